@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python code on the CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python tests/golden/make_golden.py
+Nothing here is imported by the product.  The reference modules are imported from where they lie;
+missing third-party imports of the reference (trimesh, open3d, ...) are stubbed in sys.modules, numpy.math
+is aliased to math (removed in numpy 2) and the reference's CUDA extension modules are resolved to the
+prebuilt oracle/_ref/*.so (import only -- no GPU is needed, no kernel is launched).
+
+Outputs (all float32, seeded):
+  ide.npz           IntegratedDirEncoder (ide_encoder/ide_encoder.py) for deg_view 4 and 5
+  demo_sphere.npz   BASELINE config 1: demo.ipynb cell 17 on 64x64 rays with the shipped demo/ weights
+  field_glue.npz    NeRFNetwork.forward_sigma / get_color_mlp_extra_params / forward_color of the reference
+                    (nerf/network.py, nerf/renderer.py) under configs/scenes/toaster.ini (env width 64 to keep
+                    the fixture small), driven through a differentiable stand-in position encoder
+  relight_mlps.npz  shipped ckpts/rendering_mlps.pth + ckpts/env_ckpts/env_net_3.pth, plus reference
+                    forward_color outputs on seeded inputs at those dims (env 160 / IDE deg 4)
+"""
+import argparse
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ENVIDR_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        sub = _Stub(self.__name__ + "." + name)
+        setattr(self, name, sub)
+        return sub
+
+    def __call__(self, *a, **k):
+        return _Stub("call")
+
+
+def install_shims():
+    np.math = math
+    for name in ["trimesh", "imageio", "tensorboardX", "mcubes", "lpips", "open3d", "open3d.visualization",
+                 "open3d.visualization.rendering", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "dearpygui",
+                 "dearpygui.dearpygui", "torch_ema"]:
+        sys.modules.setdefault(name, _Stub(name))
+    sys.modules["torch_ema"].ExponentialMovingAverage = object
+
+    # configargparse: argparse + "--config file.ini" (key = value lines; [a, b] lists)
+    cap = types.ModuleType("configargparse")
+
+    class ArgumentParser(argparse.ArgumentParser):
+        def add_argument(self, *a, **k):
+            self._cfg = getattr(self, "_cfg", None)
+            if k.pop("is_config_file", False):
+                self._cfg_dest = a[0].lstrip("-")
+            return super().add_argument(*a, **k)
+
+        def parse_args(self, args=None, namespace=None):
+            args = list(sys.argv[1:] if args is None else args)
+            extra = []
+            if "--config" in args:
+                path = args[args.index("--config") + 1]
+                for line in open(path):
+                    line = line.split("#")[0].split(";")[0].strip()
+                    if not line or "=" not in line:
+                        continue
+                    key, val = [s.strip() for s in line.split("=", 1)]
+                    if val in ("True", "true"):
+                        extra.append("--" + key)
+                    elif val in ("False", "false"):
+                        continue
+                    elif val.startswith("["):
+                        extra += ["--" + key] + [v.strip() for v in val.strip("[]").split(",") if v.strip()]
+                    else:
+                        extra += ["--" + key, val]
+            return super().parse_args(extra + args, namespace)
+
+    cap.ArgumentParser = ArgumentParser
+    sys.modules["configargparse"] = cap
+
+    # the reference's CUDA extension modules -> prebuilt oracle/_ref/*.so (import only)
+    sys.path.insert(0, os.path.join(REPO, "oracle", "_ref"))
+    sys.path.insert(0, REF)
+    for pkg in ["raymarching", "hashencoder", "gridencoder", "freqencoder", "shencoder"]:
+        ext = types.ModuleType(f"{pkg}._ext")
+        try:
+            mod = __import__(f"_{pkg}")
+        except Exception:
+            mod = _Stub(f"_{pkg}")
+        setattr(ext, f"_{pkg}", mod)
+        sys.modules[f"{pkg}._ext"] = ext
+        sys.modules[f"{pkg}._ext._{pkg}"] = mod
+
+
+def sd_to_np(sd, prefix=""):
+    return {prefix + k.replace(".", "_"): v.detach().cpu().numpy().astype(np.float32) for k, v in sd.items()}
+
+
+def gen_ide():
+    from ide_encoder.ide_encoder import IntegratedDirEncoder
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    for deg in (4, 5):
+        enc = IntegratedDirEncoder(deg_view=deg)
+        d = torch.nn.functional.normalize(torch.randn(64, 3, generator=g), dim=-1)
+        d[0] = torch.tensor([0.0, 0.0, 1.0]); d[1] = torch.tensor([0.0, 0.0, -1.0]); d[2] = torch.tensor([1.0, 0.0, 0.0])
+        d[3] = torch.tensor([0.0, 0.0, 0.6])       # un-normalised, x == y == 0 (ide_encoder.py:114-115)
+        rough = torch.rand(64, 1, generator=g) * 0.3
+        rough[4] = 0.0
+        out[f"dirs{deg}"] = d.numpy()
+        out[f"rough{deg}"] = rough.numpy()
+        out[f"ide{deg}_var"] = enc(d, rough).numpy()
+        out[f"ide{deg}_const"] = enc(d, 0.64).numpy()
+        out[f"mat{deg}"] = enc.mat.numpy(); out[f"ml{deg}"] = enc.ml_array.numpy(); out[f"sigma{deg}"] = enc.sigma.numpy()
+    np.savez_compressed(os.path.join(HERE, "ide.npz"), **out)
+    print("ide.npz", {k: v.shape for k, v in out.items()})
+
+
+def gen_demo():
+    """demo.ipynb cells 3-17 (the reference's CPU-runnable path), W=H=64."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from ide_encoder.ide_encoder import IntegratedDirEncoder
+
+    def get_net(i, o, h, n):
+        net = []
+        for _ in range(n - 1):
+            net += [nn.Linear(i, h), nn.ReLU(inplace=True)]
+            i = h
+        net.append(nn.Linear(i, o))
+        return nn.Sequential(*net)
+
+    sdf_net, env_net = get_net(37, 14, 64, 3), get_net(38, 12, 160, 4)
+    diffuse_net, specular_net = get_net(24, 3, 32, 2), get_net(28, 3, 64, 3)
+    ld = lambda p: torch.load(os.path.join(REF, p), map_location="cpu")
+    sdf_net.load_state_dict(ld("demo/sdf_net.pth")); diffuse_net.load_state_dict(ld("demo/diffuse_net.pth"))
+    specular_net.load_state_dict(ld("demo/specular_net.pth")); env_net.load_state_dict(ld("demo/envs/env_net_2.pth"))
+    xyz_encoding = torch.from_numpy(np.loadtxt(os.path.join(REF, "demo/xyz_encoding.txt"))).float()
+    encoder_dir = IntegratedDirEncoder(deg_view=4)
+
+    W = H = 64
+    theta, phi, radius = 123.0, 0.0, 4.0
+    roughness, metallic, base_color = 0.0, 0.2, [20 / 255., 70 / 255., 160 / 255.]
+    cam = 0.6194058656692505
+    focal = W / (2 * np.tan(cam / 2))
+    trans_t = lambda t: np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, t], [0, 0, 0, 1]])
+    rot_phi = lambda p: np.array([[1, 0, 0, 0], [0, np.cos(p), -np.sin(p), 0], [0, np.sin(p), np.cos(p), 0], [0, 0, 0, 1]])
+    rot_theta = lambda t: np.array([[np.cos(t), 0, -np.sin(t), 0], [0, 1, 0, 0], [np.sin(t), 0, np.cos(t), 0], [0, 0, 0, 1]])
+    c2w = trans_t(radius); c2w = rot_phi(-phi / 180. * np.pi) @ c2w; c2w = rot_theta(theta / 180. * np.pi) @ c2w
+    c2w = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ c2w
+    p = c2w
+    pose = np.array([[p[1, 0], -p[1, 1], -p[1, 2], p[1, 3]], [p[2, 0], -p[2, 1], -p[2, 2], p[2, 3]],
+                     [p[0, 0], -p[0, 1], -p[0, 2], p[0, 3]], [0, 0, 0, 1]], dtype=np.float32)
+    pose = torch.from_numpy(pose)[None]
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i = i.t().reshape(1, H * W) + 0.5; j = j.t().reshape(1, H * W) + 0.5
+    zs = torch.ones_like(i)
+    dirs = torch.stack(((i - W / 2) / focal * zs, (j - H / 2) / focal * zs, zs), -1)
+    dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+    rays_d = (dirs @ pose[:, :3, :3].transpose(-1, -2)).view(-1, 3)
+    rays_o = pose[..., :3, 3][..., None, :].expand(1, H * W, 3).reshape(-1, 3)
+    dot = torch.bmm(rays_d.view(-1, 1, 3), rays_o.view(-1, 3, 1)).squeeze(-1)
+    nabla = dot ** 2 - (rays_o.norm(2, 1, keepdim=True) ** 2 - 1.0)
+    near = -dot - torch.sqrt(nabla.clamp_min(0.0))
+    mask = (nabla >= -1e-4)[..., 0]
+    d = rays_d[mask]; xyz = rays_o[mask] + d * near[mask]; normals = xyz
+    with torch.no_grad():
+        h = torch.cat([xyz_encoding, torch.tensor([roughness, metallic, *base_color])])[None]
+        h = sdf_net(h)
+        geo = F.normalize(h[..., 1:13], dim=-1).repeat(xyz.shape[0], 1)
+        kappa_inv = 1.0 * F.softplus(h[..., -1] - 1)[0]
+        n_enc = encoder_dir(normals, 0.64)
+        w_o = -d
+        w_r = 2 * torch.sum(w_o * normals, -1, keepdim=True) * normals - w_o
+        w_r_enc = encoder_dir(w_r, kappa_inv)
+        n_dot_v = torch.sum(normals * w_o, -1, keepdim=True)
+        f_n = F.normalize(env_net(n_enc), dim=-1)
+        c_d = diffuse_net(torch.cat([geo, f_n], -1)).sigmoid()
+        f_r = F.normalize(env_net(w_r_enc), dim=-1)
+        c_s = specular_net(torch.cat([geo, normals, f_r, n_dot_v], -1)).sigmoid()
+    out = dict(rays_o=rays_o.numpy(), rays_d=rays_d.numpy(), mask=mask.numpy(), xyz=xyz.numpy(), dirs=d.numpy(),
+               sdf_out=h.numpy(), geo=geo[0].numpy(), kappa_inv=np.float32(kappa_inv.item()),
+               diffuse=c_d.numpy(), specular=c_s.numpy(), xyz_encoding=xyz_encoding.numpy(),
+               material=np.array([roughness, metallic, *base_color], np.float32))
+    out.update(sd_to_np(sdf_net.state_dict(), "sdf_")); out.update(sd_to_np(env_net.state_dict(), "env_"))
+    out.update(sd_to_np(diffuse_net.state_dict(), "diffuse_")); out.update(sd_to_np(specular_net.state_dict(), "specular_"))
+    np.savez_compressed(os.path.join(HERE, "demo_sphere.npz"), **out)
+    print("demo_sphere.npz: hit rays", int(mask.sum()), "of", H * W)
+
+
+class StandInEncoder(torch.nn.Module):
+    """Differentiable CPU stand-in for the (CUDA-only) hash encoder: enc = sin(xyz @ A + b)."""
+    def __init__(self, A, b):
+        super().__init__()
+        self.A, self.b = A, b
+
+    def forward(self, xyz, bound=1):
+        return torch.sin(xyz @ self.A + self.b)
+
+
+def build_model(extra_args):
+    from nerf.options import config_parser
+    argv = sys.argv
+    sys.argv = ["x", "--config", os.path.join(REF, "configs/scenes/toaster.ini")] + extra_args
+    opt = config_parser()
+    sys.argv = argv
+    opt.cuda_ray = False                    # no density-grid buffers needed for the per-sample field
+    from nerf.network import NeRFNetwork
+    torch.manual_seed(0)
+    model = NeRFNetwork(encoding="hashgrid", encoding_dir=opt.encoding_dir, bound=opt.bound, cuda_ray=False,
+                        density_scale=1, min_near=opt.min_near, density_thresh=opt.density_thresh, bg_radius=opt.bg_radius,
+                        use_sdf=opt.use_sdf, hidden_dim=opt.hidden_dim, num_layers=opt.num_layers,
+                        num_layers_color=opt.num_layers_color, hidden_dim_color=opt.hidden_dim_color,
+                        num_layers_bg=opt.num_layers_bg, num_levels=opt.num_levels, geo_feat_dim=opt.geo_feat_dim,
+                        opt=opt, env_opt=None)
+    return model, opt
+
+
+def run_field(model, opt, xyz, dirs, r_images=None, env_rot=None):
+    xyz = xyz.clone().requires_grad_(True)
+    sdfs, sigmas, geo, normals, _ = model.forward_sigma(xyz, use_sdf_sigma_grad=True, dirs=dirs, dists=None)
+    roughness = model.roughness
+    n_enc, w_r_enc, n_dot, n_env_enc = model.get_color_mlp_extra_params(normals, dirs, roughness, env_rot)
+    rgb = model.forward_color(geo, dirs, n_enc, w_r_enc, n_dot, True, n_env_enc=n_env_enc, r_images=r_images, roughness=roughness)
+    f = lambda t: t.detach().numpy().astype(np.float32)
+    blend = getattr(model, "blend_weight", None)
+    return dict(sdf=f(sdfs), sigma=f(sigmas), geo=f(geo), normal=f(normals), roughness=f(roughness), rgb=f(rgb),
+                c_diffuse=f(model.c_diffuse), c_specular=f(model.c_specular), w_r_enc=f(w_r_enc), n_env_enc=f(n_env_enc),
+                n_dot=f(n_dot), blend=f(blend) if blend is not None else np.zeros(0, np.float32))
+
+
+def model_weights(model):
+    out = {}
+    for name in ["sdf_net", "env_net", "diffuse_net", "color_net", "renv_net"]:
+        net = getattr(model, name, None)
+        if net is None:
+            continue
+        for i, lin in enumerate(net):
+            out[f"{name}_{i}_weight"] = lin.weight.detach().numpy().astype(np.float32)
+            out[f"{name}_{i}_bias"] = lin.bias.detach().numpy().astype(np.float32)
+    out["beta"] = np.float32(model.sdf_density.beta.item())
+    return out
+
+
+def gen_field_glue():
+    model, opt = build_model(["--hidden_dim_env", "64"])
+    g = torch.Generator().manual_seed(1)
+    M = 96
+    A = torch.randn(3, model.in_dim, generator=g) * 1.5
+    b = torch.rand(model.in_dim, generator=g) * 6.28
+    model.encoder = StandInEncoder(A, b)
+    # xavier init gives near-zero SDF head; scale it so sigma spans both signs of the Laplace CDF
+    with torch.no_grad():
+        model.sdf_net[-1].weight[0] *= 0.2
+        model.sdf_density.beta.fill_(0.05)
+    xyz = torch.rand(M, 3, generator=g) * 1.6 - 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    r_images = torch.rand(1, M, 4, generator=g)
+    r_images[0, ::3, 3] = 0.95 + 0.05 * r_images[0, ::3, 3]          # some visible reflections (vis > 0.9)
+    out = dict(A=A.numpy(), b=b.numpy(), xyz=xyz.numpy(), dirs=dirs.numpy(), r_images=r_images[0].numpy())
+    out.update(model_weights(model))
+    for tag, kw in [("plain", {}), ("rot", dict(env_rot=0.7)), ("renv", dict(r_images=r_images[0]))]:
+        # the renv branch indexes r_images[renv_mask] on the sample axis -> pass [M,4]
+        res = run_field(model, opt, xyz, dirs, **kw)
+        out.update({f"{tag}_{k}": v for k, v in res.items()})
+    out["opt_ide_degree"] = np.int32(opt.sh_degree)
+    out["opt_roughness_act_scale"] = np.float32(opt.roughness_act_scale)
+    out["opt_indir_roughness_thresh"] = np.float32(opt.indir_roughness_thresh)
+    out["opt_learn_indir_blend"] = np.int32(opt.learn_indir_blend)
+    out["opt_beta_min"] = np.float32(opt.beta_min); out["opt_beta_max"] = np.float32(opt.beta_max)
+    np.savez_compressed(os.path.join(HERE, "field_glue.npz"), **out)
+    print("field_glue.npz: renv-masked samples",
+          int(((out["renv_roughness"][:, 0] < 0.1) & (out["r_images"][:, 3] > 0.9)).sum()), "of", M)
+
+
+def gen_relight():
+    model, opt = build_model(["--hidden_dim_env", "160", "--sh_degree", "4"])
+    sd = torch.load(os.path.join(REF, "ckpts/rendering_mlps.pth"), map_location="cpu")["model"]
+    env = torch.load(os.path.join(REF, "ckpts/env_ckpts/env_net_3.pth"), map_location="cpu")["model"]
+    # shipped env checkpoints spell keys 'env_net0.weight' (nerf/sph_loader.py:372) -> 'env_net.0.weight'
+    env = {k.replace("env_net", "env_net."): v for k, v in env.items()}
+    missing = model.load_state_dict({**sd, **env}, strict=False)
+    assert not [k for k in missing.unexpected_keys], missing.unexpected_keys
+    g = torch.Generator().manual_seed(2)
+    M = 96
+    A = torch.randn(3, model.in_dim, generator=g) * 1.5
+    b = torch.rand(model.in_dim, generator=g) * 6.28
+    model.encoder = StandInEncoder(A, b)
+    with torch.no_grad():
+        model.sdf_net[-1].weight[0] *= 0.2
+        model.sdf_density.beta.fill_(0.05)
+    xyz = torch.rand(M, 3, generator=g) * 1.6 - 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    out = dict(A=A.numpy(), b=b.numpy(), xyz=xyz.numpy(), dirs=dirs.numpy())
+    out.update(model_weights(model))
+    res = run_field(model, opt, xyz, dirs)
+    out.update({f"plain_{k}": v for k, v in res.items()})
+    out["opt_ide_degree"] = np.int32(4)
+    np.savez_compressed(os.path.join(HERE, "relight_mlps.npz"), **out)
+    print("relight_mlps.npz written")
+
+
+if __name__ == "__main__":
+    install_shims()
+    torch.set_num_threads(1)
+    gen_ide()
+    gen_demo()
+    gen_field_glue()
+    gen_relight()

@@ -1,0 +1,110 @@
+"""Pin the torch layer of the oracle against golden vectors produced by the reference's own Python
+code (tests/golden/make_golden.py: ide_encoder.py, demo.ipynb path, nerf/network.py + nerf/renderer.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+
+def _layers(z, prefix, idxs):
+    return [(z[f"{prefix}_{i}_weight"], z[f"{prefix}_{i}_bias"]) for i in idxs]
+
+
+def _P_from_glue(z, deg):
+    n = lambda name: sorted({int(k.split("_")[2]) for k in z.files if k.startswith(name + "_")})
+    P = dict(bound=1.0, geo_feat_dim=12, roughness_act_scale=0.2, roughness_bias=-1.0, roughness_scale=1.0,
+             beta=float(z["beta"]), beta_min=float(z["opt_beta_min"]) if "opt_beta_min" in z.files else 0.0005,
+             beta_max=float(z["opt_beta_max"]) if "opt_beta_max" in z.files else 1.0,
+             ide_degree=deg, diffuse_kappa_inv=0.64, light_intensity_scale=1.0, intensity_scale=1.0,
+             indir_roughness_thresh=0.1, learn_indir_blend=True,
+             sdf=_layers(z, "sdf_net", n("sdf_net")), env=_layers(z, "env_net", n("env_net")),
+             diffuse=_layers(z, "diffuse_net", n("diffuse_net")), color=_layers(z, "color_net", n("color_net")),
+             renv=_layers(z, "renv_net", n("renv_net")) if any(k.startswith("renv_net") for k in z.files) else None)
+    return P
+
+
+def _standin(z):
+    xyz = torch.from_numpy(z["xyz"]).double()
+    A, b = torch.from_numpy(z["A"]).double(), torch.from_numpy(z["b"]).double()
+    ph = xyz @ A + b
+    enc = torch.sin(ph)
+    jac = torch.cos(ph)[:, :, None] * A.T[None]          # [M,F,3]
+    return enc.numpy(), jac.numpy()
+
+
+@pytest.mark.parametrize("deg", [4, 5])
+def test_ide_matches_reference(golden_dir, deg):
+    z = np.load(os.path.join(golden_dir, "ide.npz"))
+    ml, mat, sigma = O.ide_tables(deg)
+    np.testing.assert_array_equal(mat, z[f"mat{deg}"])
+    np.testing.assert_array_equal(ml.astype(np.float32), z[f"ml{deg}"])
+    np.testing.assert_array_equal(sigma, z[f"sigma{deg}"])
+    d = torch.from_numpy(z[f"dirs{deg}"])
+    l = np.concatenate([z[f"ml{deg}"][1]] * 2)
+    # fp32 restatement (what the reference computes): the l=16 band cancels catastrophically in the
+    # power basis, so even two fp32 evaluations of the same formula differ by ~1e-4 there.
+    atol32 = np.where(l >= 16, 2e-4, 5e-6)[None]
+    atol64 = np.where(l >= 16, 1e-3, 5e-6)[None]
+    for rough, key in ((torch.from_numpy(z[f"rough{deg}"]), "var"), (0.64, "const")):
+        ref = z[f"ide{deg}_{key}"]
+        got = O.ide_encode(d.float(), rough, deg).numpy()
+        assert (np.abs(got - ref) <= atol32 + 1e-5 * np.abs(ref)).all()
+        r64 = rough.double() if torch.is_tensor(rough) else rough
+        got = O.ide_encode(d.double(), r64, deg).float().numpy()
+        assert (np.abs(got - ref) <= atol64 + 1e-5 * np.abs(ref)).all()
+    assert got.shape[1] == (2 ** deg - 1 + deg) * 2
+
+
+@pytest.mark.parametrize("tag", ["plain", "rot", "renv"])
+def test_field_glue_matches_reference_network(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, "field_glue.npz"))
+    P = _P_from_glue(z, int(z["opt_ide_degree"]))
+    kw = {}
+    if tag == "rot":
+        kw["env_rot_radian"] = 0.7
+    if tag == "renv":
+        kw["r_images"] = z["r_images"]
+    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z), **kw)
+    tol = dict(atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(out["sdf"], z[f"{tag}_sdf"], **tol)
+    np.testing.assert_allclose(out["sigma"], z[f"{tag}_sigma"], atol=1e-4, rtol=2e-4)
+    np.testing.assert_allclose(out["geo_feat"], z[f"{tag}_geo"], **tol)
+    np.testing.assert_allclose(out["normal"], z[f"{tag}_normal"], **tol)
+    np.testing.assert_allclose(out["roughness"], z[f"{tag}_roughness"], **tol)
+    # IDE l=16 band: fp32 cancellation noise of the reference formula itself (see test_ide_matches_reference)
+    np.testing.assert_allclose(out["w_r_enc"], z[f"{tag}_w_r_enc"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(out["n_env_enc"], z[f"{tag}_n_env_enc"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(out["c_diffuse"], z[f"{tag}_c_diffuse"], **tol)
+    np.testing.assert_allclose(out["c_specular"], z[f"{tag}_c_specular"], **tol)
+    np.testing.assert_allclose(out["rgb"], z[f"{tag}_rgb"], **tol)
+
+
+def test_field_relight_dims(golden_dir):
+    z = np.load(os.path.join(golden_dir, "relight_mlps.npz"))
+    P = _P_from_glue(z, 4)
+    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z))
+    np.testing.assert_allclose(out["rgb"], z["plain_rgb"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(out["normal"], z["plain_normal"], atol=3e-5, rtol=1e-4)
+
+
+def test_demo_sphere_config1(golden_dir):
+    """BASELINE config 1 (demo.ipynb): IDE x2 + env_net x2 + diffuse + specular on the sphere hits."""
+    z = np.load(os.path.join(golden_dir, "demo_sphere.npz"))
+    env = [(z[f"env_{i}_weight"], z[f"env_{i}_bias"]) for i in (0, 2, 4, 6)]
+    dif = [(z[f"diffuse_{i}_weight"], z[f"diffuse_{i}_bias"]) for i in (0, 2)]
+    spe = [(z[f"specular_{i}_weight"], z[f"specular_{i}_bias"]) for i in (0, 2, 4)]
+    n = torch.from_numpy(z["xyz"]).double()
+    d = torch.from_numpy(z["dirs"]).double()
+    geo = torch.from_numpy(z["geo"]).double().expand(n.shape[0], -1)
+    w_o = -d
+    ndv = (n * w_o).sum(-1, keepdim=True)
+    w_r = 2 * ndv * n - w_o
+    f_n = O._unit(O._mlp(O.ide_encode(n, 0.64, 4), env), 1e-12)
+    f_r = O._unit(O._mlp(O.ide_encode(w_r, float(z["kappa_inv"]), 4), env), 1e-12)
+    c_d = torch.sigmoid(O._mlp(torch.cat([geo, f_n], -1), dif)).float().numpy()
+    c_s = torch.sigmoid(O._mlp(torch.cat([geo, n, f_r, ndv], -1), spe)).float().numpy()
+    np.testing.assert_allclose(c_d, z["diffuse"], atol=2e-5)
+    np.testing.assert_allclose(c_s, z["specular"], atol=2e-5)
