@@ -1,0 +1,425 @@
+// render.cu -- fused inference render loop for sm_100a.
+//
+// Replaces the host-driven while-loop of the reference (nerf/render_func/cuda_ray.py:238-359: per
+// iteration march_rays -> forward_sigma -> get_color_mlp_extra_params -> forward_color -> up to four
+// composite_rays launches -> boolean-mask compaction with a device->host sync) by a device-driven
+// wavefront: per iteration THREE launches (march+compact, fused field, composite+compact+advance), no
+// host synchronisation, no zero-padded sample slots, and the alive list / step schedule kept on the device.
+//
+// The reference's schedule is preserved exactly: n_step = max(min(N / n_alive, 8), 1) samples per alive ray
+// and iteration, rays_t re-synchronised from the accumulated deltas at iteration boundaries, a ray dies when
+// it produced fewer than n_step samples or when the transmittance it had before its last sample is below
+// T_thresh (raymarching/src/raymarching.cu:996-1039).  Sample positions are therefore bit-identical to the
+// reference loop; only the placement of samples in the batch differs (compact, warp-aggregated allocation).
+#include "common.cuh"
+
+namespace envidr {
+
+int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
+                         const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st);
+
+constexpr int kMarchBlock = 128;
+constexpr int kMaxNStep = 8;
+
+struct Counters {
+    uint32_t n_alive;        // alive rays entering the current iteration
+    uint32_t n_alive_next;   // filled by the compositor
+    uint32_t M;              // samples produced by the current march
+    uint32_t n_step;
+    uint32_t step_total;     // sum of n_step so far (the reference's `step`)
+    uint32_t iters;
+    uint32_t total_samples_lo, total_samples_hi;
+    uint32_t done_blocks;    // ticket for the last-block advance
+    uint32_t pad[7];
+};
+
+struct RenderBuffers {
+    float *nears, *fars, *rays_t;
+    int32_t* alive[2];
+    int2* slot;              // (offset, count) per alive slot
+    float *s_xyz, *s_dir, *s_delta, *s_rimg;
+    float *s_sigma, *s_rgb, *s_normal, *s_cd, *s_cs, *s_rough;
+    Counters* ctr;
+};
+
+struct RenderOutDev {
+    float *image, *depth, *weights_sum, *normal_image, *diffuse_image, *specular_image, *roughness_image;
+};
+
+__global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N,
+                                                    float min_near, float a0, float a1, float a2, float a3, float a4, float a5,
+                                                    RenderBuffers B, RenderOutDev O) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) {
+        Counters c{};
+        c.n_alive = N; c.n_step = 1;
+        *B.ctr = c;
+    }
+    if (n >= N) return;
+    // slab test (same arithmetic as k_near_far / reference raymarching.cu:91-145)
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    const float rdx = 1 / rays_d[3 * n], rdy = 1 / rays_d[3 * n + 1], rdz = 1 / rays_d[3 * n + 2];
+    float lo = (a0 - ox) * rdx, hi = (a3 - ox) * rdx;
+    if (lo > hi) { float s = lo; lo = hi; hi = s; }
+    float lo2 = (a1 - oy) * rdy, hi2 = (a4 - oy) * rdy;
+    if (lo2 > hi2) { float s = lo2; lo2 = hi2; hi2 = s; }
+    bool miss = (lo > hi2) || (lo2 > hi);
+    if (!miss) {
+        if (lo2 > lo) lo = lo2;
+        if (hi2 < hi) hi = hi2;
+        lo2 = (a2 - oz) * rdz; hi2 = (a5 - oz) * rdz;
+        if (lo2 > hi2) { float s = lo2; lo2 = hi2; hi2 = s; }
+        miss = (lo > hi2) || (lo2 > hi);
+        if (!miss) {
+            if (lo2 > lo) lo = lo2;
+            if (hi2 < hi) hi = hi2;
+            if (lo < min_near) lo = min_near;
+        }
+    }
+    const float near = miss ? 3.402823466e+38f : lo, far = miss ? 3.402823466e+38f : hi;
+    B.nears[n] = near; B.fars[n] = far; B.rays_t[n] = near;
+    B.alive[0][n] = (int32_t)n;
+    O.weights_sum[n] = 0; O.depth[n] = 0;
+    O.image[3 * n] = 0; O.image[3 * n + 1] = 0; O.image[3 * n + 2] = 0;
+    if (O.normal_image) { O.normal_image[3 * n] = 0; O.normal_image[3 * n + 1] = 0; O.normal_image[3 * n + 2] = 0; }
+    if (O.diffuse_image) { O.diffuse_image[3 * n] = 0; O.diffuse_image[3 * n + 1] = 0; O.diffuse_image[3 * n + 2] = 0; }
+    if (O.specular_image) { O.specular_image[3 * n] = 0; O.specular_image[3 * n + 1] = 0; O.specular_image[3 * n + 2] = 0; }
+    if (O.roughness_image) O.roughness_image[n] = 0;
+}
+
+// march n_step samples for every alive ray and append them compactly to the sample batch
+__global__ void __launch_bounds__(kMarchBlock) k_march_compact(
+        const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ r_images,
+        const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+        const float* __restrict__ noises, RenderBuffers B) {
+    __shared__ float stage[kMarchBlock][kMaxNStep][5];
+    Counters* ctr = B.ctr;
+    const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
+    if (n_alive == 0 || ctr->step_total >= max_steps) return;
+    const int32_t* __restrict__ alive = B.alive[ctr->iters & 1];
+    const bool first = ctr->iters == 0;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * kMarchBlock; base < n_alive; base += gridDim.x * kMarchBlock) {
+        const uint32_t n = base + threadIdx.x;
+        uint32_t count = 0;
+        int index = -1;
+        Dda s;
+        if (n < n_alive) {
+            index = alive[n];
+            s.init(rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H, grid);
+            const float far = B.fars[index];
+            float t = B.rays_t[index];
+            float last_t = t;
+            const float noise = (first && noises) ? noises[n] : 0.0f;
+            t += s.step_size(t) * noise;
+            float x, y, z, dt;
+            while (t < far && count < n_step) {
+                if (s.probe(t, x, y, z, dt)) {
+                    float* q = stage[threadIdx.x][count];
+                    q[0] = x; q[1] = y; q[2] = z;
+                    t += dt;
+                    q[3] = dt; q[4] = t - last_t;
+                    last_t = t;
+                    count++;
+                }
+            }
+        }
+        // warp-aggregated allocation of `count` consecutive sample slots
+        uint32_t incl = count;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t wbase = 0;
+        if (lane == 0 && total) wbase = atomicAdd(&ctr->M, total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        const uint32_t off = wbase + incl - count;
+        if (n < n_alive) {
+            B.slot[n] = make_int2((int)off, (int)count);
+            float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r_images && count) ri = *reinterpret_cast<const float4*>(r_images + 4 * (size_t)index);
+            for (uint32_t j = 0; j < count; j++) {
+                const float* q = stage[threadIdx.x][j];
+                const size_t m = (size_t)off + j;
+                B.s_xyz[3 * m] = q[0]; B.s_xyz[3 * m + 1] = q[1]; B.s_xyz[3 * m + 2] = q[2];
+                B.s_dir[3 * m] = s.dx; B.s_dir[3 * m + 1] = s.dy; B.s_dir[3 * m + 2] = s.dz;
+                *reinterpret_cast<float2*>(B.s_delta + 2 * m) = make_float2(q[3], q[4]);
+                if (r_images) *reinterpret_cast<float4*>(B.s_rimg + 4 * m) = ri;
+            }
+        }
+    }
+}
+
+// composite this iteration's samples into the per-ray accumulators, decide which rays stay alive, compact
+// the alive list, and (last block) advance the iteration counters.
+__global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, float T_thresh, uint32_t max_steps, int geometry_only,
+                                                                  int input_alpha, RenderBuffers B, RenderOutDev O) {
+    Counters* ctr = B.ctr;
+    const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
+    const bool active = !(n_alive == 0 || ctr->step_total >= max_steps);
+    const uint32_t lane = threadIdx.x & 31;
+    if (active) {
+        const int32_t* __restrict__ alive = B.alive[ctr->iters & 1];
+        int32_t* __restrict__ alive_next = B.alive[(ctr->iters & 1) ^ 1];
+        for (uint32_t base = blockIdx.x * kMarchBlock; base < n_alive; base += gridDim.x * kMarchBlock) {
+            const uint32_t n = base + threadIdx.x;
+            bool keep = false;
+            int index = -1;
+            if (n < n_alive) {
+                index = alive[n];
+                const int2 sl = B.slot[n];
+                const uint32_t cnt = (uint32_t)sl.y;
+                float t = B.rays_t[index];
+                float ws = O.weights_sum[index], d = O.depth[index];
+                // every accumulator starts from its stored value and adds sample by sample, exactly like one
+                // composite_rays call per image in the reference (cuda_ray.py:318-342)
+                float acc[3], nrm[3] = {0, 0, 0}, cd[3] = {0, 0, 0}, cs[3] = {0, 0, 0}, rgh = 0;
+                float* main_img = geometry_only ? O.normal_image : O.image;
+                acc[0] = main_img[3 * index]; acc[1] = main_img[3 * index + 1]; acc[2] = main_img[3 * index + 2];
+                const bool want_n = !geometry_only && O.normal_image;
+                if (want_n) { const float* q = O.normal_image + 3 * index; nrm[0] = q[0]; nrm[1] = q[1]; nrm[2] = q[2]; }
+                if (O.diffuse_image) { const float* q = O.diffuse_image + 3 * index; cd[0] = q[0]; cd[1] = q[1]; cd[2] = q[2]; }
+                if (O.specular_image) { const float* q = O.specular_image + 3 * index; cs[0] = q[0]; cs[1] = q[1]; cs[2] = q[2]; }
+                if (O.roughness_image) rgh = O.roughness_image[index];
+                uint32_t step = 0;
+                while (step < n_step) {
+                    if (step >= cnt) break;                       // zero-delta slot in the reference layout
+                    const size_t m = (size_t)sl.x + step;
+                    const float2 dl = *reinterpret_cast<const float2*>(B.s_delta + 2 * m);
+                    const float sg = B.s_sigma[m];
+                    const float alpha = input_alpha ? 0.0f + sg : 1.0f - __expf(-sg * dl.x);
+                    const float T = 1 - ws;
+                    const float w = alpha * T;
+                    ws += w;
+                    t = t + dl.y;
+                    d += w * t;
+                    const float* c = (geometry_only ? B.s_normal : B.s_rgb) + 3 * m;
+                    acc[0] += w * c[0]; acc[1] += w * c[1]; acc[2] += w * c[2];
+                    if (want_n) { const float* q = B.s_normal + 3 * m; nrm[0] += w * q[0]; nrm[1] += w * q[1]; nrm[2] += w * q[2]; }
+                    if (O.diffuse_image) { const float* q = B.s_cd + 3 * m; cd[0] += w * q[0]; cd[1] += w * q[1]; cd[2] += w * q[2]; }
+                    if (O.specular_image) { const float* q = B.s_cs + 3 * m; cs[0] += w * q[0]; cs[1] += w * q[1]; cs[2] += w * q[2]; }
+                    if (O.roughness_image) rgh += w * B.s_rough[m];
+                    if (T < T_thresh) break;
+                    step++;
+                }
+                keep = !(step < n_step);
+                if (keep) B.rays_t[index] = t;
+                O.weights_sum[index] = ws; O.depth[index] = d;
+                main_img[3 * index] = acc[0]; main_img[3 * index + 1] = acc[1]; main_img[3 * index + 2] = acc[2];
+                if (want_n) { float* q = O.normal_image + 3 * index; q[0] = nrm[0]; q[1] = nrm[1]; q[2] = nrm[2]; }
+                if (O.diffuse_image) { float* q = O.diffuse_image + 3 * index; q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; }
+                if (O.specular_image) { float* q = O.specular_image + 3 * index; q[0] = cs[0]; q[1] = cs[1]; q[2] = cs[2]; }
+                if (O.roughness_image) O.roughness_image[index] = rgh;
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            uint32_t wbase = 0;
+            if (lane == 0 && mask) wbase = atomicAdd(&ctr->n_alive_next, (uint32_t)__popc(mask));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (keep) alive_next[wbase + __popc(mask & ((1u << lane) - 1))] = index;
+        }
+    }
+    // last block to finish advances the iteration state
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&ctr->done_blocks, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        if (active) {
+            const uint32_t next = atomicAdd(&ctr->n_alive_next, 0u);
+            const uint32_t M = atomicAdd(&ctr->M, 0u);
+            const uint64_t tot = (((uint64_t)ctr->total_samples_hi << 32) | ctr->total_samples_lo) + M;
+            ctr->total_samples_lo = (uint32_t)tot; ctr->total_samples_hi = (uint32_t)(tot >> 32);
+            ctr->step_total += n_step;
+            ctr->iters += 1;
+            ctr->n_alive = next;
+            ctr->n_alive_next = 0;
+            ctr->M = 0;
+            uint32_t ns = next ? N / next : 1;
+            ns = ns > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : ns;
+            ctr->n_step = ns < 1 ? 1 : ns;
+        }
+        ctr->done_blocks = 0;
+    }
+}
+
+// image += (1 - ws) * bg ; normal_image <- F.normalize(normal_image, eps=1e-10)   (cuda_ray.py:348-359)
+__global__ void __launch_bounds__(256) k_render_finish(uint32_t N, float bg0, float bg1, float bg2, const float* __restrict__ bg_per_ray,
+                                                      int geometry_only, RenderOutDev O) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    if (!geometry_only) {
+        const float rem = 1 - O.weights_sum[n];
+        const float b0 = bg_per_ray ? bg_per_ray[3 * n] : bg0, b1 = bg_per_ray ? bg_per_ray[3 * n + 1] : bg1,
+                    b2 = bg_per_ray ? bg_per_ray[3 * n + 2] : bg2;
+        O.image[3 * n] += rem * b0; O.image[3 * n + 1] += rem * b1; O.image[3 * n + 2] += rem * b2;
+    }
+    if (O.normal_image) {
+        float* q = O.normal_image + 3 * n;
+        const float inv = 1.0f / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-10f);
+        q[0] *= inv; q[1] *= inv; q[2] *= inv;
+    }
+}
+
+static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+    uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, total;
+};
+static WsLayout ws_layout(uint32_t N) {
+    WsLayout L{};
+    uint64_t off = 0;
+    auto take = [&](uint64_t bytes) { const uint64_t o = off; off = align_up(off + bytes, 256); return o; };
+    const uint64_t n = N;
+    L.nears = take(4 * n); L.fars = take(4 * n); L.rays_t = take(4 * n);
+    L.alive0 = take(4 * n); L.alive1 = take(4 * n); L.slot = take(8 * n);
+    L.s_xyz = take(12 * n); L.s_dir = take(12 * n); L.s_delta = take(8 * n); L.s_rimg = take(16 * n);
+    L.s_sigma = take(4 * n); L.s_rgb = take(12 * n); L.s_normal = take(12 * n); L.s_cd = take(12 * n); L.s_cs = take(12 * n);
+    L.s_rough = take(4 * n);
+    L.ctr = take(sizeof(Counters));
+    L.total = off;
+    return L;
+}
+
+static uint32_t* g_host_flag = nullptr;     // pinned: [n_alive snapshot ring (8)] + stats[4]
+static cudaEvent_t g_events[2];
+static bool g_events_ok = false;
+
+// instrumentation (bench.py): kernel launch counter and per-launch CUDA-event timing of the field kernel
+static uint64_t g_launches = 0;
+static int g_timing = 0;
+constexpr int kMaxTimed = 4096;
+static cudaEvent_t g_tev[2 * kMaxTimed];
+static int g_tev_created = 0, g_tev_used = 0;
+
+}  // namespace envidr
+
+using namespace envidr;
+
+extern "C" {
+
+uint64_t envidr_render_workspace_bytes(uint32_t N) { return ws_layout(N).total; }
+
+int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const float* rays_o, const float* rays_d,
+                       const float* r_images, const float* noises, const float* bg_per_ray, uint32_t N,
+                       const envidr_render_opts* opts, const envidr_render_out* out, void* workspace, uint64_t workspace_bytes,
+                       envidr_stream_t stream) {
+    ENVIDR_REQUIRE(field && bitfield && rays_o && rays_d && opts && out && workspace, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(out->weights_sum && out->depth && (opts->geometry_only ? out->normal_image != nullptr : out->image != nullptr),
+                   ENVIDR_E_BADARG, "missing mandatory output buffer");
+    ENVIDR_REQUIRE(opts->cascade >= 1 && opts->cascade <= 8 && opts->grid_size >= 1 && opts->grid_size <= 1024, ENVIDR_E_UNSUPPORTED,
+                   "cascades must be 1..8, grid size <= 1024");
+    if (N == 0) return 0;
+    const WsLayout L = ws_layout(N);
+    ENVIDR_REQUIRE(workspace_bytes >= L.total, ENVIDR_E_WORKSPACE, "workspace too small (envidr_render_workspace_bytes)");
+    ENVIDR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ENVIDR_E_BADARG, "workspace must be 256-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (!g_events_ok) {
+        if (cudaHostAlloc(&g_host_flag, 64 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
+            set_error("render: pinned host allocation failed"); return (int)cudaErrorMemoryAllocation;
+        }
+        cudaEventCreateWithFlags(&g_events[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_events[1], cudaEventDisableTiming);
+        g_events_ok = true;
+    }
+    char* w = reinterpret_cast<char*>(workspace);
+    RenderBuffers B{};
+    B.nears = (float*)(w + L.nears); B.fars = (float*)(w + L.fars); B.rays_t = (float*)(w + L.rays_t);
+    B.alive[0] = (int32_t*)(w + L.alive0); B.alive[1] = (int32_t*)(w + L.alive1); B.slot = (int2*)(w + L.slot);
+    B.s_xyz = (float*)(w + L.s_xyz); B.s_dir = (float*)(w + L.s_dir); B.s_delta = (float*)(w + L.s_delta); B.s_rimg = (float*)(w + L.s_rimg);
+    B.s_sigma = (float*)(w + L.s_sigma); B.s_rgb = (float*)(w + L.s_rgb); B.s_normal = (float*)(w + L.s_normal);
+    B.s_cd = (float*)(w + L.s_cd); B.s_cs = (float*)(w + L.s_cs); B.s_rough = (float*)(w + L.s_rough);
+    B.ctr = (Counters*)(w + L.ctr);
+    RenderOutDev O{out->image, out->depth, out->weights_sum, out->normal_image, out->diffuse_image, out->specular_image,
+                   out->roughness_image};
+    if (opts->geometry_only) { O.image = out->normal_image; O.diffuse_image = nullptr; O.specular_image = nullptr; O.roughness_image = nullptr; }
+    const float* a = opts->aabb;
+    k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);
+    int rc = check_launch("render_init");
+    if (rc) return rc;
+
+    envidr_field_out fo{};
+    fo.sigma = B.s_sigma; fo.normal = B.s_normal;
+    if (!opts->geometry_only) {
+        fo.rgb = B.s_rgb;
+        if (out->diffuse_image) fo.c_diffuse = B.s_cd;
+        if (out->specular_image) fo.c_specular = B.s_cs;
+        if (out->roughness_image) fo.roughness = B.s_rough;
+    }
+    const uint32_t march_grid = min(ceil_div(N, kMarchBlock), (uint32_t)kSMs * 8);
+    const uint32_t max_iters = opts->max_steps;       // n_step >= 1 per iteration
+    const uint32_t batch = 8;
+    uint32_t it = 0, pending = 0;
+    bool done = false;
+    while (!done && it < max_iters) {
+        for (uint32_t b = 0; b < batch && it < max_iters; b++, it++) {
+            k_march_compact<<<march_grid, kMarchBlock, 0, st>>>(rays_o, rays_d, r_images, bitfield, opts->bound, opts->dt_gamma,
+                                                               opts->max_steps, opts->cascade, opts->grid_size, noises, B);
+            const bool timed = g_timing && g_tev_used < kMaxTimed;
+            if (timed) {
+                while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
+                cudaEventRecord(g_tev[2 * g_tev_used], st);
+            }
+            rc = field_forward_launch(field, B.s_xyz, B.s_dir, r_images ? B.s_rimg : nullptr, &B.ctr->M, 0,
+                                      opts->geometry_only ? 1 : 0, &fo, st);
+            if (rc) return rc;
+            if (timed) { cudaEventRecord(g_tev[2 * g_tev_used + 1], st); g_tev_used++; }
+            g_launches += 3;
+            k_composite_compact<<<march_grid, kMarchBlock, 0, st>>>(N, opts->T_thresh, opts->max_steps, opts->geometry_only,
+                                                                   opts->input_alpha, B, O);
+        }
+        rc = check_launch("render_loop");
+        if (rc) return rc;
+        // snapshot n_alive / step_total after this batch; look at the snapshot of the PREVIOUS batch so the
+        // host stays one batch ahead of the device and never stalls it
+        const uint32_t slot = pending & 1;
+        cudaMemcpyAsync(g_host_flag + 2 * slot, &B.ctr->n_alive, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(g_host_flag + 2 * slot + 1, &B.ctr->step_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(g_events[slot], st);
+        if (pending > 0) {
+            const uint32_t prev = (pending - 1) & 1;
+            cudaEventSynchronize(g_events[prev]);
+            if (g_host_flag[2 * prev] == 0 || g_host_flag[2 * prev + 1] >= opts->max_steps) done = true;
+        }
+        pending++;
+    }
+    g_launches += 2;
+    k_render_finish<<<ceil_div(N, 256), 256, 0, st>>>(N, opts->bg_color[0], opts->bg_color[1], opts->bg_color[2], bg_per_ray,
+                                                      opts->geometry_only, O);
+    cudaMemcpyAsync(g_host_flag + 8, &B.ctr->iters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(g_host_flag + 9, &B.ctr->total_samples_lo, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(g_events[0], st);
+    return check_launch("render_finish");
+}
+
+/* blocks until the last envidr_render_rays call of this process has finished; stats = {iterations, samples_lo, samples_hi, 0} */
+int envidr_render_last_stats(uint32_t stats[4]) {
+    ENVIDR_REQUIRE(stats, ENVIDR_E_BADARG, "null pointer");
+    if (!g_events_ok) { stats[0] = stats[1] = stats[2] = stats[3] = 0; return 0; }
+    cudaEventSynchronize(g_events[0]);
+    stats[0] = g_host_flag[8]; stats[1] = g_host_flag[9]; stats[2] = g_host_flag[10]; stats[3] = 0;
+    return 0;
+}
+
+/* Instrumentation for bench.py.  envidr_launch_count: kernels launched by envidr_render_rays so far in this process.
+ * envidr_render_timing(1) makes every following field-kernel launch bracketed by CUDA events on its stream;
+ * envidr_render_field_time synchronises, returns the summed duration (ms) and the number of timed launches, and resets. */
+uint64_t envidr_launch_count(void) { return g_launches; }
+int envidr_render_timing(int enable) { g_timing = enable; g_tev_used = 0; return 0; }
+int envidr_render_field_time(float* total_ms, uint32_t* launches) {
+    ENVIDR_REQUIRE(total_ms && launches, ENVIDR_E_BADARG, "null pointer");
+    float sum = 0.f;
+    for (int i = 0; i < g_tev_used; i++) {
+        cudaEventSynchronize(g_tev[2 * i + 1]);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_tev[2 * i], g_tev[2 * i + 1]) == cudaSuccess) sum += ms;
+    }
+    *total_ms = sum; *launches = (uint32_t)g_tev_used;
+    g_tev_used = 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+"""Multi-GPU rendering: rays are independent, so the path shards with NO data-path collective; the only
+exchange is the final assembly of the image (one all-gather), as SURVEY.md 8e lays out.
+
+The reference has no reachable multi-GPU path (its DDP scaffold is never activated, nerf/utils.py:360-402,
+1353-1371), so there is no reference operator to mirror here; the partitioning follows the cost structure of the
+path: pixels on the object cost 10-100x more samples than background pixels, hence rays are dealt to ranks in
+interleaved 8x8-pixel tiles, round-robin, not in contiguous row blocks.
+
+All model state (48.8 MB hash table, bit field, < 1 MB of MLP weights) is replicated on every rank.
+One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is only plumbing.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+TILE = 8
+
+
+def tile_shard_indices(H: int, W: int, rank: int, world_size: int, tile: int = TILE) -> torch.Tensor:
+    """Flat pixel indices (row-major, int64) of the rays owned by `rank`: tiles of tile x tile pixels are numbered
+    row-major and tile t belongs to rank t % world_size.  Ragged borders are handled (partial tiles)."""
+    ty = torch.arange(H) // tile
+    tx = torch.arange(W) // tile
+    tiles_x = (W + tile - 1) // tile
+    tid = ty[:, None] * tiles_x + tx[None, :]
+    return torch.nonzero((tid % world_size == rank).reshape(-1)).flatten()
+
+
+def shard_sizes(H: int, W: int, world_size: int, tile: int = TILE):
+    return [int(tile_shard_indices(H, W, r, world_size, tile).numel()) for r in range(world_size)]
+
+
+def render_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, torch.Tensor]], rays_o: torch.Tensor, rays_d: torch.Tensor,
+                   H: int, W: int, keys=("image", "depth", "weights_sum", "normal_image"), group=None) -> Dict[str, torch.Tensor]:
+    """Strong-scaling render of ONE frame: every rank renders its interleaved tiles with `render_fn(rays_o, rays_d)` and
+    one all-gather of the packed per-ray outputs ([n_r, C] fp32, C = 8 for rgb+depth+ws+normal = 32 B/ray) assembles the full
+    frame on every rank.  rays_o / rays_d are the full [H*W, 3] tensors (replicated inputs)."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    idx = tile_shard_indices(H, W, rank, ws).to(rays_o.device)
+    res = render_fn(rays_o[idx].contiguous(), rays_d[idx].contiguous())
+    cols = []
+    for k in keys:
+        v = res[k]
+        cols.append(v.reshape(v.shape[0], -1).float())
+    packed = torch.cat(cols, -1).contiguous()
+    C = packed.shape[1]
+    if ws == 1:
+        gathered = [packed]
+    else:
+        sizes = shard_sizes(H, W, ws)
+        n_max = max(sizes)
+        buf = packed.new_zeros(n_max, C)
+        buf[: packed.shape[0]] = packed
+        out = packed.new_empty(ws * n_max, C)
+        dist.all_gather_into_tensor(out, buf, group=group)           # the one collective of the path
+        gathered = [out[r * n_max: r * n_max + sizes[r]] for r in range(ws)]
+    full = packed.new_empty(H * W, C)
+    for r in range(ws):
+        full[tile_shard_indices(H, W, r, ws).to(full.device)] = gathered[r]
+    outd, c0 = {}, 0
+    for k in keys:
+        w = res[k].reshape(res[k].shape[0], -1).shape[1]
+        outd[k] = full[:, c0:c0 + w].reshape(H * W, *res[k].shape[1:])
+        c0 += w
+    return outd
+
+
+def gather_frames(frame: torch.Tensor, group=None) -> torch.Tensor:
+    """Weak-scaling sweep (one frame / light rotation per rank): all-gather the [N, C] frames -> [world, N, C]."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return frame[None]
+    ws = dist.get_world_size(group)
+    out = frame.new_empty(ws, *frame.shape)
+    dist.all_gather_into_tensor(out.view(ws * frame.shape[0], *frame.shape[1:]), frame.contiguous(), group=group)
+    return out

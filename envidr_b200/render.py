@@ -1,0 +1,254 @@
+"""Inference rendering on top of the fused CUDA loop (envidr_render_rays).
+
+Mirrors the reference entry points of this part of the hot path:
+  * run_cuda(model, rays_o, rays_d, **kwargs)   nerf/render_func/cuda_ray.py:15-364 (inference branch :238-359)
+  * NeRFRenderer.render(...)                    nerf/renderer.py:364-531 (1 pass, or the 3-pass indir_ref scheme)
+`install(render_func_module)` assigns `nerf.render_func.run_cuda = run_cuda` -- the reference looks the
+function up as a module attribute at call time (renderer.py:368-369), so main_nerf.py needs no change.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+from .field import FieldParams
+
+SQRT3 = 3 ** 0.5
+
+
+@dataclasses.dataclass
+class RenderConfig:
+    bound: float = 1.0
+    cascade: int = 1
+    grid_size: int = 128
+    min_near: float = 0.2
+    dt_gamma: float = 0.0
+    max_steps: int = 1024
+    T_thresh: float = 1e-4
+    aabb: Optional[Sequence[float]] = None
+    input_alpha: bool = False
+    # indirect-reflection passes (renderer.py:439-513)
+    indir_ref: bool = False
+    indir_max_steps: int = 1024
+    obj_aabb: Optional[Sequence[float]] = None
+
+    def aabb6(self):
+        return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3
+
+
+_workspaces: Dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(N: int, device) -> torch.Tensor:
+    key = (str(device), int(N))
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = lib().envidr_render_workspace_bytes(N)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        _workspaces.clear()          # keep one workspace alive (render sizes rarely alternate)
+        _workspaces[key] = ws
+    return ws
+
+
+def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, cfg: RenderConfig, *,
+                bg_color=1.0, r_images: Optional[torch.Tensor] = None, geometry_only: bool = False,
+                env_rot_radian: Optional[float] = None, get_normal_image: bool = True, visual_items: Sequence[str] = (),
+                perturb: bool = False, max_steps: Optional[int] = None, min_near: Optional[float] = None) -> Dict[str, torch.Tensor]:
+    """One run_cuda inference pass over N rays.  Returns image [N,3], depth [N], weights_sum [N] and
+    (optionally) normal_image / diffuse_image / specular_image / roughness_image, all on the device."""
+    if field._packed is None:
+        field.pack()
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N, dev = rays_o.shape[0], rays_o.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = _lib.RenderOut()
+    res: Dict[str, torch.Tensor] = {}
+    res["depth"] = torch.empty(N, **f32)
+    res["weights_sum"] = torch.empty(N, **f32)
+    if not geometry_only:
+        res["image"] = torch.empty(N, 3, **f32)
+    if get_normal_image or geometry_only:
+        res["normal_image"] = torch.empty(N, 3, **f32)
+    if not geometry_only:
+        if "diffuse" in visual_items:
+            res["diffuse_image"] = torch.empty(N, 3, **f32)
+        if "specular" in visual_items:
+            res["specular_image"] = torch.empty(N, 3, **f32)
+        if "roughness" in visual_items or "specular" in visual_items:
+            res["roughness_image"] = torch.empty(N, **f32)
+    for k, t in res.items():
+        setattr(out, k, t.data_ptr())
+    opts = _lib.RenderOpts()
+    opts.bound, opts.dt_gamma, opts.T_thresh = cfg.bound, cfg.dt_gamma, cfg.T_thresh
+    opts.min_near = cfg.min_near if min_near is None else min_near
+    opts.max_steps = cfg.max_steps if max_steps is None else max_steps
+    opts.cascade, opts.grid_size = cfg.cascade, cfg.grid_size
+    for i, v in enumerate(cfg.aabb6()):
+        opts.aabb[i] = float(v)
+    bg_t = None
+    if torch.is_tensor(bg_color):
+        if bg_color.numel() == 3:
+            bgc = [float(v) for v in bg_color.reshape(-1).tolist()]
+        else:
+            bg_t = bg_color.float().contiguous().view(-1, 3)
+            assert bg_t.shape[0] == N
+            bgc = [0.0, 0.0, 0.0]
+    elif isinstance(bg_color, (int, float)):
+        bgc = [float(bg_color)] * 3
+    else:
+        bgc = [float(v) for v in bg_color]
+    for i in range(3):
+        opts.bg_color[i] = bgc[i]
+    opts.geometry_only = int(geometry_only)
+    opts.input_alpha = int(cfg.input_alpha)
+    if r_images is not None:
+        r_images = r_images.float().contiguous().view(-1, 4)
+        assert r_images.shape[0] == N
+    noises = torch.rand(N, **f32) if perturb else None
+    ws = _workspace(N, dev)
+    base = ws.data_ptr()
+    aligned = (base + 255) // 256 * 256
+    f = field.cstruct(env_rot_radian)
+    check(lib().envidr_render_rays(ctypes.byref(f), ptr(bitfield), ptr(rays_o), ptr(rays_d), ptr(r_images), ptr(noises), ptr(bg_t), N,
+                                   ctypes.byref(opts), ctypes.byref(out), ctypes.c_void_p(aligned), ws.numel() - (aligned - base),
+                                   stream()), "render_rays")
+    if "roughness_image" in res:
+        res["roughness_image"] = res["roughness_image"][..., None]
+    return res
+
+
+def last_stats() -> Dict[str, int]:
+    """Blocks until the last render_rays finished; {'iterations', 'samples'} of that pass."""
+    st = (ctypes.c_uint32 * 4)()
+    check(lib().envidr_render_last_stats(st), "render_last_stats")
+    return dict(iterations=int(st[0]), samples=int(st[1]) | (int(st[2]) << 32))
+
+
+def reflect_dir(w_o: torch.Tensor, normals: torch.Tensor) -> torch.Tensor:
+    """renderer.py:20-39."""
+    return 2 * torch.sum(w_o * normals, dim=-1, keepdim=True) * normals - w_o
+
+
+def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, cfg: RenderConfig, *, bg_color=1.0,
+           get_normal_image: bool = True, env_rot_radian: Optional[float] = None, visual_items: Sequence[str] = (),
+           r_images: Optional[torch.Tensor] = None, stats: Optional[list] = None) -> Dict[str, torch.Tensor]:
+    """NeRFRenderer.render for the cuda_ray inference path (renderer.py:364-531): rays [N,3] -> dict with image,
+    depth, weights_sum, normal_image (+ visual items).  With cfg.indir_ref the three passes of renderer.py:439-513
+    are run: geometry only -> reflected secondary rays -> main pass with r_images."""
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N = rays_o.shape[0]
+    if not cfg.indir_ref:
+        results = render_rays(field, bitfield, rays_o, rays_d, cfg, bg_color=bg_color, r_images=r_images, env_rot_radian=env_rot_radian,
+                              get_normal_image=get_normal_image, visual_items=visual_items)
+        if stats is not None:
+            stats.append(last_stats())
+    else:
+        dt = 2 * SQRT3 / cfg.indir_max_steps
+        geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian)
+        if stats is not None:
+            stats.append(last_stats())
+        normals = geo["normal_image"]
+        depth = geo["depth"] - dt
+        weights_sum = geo["weights_sum"]
+        ref_mask = (depth != 0) & (weights_sum > 0.9)
+        ray_mask = (depth != 0) & (weights_sum > 0.3)
+        ref_o = rays_o + depth[:, None] * rays_d
+        ref_d = reflect_dir(-rays_d, normals)
+        if cfg.obj_aabb is not None:
+            ob = torch.tensor(cfg.obj_aabb, dtype=torch.float32, device=rays_o.device)
+            ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
+        ref = render_rays(field, bitfield, ref_o[ref_mask], ref_d[ref_mask], cfg, bg_color=0.0, env_rot_radian=env_rot_radian,
+                          get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2)
+        if stats is not None:
+            stats.append(last_stats())
+        ref_image = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)
+        ref2ray = ref_mask[ray_mask]
+        r_img = ref_image.new_zeros(ref2ray.shape[0], 4)
+        r_img[ref2ray] = ref_image
+        main = render_rays(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], cfg, bg_color=0.0, r_images=r_img,
+                           env_rot_radian=env_rot_radian, get_normal_image=get_normal_image, visual_items=visual_items)
+        if stats is not None:
+            stats.append(last_stats())
+        results = {"normal_image": normals, "depth": depth}
+        for k in ("image", "specular_image", "diffuse_image", "roughness_image"):
+            if k in main:
+                v = normals.new_zeros(N, main[k].shape[-1])
+                v[ray_mask] = main[k]
+                results[k] = v
+        ws_full = normals.new_zeros(N)
+        ws_full[ray_mask] = main["weights_sum"]
+        bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(bg_color, dtype=torch.float32, device=rays_o.device)
+        results["image"] = (torch.zeros_like(normals) + bg) * (1 - ws_full[:, None]) + results["image"]
+        results["weights_sum"] = ws_full
+    if "weights_sum" in results and get_normal_image and "normal_image" in results:
+        w = results["weights_sum"][..., None]
+        results["normal_image"] = results["normal_image"] * w + (1 - w)
+    return results
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in for the reference model
+# ---------------------------------------------------------------------------------------------
+
+_reference_run_cuda = None
+
+
+def run_cuda(model, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4,
+             get_normal_image=False, use_specular_color=True, early_stop_steps=-1, ray_depth=None, main_pass=True, r_images=None,
+             geometry_only=False, grad_ray=False, bg_sphere=True, env_rot_radian=None, **kwargs):
+    """Replacement for nerf.render_func.run_cuda.  The inference branch (cuda_ray.py:238-359) runs in the fused
+    loop; training / debug / ray_depth / background-sphere calls are forwarded to the reference implementation
+    (which then reaches our kernels through the operator-level `_backend` modules)."""
+    fused_ok = (not model.training and not model.opt.debug and ray_depth is None and not (model.bg_radius > 0 and bg_sphere)
+                and not model.opt.use_neus_sdf)
+    if not fused_ok:
+        if _reference_run_cuda is None:
+            raise _lib.EnvidrError("run_cuda: this call needs the reference training branch; call install() first")
+        return _reference_run_cuda(model, rays_o, rays_d, dt_gamma=dt_gamma, bg_color=bg_color, perturb=perturb,
+                                   force_all_rays=force_all_rays, max_steps=max_steps, T_thresh=T_thresh,
+                                   get_normal_image=get_normal_image, use_specular_color=use_specular_color,
+                                   early_stop_steps=early_stop_steps, ray_depth=ray_depth, main_pass=main_pass, r_images=r_images,
+                                   geometry_only=geometry_only, grad_ray=grad_ray, bg_sphere=bg_sphere, env_rot_radian=env_rot_radian,
+                                   **kwargs)
+    prefix = rays_o.shape[:-1]
+    field = getattr(model, "_envidr_field", None)
+    if field is None or getattr(model, "_envidr_field_dirty", True):
+        field = FieldParams.from_reference_model(model).pack()
+        model._envidr_field, model._envidr_field_dirty = field, False
+    cfg = RenderConfig(bound=float(model.bound), cascade=int(model.cascade), grid_size=int(model.grid_size), min_near=float(model.min_near),
+                       dt_gamma=float(dt_gamma), max_steps=int(max_steps), T_thresh=float(T_thresh),
+                       aabb=[float(v) for v in model.aabb_infer.tolist()])
+    res = render_rays(field, model.density_bitfield, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), cfg,
+                      bg_color=1.0 if bg_color is None else bg_color, r_images=None if r_images is None else r_images.reshape(-1, 4),
+                      geometry_only=geometry_only, env_rot_radian=env_rot_radian, get_normal_image=get_normal_image or geometry_only,
+                      visual_items=tuple(model.opt.visual_items) if model.opt.use_diffuse else (), perturb=bool(perturb))
+    results = {"depth": res["depth"].view(*prefix), "weights_sum": res["weights_sum"].view(*prefix),
+               "image": None if geometry_only else res["image"].view(*prefix, 3)}
+    if "normal_image" in res:
+        results["normal_image"] = res["normal_image"].view(*prefix, 3)
+    for k in ("diffuse_image", "specular_image", "roughness_image"):
+        if k in res:
+            results[k] = res[k]
+    return results
+
+
+def install(render_func_module=None):
+    """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop."""
+    global _reference_run_cuda
+    from .backend import install_into_sys_modules
+    install_into_sys_modules()
+    if render_func_module is None:
+        import importlib
+        render_func_module = importlib.import_module("nerf.render_func")
+    if _reference_run_cuda is None:
+        _reference_run_cuda = render_func_module.run_cuda
+    render_func_module.run_cuda = run_cuda
+    return render_func_module

@@ -1,0 +1,190 @@
+"""Seeded synthetic stand-ins for the benchmark scenes (there is no dataset / checkpoint access):
+cameras and rays restated from the reference's data path, and an analytic "toaster-like" field whose hash
+grid + MLP weights are *constructed* (not trained) so that both the CUDA path and the CPU oracle load the
+same arrays.
+
+Restated reference code (the caller side of the hot path):
+    get_rays              nerf/utils.py:110-209 (full-image branch: pixel centres + 0.5, normalised dirs)
+    pose_spherical        nerf/sph_loader.py:67-76
+    nerf_matrix_to_ngp    nerf/provider.py:32-40
+    HashEncoder offsets   hashencoder/hashgrid.py:130-146
+    net_init xavier       nerf/net_init.py (xavier_uniform weights, zero bias)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .field import FieldParams
+
+SQRT3 = 3 ** 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# cameras / rays
+# ---------------------------------------------------------------------------------------------
+
+def pose_spherical(theta_deg: float, phi_deg: float, radius: float) -> np.ndarray:
+    trans_t = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1]], np.float64)
+    p = phi_deg / 180.0 * np.pi
+    rot_phi = np.array([[1, 0, 0, 0], [0, np.cos(p), -np.sin(p), 0], [0, np.sin(p), np.cos(p), 0], [0, 0, 0, 1]])
+    t = theta_deg / 180.0 * np.pi
+    rot_th = np.array([[np.cos(t), 0, -np.sin(t), 0], [0, 1, 0, 0], [np.sin(t), 0, np.cos(t), 0], [0, 0, 0, 1]])
+    c2w = rot_th @ (rot_phi @ trans_t)
+    return np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], np.float64) @ c2w
+
+
+def nerf_matrix_to_ngp(pose: np.ndarray, scale: float = 0.33, offset=(0, 0, 0)) -> np.ndarray:
+    return np.array([
+        [pose[1, 0], -pose[1, 1], -pose[1, 2], pose[1, 3] * scale + offset[0]],
+        [pose[2, 0], -pose[2, 1], -pose[2, 2], pose[2, 3] * scale + offset[1]],
+        [pose[0, 0], -pose[0, 1], -pose[0, 2], pose[0, 3] * scale + offset[2]],
+        [0, 0, 0, 1]], dtype=np.float32)
+
+
+def intrinsics_from_fov(W: int, H: int, camera_angle_x: float) -> np.ndarray:
+    fl = W / (2 * np.tan(camera_angle_x / 2))
+    return np.array([fl, fl, W / 2, H / 2], np.float64)
+
+
+def get_rays(pose: np.ndarray, intrinsics: np.ndarray, H: int, W: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Full-image rays, [H*W, 3] each (torch fp32, CPU)."""
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    pose_t = torch.from_numpy(np.asarray(pose, np.float32))[None]
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i = i.t().reshape(1, H * W) + 0.5
+    j = j.t().reshape(1, H * W) + 0.5
+    zs = torch.ones_like(i)
+    directions = torch.stack(((i - cx) / fx * zs, (j - cy) / fy * zs, zs), dim=-1)
+    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
+    rays_d = directions @ pose_t[:, :3, :3].transpose(-1, -2)
+    rays_o = pose_t[..., :3, 3][..., None, :].expand_as(rays_d)
+    return rays_o.reshape(-1, 3).contiguous(), rays_d.reshape(-1, 3).contiguous()
+
+
+def camera_rays(W: int, H: int, theta_deg: float = 40.0, phi_deg: float = -30.0, radius: float = 4.0, scale: float = 0.65,
+                camera_angle_x: float = 0.6911112070083618):
+    pose = nerf_matrix_to_ngp(pose_spherical(theta_deg, phi_deg, radius), scale=scale)
+    return get_rays(pose, intrinsics_from_fov(W, H, camera_angle_x), H, W)
+
+
+# ---------------------------------------------------------------------------------------------
+# analytic scene
+# ---------------------------------------------------------------------------------------------
+
+def analytic_sdf(xyz: np.ndarray, scale: float = 0.65) -> np.ndarray:
+    """Rounded box (0.55 x 0.35 x 0.3) united with a sphere r=0.25 at (0.3, 0.25, 0), all times `scale`
+    (the synthetic toaster of SURVEY.md 8d).  xyz [..., 3] float64 -> signed distance."""
+    p = np.asarray(xyz, np.float64) / scale
+    half = np.array([0.55, 0.35, 0.30])
+    r = 0.08
+    q = np.abs(p) - (half - r)
+    box = np.linalg.norm(np.maximum(q, 0.0), axis=-1) + np.minimum(q.max(axis=-1), 0.0) - r
+    sph = np.linalg.norm(p - np.array([0.3, 0.25, 0.0]), axis=-1) - 0.25
+    return np.minimum(box, sph) * scale
+
+
+def hash_offsets(num_levels=16, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048, input_dim=3):
+    per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+    offsets, offset = [], 0
+    for i in range(num_levels):
+        res = int(np.ceil(base_resolution * per_level_scale ** i))
+        offsets.append(offset)
+        offset += min(2 ** log2_hashmap_size, res ** input_dim)
+    offsets.append(offset)
+    return np.array(offsets, np.int32), float(per_level_scale)
+
+
+def _xavier(rng: np.random.Generator, out_dim: int, in_dim: int) -> np.ndarray:
+    a = math.sqrt(6.0 / (in_dim + out_dim))
+    return rng.uniform(-a, a, size=(out_dim, in_dim)).astype(np.float32)
+
+
+def _mlp(rng, dims, bias_scale=0.0):
+    layers = []
+    for i in range(len(dims) - 1):
+        W = _xavier(rng, dims[i + 1], dims[i])
+        b = (rng.standard_normal(dims[i + 1]) * bias_scale).astype(np.float32)
+        layers.append((W, b))
+    return layers
+
+
+def make_synthetic_field(seed: int = 0, *, hidden_dim_env: int = 256, ide_degree: int = 5, scene_scale: float = 0.65,
+                         bound: float = 1.0, beta: float = 0.01, num_levels: int = 16, log2_hashmap_size: int = 19,
+                         desired_resolution: int = 2048, with_renv: bool = True, device="cpu") -> FieldParams:
+    """toaster.ini dimensions (hash L16/C2/base16/2048/T19, sdf 32-64-64-15, env IDE-256-256-256-12, diffuse 24-32-3,
+    color 28-64-64-3, renv 4-64-64-64-12) with weights built so that the SDF head equals the mean of the
+    smoothstep-interpolated analytic SDF stored in channel 0 of the dense levels; everything else is seeded random."""
+    rng = np.random.default_rng(seed)
+    offsets, pls = hash_offsets(num_levels, 16, log2_hashmap_size, desired_resolution * bound)
+    T = int(offsets[-1])
+    emb = rng.uniform(-0.3, 0.3, size=(T, 2)).astype(np.float32)
+    S = np.float32(np.log2(pls))
+    dense_levels = []
+    for l in range(num_levels):
+        scale = np.float32(np.exp2(np.float32(l) * S) * np.float32(16) - np.float32(1.0))
+        res = int(np.ceil(scale)) + 1
+        if res ** 3 > 2 ** log2_hashmap_size:
+            break
+        dense_levels.append(l)
+        idx = np.arange(res)
+        x01 = idx.astype(np.float64) / float(scale)
+        gx, gy, gz = np.meshgrid(x01, x01, x01, indexing="ij")
+        pts = np.stack([gx, gy, gz], -1) * 2 * bound - bound
+        sd = analytic_sdf(pts, scene_scale)
+        lin = (idx[:, None, None] + idx[None, :, None] * res + idx[None, None, :] * res * res).reshape(-1)
+        emb[offsets[l] + lin, 0] = sd.reshape(-1).astype(np.float32)
+    nd = len(dense_levels)
+    G, E, Hd = 12, 12, 64
+    in_dim = num_levels * 2
+    sdf = _mlp(rng, [in_dim, Hd, Hd, 1 + G + 2], bias_scale=0.05)
+    W1, b1 = sdf[0]; W2, b2 = sdf[1]; W3, b3 = sdf[2]
+    # units 0/1 of each hidden layer carry +u / -u with u = mean over dense levels of channel 0
+    W1[0:2] = 0; b1[0:2] = 0
+    for l in dense_levels:
+        W1[0, 2 * l] = 1.0 / nd
+        W1[1, 2 * l] = -1.0 / nd
+    W2[0:2] = 0; b2[0:2] = 0
+    W2[0, 0] = 1.0; W2[1, 1] = 1.0
+    W2[2:, 0:2] = 0                       # keep the other units independent of the SDF carrier
+    W3[0] = 0; b3[0] = 0
+    W3[0, 0] = 1.0; W3[0, 1] = -1.0
+    W3[1:, 0:2] = 0
+    P = 2 ** ide_degree - 1 + ide_degree
+    env = _mlp(rng, [2 * P, hidden_dim_env, hidden_dim_env, hidden_dim_env, E])
+    diffuse = _mlp(rng, [G + E, 32, 3])
+    color = _mlp(rng, [G + 3 + E + 1, 64, 64, 3])
+    color[-1] = (color[-1][0], color[-1][1] - np.float32(np.log(3)))        # network.py:363-364
+    renv = _mlp(rng, [4, 64, 64, 64, E]) if with_renv else None
+    tt = lambda layers: None if layers is None else [(torch.from_numpy(W.copy()), torch.from_numpy(b.copy())) for W, b in layers]
+    fp = FieldParams(embeddings=torch.from_numpy(emb), offsets=torch.from_numpy(offsets), per_level_scale=pls, base_resolution=16,
+                     bound=bound, sdf=tt(sdf), env=tt(env), diffuse=tt(diffuse), color=tt(color), renv=tt(renv), geo_feat_dim=G,
+                     ide_degree=ide_degree, beta=beta)
+    return fp.to(device) if str(device) != "cpu" else fp
+
+
+def make_bitfield(scene_scale: float = 0.65, bound: float = 1.0, grid_size: int = 128, margin_cells: float = 2.5) -> np.ndarray:
+    """Occupancy bit field (cascade 1) in the reference's layout: bit (morton3D(i,j,k) % 8) of byte
+    (morton3D(i,j,k) / 8) is set when the analytic SDF at the cell centre is below a margin -- what
+    update_extra_state + packbits converge to for an SDF field (interior and a thin shell occupied)."""
+    H = grid_size
+    c = ((np.arange(H) + 0.5) / H * 2 - 1) * bound
+    gx, gy, gz = np.meshgrid(c, c, c, indexing="ij")
+    sd = analytic_sdf(np.stack([gx, gy, gz], -1), scene_scale)
+    occ = sd < margin_cells * (2 * bound / H)
+
+    def spread(v):
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+
+    i = np.arange(H, dtype=np.uint64)
+    m = (spread(i)[:, None, None] | (spread(i)[None, :, None] << 1) | (spread(i)[None, None, :] << 2)).astype(np.int64)
+    flat = np.zeros(H ** 3, np.uint8)
+    flat[m.reshape(-1)] = occ.reshape(-1)
+    return np.packbits(flat.reshape(-1, 8), axis=-1, bitorder="little").reshape(-1)

@@ -1,0 +1,272 @@
+/*
+ * envidr_b200.h -- C ABI of libenvidr_b200.so, the B200 (sm_100a) implementation of the
+ * ENVIDR volumetric-render hot path.
+ *
+ * Every entry point replaces one function the reference exports from its pybind11 / cpp_extension
+ * modules (the drop-in boundary); the reference declaration it replaces is cited as
+ * <reference path>:<line>.  Conventions:
+ *   - plain device pointers + sizes; no torch types; all tensors fp32 / int32 / uint8, contiguous,
+ *     row-major, resident on the current CUDA device.  Outputs are caller-allocated (as in the
+ *     reference, where Python allocates every output tensor).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, what the
+ *     reference launches on).  Calls are asynchronous; nothing synchronises the device.
+ *   - return value: 0 on success; a positive cudaError_t if a launch failed; a negative
+ *     ENVIDR_E_* code for an argument the implementation rejects.  envidr_last_error() returns a
+ *     static description of the most recent failure of the calling thread.
+ *   - The library has no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef ENVIDR_B200_H_
+#define ENVIDR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ENVIDR_E_UNSUPPORTED (-1) /* unsupported D / C / degree / dims   (reference: std::runtime_error) */
+#define ENVIDR_E_BADARG      (-2) /* null pointer / inconsistent sizes    (reference: TORCH_CHECK)        */
+#define ENVIDR_E_WORKSPACE   (-3) /* workspace too small                                                 */
+
+typedef void* envidr_stream_t;
+
+const char* envidr_last_error(void);
+/* ABI version: major*100 + minor */
+int envidr_version(void);
+/* sizeof {envidr_mlp_layer, envidr_field, envidr_field_out, envidr_render_opts, envidr_render_out}: lets a
+ * foreign-language binding verify its struct mirrors. */
+int envidr_abi_sizes(uint32_t out[5]);
+
+/* ------------------------------------------------------------------------------------------------
+ * raymarching  (reference: raymarching/src/raymarching.h:7-18, bindings.cpp:5-20)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* raymarching.h:7  near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars) */
+int envidr_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                              float min_near, float* nears, float* fars, envidr_stream_t stream);
+/* raymarching.h:8  sph_from_ray(rays_o, rays_d, radius, N, coords[N,2]) */
+int envidr_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                        envidr_stream_t stream);
+/* raymarching.h:9-10  morton3D(coords[N,3] i32, N, indices[N]) / morton3D_invert */
+int envidr_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, envidr_stream_t stream);
+int envidr_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, envidr_stream_t stream);
+/* raymarching.h:11  packbits(grid f32[8N], N, density_thresh, bitfield u8[N]) */
+int envidr_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, envidr_stream_t stream);
+/* raymarching.h:12  get_scatter_idx(rays i32[N,3], N, idx_map i32[M]) */
+int envidr_get_scatter_idx(const int32_t* rays, uint32_t N, int32_t* idx_map, envidr_stream_t stream);
+
+/* raymarching.h:14  march_rays_train(...).  rays[N,3] = (ray id, offset, count); counter[2] is
+ * advanced by (total samples, N).  Unlike the reference (two atomicAdds, scheduling-dependent
+ * offsets) slot r holds ray r and offsets are the exclusive prefix sum in ray order, so the
+ * result is deterministic; per-ray counts and sample sequences are bit-identical. */
+int envidr_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t early_stop_steps, uint32_t N,
+                            uint32_t C, uint32_t H, uint32_t M, const float* nears, const float* fars,
+                            float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                            const float* noises, envidr_stream_t stream);
+/* raymarching.h:15  composite_rays_train_forward(...); weights may be NULL (reference: numel()==0) */
+int envidr_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                        const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                        uint32_t accum_deltas, uint32_t input_alpha, float* weights_sum,
+                                        float* depth, float* image, float* weights, envidr_stream_t stream);
+/* raymarching.h:16  composite_rays_train_backward(...) */
+int envidr_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                         const float* grad_depth, const float* sigmas, const float* rgbs,
+                                         const float* deltas, const int32_t* rays, const float* weights_sum,
+                                         const float* image, const float* depth, uint32_t M, uint32_t N,
+                                         float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                         uint32_t accum_deltas, uint32_t input_alpha, envidr_stream_t stream);
+/* raymarching.h:17  march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+ * max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises).  Every slot of
+ * xyzs/dirs/deltas[n_alive*n_step] is written (zeros past the end of a ray). */
+int envidr_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                      const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                      uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                      const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                      envidr_stream_t stream);
+/* raymarching.h:18  composite_rays(...): in place on rays_alive, rays_t, weights_sum, depth, image */
+int envidr_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, uint32_t accum_deltas,
+                          uint32_t input_alpha, int32_t* rays_alive, float* rays_t, const float* sigmas,
+                          const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                          float* image, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * hashencoder  (reference: hashencoder/src/hashencoder.h:13-15)  -- smoothstep, twice differentiable
+ * ---------------------------------------------------------------------------------------------- */
+/* outputs [L,B,C]; dy_dx [B, L*D*C] (ignored unless calc_grad_inputs).  D in {2,3}, C in {1,2,4,8}. */
+int envidr_hash_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets,
+                               float* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                               uint32_t H, int calc_grad_inputs, float* dy_dx, envidr_stream_t stream);
+/* grad_embeddings (pre-zeroed by the caller, as in hashgrid.py:80) is accumulated into;
+ * grad_inputs [B,D] is written when calc_grad_inputs. */
+int envidr_hash_encode_backward(const float* grad, const float* inputs, const float* embeddings,
+                                const int32_t* offsets, float* grad_embeddings, uint32_t B, uint32_t D,
+                                uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                                const float* dy_dx, float* grad_inputs, envidr_stream_t stream);
+/* grad_grad [L,B,C] is written; grad2_embeddings (pre-zeroed) is accumulated into. */
+int envidr_hash_encode_second_backward(const float* grad, const float* inputs, const float* embeddings,
+                                       const int32_t* offsets, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                                       float S, uint32_t H, int calc_grad_inputs, const float* dy_dx,
+                                       const float* grad_grad_inputs, float* grad_grad,
+                                       float* grad2_embeddings, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gridencoder  (reference: gridencoder/src/gridencoder.h:12-13)  -- linear interp, hash / tiled
+ * ---------------------------------------------------------------------------------------------- */
+/* dy_dx may be NULL (reference: at::optional).  D in 1..5, C in {1,2,4,8}.  gridtype 0 = hash, 1 = tiled. */
+int envidr_grid_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets,
+                               float* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                               uint32_t H, float* dy_dx, uint32_t gridtype, int align_corners,
+                               envidr_stream_t stream);
+int envidr_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings,
+                                const int32_t* offsets, float* grad_embeddings, uint32_t B, uint32_t D,
+                                uint32_t C, uint32_t L, float S, uint32_t H, const float* dy_dx,
+                                float* grad_inputs, uint32_t gridtype, int align_corners,
+                                envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * freqencoder / shencoder  (reference: freqencoder/src/freqencoder.h:7-10, shencoder/src/shencoder.h:9-10)
+ * ---------------------------------------------------------------------------------------------- */
+int envidr_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                               float* outputs, envidr_stream_t stream);
+int envidr_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg,
+                                uint32_t C, float* grad_inputs, envidr_stream_t stream);
+/* degree in 1..8; dy_dx [B, 3*degree^2] may be NULL */
+int envidr_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                             float* dy_dx, envidr_stream_t stream);
+/* accumulates (+=) into grad_inputs [B,D] like the reference */
+int envidr_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
+                              const float* dy_dx, float* grad_inputs, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * IDE  (reference: ide_encoder/ide_encoder.py:98-130, pure PyTorch there; no native symbol exists)
+ * ---------------------------------------------------------------------------------------------- */
+/* dirs [B,3]; kappa_inv: per-sample array [B] when kappa_inv_arr != NULL, else the scalar;
+ * out [B, 2*P], P = 2^deg_view - 1 + deg_view ([Re | Im] halves), deg_view in 1..5; out *= scale. */
+int envidr_ide_encode_forward(const float* dirs, const float* kappa_inv_arr, float kappa_inv_scalar,
+                              uint32_t B, uint32_t deg_view, float scale, float* out, envidr_stream_t stream);
+/* Host-only: the coefficient tables the kernel uses (ide_encoder.py:84-96): mat [(l_max+1), P] row-major,
+ * sigma [P], ml [2, P] (row 0 = m, row 1 = l).  l_max = 2^(deg_view-1). */
+int envidr_ide_tables(uint32_t deg_view, float* mat, float* sigma, int32_t* ml);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused per-sample field + fused inference render loop.
+ * The reference has no operator boundary here (nn.Linear stacks driven from Python:
+ * nerf/network.py:381-698, nerf/renderer.py:147-198, nerf/render_func/cuda_ray.py:238-359); the seams
+ * these replace are NeRFNetwork.forward_sigma/forward_color and nerf.render_func.run_cuda.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct envidr_mlp_layer {
+    const float* weight; /* [out_dim, in_dim] row-major (torch nn.Linear layout) */
+    const float* bias;   /* [out_dim] or NULL */
+    uint32_t in_dim, out_dim;
+} envidr_mlp_layer;
+
+#define ENVIDR_MAX_LAYERS 8
+
+typedef struct envidr_field {
+    /* hash grid (hashencoder.HashEncoder) */
+    const float* embeddings;     /* [T, 2] */
+    const int32_t* offsets;      /* [L+1] (device) */
+    uint32_t num_levels;         /* L (<= 16) */
+    uint32_t level_dim;          /* C (2) */
+    uint32_t base_resolution;    /* H */
+    float log2_per_level_scale;  /* S */
+    float bound;
+    int32_t enabled_levels;      /* <=0: all (network.py:390-393) */
+    /* MLP stacks */
+    uint32_t n_sdf, n_env, n_diffuse, n_color, n_renv;
+    envidr_mlp_layer sdf[ENVIDR_MAX_LAYERS], env[ENVIDR_MAX_LAYERS], diffuse[ENVIDR_MAX_LAYERS],
+                     color[ENVIDR_MAX_LAYERS], renv[ENVIDR_MAX_LAYERS];
+    uint32_t geo_feat_dim;       /* 12 */
+    uint32_t ide_degree;         /* deg_view: 4 or 5 */
+    /* scalars */
+    float beta;                  /* already clamped to [beta_min, beta_max] */
+    float density_scale;
+    float roughness_bias, roughness_act_scale, roughness_scale;
+    float diffuse_kappa_inv, light_intensity_scale, intensity_scale;
+    float indir_roughness_thresh;
+    int32_t learn_indir_blend;
+    int32_t has_env_rot; float env_rot[9]; /* row-major 3x3 R; w_r <- w_r @ R (renderer.py:160-161) */
+    /* device buffer of repacked (K-major, padded) weights written by envidr_field_pack; must be
+     * refreshed whenever a weight tensor changes.  Size: envidr_field_pack_bytes(). */
+    const void* packed; uint64_t packed_bytes;
+} envidr_field;
+
+/* Bytes needed for field->packed (0 if the field description is rejected; see envidr_last_error). */
+uint64_t envidr_field_pack_bytes(const envidr_field* field);
+/* Repack the torch-layout weights referenced by `field` into `packed` (device memory, async on stream). */
+int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_bytes, envidr_stream_t stream);
+
+/* Per-sample outputs of the field; any pointer may be NULL.  r_images [M,4] may be NULL. */
+typedef struct envidr_field_out {
+    float* sigma;      /* [M]   density * density_scale            */
+    float* rgb;        /* [M,3] (c_diffuse + c_specular) * intensity */
+    float* normal;     /* [M,3] unit normal                        */
+    float* sdf;        /* [M]                                      */
+    float* c_diffuse;  /* [M,3] */
+    float* c_specular; /* [M,3] */
+    float* roughness;  /* [M]   */
+    float* grad_x;     /* [M,3] un-normalised d sdf / d xyz        */
+} envidr_field_out;
+
+/* mode: 0 = full shading, 1 = geometry only (sigma, normal, sdf, roughness) */
+int envidr_field_forward(const envidr_field* field, const float* xyzs, const float* dirs,
+                         const float* r_images, uint32_t M, int mode, const envidr_field_out* out,
+                         envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused inference render loop: replaces the `else` branch of run_cuda
+ * (nerf/render_func/cuda_ray.py:238-359) -- near/far, march, field, composite, alive-list compaction and
+ * the final background mix, all device-driven (no host sync per iteration).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct envidr_render_opts {
+    float bound;            /* model.bound                                  */
+    float dt_gamma;         /* opt.dt_gamma                                 */
+    float T_thresh;         /* opt.T_thresh                                 */
+    float min_near;         /* model.min_near                               */
+    uint32_t max_steps;     /* opt.max_steps                                */
+    uint32_t cascade;       /* model.cascade                                */
+    uint32_t grid_size;     /* model.grid_size (128)                        */
+    float aabb[6];          /* model.aabb_infer                             */
+    float bg_color[3];      /* constant background (ignored when bg_per_ray is given) */
+    int32_t geometry_only;  /* composite normals instead of colours (pass 1 of indir_ref) */
+    int32_t input_alpha;    /* NeuS-style alpha input (use_neus_sdf)        */
+} envidr_render_opts;
+
+typedef struct envidr_render_out {
+    float* image;           /* [N,3]  (unused when geometry_only)           */
+    float* depth;           /* [N]                                          */
+    float* weights_sum;     /* [N]                                          */
+    float* normal_image;    /* [N,3]  optional; unit-normalised as in cuda_ray.py:356-359 */
+    float* diffuse_image;   /* [N,3]  optional ('diffuse' in visual_items)  */
+    float* specular_image;  /* [N,3]  optional ('specular' in visual_items) */
+    float* roughness_image; /* [N]    optional (composited roughness)       */
+} envidr_render_out;
+
+uint64_t envidr_render_workspace_bytes(uint32_t N);
+/* r_images [N,4] (reflected radiance + visibility per ray), noises [N] (perturb), bg_per_ray [N,3] may be NULL.
+ * workspace: 256-byte aligned device memory of at least envidr_render_workspace_bytes(N). */
+int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const float* rays_o, const float* rays_d,
+                       const float* r_images, const float* noises, const float* bg_per_ray, uint32_t N,
+                       const envidr_render_opts* opts, const envidr_render_out* out, void* workspace,
+                       uint64_t workspace_bytes, envidr_stream_t stream);
+/* Waits for the most recent envidr_render_rays of this process; stats = {iterations, samples_lo, samples_hi, 0}. */
+int envidr_render_last_stats(uint32_t stats[4]);
+
+/* Instrumentation (bench.py): launches issued by envidr_render_rays in this process; CUDA-event timing of the
+ * field kernel (the dominant kernel) on its launch stream. */
+uint64_t envidr_launch_count(void);
+int envidr_render_timing(int enable);
+int envidr_render_field_time(float* total_ms, uint32_t* launches);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENVIDR_B200_H_ */

@@ -556,3 +556,48 @@ def render_rays(P: Dict, rays_o, rays_d, bitfield, *, cascade=1, grid_size=128, 
         return dict(image=None, depth=n_depth, weights_sum=n_ws, normal_image=nrm_img.astype(np.float32))
     image = image + (1 - ws)[:, None] * np.float32(bg_color)
     return dict(image=image.astype(np.float32), depth=depth, weights_sum=ws, normal_image=nrm_img.astype(np.float32))
+
+
+def render(P: Dict, rays_o, rays_d, bitfield, *, indir_ref=False, indir_max_steps=1024, bg_color=1.0, min_near=0.2,
+           max_steps=1024, T_thresh=1e-4, env_rot_radian=None, obj_aabb=None, dtype=torch.float64, stats: Optional[list] = None, **kw):
+    """NeRFRenderer.render for the cuda_ray inference path (nerf/renderer.py:364-531): one pass, or the three passes of
+    the indirect-reflection scheme (:439-513).  normal_image is post-processed as in :529-530."""
+    rays_o, rays_d = _c32(rays_o).reshape(-1, 3), _c32(rays_d).reshape(-1, 3)
+    N = rays_o.shape[0]
+    common = dict(max_steps=max_steps, T_thresh=T_thresh, env_rot_radian=env_rot_radian, dtype=dtype, **kw)
+
+    def run(o, d, **k):
+        st = {}
+        r = render_rays(P, o, d, bitfield, stats=st, **{**common, **k})
+        if stats is not None:
+            stats.append(st)
+        return r
+
+    if not indir_ref:
+        res = run(rays_o, rays_d, bg_color=bg_color, min_near=min_near)
+    else:
+        dt = np.float32(2 * math.sqrt(3) / indir_max_steps)
+        geo = run(rays_o, rays_d, geometry_only=True, min_near=min_near)
+        normals = geo["normal_image"]
+        depth = geo["depth"] - dt
+        ws = geo["weights_sum"]
+        ref_mask = (depth != 0) & (ws > 0.9)
+        ray_mask = (depth != 0) & (ws > 0.3)
+        ref_o = rays_o + depth[:, None] * rays_d
+        w_o = -rays_d
+        ref_d = 2 * np.sum(w_o * normals, -1, keepdims=True) * normals - w_o
+        if obj_aabb is not None:
+            ob = np.asarray(obj_aabb, np.float32)
+            ref_mask &= (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
+        sec = run(ref_o[ref_mask], ref_d[ref_mask], bg_color=0.0, min_near=float(dt * 2), max_steps=indir_max_steps)
+        ref_image = np.concatenate([sec["image"], sec["weights_sum"][:, None]], -1)
+        r_img = np.zeros((int(ray_mask.sum()), 4), np.float32)
+        r_img[ref_mask[ray_mask]] = ref_image
+        main = run(rays_o[ray_mask], rays_d[ray_mask], bg_color=0.0, r_images=r_img, min_near=min_near)
+        img = np.zeros((N, 3), np.float32); img[ray_mask] = main["image"]
+        wsf = np.zeros(N, np.float32); wsf[ray_mask] = main["weights_sum"]
+        res = dict(image=(np.zeros((N, 3), np.float32) + np.float32(bg_color)) * (1 - wsf[:, None]) + img, weights_sum=wsf,
+                   depth=depth, normal_image=normals)
+    w = res["weights_sum"][:, None]
+    res["normal_image"] = res["normal_image"] * w + (1 - w)
+    return res

@@ -1,0 +1,126 @@
+"""GPU parity of the fused per-sample field kernel (envidr_field_forward) against the CPU oracle, whose torch
+layer is itself pinned to the reference's network.py / renderer.py by tests/test_oracle_golden.py.
+Tolerance: the north star asks 1e-4 on RGB; per-sample fp32-vs-fp64 differences here stay below 5e-5."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _samples(M, seed, near_surface=True):
+    from envidr_b200 import scene
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-0.75, 0.75, size=(M * 3, 3))
+    if near_surface:
+        sd = scene.analytic_sdf(x)
+        x = x[np.argsort(np.abs(sd))[:M]]                      # samples close to the surface: both signs of the Laplace CDF
+        x = x[rng.permutation(M)]
+    else:
+        x = x[:M]
+    d = rng.standard_normal((M, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    return x.astype(np.float32), d.astype(np.float32)
+
+
+@pytest.mark.parametrize("env_width,deg,M", [(64, 4, 1000), (256, 5, 2500), (160, 4, 130)])
+def test_field_forward_matches_oracle(dev, env_width, deg, M):
+    from envidr_b200 import scene
+    from oracle import oracle as O
+    fp_cpu = scene.make_synthetic_field(1, hidden_dim_env=env_width, ide_degree=deg)
+    fp = fp_cpu.to(dev).pack()
+    x, d = _samples(M, 0)
+    want = ("sigma", "rgb", "normal", "sdf", "c_diffuse", "c_specular", "roughness", "grad_x")
+    out = fp.forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), want=want)
+    ref = O.field_forward(fp_cpu.to_oracle(), x, d)
+    g = lambda k: out[k].cpu().numpy()
+    np.testing.assert_allclose(g("sdf"), ref["sdf"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(g("grad_x"), ref["grad_x"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(g("normal"), ref["normal"], atol=2e-5)
+    np.testing.assert_allclose(g("roughness"), ref["roughness"][:, 0], atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(g("sigma"), ref["sigma"], atol=5e-3, rtol=1e-3)          # d sigma/d sdf <= 1/(2 beta^2) = 5000: amplifies 1e-7 sdf rounding
+    np.testing.assert_allclose(g("c_diffuse"), ref["c_diffuse"], atol=5e-5)
+    np.testing.assert_allclose(g("c_specular"), ref["c_specular"], atol=5e-5)
+    np.testing.assert_allclose(g("rgb"), ref["rgb"], atol=1e-4)
+    assert ref["sdf"].min() < 0 < ref["sdf"].max()
+
+
+def test_field_forward_env_rotation_renv_and_masks(dev):
+    from envidr_b200 import scene
+    from oracle import oracle as O
+    fp_cpu = scene.make_synthetic_field(2, hidden_dim_env=64, ide_degree=5)
+    M = 777
+    x, d = _samples(M, 3)
+    rng = np.random.default_rng(4)
+    ri = rng.uniform(0, 1, size=(M, 4)).astype(np.float32)
+    ri[::2, 3] = 0.95 + 0.05 * ri[::2, 3]
+    P = fp_cpu.to_oracle()
+    for kw_gpu, kw_ref in ((dict(env_rot_radian=0.7), dict(env_rot_radian=0.7)),
+                           (dict(r_images=torch.from_numpy(ri)), dict(r_images=ri))):
+        fp = fp_cpu.to(dev).pack()
+        if "r_images" in kw_gpu:
+            kw_gpu = dict(r_images=kw_gpu["r_images"].to(dev))
+        out = fp.forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), want=("rgb", "c_specular", "roughness"), **kw_gpu)
+        ref = O.field_forward(P, x, d, **kw_ref)
+        np.testing.assert_allclose(out["c_specular"].cpu().numpy(), ref["c_specular"], atol=5e-5)
+        np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=1e-4)
+    ref0 = O.field_forward(P, x, d)
+    assert np.abs(ref0["c_specular"] - ref["c_specular"]).max() > 1e-3, "renv branch must change some samples"
+    # learn_indir_blend = False uses the analytic blend (network.py:632-634)
+    fp_cpu.learn_indir_blend = False
+    out = fp_cpu.to(dev).pack().forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(ri).to(dev), want=("rgb",))
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), O.field_forward(fp_cpu.to_oracle(), x, d, r_images=ri)["rgb"], atol=1e-4)
+    # enabled_levels masks the encoder output and its gradient (network.py:390-393)
+    fp_cpu.enabled_levels = 10
+    out = fp_cpu.to(dev).pack().forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), want=("rgb", "normal", "sdf"))
+    ref = O.field_forward(fp_cpu.to_oracle(), x, d)
+    np.testing.assert_allclose(out["sdf"].cpu().numpy(), ref["sdf"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(out["normal"].cpu().numpy(), ref["normal"], atol=2e-5)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=1e-4)
+
+
+def test_field_geometry_only_and_edge_sizes(dev):
+    from envidr_b200 import scene
+    fp_cpu = scene.make_synthetic_field(1, hidden_dim_env=64, ide_degree=4)
+    fp = fp_cpu.to(dev).pack()
+    for M in (1, 127, 128, 129, 148 * 128 + 5):
+        x, d = _samples(M, M, near_surface=False)
+        xt, dt = torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev)
+        full = fp.forward(xt, dt, want=("sigma", "normal", "rgb"))
+        geo = fp.forward(xt, dt, geometry_only=True, want=("sigma", "normal"))
+        assert torch.equal(full["sigma"], geo["sigma"]) and torch.equal(full["normal"], geo["normal"])
+        assert torch.isfinite(full["rgb"]).all()
+        # per-sample independence: the same sample gives the same result wherever it sits in the batch
+        perm = torch.randperm(M, device=dev)
+        shuf = fp.forward(xt[perm], dt[perm], want=("rgb", "sigma"))
+        assert torch.equal(shuf["rgb"], full["rgb"][perm]) and torch.equal(shuf["sigma"], full["sigma"][perm])
+    empty = fp.forward(torch.empty(0, 3, device=dev), torch.empty(0, 3, device=dev))
+    assert empty["rgb"].shape == (0, 3)
+
+
+def test_field_matches_reference_glue_golden(dev, golden_dir):
+    """Reference network.py outputs (golden, relight dims with the SHIPPED rendering MLPs) vs the fused kernel, the
+    position encoder being the real hash grid here: checked through the oracle on the same inputs."""
+    import os
+    from envidr_b200 import scene
+    from envidr_b200.field import FieldParams
+    from oracle import oracle as O
+    z = np.load(os.path.join(golden_dir, "relight_mlps.npz"))
+    n = lambda name: sorted({int(k.split("_")[2]) for k in z.files if k.startswith(name + "_")})
+    L = lambda name: [(torch.from_numpy(z[f"{name}_{i}_weight"]), torch.from_numpy(z[f"{name}_{i}_bias"])) for i in n(name)]
+    base = scene.make_synthetic_field(3, hidden_dim_env=160, ide_degree=4)
+    fp_cpu = FieldParams(embeddings=base.embeddings, offsets=base.offsets, per_level_scale=base.per_level_scale, base_resolution=16, bound=1.0,
+                         sdf=base.sdf, env=L("env_net"), diffuse=L("diffuse_net"), color=L("color_net"), renv=L("renv_net"),
+                         geo_feat_dim=12, ide_degree=4, beta=0.01)
+    x, d = _samples(900, 9)
+    out = fp_cpu.to(dev).pack().forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), want=("rgb", "c_diffuse", "c_specular"))
+    ref = O.field_forward(fp_cpu.to_oracle(), x, d)
+    np.testing.assert_allclose(out["c_diffuse"].cpu().numpy(), ref["c_diffuse"], atol=5e-5)
+    np.testing.assert_allclose(out["c_specular"].cpu().numpy(), ref["c_specular"], atol=5e-5)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=1e-4)
