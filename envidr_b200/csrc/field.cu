@@ -594,8 +594,8 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
     if (rc) return rc;
     ENVIDR_REQUIRE(field->packed && field->packed_bytes >= lay.floats * sizeof(float), ENVIDR_E_WORKSPACE,
                    "field->packed missing or too small (call envidr_field_pack)");
+    if (!M_dev && M_host == 0) return 0;               // empty batch: nothing to do (pointers may be NULL)
     ENVIDR_REQUIRE(xyzs && dirs && out, ENVIDR_E_BADARG, "null pointer");
-    if (!M_dev && M_host == 0) return 0;
     if ((rc = ensure_ide_field(field->ide_degree))) return rc;
     static bool attr = false;
     if (!attr) {

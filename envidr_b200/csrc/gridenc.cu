@@ -241,11 +241,23 @@ static int launch_second(const EncMode m, const float* grad, const float* inputs
         default: set_error("GridEncoding: C must be 1, 2, 4, or 8."); return ENVIDR_E_UNSUPPORTED; \
     }
 
+// per-level `scale` exactly as the encoder kernels compute it (exp2f is ex2.approx on the device)
+__global__ void k_level_scales(float S, uint32_t H, uint32_t L, float* __restrict__ out) {
+    const uint32_t level = threadIdx.x;
+    if (level < L) out[level] = exp2f(level * S) * H - 1.0f;
+}
+
 }  // namespace envidr
 
 using namespace envidr;
 
 extern "C" {
+
+int envidr_debug_level_scales(float S, uint32_t H, uint32_t L, float* scales, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(scales && L <= 64, ENVIDR_E_BADARG, "bad arguments");
+    k_level_scales<<<1, 64, 0, as_stream(stream)>>>(S, H, L, scales);
+    return check_launch("debug_level_scales");
+}
 
 int envidr_hash_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
                                uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float* dy_dx,

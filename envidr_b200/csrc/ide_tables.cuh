@@ -4,10 +4,14 @@
 // `mat`, the (m,l) list and the attenuation exponents sigma_l = l(l+1)/2 are built on the host in double
 // precision with the reference's formulas and rounded to fp32, exactly like the reference's numpy code.
 //
-// Evaluation mirrors the reference's fp32 arithmetic on purpose: z^k through powf, the z-polynomial as a
-// sequential fp32 dot product over the power basis.  For the l = 16 band (deg_view 5) that polynomial
-// cancels catastrophically (|coeff| ~ 1e5), so the reference's own result is ~5e-4 away from the exact
-// value; matching its arithmetic keeps us within ~1e-4 of what the reference produces.
+// Evaluation: the reference evaluates the z-polynomial of every (l, m) pair in the power basis
+// (vmz @ mat, fp32).  For the l = 16 band (deg_view 5) that sum cancels catastrophically (|coeff| ~ 1e5):
+// the reference's own fp32 result is up to ~5e-4 away from the exact value, and two fp32 evaluations of
+// the same formula (torch CPU / torch CUDA / this GPU) disagree by as much -- measured on B200 in round 1.
+// The kernel therefore evaluates the SAME polynomials (mat[:, i] are the power-basis coefficients of
+// K_l^m * Q_l^m(z), Q the phase-carrying associated Legendre polynomial without its sin^m factor) with the
+// fully normalised three-term recurrence in l, which is stable in fp32 (~1e-6 relative).  The result is the
+// exact encoding; its distance to the reference is the reference's own cancellation error.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -22,6 +26,11 @@ struct IdeTables {
     float mat[kIdeMaxL + 1][kIdeMaxP];   // mat[k][i]: coefficient of z^k for pair i (0 for k > l - m)
     float sigma[kIdeMaxP];
     int32_t m[kIdeMaxP], l[kIdeMaxP];
+    // normalised recurrence  q_l^m = ra[l][m] * z * q_{l-1}^m - rb[l][m] * q_{l-2}^m,  q_m^m = qmm[m]
+    float qmm[kIdeMaxL + 1];
+    float ra[kIdeMaxL + 1][kIdeMaxL + 1], rb[kIdeMaxL + 1][kIdeMaxL + 1];
+    float band_sigma[5];
+    int32_t band_base[5];
 };
 
 inline double ide_factorial(int n) { double r = 1; for (int i = 2; i <= n; i++) r *= i; return r; }
@@ -56,40 +65,57 @@ inline bool ide_build_tables(int deg_view, IdeTables* t) {
     }
     t->P = i;
     t->m_max = t->l_max;
+    for (int d = 0, base = 0; d < deg_view; d++) {
+        const int l = 1 << d;
+        t->band_base[d] = base;
+        t->band_sigma[d] = (float)(0.5 * l * (l + 1));
+        base += l + 1;
+    }
+    for (int m = 0; m <= (int)t->l_max; m++) {
+        double dfact = 1.0;                                   // (2m-1)!!
+        for (int k = 2 * m - 1; k > 1; k -= 2) dfact *= k;
+        t->qmm[m] = (float)(sqrt((2.0 * m + 1.0) / (4.0 * M_PI) / ide_factorial(2 * m)) * ((m & 1) ? -1.0 : 1.0) * dfact);
+        for (int l = m + 1; l <= (int)t->l_max; l++) {
+            t->ra[l][m] = (float)sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
+            t->rb[l][m] = (l - m - 1 > 0)
+                ? (float)sqrt((2.0 * l + 1.0) * (l + m - 1.0) * (l - m - 1.0) / ((2.0 * l - 3.0) * (l - m) * (double)(l + m))) : 0.0f;
+        }
+    }
     return true;
 }
 
 #ifdef __CUDACC__
-// out_re[i*sr], out_im[i*si], i < P:  [Re | Im] of  (x+iy)^m * (sum_k z^k mat[k][i]) * exp(-sigma_i * kappa_inv) * scale
+// out_re[i*sr], out_im[i*si], i < P:  [Re | Im] of  (x+iy)^m * K_l^m Q_l^m(z) * exp(-sigma_l * kappa_inv) * scale
 __device__ __forceinline__ void ide_eval(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale,
                                          float* out_re, int sr, float* out_im, int si) {
     if (x == 0.0f && y == 0.0f) y += 1.0f;         // "avoid 0 + 0j exponentiation" (ide_encoder.py:113-115)
-    float zp[kIdeMaxL + 1], re[kIdeMaxL + 1], im[kIdeMaxL + 1];
-    zp[0] = 1.0f; re[0] = 1.0f; im[0] = 0.0f;
+    float att[5];
     #pragma unroll
-    for (int k = 1; k <= kIdeMaxL; k++) {
-        if (k <= (int)T.l_max) {
-            zp[k] = powf(z, (float)k);
-            re[k] = re[k - 1] * x - im[k - 1] * y;
-            im[k] = re[k - 1] * y + im[k - 1] * x;
-        } else {
-            zp[k] = 0.0f; re[k] = 0.0f; im[k] = 0.0f;
+    for (int b = 0; b < 5; b++) att[b] = (b < (int)T.deg) ? expf(-T.band_sigma[b] * kappa_inv) * scale : 0.0f;
+    const int l_max = (int)T.l_max;
+    float re = 1.0f, im = 0.0f;
+    for (int m = 0; m <= l_max; m++) {
+        if (m > 0) {
+            const float nr = re * x - im * y;
+            im = re * y + im * x;
+            re = nr;
         }
-    }
-    // pairs are grouped by band l = 1, 2, 4, ...; within a band m = 0..l
-    uint32_t i = 0;
-    #pragma unroll
-    for (int band = 0; band < 5; band++) {
-        if (band >= (int)T.deg) break;
-        const int l = 1 << band;
-        const float att = expf(-T.sigma[i] * kappa_inv) * 1.0f;
-        #pragma unroll
-        for (int m = 0; m <= l; m++, i++) {
-            float acc = 0.0f;
-            #pragma unroll
-            for (int k = 0; k <= l - m; k++) acc = fmaf(zp[k], T.mat[k][i], acc);
-            out_re[i * sr] = re[m] * acc * att * scale;
-            out_im[i * si] = im[m] * acc * att * scale;
+        float p2 = 0.0f, p1 = T.qmm[m];
+        if (m > 0 && (m & (m - 1)) == 0) {            // l == m is itself a band (m = 1, 2, 4, 8, 16)
+            const int b = 31 - __clz(m);
+            const int i = T.band_base[b] + m;
+            out_re[i * sr] = re * p1 * att[b];
+            out_im[i * si] = im * p1 * att[b];
+        }
+        for (int l = m + 1; l <= l_max; l++) {
+            const float q = T.ra[l][m] * z * p1 - T.rb[l][m] * p2;
+            p2 = p1; p1 = q;
+            if ((l & (l - 1)) == 0) {
+                const int b = 31 - __clz(l);
+                const int i = T.band_base[b] + m;
+                out_re[i * sr] = re * q * att[b];
+                out_im[i * si] = im * q * att[b];
+            }
         }
     }
 }

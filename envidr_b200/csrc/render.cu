@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) k_render_finish(uint32_t N, float bg0, fl
     }
     if (O.normal_image) {
         float* q = O.normal_image + 3 * n;
-        const float inv = 1.0f / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-10f);
-        q[0] *= inv; q[1] *= inv; q[2] *= inv;
+        const float den = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-10f);      // F.normalize: v / max(|v|, eps)
+        q[0] = q[0] / den; q[1] = q[1] / den; q[2] = q[2] / den;
     }
 }
 

@@ -113,6 +113,10 @@ int envidr_hash_encode_second_backward(const float* grad, const float* inputs, c
                                        const float* grad_grad_inputs, float* grad_grad,
                                        float* grad2_embeddings, envidr_stream_t stream);
 
+/* Test hook: the per-level fp32 `scale = exp2f(level*S)*H - 1` exactly as the kernels evaluate it (exp2f is the
+ * ex2.approx instruction on the device, up to 2 ulp from libm).  Lets a CPU checker use the device's level geometry. */
+int envidr_debug_level_scales(float S, uint32_t H, uint32_t L, float* scales /* device [L] */, envidr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * gridencoder  (reference: gridencoder/src/gridencoder.h:12-13)  -- linear interp, hash / tiled
  * ---------------------------------------------------------------------------------------------- */
@@ -256,6 +260,10 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
                        uint64_t workspace_bytes, envidr_stream_t stream);
 /* Waits for the most recent envidr_render_rays of this process; stats = {iterations, samples_lo, samples_hi, 0}. */
 int envidr_render_last_stats(uint32_t stats[4]);
+
+/* Test hook: D[128 x N] (fp32, row-major) = A[128 x K] * B[N x K]^T with both operands rounded to fp16, computed by one
+ * tcgen05.mma chain (pins the UMMA descriptor / operand layout conventions of the tensor-core path on hardware). */
+int envidr_tc_probe(const float* A, const float* B, float* D, uint32_t N, uint32_t K, uint32_t variant, envidr_stream_t stream);
 
 /* Instrumentation (bench.py): launches issued by envidr_render_rays in this process; CUDA-event timing of the
  * field kernel (the dominant kernel) on its launch stream. */

