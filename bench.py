@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_SAMPLE = 651_008            # toaster dims, forward (sdf + normal + env x2 + diffuse + colour)
 FLOP_RENV_EXTRA = 18_432 + 12_160     # renv_net + second colour evaluation (main pass with r_images)
 FLOP_GEOMETRY = 14_208 + 12_416 + 192  # sdf fwd + reverse pass + jacobian contraction (geometry-only pass)
+FLOP_ENV = 610_304                    # env_net 72-256-256-256-12 evaluated twice per sample
 
 
 def parse():
@@ -42,6 +43,8 @@ def parse():
     ap.add_argument("--no-indir", action="store_true", help="single pass (BASELINE config 2 style)")
     ap.add_argument("--cpu-sample", type=int, default=12288, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
+                    help="env_net arithmetic: tc = tcgen05 tensor cores with fp16 hi/lo split operands (default), fp32 = FFMA path")
     return ap.parse_args()
 
 
@@ -162,6 +165,7 @@ def main():
     fp_cpu, bf, ro, rd, W, H = workload(args)
     N = W * H
     indir = not args.no_indir
+    fp_cpu.precision = args.precision
     fp = fp_cpu.to(dev).pack()
     bft = torch.from_numpy(bf).to(dev)
     rot = (2 * np.pi * rank / world) if world > 1 else None
@@ -231,12 +235,18 @@ def main():
     value = world * N / (ms_per_step * 1e-3)
     e2e_value = world * N / (e2e_ms / args.steps * 1e-3)
 
-    # roofline of the dominant kernel (k_field): algorithmic FLOP per sample x samples, over its CUDA-event time
+    # roofline of the dominant kernel: algorithmic FLOP per sample x samples, over its CUDA-event time.
+    #   fp32 : k_field does everything          -> all FLOPs of the pass
+    #   tc   : k_env_tc does the env_net passes -> 610,304 FLOP per shaded sample (2 x 152,576 MAC), geometry pass excluded
+    tcp = args.precision == "tc"
     if indir:
-        flop_step = (stats[0]["samples"] * FLOP_GEOMETRY + stats[1]["samples"] * FLOP_PER_SAMPLE
-                     + stats[2]["samples"] * (FLOP_PER_SAMPLE + FLOP_RENV_EXTRA))
+        if tcp:
+            flop_step = (stats[1]["samples"] + stats[2]["samples"]) * FLOP_ENV
+        else:
+            flop_step = (stats[0]["samples"] * FLOP_GEOMETRY + stats[1]["samples"] * FLOP_PER_SAMPLE
+                         + stats[2]["samples"] * (FLOP_PER_SAMPLE + FLOP_RENV_EXTRA))
     else:
-        flop_step = stats[0]["samples"] * FLOP_PER_SAMPLE
+        flop_step = stats[0]["samples"] * (FLOP_ENV if tcp else FLOP_PER_SAMPLE)
     field_ms_per_step = fms.value / args.steps
     peaks = {}
     try:
@@ -245,12 +255,15 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = flop_step / (field_ms_per_step * 1e-3) / 1e12 if field_ms_per_step > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_field (fused per-sample field: hash gather + SDF + normal + IDE + env/diffuse/colour MLPs)",
+    kname = ("k_env_tc (IDE + env_net x2 on tcgen05, fp16 hi/lo split operands: 3 MMAs per K step, fp32 accumulate in TMEM)" if tcp else
+             "k_field (fused per-sample field: hash gather + SDF + normal + IDE + env/diffuse/colour MLPs, fp32 FFMA)")
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
                 "traffic": None, "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
                 "kernel_share_of_step": field_ms_per_step / ms_per_step, "algorithmic_flop_per_step": flop_step,
-                "arithmetic": "fp32 FFMA (exact path); tensor-core path not enabled in this round's default"}
+                "arithmetic": ("tcgen05.mma kind::f16, 3 MMAs per K step (hi*hi + lo*hi + hi*lo): the tensor pipe executes 3x the "
+                               "algorithmic FLOPs counted here") if tcp else "fp32 FFMA (exact path)"}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -259,7 +272,8 @@ def main():
                    "sample": f"{n} rays (stride sample of the {W}x{H} frame, {s} samples) in {dt:.1f} s; oracle CPU port "
                              f"(C march/hash/composite + torch-CPU fp32 MLPs, all host threads)"}
         line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (env_net: fp16 hi+lo split operands on tensor cores, fp32 accumulate)" if tcp else "f32",
                 "data": "synthetic", "config": config_dict(args, W, H, indir),
                 "samples_per_sec": world * samples_per_step / (ms_per_step * 1e-3), "samples_per_step_per_gpu": samples_per_step,
                 "march_iterations_per_step": iters_per_step,

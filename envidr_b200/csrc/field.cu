@@ -21,6 +21,7 @@
 #include <math.h>
 #include "gridenc.cuh"
 #include "ide_tables.cuh"
+#include "field_tc.cuh"
 
 namespace envidr {
 
@@ -201,9 +202,15 @@ __device__ void run_stack(const float* __restrict__ blob, const LayerDesc* layer
     }
 }
 
+// phases: bit 0 = geometry (P1-P4), bit 1 = env_net on the FFMA path (P5), bit 2 = shading heads (P6-P7).
+// With the tensor-core env_net (field_tc.cu) the kernel is launched twice: phases = 1 writes a per-sample record
+// `rec` [M][32] (geo 0-15, n 16-18, n.w_o 19, roughness 20, blend 21, n_env 22-24, w_r 25-27), k_env_tc turns it into
+// unit-normalised env features `feat` [M][32] (f_n 0-15, f_r 16-31), and phases = 4 shades from rec + feat.
+constexpr int kRecFloats = 32;
 __global__ void __launch_bounds__(kThreads, 1)
 k_field(const FieldDev F, const float* __restrict__ xyzs, const float* __restrict__ dirs, const float* __restrict__ r_images,
-        const uint32_t* __restrict__ M_dev, uint32_t M_host, int mode, const FieldOutDev O) {
+        const uint32_t* __restrict__ M_dev, uint32_t M_host, int mode, int phases, float* __restrict__ rec, float* __restrict__ feat,
+        const FieldOutDev O) {
     extern __shared__ __align__(16) float smem[];
     float* act = smem;                         // [128][260]
     float* wbuf = act + kTile * kLd;           // [2][16*256]
@@ -217,6 +224,7 @@ k_field(const FieldDev F, const float* __restrict__ xyzs, const float* __restric
 
     for (uint32_t tile = blockIdx.x; (size_t)tile * kTile < M; tile += gridDim.x) {
         const uint32_t m0 = tile * kTile;
+        if (phases & 1) {
         // ---- P1: hash-grid gather: thread = (sample, level parity) ---------------------------------------
         {
             const int s = tid & (kTile - 1), g = tid >> 7;
@@ -363,12 +371,32 @@ k_field(const FieldDev F, const float* __restrict__ xyzs, const float* __restric
                 if (O.roughness) O.roughness[m] = rough;
                 if (O.normal) { O.normal[3 * (size_t)m] = nx; O.normal[3 * (size_t)m + 1] = ny; O.normal[3 * (size_t)m + 2] = nz; }
                 if (O.grad_x) { O.grad_x[3 * (size_t)m] = gx; O.grad_x[3 * (size_t)m + 1] = gy; O.grad_x[3 * (size_t)m + 2] = gz; }
+                if (rec && mode != 1) {
+                    float* q = rec + (size_t)m * kRecFloats;
+                    for (int i = 0; i < G; i++) q[i] = side[(S_GEO + i) * kTile + s];
+                    q[16] = nx; q[17] = ny; q[18] = nz; q[19] = ndot; q[20] = rough; q[21] = blend;
+                    q[22] = nex; q[23] = ney; q[24] = nez; q[25] = wrx; q[26] = wry; q[27] = wrz;
+                }
             }
         }
         __syncthreads();
+        }  // phases & 1
         if (mode == 1) continue;   // geometry only (block-uniform)
+        if (!(phases & 1)) {       // shading-only launch: reload the per-sample record written by the geometry launch
+            if (tid < kTile) {
+                const int s = tid;
+                const uint32_t m = m0 + s;
+                const float* q = rec + (size_t)min(m, M - 1) * kRecFloats;
+                for (int i = 0; i < G; i++) side[(S_GEO + i) * kTile + s] = q[i];
+                side[(S_N + 0) * kTile + s] = q[16]; side[(S_N + 1) * kTile + s] = q[17]; side[(S_N + 2) * kTile + s] = q[18];
+                side[S_NDOT * kTile + s] = q[19]; side[S_ROUGH * kTile + s] = q[20]; side[S_BLEND * kTile + s] = q[21];
+            }
+            __syncthreads();
+        }
+        if (!(phases & 6)) continue;
 
         // ---- P5: env_net on IDE(n, kappa_diffuse) and IDE(w_r, roughness) --------------------------------
+        if (phases & 2)
         for (int branch = 0; branch < 2; branch++) {
             if (tid < kTile) {
                 const int s = tid;
@@ -392,10 +420,16 @@ k_field(const FieldDev F, const float* __restrict__ xyzs, const float* __restric
         }
         // ---- P6: shading heads ---------------------------------------------------------------------------------
         const int E = (int)F.env[F.n_env - 1].N;       // env feature dim
+        if (!(phases & 4)) continue;
         if (tid < kTile) {
             const int s = tid;
-            unit_norm(side, S_FN, E, s, 1e-12f);
-            unit_norm(side, S_FR, E, s, 1e-12f);
+            if (phases & 2) {
+                unit_norm(side, S_FN, E, s, 1e-12f);
+                unit_norm(side, S_FR, E, s, 1e-12f);
+            } else {                                    // features come unit-normalised from the tensor-core kernel
+                const float* q = feat + (size_t)min(m0 + s, M - 1) * kRecFloats;
+                for (int i = 0; i < E; i++) { side[(S_FN + i) * kTile + s] = q[i]; side[(S_FR + i) * kTile + s] = q[16 + i]; }
+            }
             float* a = act + s * kLd;
             for (int i = 0; i < G; i++) a[i] = side[(S_GEO + i) * kTile + s];
             for (int i = 0; i < E; i++) a[G + i] = side[(S_FN + i) * kTile + s];
@@ -587,12 +621,15 @@ static int ensure_ide_field(uint32_t deg) {
 
 constexpr size_t kFieldSmem = (size_t)(kTile * kLd + 2 * kWbuf + S_COUNT * kTile) * sizeof(float);
 
+// timing hook (bench.py): when non-null, ev[0]/ev[1] are recorded around the dominant kernel of this call
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
-                         const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st) {
+                         const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
+                         cudaEvent_t* ev) {
     Layout lay;
     int rc = build_layout(field, &lay);
     if (rc) return rc;
-    ENVIDR_REQUIRE(field->packed && field->packed_bytes >= lay.floats * sizeof(float), ENVIDR_E_WORKSPACE,
+    const uint64_t simt_bytes = lay.floats * sizeof(float);
+    ENVIDR_REQUIRE(field->packed && field->packed_bytes >= simt_bytes, ENVIDR_E_WORKSPACE,
                    "field->packed missing or too small (call envidr_field_pack)");
     if (!M_dev && M_host == 0) return 0;               // empty batch: nothing to do (pointers may be NULL)
     ENVIDR_REQUIRE(xyzs && dirs && out, ENVIDR_E_BADARG, "null pointer");
@@ -606,8 +643,31 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
     FieldOutDev O{out->sigma, out->rgb, out->normal, out->sdf, out->c_diffuse, out->c_specular, out->roughness, out->grad_x};
     uint32_t grid = kSMs;
     if (!M_dev) grid = min((uint32_t)kSMs, ceil_div(M_host, kTile));
-    k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, O);
-    return check_launch("field_forward");
+    const bool tensor = field->precision == 1 && mode != 1;
+    if (!tensor) {
+        if (ev) cudaEventRecord(ev[0], st);
+        k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, mode == 1 ? 1 : 7, nullptr, nullptr, O);
+        if (ev) cudaEventRecord(ev[1], st);
+        return check_launch("field_forward");
+    }
+    // tensor-core env_net: geometry -> record, tcgen05 env_net -> features, shading heads
+    TcEnv tcenv;
+    uint64_t total = 0;
+    ENVIDR_REQUIRE(tc_layout(field, simt_bytes, &tcenv, &total), ENVIDR_E_UNSUPPORTED,
+                   "precision=1: env_net shape outside the tensor-core kernel (hidden widths must be multiples of 32, <= 256; env_feat <= 16)");
+    ENVIDR_REQUIRE(field->packed_bytes >= total, ENVIDR_E_WORKSPACE, "field->packed too small for the tensor-core images (envidr_field_pack_bytes)");
+    const uint64_t cap = M_dev ? field->scratch_samples : M_host;
+    ENVIDR_REQUIRE(field->scratch && field->scratch_samples >= cap && cap > 0, ENVIDR_E_WORKSPACE,
+                   "precision=1 needs field->scratch (256 B per sample)");
+    float* rec = reinterpret_cast<float*>(field->scratch);
+    float* feat = rec + (size_t)field->scratch_samples * kRecFloats;
+    k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, 1, rec, feat, O);
+    if (ev) cudaEventRecord(ev[0], st);
+    rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, M_dev, M_host, st);
+    if (ev) cudaEventRecord(ev[1], st);
+    if (rc) return rc;
+    k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, 4, rec, feat, O);
+    return check_launch("field_forward(tc)");
 }
 
 }  // namespace envidr
@@ -619,6 +679,9 @@ extern "C" {
 uint64_t envidr_field_pack_bytes(const envidr_field* field) {
     Layout lay;
     if (build_layout(field, &lay)) return 0;
+    TcEnv t;
+    uint64_t total = 0;
+    if (tc_layout(field, lay.floats * sizeof(float), &t, &total)) return total;      // FFMA images + tensor-core images
     return lay.floats * sizeof(float);
 }
 
@@ -648,12 +711,19 @@ int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_b
     const envidr_mlp_layer& last = field->sdf[field->n_sdf - 1];
     cudaMemsetAsync(blob + lay.dev.sdf_row0_off, 0, kMaxHidden * sizeof(float), st);
     cudaMemcpyAsync(blob + lay.dev.sdf_row0_off, last.weight, last.in_dim * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    return check_launch("field_pack");
+    rc = check_launch("field_pack");
+    if (rc) return rc;
+    envidr_field tmp = *field;
+    tmp.packed = packed; tmp.packed_bytes = packed_bytes;
+    TcEnv t;
+    uint64_t total = 0;
+    if (tc_layout(&tmp, lay.floats * sizeof(float), &t, &total) && packed_bytes >= total) return tc_pack(field, t, packed, st);
+    return 0;
 }
 
 int envidr_field_forward(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images, uint32_t M, int mode,
                          const envidr_field_out* out, envidr_stream_t stream) {
-    return field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream));
+    return field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), nullptr);
 }
 
 }  // extern "C"

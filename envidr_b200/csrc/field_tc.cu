@@ -1,0 +1,312 @@
+// field_tc.cu -- env_net (IDE -> hidden x (n-1) -> env_feat, evaluated for the normal and the reflected direction of
+// every sample) on the 5th-generation tensor cores of sm_100a.
+//
+// This is >90 % of the FLOPs of the render path (610,304 of 651,008 FLOP/sample at toaster dims).
+// The reference runs it as 8 cuBLAS fp32 GEMMs + 8 elementwise launches per render iteration (network.py:527-607).
+//
+// Design (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      producer: streams the pre-packed weight images of every layer from L2 into a 4-stage shared-memory
+//               ring with 1-D bulk async copies (TMA engine, cp.async.bulk -> UBLKCP), one 16-wide K step per stage
+//   warp 1      issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128 rows, N = layer width,
+//               K = 16) with the fp32 accumulator tile [128 x N] in tensor memory (TMEM, 256 columns)
+//   warp 2      TMEM allocator
+//   warps 4-11  workers (2 per accumulator row): compute the IDE features of the tile straight into the A-operand
+//               layout, and after each layer read their 32-column slices of the accumulator with tcgen05.ld, apply
+//               bias + ReLU and write the next layer's A operand back to shared memory (in place); the last layer's
+//               epilogue unit-normalises the env feature and stores it.
+//   Synchronisation is mbarrier-only between roles (full/empty ring, accumulator-ready via tcgen05.commit,
+//   operand-ready via arrive after fence.proxy.async).
+//
+// Precision: the reference computes these layers in fp32 and the parity bar is 1e-4 on RGB, which a single fp16/bf16/
+// tf32 pass does not meet (measured ~1e-3 on the env feature).  Every operand is therefore split x = hi + lo into two
+// fp16 values (22 significant bits) and each K step issues three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32;
+// the dropped lo*lo term is below 2^-22 relative.  Effective tensor throughput is a third of the fp16 rate.
+#include <math.h>
+#include "common.cuh"
+#include "ide_tables.cuh"
+#include "tc_common.cuh"
+#include "field_tc.cuh"
+
+namespace envidr {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcStages = 4;
+constexpr uint32_t kTcStageBytes = 16384;          // one K step (16) of a 256-wide layer: 2 (hi,lo) x 2 chunks x 256 x 16 B
+constexpr uint32_t kTcARegion = 65536;             // 128 rows x 256 K x 2 B
+__constant__ IdeTables c_ide_tc;
+static int g_ide_tc_deg = 0;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = smem + kTcARegion;
+    uint8_t* ring = smem + 2 * kTcARegion;
+    float* s_bias = reinterpret_cast<float*>(ring + kTcStages * kTcStageBytes);         // [8 * 256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kTcMaxLayers * 256);
+    uint64_t* full = bars;                  // [4]  producer -> issuer (TMA bytes landed)
+    uint64_t* empty = bars + kTcStages;     // [4]  issuer -> producer (MMAs reading the stage retired)
+    uint64_t* acc_ready = bars + 2 * kTcStages;      // issuer -> workers
+    uint64_t* a_ready = bars + 2 * kTcStages + 1;    // workers -> issuer (256 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t M = M_dev ? *M_dev : M_host;
+    const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
+    const int nl = (int)E.n_layers;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(acc_ready, 1);
+        tc::mbar_init(a_ready, 256);
+        tc::mbar_fence_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+    for (uint32_t i = tid; i < (uint32_t)nl * 256; i += kTcThreads) {
+        const uint32_t l = i >> 8, c = i & 255;
+        s_bias[i] = (c < E.L[l].Np) ? __ldg(E.bias + E.L[l].bias_off + c) : 0.0f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int l = 0; l < nl; l++) {
+                const uint32_t ksteps = E.L[l].Kp / 16, bytes = E.L[l].Np * 64;
+                const uint8_t* src = E.blob + E.L[l].img_off;
+                for (uint32_t s = 0; s < ksteps; s++) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    if (lane == 0) {
+                        tc::mbar_arrive_expect_tx(&full[stage], bytes);
+                        tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * bytes, bytes, &full[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        uint32_t stage = 0, phase = 0, a_par = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int l = 0; l < nl; l++) {
+                const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np;
+                const uint32_t idesc = tc::make_idesc_f16(128, Np);
+                tc::mbar_wait(a_ready, a_par); a_par ^= 1;
+                tc::tc_fence_after();
+                for (uint32_t s = 0; s < ksteps; s++) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_hi = tc::smem_u32(sA_hi) + s * 4096, a_lo = tc::smem_u32(sA_lo) + s * 4096;
+                        const uint32_t b_hi = tc::smem_u32(ring + stage * kTcStageBytes), b_lo = b_hi + Np * 32;
+                        const uint64_t da_hi = tc::make_smem_desc(a_hi, 2048, 128), da_lo = tc::make_smem_desc(a_lo, 2048, 128);
+                        const uint64_t db_hi = tc::make_smem_desc(b_hi, Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, Np * 16, 128);
+                        tc::mma_f16_ss(tmem, da_hi, db_hi, idesc, s > 0);
+                        tc::mma_f16_ss(tmem, da_lo, db_hi, idesc, 1);
+                        tc::mma_f16_ss(tmem, da_hi, db_lo, idesc, 1);
+                        tc::mma_commit(&empty[stage]);            // frees the ring slot when these MMAs retire
+                    }
+                    __syncwarp();
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+                if (lane == 0) tc::mma_commit(acc_ready);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== workers =====================
+        const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t branch = row >> 6;
+        const uint32_t lane_addr = (quarter * 32u) << 16;
+        uint32_t acc_par = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t m = tile * 64 + (row & 63);
+            const bool valid = m < M;
+            // ---- IDE features of this row -> A operand of layer 0 -------------------------------------
+            if (g == 0) {
+                const uint32_t Kp0 = E.L[0].Kp;
+                if (valid) {
+                    const float* q = rec + (size_t)m * kTcRecFloats;
+                    const float dx = q[22 + 3 * branch], dy = q[23 + 3 * branch], dz = q[24 + 3 * branch];
+                    const float kap = branch ? q[20] : E.kappa_diffuse;
+                    const uint32_t P = E.P;
+                    ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, [&](int i, float re, float im) {
+                        __half h, lo;
+                        tc::split_f16(re, h, lo);
+                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, i)) = h;
+                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, i)) = lo;
+                        tc::split_f16(im, h, lo);
+                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, P + i)) = h;
+                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, P + i)) = lo;
+                    });
+                    for (uint32_t k = 2 * P; k < Kp0; k++) {
+                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, k)) = __float2half_rn(0.f);
+                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, k)) = __float2half_rn(0.f);
+                    }
+                } else {
+                    for (uint32_t k = 0; k < Kp0; k += 8) {
+                        *reinterpret_cast<uint4*>(sA_hi + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(sA_lo + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(a_ready);
+            // ---- per-layer epilogues ---------------------------------------------------------------------------
+            for (int l = 0; l < nl; l++) {
+                tc::mbar_wait(acc_ready, acc_par); acc_par ^= 1;
+                tc::tc_fence_after();
+                const float* bias = s_bias + l * 256;
+                if (l < nl - 1) {
+                    const uint32_t nchunks = E.L[l].N / 32;
+                    for (uint32_t cb = g; cb < nchunks; cb += 2) {
+                        uint32_t r[32];
+                        tc::tmem_ld32(tmem + lane_addr + cb * 32, r);
+                        tc::tmem_ld_wait();
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            uint32_t ph[4], pl[4];
+                            #pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const int c0 = j * 8 + e * 2;
+                                const float v0 = fmaxf(__uint_as_float(r[c0]) + bias[cb * 32 + c0], 0.0f);
+                                const float v1 = fmaxf(__uint_as_float(r[c0 + 1]) + bias[cb * 32 + c0 + 1], 0.0f);
+                                __half h0, l0, h1, l1;
+                                tc::split_f16(v0, h0, l0);
+                                tc::split_f16(v1, h1, l1);
+                                ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            }
+                            const uint32_t off = tc::op_off(128, row, cb * 32 + j * 8);
+                            *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        }
+                    }
+                    tc::tc_fence_before();
+                    tc::fence_proxy_async_smem();
+                    tc::mbar_arrive(a_ready);
+                } else if (g == 0) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tmem + lane_addr, r);
+                    tc::tmem_ld_wait();
+                    const int Ef = (int)E.E;
+                    float f[16], ss = 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
+                        ss += f[i] * f[i];
+                    }
+                    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * kTcRecFloats + 16 * branch);
+                        dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+                        dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+                        dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
+                        dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
+                    }
+                    tc::tc_fence_before();
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem, 256);
+}
+
+// weight image of one layer: for every K step s: [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1], chunk = [Np][8] halfs
+__global__ void k_pack_tc(const float* __restrict__ W, const float* __restrict__ b, uint8_t* __restrict__ img, float* __restrict__ bias,
+                          uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+    const uint32_t total = Kp * Np;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t n = i / Kp, k = i - n * Kp;
+        const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+        __half h, lo;
+        tc::split_f16(v, h, lo);
+        const uint32_t s = k >> 4, kk = k & 15;
+        const size_t base = (size_t)s * Np * 64 + (kk >> 3) * (Np * 16) + n * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(img + base) = h;
+        *reinterpret_cast<__half*>(img + base + (size_t)Np * 32) = lo;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x) bias[i] = (b && i < N) ? b[i] : 0.0f;
+}
+
+static uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// Lays the tensor-core images out after `base_bytes` of the packed blob.  Returns false if the env_net shape is outside
+// what the tensor-core kernel handles (the FFMA path then has to be used).
+bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes) {
+    TcEnv& t = *out;
+    t = TcEnv{};
+    if (f->n_env < 2 || f->n_env > (uint32_t)kTcMaxLayers) return false;
+    const uint32_t P = (1u << f->ide_degree) - 1 + f->ide_degree;
+    uint64_t off = rup((uint32_t)base_bytes, 1024);
+    uint32_t boff = 0;
+    for (uint32_t i = 0; i < f->n_env; i++) {
+        const bool last = (i == f->n_env - 1);
+        const uint32_t K = f->env[i].in_dim, N = f->env[i].out_dim;
+        if (!last && (N % 32 != 0 || N > 256 || N < 32)) return false;
+        if (last && N > 16) return false;
+        if (i > 0 && K != f->env[i - 1].out_dim) return false;
+        TcLayer& L = t.L[i];
+        L.K = K; L.Kp = rup(K, 16); L.N = N; L.Np = last ? 16 : N;
+        if (L.Kp > 256) return false;
+        L.img_off = (uint32_t)off;
+        off += (uint64_t)(L.Kp / 16) * L.Np * 64;
+        L.bias_off = boff;
+        boff += L.Np;
+    }
+    if (f->env[0].in_dim != 2 * P) return false;
+    off = rup((uint32_t)off, 256);
+    const uint64_t bias_bytes_off = off;
+    off += (uint64_t)boff * 4;
+    t.n_layers = f->n_env; t.P = P; t.E = f->env[f->n_env - 1].out_dim;
+    t.kappa_diffuse = f->diffuse_kappa_inv; t.light_scale = f->light_intensity_scale;
+    if (f->packed) {
+        t.blob = reinterpret_cast<const uint8_t*>(f->packed);
+        t.bias = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(f->packed) + bias_bytes_off);
+    }
+    *total_bytes = off;
+    return true;
+}
+
+int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st) {
+    uint8_t* blob = reinterpret_cast<uint8_t*>(packed);
+    float* bias = const_cast<float*>(reinterpret_cast<const float*>(blob + (reinterpret_cast<const uint8_t*>(t.bias) - t.blob)));
+    for (uint32_t i = 0; i < t.n_layers; i++) {
+        const TcLayer& L = t.L[i];
+        k_pack_tc<<<128, 256, 0, st>>>(f->env[i].weight, f->env[i].bias, blob + L.img_off, bias + L.bias_off, L.K, L.N, L.Kp, L.Np);
+    }
+    return check_launch("field_pack_tc");
+}
+
+constexpr size_t kTcSmem = 2 * kTcARegion + kTcStages * kTcStageBytes + kTcMaxLayers * 256 * sizeof(float) + 128;
+
+int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
+    if ((int)ide_degree != g_ide_tc_deg) {
+        IdeTables tab;
+        if (!ide_build_tables((int)ide_degree, &tab)) return ENVIDR_E_UNSUPPORTED;
+        cudaError_t e = cudaMemcpyToSymbol(c_ide_tc, &tab, sizeof(tab));
+        if (e != cudaSuccess) { set_error("ide tables: %s", cudaGetErrorString(e)); return (int)e; }
+        g_ide_tc_deg = (int)ide_degree;
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_env_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e != cudaSuccess) { set_error("env_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    uint32_t grid = kSMs;
+    if (!M_dev) grid = min((uint32_t)kSMs, (2 * M_host + 127) / 128);
+    if (grid == 0) return 0;
+    k_env_tc<<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host);
+    return check_launch("env_tc");
+}
+
+}  // namespace envidr

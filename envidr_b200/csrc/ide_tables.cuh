@@ -85,9 +85,9 @@ inline bool ide_build_tables(int deg_view, IdeTables* t) {
 }
 
 #ifdef __CUDACC__
-// out_re[i*sr], out_im[i*si], i < P:  [Re | Im] of  (x+iy)^m * K_l^m Q_l^m(z) * exp(-sigma_l * kappa_inv) * scale
-__device__ __forceinline__ void ide_eval(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale,
-                                         float* out_re, int sr, float* out_im, int si) {
+// emit(i, re_i, im_i), i < P, with [Re | Im]_i = (x+iy)^m * K_l^m Q_l^m(z) * exp(-sigma_l * kappa_inv) * scale
+template <class Emit>
+__device__ __forceinline__ void ide_eval_emit(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale, Emit&& emit) {
     if (x == 0.0f && y == 0.0f) y += 1.0f;         // "avoid 0 + 0j exponentiation" (ide_encoder.py:113-115)
     float att[5];
     #pragma unroll
@@ -103,21 +103,22 @@ __device__ __forceinline__ void ide_eval(const IdeTables& T, float x, float y, f
         float p2 = 0.0f, p1 = T.qmm[m];
         if (m > 0 && (m & (m - 1)) == 0) {            // l == m is itself a band (m = 1, 2, 4, 8, 16)
             const int b = 31 - __clz(m);
-            const int i = T.band_base[b] + m;
-            out_re[i * sr] = re * p1 * att[b];
-            out_im[i * si] = im * p1 * att[b];
+            emit(T.band_base[b] + m, re * p1 * att[b], im * p1 * att[b]);
         }
         for (int l = m + 1; l <= l_max; l++) {
             const float q = T.ra[l][m] * z * p1 - T.rb[l][m] * p2;
             p2 = p1; p1 = q;
             if ((l & (l - 1)) == 0) {
                 const int b = 31 - __clz(l);
-                const int i = T.band_base[b] + m;
-                out_re[i * sr] = re * q * att[b];
-                out_im[i * si] = im * q * att[b];
+                emit(T.band_base[b] + m, re * q * att[b], im * q * att[b]);
             }
         }
     }
+}
+// out_re[i*sr], out_im[i*si], i < P
+__device__ __forceinline__ void ide_eval(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale,
+                                         float* out_re, int sr, float* out_im, int si) {
+    ide_eval_emit(T, x, y, z, kappa_inv, scale, [&](int i, float re, float im) { out_re[i * sr] = re; out_im[i * si] = im; });
 }
 #endif
 

@@ -16,7 +16,8 @@
 namespace envidr {
 
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
-                         const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st);
+                         const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
+                         cudaEvent_t* ev);
 
 constexpr int kMarchBlock = 128;
 constexpr int kMaxNStep = 8;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256) k_render_finish(uint32_t N, float bg0, fl
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, total;
+    uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, scratch, total;
 };
 static WsLayout ws_layout(uint32_t N) {
     WsLayout L{};
@@ -280,6 +281,7 @@ static WsLayout ws_layout(uint32_t N) {
     L.s_sigma = take(4 * n); L.s_rgb = take(12 * n); L.s_normal = take(12 * n); L.s_cd = take(12 * n); L.s_cs = take(12 * n);
     L.s_rough = take(4 * n);
     L.ctr = take(sizeof(Counters));
+    L.scratch = take(256 * n);             // tensor-core path: per-sample record + env features (2 x 32 floats)
     L.total = off;
     return L;
 }
@@ -341,6 +343,8 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     int rc = check_launch("render_init");
     if (rc) return rc;
 
+    envidr_field fld = *field;                       // per-iteration sample count is bounded by N
+    fld.scratch = w + L.scratch; fld.scratch_samples = N;
     envidr_field_out fo{};
     fo.sigma = B.s_sigma; fo.normal = B.s_normal;
     if (!opts->geometry_only) {
@@ -359,15 +363,12 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
             k_march_compact<<<march_grid, kMarchBlock, 0, st>>>(rays_o, rays_d, r_images, bitfield, opts->bound, opts->dt_gamma,
                                                                opts->max_steps, opts->cascade, opts->grid_size, noises, B);
             const bool timed = g_timing && g_tev_used < kMaxTimed;
-            if (timed) {
-                while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
-                cudaEventRecord(g_tev[2 * g_tev_used], st);
-            }
-            rc = field_forward_launch(field, B.s_xyz, B.s_dir, r_images ? B.s_rimg : nullptr, &B.ctr->M, 0,
-                                      opts->geometry_only ? 1 : 0, &fo, st);
+            if (timed) while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
+            rc = field_forward_launch(&fld, B.s_xyz, B.s_dir, r_images ? B.s_rimg : nullptr, &B.ctr->M, 0,
+                                      opts->geometry_only ? 1 : 0, &fo, st, timed ? &g_tev[2 * g_tev_used] : nullptr);
             if (rc) return rc;
-            if (timed) { cudaEventRecord(g_tev[2 * g_tev_used + 1], st); g_tev_used++; }
-            g_launches += 3;
+            if (timed) g_tev_used++;
+            g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;
             k_composite_compact<<<march_grid, kMarchBlock, 0, st>>>(N, opts->T_thresh, opts->max_steps, opts->geometry_only,
                                                                    opts->input_alpha, B, O);
         }

@@ -55,7 +55,9 @@ class FieldParams:
     indir_roughness_thresh: float = 0.1
     learn_indir_blend: bool = True
     enabled_levels: int = -1
+    precision: str = "fp32"             # "fp32": exact FFMA path; "tc": tcgen05 tensor cores, fp16 hi/lo split operands (3 MMAs)
     _packed: Optional[torch.Tensor] = None
+    _scratch: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -77,6 +79,7 @@ class FieldParams:
         for name, st in self.stacks().items():
             kw[name] = None if st is None else [(mv(W), mv(b)) for W, b in st]
         kw["_packed"] = None
+        kw["_scratch"] = None
         return FieldParams(**kw)
 
     def clamped_beta(self) -> float:
@@ -137,6 +140,12 @@ class FieldParams:
         if self._packed is not None:
             f.packed = self._packed.data_ptr()
             f.packed_bytes = self._packed.numel() * 4
+        if self.precision not in ("fp32", "tc"):
+            raise _lib.EnvidrError(f"unknown precision {self.precision!r} (fp32 | tc)")
+        f.precision = 1 if self.precision == "tc" else 0
+        if self._scratch is not None:
+            f.scratch = self._scratch.data_ptr()
+            f.scratch_samples = self._scratch.numel() // 64
         return f
 
     def pack(self) -> "FieldParams":
@@ -167,6 +176,8 @@ class FieldParams:
         if r_images is not None:
             r_images = r_images.float().contiguous().view(-1, 4)
             assert r_images.shape[0] == M
+        if self.precision == "tc" and not geometry_only and (self._scratch is None or self._scratch.numel() < 64 * M):
+            self._scratch = torch.empty(64 * max(M, 1), dtype=torch.float32, device=xyzs.device)
         f = self.cstruct(env_rot_radian)
         check(lib().envidr_field_forward(ctypes.byref(f), ptr(xyzs), ptr(dirs), ptr(r_images), M, 1 if geometry_only else 0,
                                          ctypes.byref(fo), stream()), "field_forward")

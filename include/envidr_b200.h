@@ -198,6 +198,11 @@ typedef struct envidr_field {
     /* device buffer of repacked (K-major, padded) weights written by envidr_field_pack; must be
      * refreshed whenever a weight tensor changes.  Size: envidr_field_pack_bytes(). */
     const void* packed; uint64_t packed_bytes;
+    /* arithmetic of the env_net passes: 0 = fp32 FFMA (bit-faithful path); 1 = tcgen05 tensor cores with every operand
+     * split into two fp16 values and three MMAs per K step (fp32 accumulate; ~1e-6 relative to the fp32 path). */
+    int32_t precision; int32_t reserved;
+    /* precision = 1 only: device scratch of 256 bytes per sample for at least scratch_samples >= M samples */
+    void* scratch; uint64_t scratch_samples;
 } envidr_field;
 
 /* Bytes needed for field->packed (0 if the field description is rejected; see envidr_last_error). */
