@@ -351,8 +351,10 @@ def _sph_harm_coeff(l: int, m: int, k: int) -> float:
     return math.sqrt((2.0 * l + 1.0) * math.factorial(l - m) / (4.0 * math.pi * math.factorial(l + m))) * legendre
 
 
-def ide_tables(deg_view: int):
-    """(ml[2,P] int, mat[l_max+1,P] float32, sigma[P] float32); ide_encoder.py:45-96."""
+def ide_tables(deg_view: int, exact: bool = False):
+    """(ml[2,P] int, mat[l_max+1,P] float32, sigma[P] float32); ide_encoder.py:45-96.
+    exact=True keeps the coefficients in float64 (the reference rounds them to fp32 when it registers the buffer, which
+    by itself moves the l = 16 band by up to ~6e-4: |coeff| ~ 1e5 x 6e-8)."""
     if deg_view > 5:
         raise ValueError("Only deg_view of at most 5 is numerically stable.")
     ml = [(m, 2 ** i) for i in range(deg_view) for m in range(2 ** i + 1)]
@@ -363,13 +365,16 @@ def ide_tables(deg_view: int):
             mat[k, i] = _sph_harm_coeff(l, m, k)
     ml_a = np.array(ml).T
     sigma = 0.5 * ml_a[1] * (ml_a[1] + 1)
+    if exact:
+        return ml_a.astype(np.int32), mat, sigma.astype(np.float64)
     return ml_a.astype(np.int32), mat.astype(np.float32), sigma.astype(np.float32)
 
 
-def ide_encode(xyz: torch.Tensor, kappa_inv, deg_view: int) -> torch.Tensor:
+def ide_encode(xyz: torch.Tensor, kappa_inv, deg_view: int, exact_tables: bool = False) -> torch.Tensor:
     """IntegratedDirEncoder.forward (ide_encoder.py:98-130) with repeated complex products instead of
-    complex pow.  dtype follows xyz (float32 or float64); the tables are the fp32-rounded ones."""
-    ml, mat, sigma = ide_tables(deg_view)
+    complex pow.  dtype follows xyz (float32 or float64); the tables are the fp32-rounded ones of the reference unless
+    exact_tables (then, in float64, the result is the mathematically exact encoding)."""
+    ml, mat, sigma = ide_tables(deg_view, exact_tables)
     dt = xyz.dtype
     x, y, z = xyz[..., 0:1], xyz[..., 1:2], xyz[..., 2:3]
     y = y + ((x == 0) & (y == 0)).to(dt)                      # "avoid 0 + 0j exponentiation"

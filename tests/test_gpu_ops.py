@@ -476,9 +476,9 @@ def test_ide_kernel_vs_reference_golden(dev, golden_dir, deg):
         ref = z[f"ide{deg}_{key}"]
         assert got.shape == ref.shape
         assert (np.abs(got - ref) <= atol + 2e-5 * np.abs(ref)).all(), np.abs(got - ref).max()
-        # against the exact (fp64) encoding the kernel is accurate in every band
+        # against the exact encoding (float64 arithmetic AND float64 coefficients) the kernel is accurate in every band
         r64 = rough.double().cpu() if torch.is_tensor(rough) else rough
-        exact = O.ide_encode(d.double().cpu(), r64, deg).numpy()
+        exact = O.ide_encode(d.double().cpu(), r64, deg, exact_tables=True).numpy()
         assert (np.abs(got - exact) <= 2e-6 + 2e-5 * np.abs(exact)).all(), np.abs(got - exact).max()   # values reach 90 at z = +-1
     # autograd path (torch formulation) agrees with the kernel
     d2 = d.clone().requires_grad_(True)
