@@ -5,17 +5,18 @@
 // The reference runs it as 8 cuBLAS fp32 GEMMs + 8 elementwise launches per render iteration (network.py:527-607).
 //
 // Design (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      producer: streams the pre-packed weight images of every layer from L2 into a 4-stage shared-memory
+//   warp 0      producer: streams the pre-packed weight images of every layer from L2 into a 3-stage shared-memory
 //               ring with 1-D bulk async copies (TMA engine, cp.async.bulk -> UBLKCP), one 16-wide K step per stage
 //   warp 1      issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128 rows, N = layer width,
 //               K = 16) with the fp32 accumulator tile [128 x N] in tensor memory (TMEM, 256 columns)
 //   warp 2      TMEM allocator
-//   warps 4-11  workers (2 per accumulator row): compute the IDE features of the tile straight into the A-operand
-//               layout, and after each layer read their 32-column slices of the accumulator with tcgen05.ld, apply
-//               bias + ReLU and write the next layer's A operand back to shared memory (in place); the last layer's
-//               epilogue unit-normalises the env feature and stores it.
-//   Synchronisation is mbarrier-only between roles (full/empty ring, accumulator-ready via tcgen05.commit,
-//   operand-ready via arrive after fence.proxy.async).
+//   warps 4-11  epilogue (2 threads per accumulator row): after each layer read their 32-column slices of the
+//               accumulator with tcgen05.ld, apply bias + ReLU, re-split into fp16 hi/lo and write the next layer's
+//               A operand to shared memory (in place); the last layer's epilogue unit-normalises the env feature
+//   warps 12-19 IDE (2 threads per row, even / odd orders m): directional encoding of the NEXT tile straight into a
+//               separate layer-0 A-operand buffer while the current tile occupies the tensor pipe
+//   Synchronisation is mbarrier-only between roles (full/empty ring, accumulator-ready / IDE-buffer-free via
+//   tcgen05.commit, operand-ready via arrive after fence.proxy.async).
 //
 // Precision: the reference computes these layers in fp32 and the parity bar is 1e-4 on RGB, which a single fp16/bf16/
 // tf32 pass does not meet (measured ~1e-3 on the env feature).  Every operand is therefore split x = hi + lo into two
@@ -29,26 +30,41 @@
 
 namespace envidr {
 
-constexpr int kTcThreads = 384;
-constexpr int kTcStages = 4;
+constexpr int kTcThreads = 640;                    // 4 control warps + 8 epilogue warps + 8 IDE warps
+constexpr int kTcStages = 3;
 constexpr uint32_t kTcStageBytes = 16384;          // one K step (16) of a 256-wide layer: 2 (hi,lo) x 2 chunks x 256 x 16 B
 constexpr uint32_t kTcARegion = 65536;             // 128 rows x 256 K x 2 B
+constexpr uint32_t kTcIdeRegion = 20480;           // 128 rows x 80 K x 2 B (IDE features, deg_view <= 5, K padded to 16)
 __constant__ IdeTables c_ide_tc;
 static int g_ide_tc_deg = 0;
+
+// fp32 pair -> packed fp16 (hi) pair and packed fp16 (lo = x - hi) pair
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sA_hi = smem;
+    uint8_t* sA_hi = smem;                                   // hidden-layer A operand (written by the epilogues)
     uint8_t* sA_lo = smem + kTcARegion;
-    uint8_t* ring = smem + 2 * kTcARegion;
+    uint8_t* sI_hi = smem + 2 * kTcARegion;                  // layer-0 A operand (written by the IDE warps)
+    uint8_t* sI_lo = sI_hi + kTcIdeRegion;
+    uint8_t* ring = sI_lo + kTcIdeRegion;
     float* s_bias = reinterpret_cast<float*>(ring + kTcStages * kTcStageBytes);         // [8 * 256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kTcMaxLayers * 256);
-    uint64_t* full = bars;                  // [4]  producer -> issuer (TMA bytes landed)
-    uint64_t* empty = bars + kTcStages;     // [4]  issuer -> producer (MMAs reading the stage retired)
-    uint64_t* acc_ready = bars + 2 * kTcStages;      // issuer -> workers
-    uint64_t* a_ready = bars + 2 * kTcStages + 1;    // workers -> issuer (256 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2);
+    uint64_t* full = bars;                           // [3]  producer -> issuer (TMA bytes landed)
+    uint64_t* empty = bars + kTcStages;              // [3]  issuer -> producer (MMAs reading the stage retired)
+    uint64_t* acc_ready = bars + 2 * kTcStages;      // issuer -> epilogue warps (accumulator of a layer complete)
+    uint64_t* a_ready = acc_ready + 1;               // epilogue warps -> issuer (next layer's A operand in smem; 256 arrivals)
+    uint64_t* d_free = acc_ready + 2;                // epilogue warps -> issuer (last accumulator of the tile drained; 256 arrivals)
+    uint64_t* ide_full = acc_ready + 3;              // IDE warps -> issuer (256 arrivals)
+    uint64_t* ide_empty = acc_ready + 4;             // issuer -> IDE warps (layer-0 MMAs retired)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 5);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t M = M_dev ? *M_dev : M_host;
@@ -59,6 +75,9 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(acc_ready, 1);
         tc::mbar_init(a_ready, 256);
+        tc::mbar_init(d_free, 256);
+        tc::mbar_init(ide_full, 256);
+        tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
@@ -91,18 +110,26 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        uint32_t stage = 0, phase = 0, a_par = 0;
+        uint32_t stage = 0, phase = 0, a_par = 0, ide_par = 0, dfree_par = 1;    // dfree_par = 1: the first wait passes
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int l = 0; l < nl; l++) {
                 const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np;
                 const uint32_t idesc = tc::make_idesc_f16(128, Np);
-                tc::mbar_wait(a_ready, a_par); a_par ^= 1;
+                uint32_t base_hi, base_lo;
+                if (l == 0) {
+                    tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;          // IDE operand of this tile is in smem
+                    tc::mbar_wait(d_free, dfree_par); dfree_par ^= 1;        // previous tile's last accumulator has been read
+                    base_hi = tc::smem_u32(sI_hi); base_lo = tc::smem_u32(sI_lo);
+                } else {
+                    tc::mbar_wait(a_ready, a_par); a_par ^= 1;
+                    base_hi = tc::smem_u32(sA_hi); base_lo = tc::smem_u32(sA_lo);
+                }
                 tc::tc_fence_after();
                 for (uint32_t s = 0; s < ksteps; s++) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t a_hi = tc::smem_u32(sA_hi) + s * 4096, a_lo = tc::smem_u32(sA_lo) + s * 4096;
+                        const uint32_t a_hi = base_hi + s * 4096, a_lo = base_lo + s * 4096;
                         const uint32_t b_hi = tc::smem_u32(ring + stage * kTcStageBytes), b_lo = b_hi + Np * 32;
                         const uint64_t da_hi = tc::make_smem_desc(a_hi, 2048, 128), da_lo = tc::make_smem_desc(a_lo, 2048, 128);
                         const uint64_t db_hi = tc::make_smem_desc(b_hi, Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, Np * 16, 128);
@@ -114,12 +141,15 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     __syncwarp();
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
-                if (lane == 0) tc::mma_commit(acc_ready);
+                if (lane == 0) {
+                    if (l == 0) tc::mma_commit(ide_empty);        // IDE buffer may be refilled for the next tile
+                    tc::mma_commit(acc_ready);
+                }
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
-        // ===================== workers =====================
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== epilogue warps =====================
         const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
         const uint32_t row = quarter * 32 + lane;
         const uint32_t branch = row >> 6;
@@ -128,37 +158,6 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
-            // ---- IDE features of this row -> A operand of layer 0 -------------------------------------
-            if (g == 0) {
-                const uint32_t Kp0 = E.L[0].Kp;
-                if (valid) {
-                    const float* q = rec + (size_t)m * kTcRecFloats;
-                    const float dx = q[22 + 3 * branch], dy = q[23 + 3 * branch], dz = q[24 + 3 * branch];
-                    const float kap = branch ? q[20] : E.kappa_diffuse;
-                    const uint32_t P = E.P;
-                    ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, [&](int i, float re, float im) {
-                        __half h, lo;
-                        tc::split_f16(re, h, lo);
-                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, i)) = h;
-                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, i)) = lo;
-                        tc::split_f16(im, h, lo);
-                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, P + i)) = h;
-                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, P + i)) = lo;
-                    });
-                    for (uint32_t k = 2 * P; k < Kp0; k++) {
-                        *reinterpret_cast<__half*>(sA_hi + tc::op_off(128, row, k)) = __float2half_rn(0.f);
-                        *reinterpret_cast<__half*>(sA_lo + tc::op_off(128, row, k)) = __float2half_rn(0.f);
-                    }
-                } else {
-                    for (uint32_t k = 0; k < Kp0; k += 8) {
-                        *reinterpret_cast<uint4*>(sA_hi + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(sA_lo + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
-                    }
-                }
-            }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(a_ready);
-            // ---- per-layer epilogues ---------------------------------------------------------------------------
             for (int l = 0; l < nl; l++) {
                 tc::mbar_wait(acc_ready, acc_par); acc_par ^= 1;
                 tc::tc_fence_after();
@@ -169,20 +168,15 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         uint32_t r[32];
                         tc::tmem_ld32(tmem + lane_addr + cb * 32, r);
                         tc::tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
                         #pragma unroll
                         for (int j = 0; j < 4; j++) {
+                            const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
                             uint32_t ph[4], pl[4];
-                            #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int c0 = j * 8 + e * 2;
-                                const float v0 = fmaxf(__uint_as_float(r[c0]) + bias[cb * 32 + c0], 0.0f);
-                                const float v1 = fmaxf(__uint_as_float(r[c0 + 1]) + bias[cb * 32 + c0 + 1], 0.0f);
-                                __half h0, l0, h1, l1;
-                                tc::split_f16(v0, h0, l0);
-                                tc::split_f16(v1, h1, l1);
-                                ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                            }
+                            split2(fmaxf(__uint_as_float(r[8 * j + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(r[8 * j + 1]) + ba.y, 0.f), ph[0], pl[0]);
+                            split2(fmaxf(__uint_as_float(r[8 * j + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r[8 * j + 3]) + ba.w, 0.f), ph[1], pl[1]);
+                            split2(fmaxf(__uint_as_float(r[8 * j + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[8 * j + 5]) + bb.y, 0.f), ph[2], pl[2]);
+                            split2(fmaxf(__uint_as_float(r[8 * j + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(r[8 * j + 7]) + bb.w, 0.f), ph[3], pl[3]);
                             const uint32_t off = tc::op_off(128, row, cb * 32 + j * 8);
                             *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                             *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -191,28 +185,73 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     tc::tc_fence_before();
                     tc::fence_proxy_async_smem();
                     tc::mbar_arrive(a_ready);
-                } else if (g == 0) {
-                    uint32_t r[16];
-                    tc::tmem_ld16(tmem + lane_addr, r);
-                    tc::tmem_ld_wait();
-                    const int Ef = (int)E.E;
-                    float f[16], ss = 0.f;
-                    #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
-                        ss += f[i] * f[i];
-                    }
-                    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
-                    if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * kTcRecFloats + 16 * branch);
-                        dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-                        dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
-                        dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
-                        dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
+                } else {
+                    if (g == 0) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(tmem + lane_addr, r);
+                        tc::tmem_ld_wait();
+                        const int Ef = (int)E.E;
+                        float f[16], ss = 0.f;
+                        #pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
+                            ss += f[i] * f[i];
+                        }
+                        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
+                        if (valid) {
+                            float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * kTcRecFloats + 16 * branch);
+                            dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+                            dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+                            dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
+                            dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
+                        }
                     }
                     tc::tc_fence_before();
+                    tc::mbar_arrive(d_free);
                 }
             }
+        }
+    } else if (warp >= 12) {
+        // ===================== IDE warps: directional encoding of the NEXT tile while the current one is in the MMA pipe ====
+        const uint32_t t2 = tid - 12 * 32;               // 0..255
+        const uint32_t row = t2 & 127, mpar = t2 >> 7;   // two threads per row: even / odd orders m
+        const uint32_t branch = row >> 6;
+        const uint32_t Kp0 = E.L[0].Kp, P = E.P;
+        uint32_t empty_par = 1;                          // first wait passes
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t m = tile * 64 + (row & 63);
+            const bool valid = m < M;
+            float dx = 0.f, dy = 0.f, dz = 1.f, kap = 0.f;
+            if (valid) {
+                const float* q = rec + (size_t)m * kTcRecFloats;
+                dx = q[22 + 3 * branch]; dy = q[23 + 3 * branch]; dz = q[24 + 3 * branch];
+                kap = branch ? q[20] : E.kappa_diffuse;
+            }
+            tc::mbar_wait(ide_empty, empty_par); empty_par ^= 1;
+            if (valid) {
+                ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, [&](int i, float re, float im) {
+                    __half h, lo;
+                    tc::split_f16(re, h, lo);
+                    *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, i)) = h;
+                    *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, i)) = lo;
+                    tc::split_f16(im, h, lo);
+                    *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, P + i)) = h;
+                    *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, P + i)) = lo;
+                }, (int)mpar, 2);
+                if (mpar == 0) {
+                    for (uint32_t k = 2 * P; k < Kp0; k++) {
+                        *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, k)) = __float2half_rn(0.f);
+                        *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, k)) = __float2half_rn(0.f);
+                    }
+                }
+            } else if (mpar == 0) {
+                for (uint32_t k = 0; k < Kp0; k += 8) {
+                    *reinterpret_cast<uint4*>(sI_hi + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(sI_lo + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(ide_full);
         }
     }
     tc::tc_fence_before();
@@ -256,7 +295,7 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
         if (i > 0 && K != f->env[i - 1].out_dim) return false;
         TcLayer& L = t.L[i];
         L.K = K; L.Kp = rup(K, 16); L.N = N; L.Np = last ? 16 : N;
-        if (L.Kp > 256) return false;
+        if (L.Kp > 256 || (i == 0 && L.Kp > 80)) return false;
         L.img_off = (uint32_t)off;
         off += (uint64_t)(L.Kp / 16) * L.Np * 64;
         L.bias_off = boff;
@@ -286,7 +325,7 @@ int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st
     return check_launch("field_pack_tc");
 }
 
-constexpr size_t kTcSmem = 2 * kTcARegion + kTcStages * kTcStageBytes + kTcMaxLayers * 256 * sizeof(float) + 128;
+constexpr size_t kTcSmem = 2 * kTcARegion + 2 * kTcIdeRegion + kTcStages * kTcStageBytes + kTcMaxLayers * 256 * sizeof(float) + 256;
 
 int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
     if ((int)ide_degree != g_ide_tc_deg) {

@@ -85,32 +85,44 @@ inline bool ide_build_tables(int deg_view, IdeTables* t) {
 }
 
 #ifdef __CUDACC__
-// emit(i, re_i, im_i), i < P, with [Re | Im]_i = (x+iy)^m * K_l^m Q_l^m(z) * exp(-sigma_l * kappa_inv) * scale
+// emit(i, re_i, im_i), i < P, with [Re | Im]_i = (x+iy)^m * K_l^m Q_l^m(z) * exp(-sigma_l * kappa_inv) * scale.
+// Only the orders m = m_start, m_start + m_step, ... are visited (lets several threads share one direction).
 template <class Emit>
-__device__ __forceinline__ void ide_eval_emit(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale, Emit&& emit) {
+__device__ __forceinline__ void ide_eval_emit(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale, Emit&& emit,
+                                              int m_start = 0, int m_step = 1) {
     if (x == 0.0f && y == 0.0f) y += 1.0f;         // "avoid 0 + 0j exponentiation" (ide_encoder.py:113-115)
-    float att[5];
-    #pragma unroll
-    for (int b = 0; b < 5; b++) att[b] = (b < (int)T.deg) ? expf(-T.band_sigma[b] * kappa_inv) * scale : 0.0f;
+    float att0 = 0.f, att1 = 0.f, att2 = 0.f, att3 = 0.f, att4 = 0.f;
+    const int deg = (int)T.deg;
+    if (deg > 0) att0 = expf(-T.band_sigma[0] * kappa_inv) * scale;
+    if (deg > 1) att1 = expf(-T.band_sigma[1] * kappa_inv) * scale;
+    if (deg > 2) att2 = expf(-T.band_sigma[2] * kappa_inv) * scale;
+    if (deg > 3) att3 = expf(-T.band_sigma[3] * kappa_inv) * scale;
+    if (deg > 4) att4 = expf(-T.band_sigma[4] * kappa_inv) * scale;
+    auto att_of = [&](int b) { return b == 0 ? att0 : (b == 1 ? att1 : (b == 2 ? att2 : (b == 3 ? att3 : att4))); };
     const int l_max = (int)T.l_max;
-    float re = 1.0f, im = 0.0f;
-    for (int m = 0; m <= l_max; m++) {
-        if (m > 0) {
-            const float nr = re * x - im * y;
-            im = re * y + im * x;
+    // (x+iy)^m_start and the per-iteration multiplier (x+iy)^m_step
+    float re = 1.0f, im = 0.0f, sr = 1.0f, si = 0.0f;
+    for (int k = 0; k < m_start; k++) { const float nr = re * x - im * y; im = re * y + im * x; re = nr; }
+    for (int k = 0; k < m_step; k++) { const float nr = sr * x - si * y; si = sr * y + si * x; sr = nr; }
+    for (int m = m_start; m <= l_max; m += m_step) {
+        if (m > m_start) {
+            const float nr = re * sr - im * si;
+            im = re * si + im * sr;
             re = nr;
         }
         float p2 = 0.0f, p1 = T.qmm[m];
         if (m > 0 && (m & (m - 1)) == 0) {            // l == m is itself a band (m = 1, 2, 4, 8, 16)
             const int b = 31 - __clz(m);
-            emit(T.band_base[b] + m, re * p1 * att[b], im * p1 * att[b]);
+            const float a = att_of(b);
+            emit(T.band_base[b] + m, re * p1 * a, im * p1 * a);
         }
         for (int l = m + 1; l <= l_max; l++) {
             const float q = T.ra[l][m] * z * p1 - T.rb[l][m] * p2;
             p2 = p1; p1 = q;
             if ((l & (l - 1)) == 0) {
                 const int b = 31 - __clz(l);
-                emit(T.band_base[b] + m, re * q * att[b], im * q * att[b]);
+                const float a = att_of(b);
+                emit(T.band_base[b] + m, re * q * a, im * q * a);
             }
         }
     }
