@@ -643,25 +643,36 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
     FieldOutDev O{out->sigma, out->rgb, out->normal, out->sdf, out->c_diffuse, out->c_specular, out->roughness, out->grad_x};
     uint32_t grid = kSMs;
     if (!M_dev) grid = min((uint32_t)kSMs, ceil_div(M_host, kTile));
-    const bool tensor = field->precision == 1 && mode != 1;
-    if (!tensor) {
+    if (field->precision != 1) {
         if (ev) cudaEventRecord(ev[0], st);
         k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, mode == 1 ? 1 : 7, nullptr, nullptr, O);
         if (ev) cudaEventRecord(ev[1], st);
         return check_launch("field_forward");
     }
-    // tensor-core env_net: geometry -> record, tcgen05 env_net -> features, shading heads
+    // tensor-core path: geometry (k_geom_tc) -> record, env_net (k_env_tc) -> features, shading heads (k_field phases = 4)
     TcEnv tcenv;
-    uint64_t total = 0;
+    TcGeom tcgeom;
+    uint64_t total = 0, total2 = 0;
     ENVIDR_REQUIRE(tc_layout(field, simt_bytes, &tcenv, &total), ENVIDR_E_UNSUPPORTED,
                    "precision=1: env_net shape outside the tensor-core kernel (hidden widths must be multiples of 32, <= 256; env_feat <= 16)");
-    ENVIDR_REQUIRE(field->packed_bytes >= total, ENVIDR_E_WORKSPACE, "field->packed too small for the tensor-core images (envidr_field_pack_bytes)");
-    const uint64_t cap = M_dev ? field->scratch_samples : M_host;
-    ENVIDR_REQUIRE(field->scratch && field->scratch_samples >= cap && cap > 0, ENVIDR_E_WORKSPACE,
-                   "precision=1 needs field->scratch (256 B per sample)");
-    float* rec = reinterpret_cast<float*>(field->scratch);
-    float* feat = rec + (size_t)field->scratch_samples * kRecFloats;
-    k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, 1, rec, feat, O);
+    const bool geom_tc = geom_tc_layout(field, total, &tcgeom, &total2);
+    ENVIDR_REQUIRE(field->packed_bytes >= (geom_tc ? total2 : total), ENVIDR_E_WORKSPACE,
+                   "field->packed too small for the tensor-core images (envidr_field_pack_bytes)");
+    float* rec = nullptr;
+    float* feat = nullptr;
+    if (mode != 1) {
+        const uint64_t cap = M_dev ? field->scratch_samples : M_host;
+        ENVIDR_REQUIRE(field->scratch && field->scratch_samples >= cap && cap > 0, ENVIDR_E_WORKSPACE,
+                       "precision=1 needs field->scratch (256 B per sample)");
+        rec = reinterpret_cast<float*>(field->scratch);
+        feat = rec + (size_t)field->scratch_samples * kRecFloats;
+    }
+    if (geom_tc) {
+        if ((rc = geom_tc_launch(tcgeom, xyzs, dirs, M_dev, M_host, mode, rec, out, st))) return rc;
+    } else {
+        k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, 1, rec, feat, O);
+    }
+    if (mode == 1) return check_launch("field_forward(tc, geometry)");
     if (ev) cudaEventRecord(ev[0], st);
     rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, M_dev, M_host, st);
     if (ev) cudaEventRecord(ev[1], st);
@@ -680,9 +691,11 @@ uint64_t envidr_field_pack_bytes(const envidr_field* field) {
     Layout lay;
     if (build_layout(field, &lay)) return 0;
     TcEnv t;
-    uint64_t total = 0;
-    if (tc_layout(field, lay.floats * sizeof(float), &t, &total)) return total;      // FFMA images + tensor-core images
-    return lay.floats * sizeof(float);
+    TcGeom g;
+    uint64_t total = 0, total2 = 0;
+    if (!tc_layout(field, lay.floats * sizeof(float), &t, &total)) return lay.floats * sizeof(float);
+    if (geom_tc_layout(field, total, &g, &total2)) return total2;                    // FFMA + env_net + sdf_net tensor-core images
+    return total;
 }
 
 int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_bytes, envidr_stream_t stream) {
@@ -716,8 +729,12 @@ int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_b
     envidr_field tmp = *field;
     tmp.packed = packed; tmp.packed_bytes = packed_bytes;
     TcEnv t;
-    uint64_t total = 0;
-    if (tc_layout(&tmp, lay.floats * sizeof(float), &t, &total) && packed_bytes >= total) return tc_pack(field, t, packed, st);
+    TcGeom g;
+    uint64_t total = 0, total2 = 0;
+    if (tc_layout(&tmp, lay.floats * sizeof(float), &t, &total) && packed_bytes >= total) {
+        if ((rc = tc_pack(field, t, packed, st))) return rc;
+        if (geom_tc_layout(&tmp, total, &g, &total2) && packed_bytes >= total2) return geom_tc_pack(field, g, packed, st);
+    }
     return 0;
 }
 

@@ -21,6 +21,23 @@ struct TcEnv {
 };
 
 
+// ---- geometry phase on tensor cores (geom_tc.cu) ---------------------------------------------------------
+struct TcImg { uint32_t Kp, N, Np, off; };     // operand image of one layer inside the resident region (byte offset)
+struct TcGeom {
+    const uint8_t* blob;                       // start of the resident region in the packed blob
+    uint64_t blob_off;                         // its byte offset inside field->packed
+    uint32_t res_bytes, res_bytes_al, float_off, n_layers;
+    TcImg F[4], R[4];                          // forward layers 0..n-1; reverse (transposed) images of layers 0..n-2
+    const float* table; const int* offsets;
+    uint32_t L, H; float S, bound; int enabled_levels; uint32_t geo_dim;
+    float beta, density_scale, rough_bias, rough_act_scale, rough_scale;
+    int has_rot; float rot[9];
+};
+bool geom_tc_layout(const envidr_field* f, uint64_t base_bytes, TcGeom* out, uint64_t* total_bytes);
+int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStream_t st);
+int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
+                   const envidr_field_out* out, cudaStream_t st);
+
 // layout / packing / launch (field_tc.cu)
 bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes);
 int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st);

@@ -58,11 +58,14 @@ def test_tensor_core_env_net_matches_fp32_path(dev, env_width, deg, M):
     fp_tc.precision = "tc"
     out = fp_tc.pack().forward(xt, dt, want=want)
     torch.cuda.synchronize()
-    assert torch.equal(out["sigma"], ref32["sigma"]) and torch.equal(out["normal"], ref32["normal"])     # geometry phase is shared
+    # geometry on tensor cores (fp16 hi/lo split, fp32 accumulate): the SDF agrees to ~2e-7, which the Laplace density
+    # amplifies by up to 1/(2 beta^2) = 5000
+    torch.testing.assert_close(out["sigma"], ref32["sigma"], atol=5e-3, rtol=2e-4)
+    assert (out["normal"] - ref32["normal"]).abs().max().item() <= 2e-5
     err = (out["rgb"] - ref32["rgb"]).abs().max().item()
-    assert err <= 2e-5, f"tensor-core env_net vs fp32 path: rgb max err {err}"
-    assert (out["c_diffuse"] - ref32["c_diffuse"]).abs().max().item() <= 1e-5
-    assert (out["c_specular"] - ref32["c_specular"]).abs().max().item() <= 1e-5
+    assert err <= 3e-5, f"tensor-core path vs fp32 path: rgb max err {err}"
+    assert (out["c_diffuse"] - ref32["c_diffuse"]).abs().max().item() <= 2e-5
+    assert (out["c_specular"] - ref32["c_specular"]).abs().max().item() <= 2e-5
     if M <= 3000:
         ref = O.field_forward(fp_cpu.to_oracle(), x, d)
         np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=1e-4)
@@ -72,7 +75,13 @@ def test_tensor_core_env_net_matches_fp32_path(dev, env_width, deg, M):
     ri[::2, 3] = 0.97
     a = fp_tc.forward(xt, dt, ri, env_rot_radian=0.4, want=("rgb",))["rgb"]
     b = fp_cpu.to(dev).pack().forward(xt, dt, ri, env_rot_radian=0.4, want=("rgb",))["rgb"]
-    assert (a - b).abs().max().item() <= 2e-5
+    assert (a - b).abs().max().item() <= 3e-5
+    # geometry-only mode and extra outputs of the tensor-core geometry kernel
+    ga = fp_tc.forward(xt, dt, geometry_only=True, want=("sigma", "normal", "sdf", "roughness", "grad_x"))
+    gb = fp_cpu.to(dev).pack().forward(xt, dt, geometry_only=True, want=("sigma", "normal", "sdf", "roughness", "grad_x"))
+    torch.testing.assert_close(ga["sdf"], gb["sdf"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(ga["grad_x"], gb["grad_x"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(ga["roughness"], gb["roughness"], atol=1e-6, rtol=1e-5)
 
 
 def test_render_with_tensor_cores(dev):
@@ -87,6 +96,8 @@ def test_render_with_tensor_cores(dev):
     st = []
     out = render.render(fp_tc.pack(), bft, ro, rd, cfg, stats=st)
     assert len(st) == 3
-    assert torch.equal(out["weights_sum"], ref["weights_sum"]) and torch.equal(out["depth"], ref["depth"])
+    torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(out["depth"], ref["depth"], atol=3e-4, rtol=0)
     err = (out["image"] - ref["image"]).abs().max().item()
-    assert err <= 2e-5, f"image L-inf tensor-core vs fp32 path {err}"
+    assert err <= 1e-4, f"image L-inf tensor-core vs fp32 path {err}"
+    assert (out["image"] - ref["image"]).abs().mean().item() <= 2e-6
