@@ -624,7 +624,8 @@ constexpr size_t kFieldSmem = (size_t)(kTile * kLd + 2 * kWbuf + S_COUNT * kTile
 // timing hook (bench.py): when non-null, ev[0]/ev[1] are recorded around the dominant kernel of this call
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
                          const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
-                         cudaEvent_t* ev) {
+                         cudaEvent_t* ev, int* ev_recorded) {
+    if (ev_recorded) *ev_recorded = 0;
     Layout lay;
     int rc = build_layout(field, &lay);
     if (rc) return rc;
@@ -646,17 +647,21 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
     if (field->precision != 1) {
         if (ev) cudaEventRecord(ev[0], st);
         k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, mode == 1 ? 1 : 7, nullptr, nullptr, O);
-        if (ev) cudaEventRecord(ev[1], st);
+        if (ev) { cudaEventRecord(ev[1], st); if (ev_recorded) *ev_recorded = 1; }
         return check_launch("field_forward");
     }
     // tensor-core path: geometry (k_geom_tc) -> record, env_net (k_env_tc) -> features, shading heads (k_field phases = 4)
     TcEnv tcenv;
     TcGeom tcgeom;
-    uint64_t total = 0, total2 = 0;
+    TcShade tcshade;
+    uint64_t total = 0, total2 = 0, total3 = 0;
     ENVIDR_REQUIRE(tc_layout(field, simt_bytes, &tcenv, &total), ENVIDR_E_UNSUPPORTED,
                    "precision=1: env_net shape outside the tensor-core kernel (hidden widths must be multiples of 32, <= 256; env_feat <= 16)");
     const bool geom_tc = geom_tc_layout(field, total, &tcgeom, &total2);
-    ENVIDR_REQUIRE(field->packed_bytes >= (geom_tc ? total2 : total), ENVIDR_E_WORKSPACE,
+    if (!geom_tc) total2 = total;
+    const bool shade_tc = shade_tc_layout(field, total2, &tcshade, &total3);
+    if (!shade_tc) total3 = total2;
+    ENVIDR_REQUIRE(field->packed_bytes >= total3, ENVIDR_E_WORKSPACE,
                    "field->packed too small for the tensor-core images (envidr_field_pack_bytes)");
     float* rec = nullptr;
     float* feat = nullptr;
@@ -675,8 +680,9 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
     if (mode == 1) return check_launch("field_forward(tc, geometry)");
     if (ev) cudaEventRecord(ev[0], st);
     rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, M_dev, M_host, st);
-    if (ev) cudaEventRecord(ev[1], st);
+    if (ev) { cudaEventRecord(ev[1], st); if (ev_recorded) *ev_recorded = 1; }
     if (rc) return rc;
+    if (shade_tc) return shade_tc_launch(tcshade, rec, feat, r_images, M_dev, M_host, out, st);
     k_field<<<grid, kThreads, kFieldSmem, st>>>(lay.dev, xyzs, dirs, r_images, M_dev, M_host, mode, 4, rec, feat, O);
     return check_launch("field_forward(tc)");
 }
@@ -692,10 +698,12 @@ uint64_t envidr_field_pack_bytes(const envidr_field* field) {
     if (build_layout(field, &lay)) return 0;
     TcEnv t;
     TcGeom g;
-    uint64_t total = 0, total2 = 0;
+    TcShade sh;
+    uint64_t total = 0, total2 = 0, total3 = 0;
     if (!tc_layout(field, lay.floats * sizeof(float), &t, &total)) return lay.floats * sizeof(float);
-    if (geom_tc_layout(field, total, &g, &total2)) return total2;                    // FFMA + env_net + sdf_net tensor-core images
-    return total;
+    if (!geom_tc_layout(field, total, &g, &total2)) total2 = total;                  // FFMA + env_net (+ sdf_net) (+ heads) images
+    if (!shade_tc_layout(field, total2, &sh, &total3)) total3 = total2;
+    return total3;
 }
 
 int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_bytes, envidr_stream_t stream) {
@@ -730,17 +738,20 @@ int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_b
     tmp.packed = packed; tmp.packed_bytes = packed_bytes;
     TcEnv t;
     TcGeom g;
-    uint64_t total = 0, total2 = 0;
+    TcShade sh;
+    uint64_t total = 0, total2 = 0, total3 = 0;
     if (tc_layout(&tmp, lay.floats * sizeof(float), &t, &total) && packed_bytes >= total) {
         if ((rc = tc_pack(field, t, packed, st))) return rc;
-        if (geom_tc_layout(&tmp, total, &g, &total2) && packed_bytes >= total2) return geom_tc_pack(field, g, packed, st);
+        if (geom_tc_layout(&tmp, total, &g, &total2) && packed_bytes >= total2) { if ((rc = geom_tc_pack(field, g, packed, st))) return rc; }
+        else total2 = total;
+        if (shade_tc_layout(&tmp, total2, &sh, &total3) && packed_bytes >= total3) return shade_tc_pack(field, sh, packed, st);
     }
     return 0;
 }
 
 int envidr_field_forward(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images, uint32_t M, int mode,
                          const envidr_field_out* out, envidr_stream_t stream) {
-    return field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), nullptr);
+    return field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -70,6 +70,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
     const int nl = (int)E.n_layers;
+    if (blockIdx.x >= n_tiles) return;                // nothing to do for this CTA (tail iterations of the render loop)
 
     if (tid == 0) {
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }

@@ -38,6 +38,22 @@ int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStrea
 int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
                    const envidr_field_out* out, cudaStream_t st);
 
+// ---- shading heads on tensor cores (shade_tc.cu) -----------------------------------------------------------
+struct TcShade {
+    const uint8_t* blob;
+    uint64_t blob_off;
+    uint32_t res_bytes, res_bytes_al, float_off;
+    uint32_t net_layers[3];                    // 0 diffuse, 1 color, 2 renv
+    TcImg img[3][4];
+    uint32_t geo_dim, env_dim;
+    float rough_scale, indir_rough_thresh, intensity_scale;
+    int learn_blend;
+};
+bool shade_tc_layout(const envidr_field* f, uint64_t base_bytes, TcShade* out, uint64_t* total_bytes);
+int shade_tc_pack(const envidr_field* f, const TcShade& s, void* packed, cudaStream_t st);
+int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const float* r_images, const uint32_t* M_dev, uint32_t M_host,
+                    const envidr_field_out* out, cudaStream_t st);
+
 // layout / packing / launch (field_tc.cu)
 bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes);
 int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st);

@@ -53,6 +53,7 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (M + 127) / 128;
+    if (blockIdx.x >= n_tiles) return;             // nothing to do for this CTA (tail iterations of the render loop)
     const int n = (int)G.n_layers;                 // forward layers; n - 1 reverse stages
     const int n_stages = 2 * n - 1;
     const float* s_f = reinterpret_cast<const float*>(s_w + G.float_off);     // biases [n][64], then w_row0[64]

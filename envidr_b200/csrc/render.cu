@@ -17,7 +17,7 @@ namespace envidr {
 
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
                          const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
-                         cudaEvent_t* ev);
+                         cudaEvent_t* ev, int* ev_recorded);
 
 constexpr int kMarchBlock = 128;
 constexpr int kMaxNStep = 8;
@@ -363,12 +363,13 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
             k_march_compact<<<march_grid, kMarchBlock, 0, st>>>(rays_o, rays_d, r_images, bitfield, opts->bound, opts->dt_gamma,
                                                                opts->max_steps, opts->cascade, opts->grid_size, noises, B);
             const bool timed = g_timing && g_tev_used < kMaxTimed;
+            int recorded = 0;
             if (timed) while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
             rc = field_forward_launch(&fld, B.s_xyz, B.s_dir, r_images ? B.s_rimg : nullptr, &B.ctr->M, 0,
-                                      opts->geometry_only ? 1 : 0, &fo, st, timed ? &g_tev[2 * g_tev_used] : nullptr);
+                                      opts->geometry_only ? 1 : 0, &fo, st, timed ? &g_tev[2 * g_tev_used] : nullptr, &recorded);
             if (rc) return rc;
-            if (timed) g_tev_used++;
-            g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;
+            if (timed && recorded) g_tev_used++;
+            g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;      // march, [geom, env, shade | field], composite
             k_composite_compact<<<march_grid, kMarchBlock, 0, st>>>(N, opts->T_thresh, opts->max_steps, opts->geometry_only,
                                                                    opts->input_alpha, B, O);
         }
@@ -418,6 +419,7 @@ int envidr_render_field_time(float* total_ms, uint32_t* launches) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, g_tev[2 * i], g_tev[2 * i + 1]) == cudaSuccess) sum += ms;
     }
+    (void)cudaGetLastError();
     *total_ms = sum; *launches = (uint32_t)g_tev_used;
     g_tev_used = 0;
     return 0;

@@ -104,8 +104,52 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
 }
+// fp32 pair -> packed fp16 (hi) pair and packed fp16 (lo = x - hi) pair
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // byte offset of element (r, k) inside a chunk-major [R x K] fp16 operand
 __host__ __device__ constexpr uint32_t op_off(uint32_t R, uint32_t r, uint32_t k) { return (k >> 3) * (R * 16) + r * 16 + (k & 7) * 2; }
+
+// Epilogue of a hidden layer for one 32-column chunk of one accumulator row: v = relu(D + bias) -> fp16 hi/lo ->
+// next A operand (128-row chunk-major buffers dst_hi / dst_lo).  Returns the ReLU mask of the 32 columns.
+__device__ __forceinline__ uint32_t hidden_epilogue32(uint32_t taddr, const float* bias32, uint8_t* dst_hi, uint8_t* dst_lo, uint32_t row,
+                                                     uint32_t col0) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
+    uint32_t mk = 0;
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        uint32_t ph[4], pl[4];
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int c = jj * 8 + e * 2;
+            const float v0 = __uint_as_float(r[c]) + bias32[c], v1 = __uint_as_float(r[c + 1]) + bias32[c + 1];
+            mk |= (v0 > 0.f ? 1u : 0u) << c;
+            mk |= (v1 > 0.f ? 1u : 0u) << (c + 1);
+            split2(fmaxf(v0, 0.f), fmaxf(v1, 0.f), ph[e], pl[e]);
+        }
+        const uint32_t off = op_off(128, row, col0 + jj * 8);
+        *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+    return mk;
+}
+// write 8 consecutive K values of one row of an A operand
+__device__ __forceinline__ void store_chunk8(uint8_t* dst_hi, uint8_t* dst_lo, uint32_t row, uint32_t k0, const float (&v)[8]) {
+    uint32_t ph[4], pl[4];
+    #pragma unroll
+    for (int e = 0; e < 4; e++) split2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
+    const uint32_t off = op_off(128, row, k0);
+    *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
 
 }  // namespace tc
 }  // namespace envidr
