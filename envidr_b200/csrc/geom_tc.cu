@@ -18,22 +18,50 @@
 
 namespace envidr {
 
-constexpr int kGThreads = 384;                     // 4 control warps + 8 worker warps
-constexpr uint32_t kGOperand = 32768;              // one A-operand buffer: 128 rows x 64 K x 2 B x (hi, lo)
-constexpr uint32_t kGOperandHalf = 16384;
-constexpr int kGJacLd = 100;                       // floats per row of the jacobian tile (96 + pad)
+constexpr int kGThreads = 576;                     // warps 0-7 chain (2 groups x 4), 8-15 gather, 16 MMA issuer, 17 TMEM / weights
+constexpr uint32_t kGEnc = 16384, kGEncHalf = 8192;    // encoding operand: 128 rows x 32 K x 2 B, hi | lo
+constexpr uint32_t kGHid = 32768, kGHidHalf = 16384;   // hidden operand:   128 rows x 64 K x 2 B, hi | lo
+constexpr uint32_t kGJacBase = 128, kGJacCols = 96;    // TMEM columns: 2 accumulators x 64, then 4 jacobian slots x 96
 
 struct GeomOutDev { float *sigma, *normal, *sdf, *roughness, *grad_x; };
+struct GLevel { uint32_t off2, size, res, hashed, pow2, on; float scale; uint32_t pad; };
 
 __device__ __forceinline__ float g_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float g_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
-__device__ __forceinline__ void g_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// hash-grid cell index with the level's indexing mode decided once per level (same value as cell_index<3>, gridenc.cuh)
+__device__ __forceinline__ uint32_t g_index(const GLevel& lv, uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t idx;
+    if (lv.hashed) {
+        idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+        idx = lv.pow2 ? (idx & (lv.size - 1)) : (idx % lv.size);
+    } else {
+        idx = x + lv.res * (y + lv.res * z);
+        if (idx >= lv.size) idx %= lv.size;
+    }
+    return idx;
+}
+
+// write `vals` (32 columns col0..col0+31 of row `row`) into a 128-row hidden operand as fp16 hi / lo
+__device__ __forceinline__ void g_store32(uint8_t* hid, uint32_t row, uint32_t col0, const float (&v)[32]) {
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        uint32_t ph[4], pl[4];
+        #pragma unroll
+        for (int e = 0; e < 4; e++) tc::split2(v[jj * 8 + 2 * e], v[jj * 8 + 2 * e + 1], ph[e], pl[e]);
+        const uint32_t off = tc::op_off(128, row, col0 + jj * 8);
+        *reinterpret_cast<uint4*>(hid + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(hid + kGHidHalf + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
 }
 
 __global__ void __launch_bounds__(kGThreads, 1)
@@ -41,299 +69,363 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
           uint32_t M_host, int mode, float* __restrict__ rec, const GeomOutDev O) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem;                                           // resident weight images + float region
-    uint8_t* s_op = smem + G.res_bytes_al;                         // two operand buffers
-    float* s_jac = reinterpret_cast<float*>(s_op + 2 * kGOperand); // [128][100]
-    float* s_side = s_jac + 128 * kGJacLd;                         // [16][128] last-layer outputs
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_side + 16 * 128);
-    uint64_t* w_full = bars;          // resident weights landed
-    uint64_t* acc_ready = bars + 1;   // issuer -> workers
-    uint64_t* a_ready = bars + 2;     // workers -> issuer (256 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint8_t* s_enc = smem + G.res_bytes_al;                        // two encoding operands (gather -> stage 0)
+    uint8_t* s_hid = s_enc + 2 * kGEnc;                            // one hidden operand per chain group (rewritten in place)
+    GLevel* s_lvl = reinterpret_cast<GLevel*>(s_hid + 2 * kGHid);  // [16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_lvl + 16);
+    uint64_t* w_full = bars;              // resident weights landed
+    uint64_t* enc_full = bars + 1;        // [2] gather -> issuer (256 arrivals)
+    uint64_t* enc_free = bars + 3;        // [2] issuer (commit of the stage-0 MMA) -> gather
+    uint64_t* acc_ready = bars + 5;       // [2] issuer -> chain group
+    uint64_t* a_ready = bars + 7;         // [2] chain group -> issuer (128 arrivals)
+    uint64_t* jac_free = bars + 9;        // [4] chain group -> gather (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (M + 127) / 128;
     if (blockIdx.x >= n_tiles) return;             // nothing to do for this CTA (tail iterations of the render loop)
+    const uint32_t T = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;       // tiles of this CTA: blockIdx.x + j * gridDim.x
     const int n = (int)G.n_layers;                 // forward layers; n - 1 reverse stages
     const int n_stages = 2 * n - 1;
     const float* s_f = reinterpret_cast<const float*>(s_w + G.float_off);     // biases [n][64], then w_row0[64]
 
     if (tid == 0) {
         tc::mbar_init(w_full, 1);
-        tc::mbar_init(acc_ready, 1);
-        tc::mbar_init(a_ready, 256);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(enc_full + i, 256);
+            tc::mbar_init(enc_free + i, 1);
+            tc::mbar_init(acc_ready + i, 1);
+            tc::mbar_init(a_ready + i, 128);
+        }
+        for (int i = 0; i < 4; i++) tc::mbar_init(jac_free + i, 128);
         tc::mbar_fence_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 64);
+    if (tid < G.L) {                               // per-level constants (reference: hashencoder.cu:118-124, 54-72)
+        GLevel lv;
+        const uint32_t l = tid;
+        lv.off2 = (uint32_t)G.offsets[l] * 2;
+        lv.size = (uint32_t)(G.offsets[l + 1] - G.offsets[l]);
+        lv.scale = exp2f(l * G.S) * G.H - 1.0f;
+        lv.res = (uint32_t)ceilf(lv.scale) + 1;
+        uint32_t stride = 1;
+        for (int d = 0; d < 3; d++) if (stride <= lv.size) stride *= lv.res;
+        lv.hashed = stride > lv.size ? 1u : 0u;
+        lv.pow2 = (lv.size & (lv.size - 1)) == 0 ? 1u : 0u;
+        lv.on = !(G.enabled_levels > 0 && (int)l >= G.enabled_levels) ? 1u : 0u;
+        lv.pad = 0;
+        s_lvl[l] = lv;
+    }
+    if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp == 0 && lane == 0) {                  // one-time: pull the resident region in with a few bulk copies
+    if (warp == 17 && lane == 0) {                 // one-time: pull the resident region in with a few bulk copies
         tc::mbar_arrive_expect_tx(w_full, G.res_bytes);
         for (uint32_t o = 0; o < G.res_bytes; o += 16384) {
             const uint32_t b = min(16384u, G.res_bytes - o);
             tc::bulk_g2s(s_w + o, G.blob + o, b, w_full);
         }
     }
-    tc::mbar_wait(w_full, 0);
 
-    if (warp == 0) {
-        // ===================== MMA issuer =====================
-        uint32_t a_par = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (warp == 16) {
+        // ===================== MMA issuer: two tiles in flight, stages interleaved =====================
+        tc::mbar_wait(w_full, 0);
+        uint32_t encf_par = 0, a_par = 0;          // bit u = parity of the next phase to wait for
+        for (uint32_t p = 0; p < T; p += 2) {
+            const uint32_t ntp = min(2u, T - p);
             for (int st = 0; st < n_stages; st++) {
                 const TcImg& I = (st < n) ? G.F[st] : G.R[n_stages - 1 - st];      // reverse stages use layers n-2 .. 0
-                tc::mbar_wait(a_ready, a_par); a_par ^= 1;
-                tc::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
-                    const uint32_t a_hi0 = tc::smem_u32(s_op + (st & 1) * kGOperand), a_lo0 = a_hi0 + kGOperandHalf;
-                    const uint32_t b0 = tc::smem_u32(s_w + I.off);
-                    for (uint32_t s = 0; s < I.Kp / 16; s++) {
-                        const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
-                        const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
-                        const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
-                        tc::mma_f16_ss(tmem, da_hi, db_hi, idesc, s > 0);
-                        tc::mma_f16_ss(tmem, da_lo, db_hi, idesc, 1);
-                        tc::mma_f16_ss(tmem, da_hi, db_lo, idesc, 1);
+                for (uint32_t u = 0; u < ntp; u++) {
+                    if (st == 0) {
+                        tc::mbar_wait(enc_full + u, (encf_par >> u) & 1u); encf_par ^= 1u << u;
+                        if (p >= 2) { tc::mbar_wait(a_ready + u, (a_par >> u) & 1u); a_par ^= 1u << u; }   // accumulator drained
+                    } else {
+                        tc::mbar_wait(a_ready + u, (a_par >> u) & 1u); a_par ^= 1u << u;
                     }
-                    tc::mma_commit(acc_ready);
+                    tc::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
+                        const uint32_t a_hi0 = tc::smem_u32(st == 0 ? s_enc + u * kGEnc : s_hid + u * kGHid);
+                        const uint32_t a_lo0 = a_hi0 + (st == 0 ? kGEncHalf : kGHidHalf);
+                        const uint32_t b0 = tc::smem_u32(s_w + I.off);
+                        const uint32_t d = tmem + u * 64;
+                        for (uint32_t s = 0; s < I.Kp / 16; s++) {
+                            const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
+                            const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
+                            const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
+                            tc::mma_f16_ss(d, da_hi, db_hi, idesc, s > 0);
+                            tc::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
+                            tc::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
+                        }
+                        tc::mma_commit(acc_ready + u);
+                        if (st == 0) tc::mma_commit(enc_free + u);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
-    } else if (warp >= 4) {
-        // ===================== workers =====================
-        const uint32_t wt = tid - 128;                     // 0..255
-        const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
-        const uint32_t row = quarter * 32 + lane;          // accumulator row of this thread (2 threads per row: g = 0, 1)
+    } else if (warp >= 8 && warp < 16) {
+        // ===================== gather: thread = (sample, level parity) =====================
+        const uint32_t quarter = warp & 3, par = (warp - 8) >> 2;
+        const uint32_t s = quarter * 32 + lane;
         const uint32_t lane_addr = (quarter * 32u) << 16;
-        const uint32_t Hd = G.F[0].N;                      // hidden width (32 or 64)
-        const uint32_t hchunks = Hd / 32;
-        uint32_t acc_par = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint32_t m0 = tile * 128;
-            // ---- gather: thread = (sample, level parity); encoding -> operand buffer 0 (fp16 hi/lo), jacobian -> smem fp32
-            {
-                const uint32_t s = wt & 127, par = wt >> 7;
-                const uint32_t m = m0 + s;
-                const bool valid = m < M;
-                float x01[3] = {0.f, 0.f, 0.f};
-                if (valid) {
+        float xn[3] = {0.f, 0.f, 0.f};
+        {
+            const uint32_t m = blockIdx.x * 128 + s;
+            if (m < M) {
+                #pragma unroll
+                for (int d = 0; d < 3; d++) xn[d] = __ldg(xyzs + 3 * (size_t)m + d);
+            }
+        }
+        for (uint32_t j = 0; j < T; j++) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x;
+            const uint32_t m = tile * 128 + s;
+            const bool valid = m < M;
+            float x01[3];
+            bool inside = valid;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+                x01[d] = (xn[d] + G.bound) / (2 * G.bound);
+                if (x01[d] < 0 || x01[d] > 1) inside = false;
+            }
+            if (j + 1 < T) {                       // prefetch the next tile's position
+                const uint32_t mn = (tile + gridDim.x) * 128 + s;
+                #pragma unroll
+                for (int d = 0; d < 3; d++) xn[d] = mn < M ? __ldg(xyzs + 3 * (size_t)mn + d) : 0.f;
+            }
+            const uint32_t b = j & 1, q = j & 3;
+            if (j >= 2) tc::mbar_wait(enc_free + b, ((j >> 1) - 1) & 1u);
+            if (j >= 4) tc::mbar_wait(jac_free + q, ((j >> 2) - 1) & 1u);
+            tc::tc_fence_after();
+            uint8_t* enc = s_enc + b * kGEnc;
+            const uint32_t jac_t = tmem + lane_addr + kGJacBase + q * kGJacCols + par * 48;
+            for (uint32_t l0 = par; l0 < G.L; l0 += 4) {
+                float rows[2][8][2], w[2][3], dw[2][3], sc[2];
+                #pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t l = l0 + 2 * u;
                     #pragma unroll
-                    for (int d = 0; d < 3; d++) x01[d] = (xyzs[3 * (size_t)m + d] + G.bound) / (2 * G.bound);
-                }
-                const EncMode em{1, 0, 0};
-                for (uint32_t l = par; l < G.L; l += 2) {
-                    float e0 = 0.f, e1 = 0.f, j[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    Cell<3> cell;
-                    const bool lvl_on = !(G.enabled_levels > 0 && (int)l >= G.enabled_levels);
-                    if (valid && lvl_on && cell.setup(em, x01, G.offsets, l, G.S, G.H)) {
-                        const float* grid = G.table + (size_t)(uint32_t)G.offsets[l] * 2;
-                        float rows[8][2];
-                        #pragma unroll
-                        for (uint32_t corner = 0; corner < 8; corner++) {
-                            uint32_t pl[3];
+                    for (int c = 0; c < 8; c++) { rows[u][c][0] = 0.f; rows[u][c][1] = 0.f; }
+                    #pragma unroll
+                    for (int d = 0; d < 3; d++) { w[u][d] = 0.f; dw[u][d] = 0.f; }
+                    sc[u] = 0.f;
+                    if (l < G.L) {
+                        const GLevel lv = s_lvl[l];
+                        if (inside && lv.on) {
+                            uint32_t pg[3];
                             #pragma unroll
-                            for (int d = 0; d < 3; d++) pl[d] = cell.pg[d] + ((corner >> d) & 1u);
-                            load_row<2>(grid + (size_t)cell_index<3>(em, cell.hashmap_size, cell.resolution, pl) * 2, rows[corner]);
+                            for (int d = 0; d < 3; d++) {
+                                float p = x01[d] * lv.scale;
+                                pg[d] = (uint32_t)floorf(p);
+                                p -= (float)pg[d];
+                                dw[u][d] = 6 * p * (1.0f - p);
+                                w[u][d] = p * p * (3.0f - 2.0f * p);
+                            }
+                            sc[u] = lv.scale;
+                            const float2* grid = reinterpret_cast<const float2*>(G.table + lv.off2);
+                            #pragma unroll
+                            for (uint32_t c = 0; c < 8; c++) {
+                                const float2 t = __ldg(grid + g_index(lv, pg[0] + (c & 1u), pg[1] + ((c >> 1) & 1u), pg[2] + ((c >> 2) & 1u)));
+                                rows[u][c][0] = t.x; rows[u][c][1] = t.y;
+                            }
                         }
+                    }
+                }
+                #pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t l = l0 + 2 * u;
+                    if (l < G.L) {
+                        float e0 = 0.f, e1 = 0.f, jv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         #pragma unroll
-                        for (uint32_t corner = 0; corner < 8; corner++) {
+                        for (uint32_t c = 0; c < 8; c++) {
                             float wt_ = 1;
                             #pragma unroll
-                            for (int d = 0; d < 3; d++) wt_ *= ((corner >> d) & 1u) ? cell.w[d] : 1 - cell.w[d];
-                            e0 += wt_ * rows[corner][0];
-                            e1 += wt_ * rows[corner][1];
+                            for (int d = 0; d < 3; d++) wt_ *= ((c >> d) & 1u) ? w[u][d] : 1 - w[u][d];
+                            e0 += wt_ * rows[u][c][0];
+                            e1 += wt_ * rows[u][c][1];
                         }
                         #pragma unroll
                         for (int gd = 0; gd < 3; gd++) {
                             #pragma unroll
                             for (uint32_t sub = 0; sub < 4; sub++) {
-                                float wt_ = cell.scale;
-                                uint32_t corner = 0;
+                                float wt_ = sc[u];
+                                uint32_t c = 0;
                                 #pragma unroll
                                 for (int nd = 0; nd < 2; nd++) {
                                     const int d = nd >= gd ? nd + 1 : nd;
-                                    if ((sub >> nd) & 1u) { wt_ *= cell.w[d]; corner |= 1u << d; }
-                                    else                  { wt_ *= 1 - cell.w[d]; }
+                                    if ((sub >> nd) & 1u) { wt_ *= w[u][d]; c |= 1u << d; }
+                                    else                  { wt_ *= 1 - w[u][d]; }
                                 }
-                                j[gd * 2 + 0] += wt_ * (rows[corner | (1u << gd)][0] - rows[corner][0]) * cell.dw[gd];
-                                j[gd * 2 + 1] += wt_ * (rows[corner | (1u << gd)][1] - rows[corner][1]) * cell.dw[gd];
+                                jv[gd * 2 + 0] += wt_ * (rows[u][c | (1u << gd)][0] - rows[u][c][0]) * dw[u][gd];
+                                jv[gd * 2 + 1] += wt_ * (rows[u][c | (1u << gd)][1] - rows[u][c][1]) * dw[u][gd];
                             }
                         }
+                        uint32_t hi, lo;
+                        tc::split2(e0, e1, hi, lo);
+                        const uint32_t off = tc::op_off(128, s, 2 * l);
+                        *reinterpret_cast<uint32_t*>(enc + off) = hi;
+                        *reinterpret_cast<uint32_t*>(enc + kGEncHalf + off) = lo;
+                        const uint32_t jt = jac_t + 6 * (l >> 1);
+                        tmem_st4(jt, jv[0], jv[1], jv[2], jv[3]);
+                        tmem_st2(jt + 4, jv[4], jv[5]);
                     }
-                    uint32_t hi, lo;
-                    g_split2(e0, e1, hi, lo);
-                    const uint32_t off = tc::op_off(128, s, 2 * l);
-                    *reinterpret_cast<uint32_t*>(s_op + off) = hi;
-                    *reinterpret_cast<uint32_t*>(s_op + kGOperandHalf + off) = lo;
-                    float* jq = s_jac + s * kGJacLd + 6 * l;
-                    #pragma unroll
-                    for (int q = 0; q < 6; q++) jq[q] = j[q];
-                }
-                // zero the encoder columns between 2L and the padded K of the first layer
-                if (par == 0) for (uint32_t k = 2 * G.L; k < G.F[0].Kp; k += 2) {
-                    const uint32_t off = tc::op_off(128, s, k);
-                    *reinterpret_cast<uint32_t*>(s_op + off) = 0u;
-                    *reinterpret_cast<uint32_t*>(s_op + kGOperandHalf + off) = 0u;
                 }
             }
+            tmem_st_wait();
+            tc::tc_fence_before();
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(a_ready);
-
-            uint32_t mask[2] = {0u, 0u};                   // ReLU masks of hidden layers 0 and 1 for this thread's 32 columns
+            tc::mbar_arrive(enc_full + b);
+        }
+    } else if (warp < 8) {
+        // ===================== chain: group u = warp / 4 owns every other tile; thread = accumulator row =====================
+        const uint32_t u = warp >> 2, quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t lane_addr = (quarter * 32u) << 16;
+        const uint32_t acc_t = tmem + lane_addr + u * 64;
+        uint8_t* hid = s_hid + u * kGHid;
+        const uint32_t Hd = G.F[0].N;                      // hidden width (32 or 64)
+        const uint32_t hchunks = Hd / 32;
+        const int Gd = (int)G.geo_dim;
+        const bool want_rec = rec && mode != 1;
+        tc::mbar_wait(w_full, 0);
+        uint32_t acc_par = 0;
+        for (uint32_t j = u; j < T; j += 2) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x;
+            const uint32_t m = tile * 128 + row;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (want_rec && m < M) { dx = __ldg(dirs + 3 * (size_t)m); dy = __ldg(dirs + 3 * (size_t)m + 1); dz = __ldg(dirs + 3 * (size_t)m + 2); }
+            uint32_t mk[2][2] = {{0u, 0u}, {0u, 0u}};      // ReLU masks [hidden layer][32-column chunk]
+            float outv[16];
+            #pragma unroll
+            for (int i = 0; i < 16; i++) outv[i] = 0.f;
             for (int st = 0; st < n_stages; st++) {
-                tc::mbar_wait(acc_ready, acc_par); acc_par ^= 1;
+                tc::mbar_wait(acc_ready + u, acc_par); acc_par ^= 1;
                 tc::tc_fence_after();
-                uint8_t* dst = s_op + ((st + 1) & 1) * kGOperand;          // operand buffer of the next stage
                 if (st < n - 1) {
-                    // hidden forward layer st: h = relu(D + b), keep the mask, write the next operand
-                    if (g < hchunks) {
-                        uint32_t r[32];
-                        tc::tmem_ld32(tmem + lane_addr + g * 32, r);
-                        tc::tmem_ld_wait();
-                        const float* bias = s_f + st * 64 + g * 32;
-                        uint32_t mk = 0;
-                        #pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            uint32_t ph[4], pl[4];
-                            #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int c = jj * 8 + e * 2;
-                                const float v0 = __uint_as_float(r[c]) + bias[c], v1 = __uint_as_float(r[c + 1]) + bias[c + 1];
-                                mk |= (v0 > 0.f ? 1u : 0u) << c;
-                                mk |= (v1 > 0.f ? 1u : 0u) << (c + 1);
-                                g_split2(fmaxf(v0, 0.f), fmaxf(v1, 0.f), ph[e], pl[e]);
-                            }
-                            const uint32_t off = tc::op_off(128, row, g * 32 + jj * 8);
-                            *reinterpret_cast<uint4*>(dst + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            *reinterpret_cast<uint4*>(dst + kGOperandHalf + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        }
-                        mask[st] = mk;
+                    // hidden forward layer st: h = relu(D + b), keep the mask, write the next operand (in place)
+                    #pragma unroll
+                    for (uint32_t ch = 0; ch < 2; ch++) if (ch < hchunks) {
+                        const uint32_t v = tc::hidden_epilogue32(acc_t + ch * 32, s_f + st * 64 + ch * 32, hid, hid + kGHidHalf, row, ch * 32);
+                        if (st == 0) mk[0][ch] = v; else mk[1][ch] = v;
                     }
                 } else if (st == n - 1) {
                     // last forward layer: keep its outputs, start the reverse pass: g = W_last[0,:] * relu'(h_{n-2})
-                    if (g == 0) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem + lane_addr, r);
-                        tc::tmem_ld_wait();
-                        const float* bias = s_f + st * 64;
+                    uint32_t r[16];
+                    tc::tmem_ld16(acc_t, r);
+                    tc::tmem_ld_wait();
+                    const float* bias = s_f + st * 64;
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) outv[i] = __uint_as_float(r[i]) + bias[i];
+                    #pragma unroll
+                    for (uint32_t ch = 0; ch < 2; ch++) if (ch < hchunks) {
+                        const float* w0 = s_f + n * 64 + ch * 32;
+                        const uint32_t mask = (n - 2 == 0) ? mk[0][ch] : mk[1][ch];
+                        float v[32];
                         #pragma unroll
-                        for (int i = 0; i < 16; i++) s_side[i * 128 + row] = __uint_as_float(r[i]) + bias[i];
-                    }
-                    if (g < hchunks) {
-                        const float* w0 = s_f + n * 64 + g * 32;
-                        const uint32_t mk = mask[n - 2];
-                        #pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            uint32_t ph[4], pl[4];
-                            #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int c = jj * 8 + e * 2;
-                                g_split2(((mk >> c) & 1u) ? w0[c] : 0.f, ((mk >> (c + 1)) & 1u) ? w0[c + 1] : 0.f, ph[e], pl[e]);
-                            }
-                            const uint32_t off = tc::op_off(128, row, g * 32 + jj * 8);
-                            *reinterpret_cast<uint4*>(dst + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            *reinterpret_cast<uint4*>(dst + kGOperandHalf + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        }
+                        for (int c = 0; c < 32; c++) v[c] = ((mask >> c) & 1u) ? w0[c] : 0.f;
+                        g_store32(hid, row, ch * 32, v);
                     }
                 } else if (st < n_stages - 1) {
                     // reverse stage through layer i = n_stages - 1 - st (>= 1): g_{i-1} = D * relu'(h_{i-1})
                     const int i = n_stages - 1 - st;
-                    if (g < hchunks) {
+                    #pragma unroll
+                    for (uint32_t ch = 0; ch < 2; ch++) if (ch < hchunks) {
                         uint32_t r[32];
-                        tc::tmem_ld32(tmem + lane_addr + g * 32, r);
+                        tc::tmem_ld32(acc_t + ch * 32, r);
                         tc::tmem_ld_wait();
-                        const uint32_t mk = mask[i - 1];
+                        const uint32_t mask = (i - 1 == 0) ? mk[0][ch] : mk[1][ch];
+                        float v[32];
                         #pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            uint32_t ph[4], pl[4];
-                            #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int c = jj * 8 + e * 2;
-                                g_split2(((mk >> c) & 1u) ? __uint_as_float(r[c]) : 0.f, ((mk >> (c + 1)) & 1u) ? __uint_as_float(r[c + 1]) : 0.f,
-                                         ph[e], pl[e]);
-                            }
-                            const uint32_t off = tc::op_off(128, row, g * 32 + jj * 8);
-                            *reinterpret_cast<uint4*>(dst + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            *reinterpret_cast<uint4*>(dst + kGOperandHalf + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        }
+                        for (int c = 0; c < 32; c++) v[c] = ((mask >> c) & 1u) ? __uint_as_float(r[c]) : 0.f;
+                        g_store32(hid, row, ch * 32, v);
                     }
                 } else {
-                    // last reverse stage: D = d sdf / d enc; contract with the jacobian, finish the sample
-                    if (g == 0) {
+                    // last reverse stage: D = d sdf / d enc; contract with the jacobian (TMEM slot j & 3), finish the sample
+                    uint32_t g[32];
+                    tc::tmem_ld32(acc_t, g);
+                    float gx = 0.f, gy = 0.f, gz = 0.f;
+                    const uint32_t jt = tmem + lane_addr + kGJacBase + (j & 3) * kGJacCols;
+                    #pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
                         uint32_t r[32];
-                        tc::tmem_ld32(tmem + lane_addr, r);
+                        tc::tmem_ld32(jt + cc * 32, r);
                         tc::tmem_ld_wait();
-                        const uint32_t m = m0 + row;
-                        const float* jq = s_jac + row * kGJacLd;
-                        float gx = 0.f, gy = 0.f, gz = 0.f;
-                        for (uint32_t l = 0; l < G.L; l++) {
-                            const float g0 = __uint_as_float(r[2 * l]), g1 = __uint_as_float(r[2 * l + 1]);
-                            gx += g0 * jq[6 * l + 0] + g1 * jq[6 * l + 1];
-                            gy += g0 * jq[6 * l + 2] + g1 * jq[6 * l + 3];
-                            gz += g0 * jq[6 * l + 4] + g1 * jq[6 * l + 5];
-                        }
-                        const float inv2b = 1.0f / (2 * G.bound);
-                        gx *= inv2b; gy *= inv2b; gz *= inv2b;
-                        const float gn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-10f);
-                        const float nx = gx / gn, ny = gy / gn, nz = gz / gn;
-                        const int Gd = (int)G.geo_dim;
-                        const float sdf = s_side[0 * 128 + row];
-                        const float sg = (sdf > 0.f) ? 1.f : ((sdf < 0.f) ? -1.f : 0.f);
-                        const float sigma = (1.0f / G.beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(sdf) / G.beta)) * G.density_scale;
-                        if (m < M) {
-                            if (O.sigma) O.sigma[m] = sigma;
-                            if (O.sdf) O.sdf[m] = sdf;
-                            if (O.normal) { O.normal[3 * (size_t)m] = nx; O.normal[3 * (size_t)m + 1] = ny; O.normal[3 * (size_t)m + 2] = nz; }
-                            if (O.grad_x) { O.grad_x[3 * (size_t)m] = gx; O.grad_x[3 * (size_t)m + 1] = gy; O.grad_x[3 * (size_t)m + 2] = gz; }
-                            const float rough = G.rough_act_scale * g_softplus(s_side[(1 + Gd) * 128 + row] + G.rough_bias) * G.rough_scale;
-                            if (O.roughness) O.roughness[m] = rough;
-                            if (rec && mode != 1) {
-                                float ss = 0.f;
-                                for (int i = 0; i < Gd; i++) { const float v = s_side[(1 + i) * 128 + row]; ss += v * v; }
-                                const float ginv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-                                const float blend = g_sigmoid(s_side[(2 + Gd) * 128 + row]);
-                                const float dx = dirs[3 * (size_t)m], dy = dirs[3 * (size_t)m + 1], dz = dirs[3 * (size_t)m + 2];
-                                const float wox = -dx, woy = -dy, woz = -dz;
-                                const float ndot = nx * wox + ny * woy + nz * woz;
-                                float wrx = 2 * ndot * nx - wox, wry = 2 * ndot * ny - woy, wrz = 2 * ndot * nz - woz;
-                                float nex = nx, ney = ny, nez = nz;
-                                if (G.has_rot) {
-                                    const float* R = G.rot;
-                                    const float a0 = wrx * R[0] + wry * R[3] + wrz * R[6], a1 = wrx * R[1] + wry * R[4] + wrz * R[7],
-                                                a2 = wrx * R[2] + wry * R[5] + wrz * R[8];
-                                    wrx = a0; wry = a1; wrz = a2;
-                                    const float b0 = nx * R[0] + ny * R[3] + nz * R[6], b1 = nx * R[1] + ny * R[4] + nz * R[7],
-                                                b2 = nx * R[2] + ny * R[5] + nz * R[8];
-                                    nex = b0; ney = b1; nez = b2;
-                                }
-                                float* q = rec + (size_t)m * kTcRecFloats;
-                                for (int i = 0; i < Gd; i++) q[i] = s_side[(1 + i) * 128 + row] * ginv;
-                                q[16] = nx; q[17] = ny; q[18] = nz; q[19] = ndot; q[20] = rough; q[21] = blend;
-                                q[22] = nex; q[23] = ney; q[24] = nez; q[25] = wrx; q[26] = wry; q[27] = wrz;
+                        #pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const int col = cc * 32 + i, jp = col / 48, rem = col % 48, li = rem / 6, qq = rem % 6;
+                            const int l = 2 * li + jp;
+                            if (l < (int)G.L) {
+                                const float t = __uint_as_float(g[2 * l + (qq & 1)]) * __uint_as_float(r[i]);
+                                if ((qq >> 1) == 0) gx += t; else if ((qq >> 1) == 1) gy += t; else gz += t;
                             }
+                        }
+                    }
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(a_ready + u);          // accumulator and jacobian slot are drained
+                    tc::mbar_arrive(jac_free + (j & 3));
+                    const float inv2b = 1.0f / (2 * G.bound);
+                    gx *= inv2b; gy *= inv2b; gz *= inv2b;
+                    const float gn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-10f);
+                    const float nx = gx / gn, ny = gy / gn, nz = gz / gn;
+                    const float sdf = outv[0];
+                    const float sg = (sdf > 0.f) ? 1.f : ((sdf < 0.f) ? -1.f : 0.f);
+                    const float sigma = (1.0f / G.beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(sdf) / G.beta)) * G.density_scale;
+                    if (m < M) {
+                        if (O.sigma) O.sigma[m] = sigma;
+                        if (O.sdf) O.sdf[m] = sdf;
+                        if (O.normal) { O.normal[3 * (size_t)m] = nx; O.normal[3 * (size_t)m + 1] = ny; O.normal[3 * (size_t)m + 2] = nz; }
+                        if (O.grad_x) { O.grad_x[3 * (size_t)m] = gx; O.grad_x[3 * (size_t)m + 1] = gy; O.grad_x[3 * (size_t)m + 2] = gz; }
+                        float rough_raw = 0.f, blend_raw = 0.f, ss = 0.f;
+                        #pragma unroll
+                        for (int i = 1; i < 16; i++) {
+                            if (i <= Gd) ss += outv[i] * outv[i];
+                            if (i == 1 + Gd) rough_raw = outv[i];
+                            if (i == 2 + Gd) blend_raw = outv[i];
+                        }
+                        const float rough = G.rough_act_scale * g_softplus(rough_raw + G.rough_bias) * G.rough_scale;
+                        if (O.roughness) O.roughness[m] = rough;
+                        if (want_rec) {
+                            const float ginv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                            const float blend = g_sigmoid(blend_raw);
+                            const float wox = -dx, woy = -dy, woz = -dz;
+                            const float ndot = nx * wox + ny * woy + nz * woz;
+                            float wrx = 2 * ndot * nx - wox, wry = 2 * ndot * ny - woy, wrz = 2 * ndot * nz - woz;
+                            float nex = nx, ney = ny, nez = nz;
+                            if (G.has_rot) {
+                                const float* R = G.rot;
+                                const float a0 = wrx * R[0] + wry * R[3] + wrz * R[6], a1 = wrx * R[1] + wry * R[4] + wrz * R[7],
+                                            a2 = wrx * R[2] + wry * R[5] + wrz * R[8];
+                                wrx = a0; wry = a1; wrz = a2;
+                                const float b0 = nx * R[0] + ny * R[3] + nz * R[6], b1 = nx * R[1] + ny * R[4] + nz * R[7],
+                                            b2 = nx * R[2] + ny * R[5] + nz * R[8];
+                                nex = b0; ney = b1; nez = b2;
+                            }
+                            float4* q4 = reinterpret_cast<float4*>(rec + (size_t)m * kTcRecFloats);
+                            float gq[16];
+                            #pragma unroll
+                            for (int i = 0; i < 15; i++) gq[i] = (i < Gd) ? outv[1 + i] * ginv : 0.f;
+                            gq[15] = 0.f;
+                            #pragma unroll
+                            for (int i = 0; i < 4; i++) q4[i] = make_float4(gq[4 * i], gq[4 * i + 1], gq[4 * i + 2], gq[4 * i + 3]);
+                            q4[4] = make_float4(nx, ny, nz, ndot);
+                            q4[5] = make_float4(rough, blend, nex, ney);
+                            q4[6] = make_float4(nez, wrx, wry, wrz);
                         }
                     }
                 }
                 if (st < n_stages - 1) {
                     tc::tc_fence_before();
                     tc::fence_proxy_async_smem();
-                    tc::mbar_arrive(a_ready);
-                } else {
-                    tc::tc_fence_before();
-                    __syncwarp();
+                    tc::mbar_arrive(a_ready + u);
                 }
             }
-            // all 8 worker warps must be done with s_jac / s_side / TMEM before the next tile's gather overwrites them
-            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 64);
+    if (warp == 17) tc::tmem_dealloc(tmem, 512);
 }
 
 // image of B[n][k] (N x K, K-major) for one layer; transpose = 1 reads W as [K][N] (reverse pass: B = W^T)
@@ -406,7 +498,7 @@ int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStrea
 
 int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
                    const envidr_field_out* out, cudaStream_t st) {
-    const size_t smem = (size_t)g.res_bytes_al + 2 * kGOperand + 128 * kGJacLd * 4 + 16 * 128 * 4 + 64;
+    const size_t smem = (size_t)g.res_bytes_al + 2 * kGEnc + 2 * kGHid + 16 * sizeof(GLevel) + 16 * 8;
     static size_t attr_set = 0;
     if (attr_set < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_geom_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
