@@ -14,175 +14,200 @@
 
 namespace envidr {
 
-constexpr int kSThreads = 384;                     // 4 control warps + 8 worker warps
-constexpr uint32_t kSOperand = 32768;              // one A-operand buffer: 128 rows x 64 K x 2 B x (hi, lo)
+constexpr int kSThreads = 576;                     // warps 0-15 chain (4 groups x 4), 16 MMA issuer, 17 TMEM / weights
+constexpr int kSGroups = 4;                        // tiles in flight per CTA
+constexpr uint32_t kSOperand = 32768;              // one A-operand buffer per group: 128 rows x 64 K x 2 B x (hi, lo), rewritten in place
 constexpr uint32_t kSOperandHalf = 16384;
 
 struct ShadeOutDev { float *rgb, *c_diffuse, *c_specular; };
 
 __device__ __forceinline__ float s_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Operand column layout of the first layers (the weight images are packed with the same permutation, see k_pack_tc3):
+//   diffuse_net : [ geo 0..11 | 0 0 0 0 | f_n 0..15 ]
+//   color_net   : [ geo 0..11 | n.x n.y n.z n.w_o | f_r (or f_e) 0..15 ]
+//   renv_net    : [ r*vis (3) rho | 0 ... ]   (K = 16)
 __global__ void __launch_bounds__(kSThreads, 1)
 k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restrict__ feat, const float* __restrict__ r_images,
            const uint32_t* __restrict__ M_dev, uint32_t M_host, const ShadeOutDev O) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem;
     uint8_t* s_op = smem + S.res_bytes_al;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_op + 2 * kSOperand);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_op + kSGroups * kSOperand);
     uint64_t* w_full = bars;
-    uint64_t* acc_ready = bars + 1;
-    uint64_t* a_ready = bars + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* acc_ready = bars + 1;                // [4] issuer -> chain group
+    uint64_t* a_ready = bars + 1 + kSGroups;       // [4] chain group -> issuer (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kSGroups);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (M + 127) / 128;
     if (blockIdx.x >= n_tiles) return;             // nothing to do for this CTA (tail iterations of the render loop)
+    const uint32_t T = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;       // tiles of this CTA: blockIdx.x + j * gridDim.x
     const bool do_renv = (r_images != nullptr) && S.net_layers[2] > 0;
     const int n_nets = do_renv ? 4 : 2;            // diffuse, color, [renv, color again]
     const float* s_f = reinterpret_cast<const float*>(s_w + S.float_off);     // biases: [net 0..2][layer][64]
 
     if (tid == 0) {
         tc::mbar_init(w_full, 1);
-        tc::mbar_init(acc_ready, 1);
-        tc::mbar_init(a_ready, 256);
+        for (int i = 0; i < kSGroups; i++) { tc::mbar_init(acc_ready + i, 1); tc::mbar_init(a_ready + i, 128); }
         tc::mbar_fence_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 64);
+    if (warp == 17) tc::tmem_alloc(tmem_slot, 64 * kSGroups);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp == 0 && lane == 0) {
+    if (warp == 17 && lane == 0) {
         tc::mbar_arrive_expect_tx(w_full, S.res_bytes);
         for (uint32_t o = 0; o < S.res_bytes; o += 16384) tc::bulk_g2s(s_w + o, S.blob + o, min(16384u, S.res_bytes - o), w_full);
     }
-    tc::mbar_wait(w_full, 0);
 
-    if (warp == 0) {
-        // ===================== MMA issuer =====================
-        uint32_t a_par = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            uint32_t st = 0;
+    if (warp == 16) {
+        // ===================== MMA issuer: up to 4 tiles in flight, stages interleaved round-robin =====================
+        tc::mbar_wait(w_full, 0);
+        uint32_t a_par = 0;                        // bit u = parity of the next a_ready[u] phase
+        for (uint32_t p = 0; p < T; p += kSGroups) {
+            const uint32_t ntp = min((uint32_t)kSGroups, T - p);
             for (int net = 0; net < n_nets; net++) {
                 const int w = (net == 3) ? 1 : net;                    // weight set: 0 diffuse, 1 color, 2 renv
-                for (uint32_t l = 0; l < S.net_layers[w]; l++, st++) {
+                for (uint32_t l = 0; l < S.net_layers[w]; l++) {
                     const TcImg& I = S.img[w][l];
-                    tc::mbar_wait(a_ready, a_par); a_par ^= 1;
-                    tc::tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
-                        const uint32_t a_hi0 = tc::smem_u32(s_op + (st & 1) * kSOperand), a_lo0 = a_hi0 + kSOperandHalf;
-                        const uint32_t b0 = tc::smem_u32(s_w + I.off);
-                        for (uint32_t s = 0; s < I.Kp / 16; s++) {
-                            const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
-                            const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
-                            const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
-                            tc::mma_f16_ss(tmem, da_hi, db_hi, idesc, s > 0);
-                            tc::mma_f16_ss(tmem, da_lo, db_hi, idesc, 1);
-                            tc::mma_f16_ss(tmem, da_hi, db_lo, idesc, 1);
+                    for (uint32_t u = 0; u < ntp; u++) {
+                        tc::mbar_wait(a_ready + u, (a_par >> u) & 1u); a_par ^= 1u << u;
+                        tc::tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
+                            const uint32_t a_hi0 = tc::smem_u32(s_op + u * kSOperand), a_lo0 = a_hi0 + kSOperandHalf;
+                            const uint32_t b0 = tc::smem_u32(s_w + I.off);
+                            const uint32_t d = tmem + u * 64;
+                            for (uint32_t s = 0; s < I.Kp / 16; s++) {
+                                const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
+                                const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
+                                const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
+                                tc::mma_f16_ss(d, da_hi, db_hi, idesc, s > 0);
+                                tc::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
+                                tc::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
+                            }
+                            tc::mma_commit(acc_ready + u);
                         }
-                        tc::mma_commit(acc_ready);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===================== workers =====================
-        const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
+    } else if (warp < 16) {
+        // ===================== chain: group u = warp / 4 owns every 4th tile; thread = accumulator row =====================
+        const uint32_t u = warp >> 2, quarter = warp & 3;
         const uint32_t row = quarter * 32 + lane;
-        const uint32_t lane_addr = (quarter * 32u) << 16;
+        const uint32_t acc_t = tmem + ((quarter * 32u) << 16) + u * 64;
+        uint8_t* op = s_op + u * kSOperand;
         const int Gd = (int)S.geo_dim, Ed = (int)S.env_dim;
+        tc::mbar_wait(w_full, 0);
         uint32_t acc_par = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t j = u; j < T; j += kSGroups) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x;
             const uint32_t m = tile * 128 + row;
             const bool valid = m < M;
-            const float* q = rec + (size_t)min(m, M - 1) * kTcRecFloats;
-            const float* ft = feat + (size_t)min(m, M - 1) * kTcRecFloats;
+            const float4* q4 = reinterpret_cast<const float4*>(rec + (size_t)min(m, M - 1) * kTcRecFloats);
+            const float4* f4 = reinterpret_cast<const float4*>(feat + (size_t)min(m, M - 1) * kTcRecFloats);
+            float geo[16];                         // geo 0..11, then n.xyz, n.w_o
+            {
+                const float4 a = __ldg(q4), b = __ldg(q4 + 1), c = __ldg(q4 + 2), d = __ldg(q4 + 4);
+                const float t[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                #pragma unroll
+                for (int i = 0; i < 12; i++) geo[i] = (i < Gd) ? t[i] : 0.f;
+                geo[12] = d.x; geo[13] = d.y; geo[14] = d.z; geo[15] = d.w;
+            }
+            const float4 q5 = __ldg(q4 + 5);       // rough, blend, ...
+            const float rough = q5.x, blend = q5.y;
             float outv[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};      // raw heads: diffuse, color, color(renv)
             float fe[16];
+            #pragma unroll
+            for (int i = 0; i < 16; i++) fe[i] = 0.f;
             float rr = 0.f, vis = 0.f;
-            uint32_t st = 0;
             for (int net = 0; net < n_nets; net++) {
                 const int w = (net == 3) ? 1 : net;
                 const uint32_t nl = S.net_layers[w];
-                // ---- assemble this net's input row (K <= 32) into the operand buffer of its first stage -----------------
-                if (g == 0) {
-                    float in[32];
+                // ---- assemble this net's input row into the operand buffer (the previous MMA reading it has completed) ---------
+                if (net == 2) {
+                    float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) ri = __ldg(reinterpret_cast<const float4*>(r_images) + m);
+                    vis = ri.w;
+                    rr = sqrtf(rough / S.rough_scale / 0.75f);
+                    const float v0[8] = {ri.x * vis, ri.y * vis, ri.z * vis, rr, 0.f, 0.f, 0.f, 0.f};
+                    const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 0, v0);
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 8, z8);
+                } else {
+                    float v0[8], v1[8];
                     #pragma unroll
-                    for (int i = 0; i < 32; i++) in[i] = 0.f;
-                    if (net == 0) {
-                        for (int i = 0; i < Gd; i++) in[i] = q[i];
-                        for (int i = 0; i < Ed; i++) in[Gd + i] = ft[i];
-                    } else if (net == 1 || net == 3) {
-                        for (int i = 0; i < Gd; i++) in[i] = q[i];
-                        in[Gd] = q[16]; in[Gd + 1] = q[17]; in[Gd + 2] = q[18];
-                        for (int i = 0; i < Ed; i++) in[Gd + 3 + i] = (net == 1) ? ft[16 + i] : fe[i];
-                        in[Gd + 3 + Ed] = q[19];
+                    for (int i = 0; i < 8; i++) { v0[i] = geo[i]; v1[i] = (net == 0 && i >= 4) ? 0.f : geo[8 + i]; }
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 0, v0);
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 8, v1);
+                    float f[16];
+                    if (net == 3) {
+                        #pragma unroll
+                        for (int i = 0; i < 16; i++) f[i] = fe[i];
                     } else {
-                        float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) ri = *reinterpret_cast<const float4*>(r_images + 4 * (size_t)m);
-                        vis = ri.w;
-                        rr = sqrtf(q[20] / S.rough_scale / 0.75f);
-                        in[0] = ri.x * vis; in[1] = ri.y * vis; in[2] = ri.z * vis; in[3] = rr;
-                    }
-                    uint8_t* dst = s_op + (st & 1) * kSOperand;
-                    const uint32_t Kp = S.img[w][0].Kp;
-                    #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        if ((uint32_t)c * 8 < Kp) {
-                            float v8[8];
-                            #pragma unroll
-                            for (int e = 0; e < 8; e++) v8[e] = in[c * 8 + e];
-                            tc::store_chunk8(dst, dst + kSOperandHalf, row, c * 8, v8);
+                        const float4* src = f4 + (net == 1 ? 4 : 0);           // f_r at float 16, f_n at float 0
+                        #pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float4 t = __ldg(src + i);
+                            f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
                         }
+                        #pragma unroll
+                        for (int i = 0; i < 16; i++) f[i] = (i < Ed) ? f[i] : 0.f;
                     }
+                    float v2[8], v3[8];
+                    #pragma unroll
+                    for (int i = 0; i < 8; i++) { v2[i] = f[i]; v3[i] = f[8 + i]; }
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 16, v2);
+                    tc::store_chunk8(op, op + kSOperandHalf, row, 24, v3);
                 }
                 tc::fence_proxy_async_smem();
-                tc::mbar_arrive(a_ready);
+                tc::mbar_arrive(a_ready + u);
                 // ---- layers ------------------------------------------------------------------------------------------------
-                for (uint32_t l = 0; l < nl; l++, st++) {
-                    tc::mbar_wait(acc_ready, acc_par); acc_par ^= 1;
+                for (uint32_t l = 0; l < nl; l++) {
+                    tc::mbar_wait(acc_ready + u, acc_par); acc_par ^= 1;
                     tc::tc_fence_after();
                     const float* bias = s_f + (w * 4 + l) * 64;
                     if (l + 1 < nl) {
                         const uint32_t chunks = S.img[w][l].N / 32;
-                        uint8_t* dst = s_op + ((st + 1) & 1) * kSOperand;
-                        if (g < chunks) tc::hidden_epilogue32(tmem + lane_addr + g * 32, bias + g * 32, dst, dst + kSOperandHalf, row, g * 32);
+                        #pragma unroll
+                        for (uint32_t ch = 0; ch < 2; ch++)
+                            if (ch < chunks) tc::hidden_epilogue32(acc_t + ch * 32, bias + ch * 32, op, op + kSOperandHalf, row, ch * 32);
                         tc::tc_fence_before();
                         tc::fence_proxy_async_smem();
-                        tc::mbar_arrive(a_ready);
+                        tc::mbar_arrive(a_ready + u);
                     } else {
-                        if (g == 0) {
-                            uint32_t r[16];
-                            tc::tmem_ld16(tmem + lane_addr, r);
-                            tc::tmem_ld_wait();
-                            if (net == 2) {
-                                float ss = 0.f;
-                                #pragma unroll
-                                for (int i = 0; i < 16; i++) { fe[i] = (i < Ed) ? __uint_as_float(r[i]) + bias[i] : 0.f; ss += fe[i] * fe[i]; }
-                                const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-                                #pragma unroll
-                                for (int i = 0; i < 16; i++) fe[i] *= inv;
-                            } else {
-                                const int slot = net == 0 ? 0 : (net == 1 ? 1 : 2);
-                                #pragma unroll
-                                for (int i = 0; i < 3; i++) outv[slot][i] = __uint_as_float(r[i]) + bias[i];
+                        uint32_t r[16];
+                        tc::tmem_ld16(acc_t, r);
+                        tc::tmem_ld_wait();
+                        if (net == 2) {
+                            float ss = 0.f;
+                            #pragma unroll
+                            for (int i = 0; i < 16; i++) { fe[i] = (i < Ed) ? __uint_as_float(r[i]) + bias[i] : 0.f; ss += fe[i] * fe[i]; }
+                            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                            #pragma unroll
+                            for (int i = 0; i < 16; i++) fe[i] *= inv;
+                        } else {
+                            #pragma unroll
+                            for (int i = 0; i < 3; i++) {
+                                const float v = __uint_as_float(r[i]) + bias[i];
+                                if (net == 0) outv[0][i] = v; else if (net == 1) outv[1][i] = v; else outv[2][i] = v;
                             }
                         }
-                        tc::tc_fence_before();
-                        // every worker warp must be past its TMEM read before the next net's first MMA may overwrite D:
-                        // that MMA waits for a_ready, which all 256 workers arrive on after this point (program order)
+                        tc::tc_fence_before();     // the next MMA into this accumulator waits for this thread's next a_ready arrival
                     }
                 }
             }
-            if (g == 0 && valid) {
+            if (valid) {
                 float cd[3], cs[3];
                 #pragma unroll
                 for (int i = 0; i < 3; i++) { cd[i] = s_sigmoid(outv[0][i]); cs[i] = s_sigmoid(outv[1][i]); }
-                if (do_renv && q[20] < S.indir_rough_thresh && vis > 0.9f) {
-                    const float bw = S.learn_blend ? 0.98f * q[21] : 0.95f * s_sigmoid(80.0f * (rr - 0.18f));
+                if (do_renv && rough < S.indir_rough_thresh && vis > 0.9f) {
+                    const float bw = S.learn_blend ? 0.98f * blend : 0.95f * s_sigmoid(80.0f * (rr - 0.18f));
                     #pragma unroll
                     for (int i = 0; i < 3; i++) cs[i] = cs[i] * bw + s_sigmoid(outv[2][i]) * (1 - bw);
                 }
@@ -197,17 +222,27 @@ k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restri
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 64);
+    if (warp == 17) tc::tmem_dealloc(tmem, 64 * kSGroups);
 }
 
-__global__ void k_pack_tc3(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np);
+__global__ void k_pack_tc3(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np, int kmap,
+                           uint32_t Gd, uint32_t Ed);
 __global__ void k_pack_floats3(const float* __restrict__ src, float* __restrict__ dst, uint32_t n, uint32_t n_pad);
 
-__global__ void k_pack_tc3(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+// kmap: 0 identity; 1 diffuse_net layer 0 ([geo | f] -> geo at 0.., f at 16..); 2 color_net layer 0
+// ([geo | n | f | n.w_o] -> geo at 0.., n at 12..14, n.w_o at 15, f at 16..).  k below is the operand column; src the weight column.
+__global__ void k_pack_tc3(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np, int kmap,
+                           uint32_t Gd, uint32_t Ed) {
     const uint32_t total = Kp * Np;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t nn = i / Kp, k = i - nn * Kp;
-        const float v = (nn < N && k < K) ? W[(size_t)nn * K + k] : 0.0f;
+        int src = (int)k;
+        if (kmap == 1) {
+            src = k < 12 ? (k < Gd ? (int)k : -1) : (k < 16 ? -1 : (k - 16 < Ed ? (int)(Gd + k - 16) : -1));
+        } else if (kmap == 2) {
+            src = k < 12 ? (k < Gd ? (int)k : -1) : (k < 15 ? (int)(Gd + k - 12) : (k == 15 ? (int)(Gd + 3 + Ed) : (k - 16 < Ed ? (int)(Gd + 3 + k - 16) : -1)));
+        }
+        const float v = (nn < N && src >= 0 && (uint32_t)src < K) ? W[(size_t)nn * K + src] : 0.0f;
         __half h, lo;
         tc::split_f16(v, h, lo);
         const uint32_t s = k >> 4, kk = k & 15;
@@ -228,7 +263,7 @@ bool shade_tc_layout(const envidr_field* f, uint64_t base_bytes, TcShade* out, u
     const envidr_mlp_layer* nets[3] = {f->diffuse, f->color, f->renv};
     const uint32_t nl[3] = {f->n_diffuse, f->n_color, f->n_renv};
     const uint32_t G = f->geo_feat_dim, E = f->env[f->n_env - 1].out_dim;
-    if (G > 13 || E > 16 || G + 4 + E > 32) return false;
+    if (G > 12 || E > 16) return false;
     uint32_t off = 0;
     for (int w = 0; w < 3; w++) {
         if (nl[w] > 4 || (w < 2 && nl[w] < 1)) return false;
@@ -240,7 +275,7 @@ bool shade_tc_layout(const envidr_field* f, uint64_t base_bytes, TcShade* out, u
             if (last && N > 16) return false;
             if (l > 0 && K != nets[w][l - 1].out_dim) return false;
             TcImg& I = s.img[w][l];
-            I.Kp = rup3(K, 16); I.N = N; I.Np = last ? 16 : N; I.off = off;
+            I.Kp = (l == 0 && w < 2) ? 32 : rup3(K, 16); I.N = N; I.Np = last ? 16 : N; I.off = off;
             off += (I.Kp / 16) * I.Np * 64;
         }
         s.net_layers[w] = nl[w];
@@ -269,7 +304,8 @@ int shade_tc_pack(const envidr_field* f, const TcShade& s, void* packed, cudaStr
     for (int w = 0; w < 3; w++)
         for (uint32_t l = 0; l < s.net_layers[w]; l++) {
             const TcImg& I = s.img[w][l];
-            k_pack_tc3<<<32, 256, 0, st>>>(nets[w][l].weight, blob + I.off, nets[w][l].in_dim, nets[w][l].out_dim, I.Kp, I.Np);
+            k_pack_tc3<<<32, 256, 0, st>>>(nets[w][l].weight, blob + I.off, nets[w][l].in_dim, nets[w][l].out_dim, I.Kp, I.Np,
+                                       (l == 0 && w < 2) ? w + 1 : 0, s.geo_dim, s.env_dim);
             k_pack_floats3<<<1, 64, 0, st>>>(nets[w][l].bias, fl + (w * 4 + l) * 64, nets[w][l].out_dim, 64);
         }
     return check_launch("shade_tc_pack");
@@ -277,7 +313,7 @@ int shade_tc_pack(const envidr_field* f, const TcShade& s, void* packed, cudaStr
 
 int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const float* r_images, const uint32_t* M_dev, uint32_t M_host,
                     const envidr_field_out* out, cudaStream_t st) {
-    const size_t smem = (size_t)s.res_bytes_al + 2 * kSOperand + 64;
+    const size_t smem = (size_t)s.res_bytes_al + kSGroups * kSOperand + 128;
     static size_t attr_set = 0;
     if (attr_set < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
