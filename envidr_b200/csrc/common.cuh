@@ -121,6 +121,74 @@ struct Dda {
         } while (t < tt);
         return false;
     }
+
+    // ---- single-cascade, constant-step variant (cascade == 1, dt_gamma == 0, H <= 256: every shipped config) ----------
+    // With one cascade the mip level is always 0 and with dt_gamma == 0 the step is the constant min(dt_max, dt_min), so
+    // probe() collapses to the arithmetic below: same operations on the same values, hence the same samples bit for bit.
+    // box = {x0, x1, y0, y1, z0, z1}: bounding box of the occupied cells.  A ray whose current cell lies beyond the box
+    // on an axis along which it moves away (cell indices are monotone in t) can never meet an occupied cell again: the
+    // reference would step through empty cells up to `far` and emit nothing, so the march stops right there (t = far).
+    float c_mipb, c_rmipb, c_dt, hx, hy, hz;
+    int bx0, bx1, by0, by1, bz0, bz1;
+
+    __device__ __forceinline__ void init_fast(const int* __restrict__ box) {
+        c_mipb = fminf(scalbnf(1.0f, 0), bound);
+        c_rmipb = 1 / c_mipb;
+        c_dt = clampf(0.0f, dt_min, dt_max);
+        hx = 0.5f + 0.5f * copysignf(1.0f, dx);
+        hy = 0.5f + 0.5f * copysignf(1.0f, dy);
+        hz = 0.5f + 0.5f * copysignf(1.0f, dz);
+        bx0 = box[0]; bx1 = box[1]; by0 = box[2]; by1 = box[3]; bz0 = box[4]; bz1 = box[5];
+    }
+
+    // conservative slab test of the ray against the occupied box grown by one cell (sides on the grid border are open)
+    __device__ __forceinline__ bool misses_box() const {
+        if (bx0 > bx1) return true;                  // no occupied cell at all
+        const float cell = 2.0f * c_mipb * rH;
+        float t0 = -3.402823466e+38f, t1 = 3.402823466e+38f;
+        const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+        const int lo[3] = {bx0, by0, bz0}, hi[3] = {bx1, by1, bz1};
+        #pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float pl = lo[a] <= 0 ? -3.402823466e+38f : (lo[a] - 1) * cell - c_mipb;
+            const float ph = hi[a] >= (int)H - 1 ? 3.402823466e+38f : (hi[a] + 2) * cell - c_mipb;
+            if (d[a] == 0.0f) {
+                if (o[a] < pl || o[a] > ph) return true;
+            } else {
+                const float r = 1 / d[a];
+                float ta = (pl - o[a]) * r, tb = (ph - o[a]) * r;
+                if (ta > tb) { const float sw = ta; ta = tb; tb = sw; }
+                t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+            }
+        }
+        return t0 > t1 + 1e-3f;
+    }
+
+    __device__ __forceinline__ bool probe_fast(float& t, float& x, float& y, float& z, float& dt, float far) const {
+        x = clampf(ox + t * dx, -bound, bound);
+        y = clampf(oy + t * dy, -bound, bound);
+        z = clampf(oz + t * dz, -bound, bound);
+        dt = c_dt;
+        const int nx = (int)clampf(0.5f * (x * c_rmipb + 1) * Hf, 0.0f, (float)(H - 1));
+        const int ny = (int)clampf(0.5f * (y * c_rmipb + 1) * Hf, 0.0f, (float)(H - 1));
+        const int nz = (int)clampf(0.5f * (z * c_rmipb + 1) * Hf, 0.0f, (float)(H - 1));
+        const uint32_t index = morton3(nx, ny, nz);
+        const bool occ = grid[index >> 3] & (1u << (index & 7u));
+        if (occ) return true;
+        if ((nx > bx1 && dx >= 0.0f) || (nx < bx0 && dx <= 0.0f) || (ny > by1 && dy >= 0.0f) || (ny < by0 && dy <= 0.0f) ||
+            (nz > bz1 && dz >= 0.0f) || (nz < bz0 && dz <= 0.0f)) {
+            t = far;
+            return false;
+        }
+        const float tx = (((nx + hx) * rH * 2 - 1) * c_mipb - x) * rdx;
+        const float ty = (((ny + hy) * rH * 2 - 1) * c_mipb - y) * rdy;
+        const float tz = (((nz + hz) * rH * 2 - 1) * c_mipb - z) * rdz;
+        const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+        do {
+            t += c_dt;
+        } while (t < tt);
+        return false;
+    }
 };
 
 }  // namespace envidr

@@ -41,6 +41,7 @@ struct RenderBuffers {
     float *s_xyz, *s_dir, *s_delta, *s_rimg;
     float *s_sigma, *s_rgb, *s_normal, *s_cd, *s_cs, *s_rough;
     Counters* ctr;
+    int* occ_box;            // {x0, x1, y0, y1, z0, z1}: bounding box of the occupied level-0 cells (single-cascade fast path)
 };
 
 struct RenderOutDev {
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ r
         Counters c{};
         c.n_alive = N; c.n_step = 1;
         *B.ctr = c;
+        for (int a = 0; a < 3; a++) { B.occ_box[2 * a] = 0x7fffffff; B.occ_box[2 * a + 1] = -1; }
     }
     if (n >= N) return;
     // slab test (same arithmetic as k_near_far / reference raymarching.cu:91-145)
@@ -88,11 +90,37 @@ __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ r
     if (O.roughness_image) O.roughness_image[n] = 0;
 }
 
+// bounding box of the occupied cells of cascade level 0 (bit = Morton(x, y, z), reference raymarching.cu:56-81)
+__global__ void __launch_bounds__(256) k_occ_box(const uint8_t* __restrict__ grid, uint32_t n_words, int* __restrict__ box) {
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
+    const uint32_t* __restrict__ g32 = reinterpret_cast<const uint32_t*>(grid);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+        uint32_t w = g32[i];
+        while (w) {
+            const uint32_t b = __ffs(w) - 1;
+            w &= w - 1;
+            const uint32_t idx = i * 32 + b;
+            const int c[3] = {(int)compact3(idx), (int)compact3(idx >> 1), (int)compact3(idx >> 2)};
+            #pragma unroll
+            for (int a = 0; a < 3; a++) { lo[a] = min(lo[a], c[a]); hi[a] = max(hi[a], c[a]); }
+        }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0 && hi[a] >= 0) { atomicMin(box + 2 * a, lo[a]); atomicMax(box + 2 * a + 1, hi[a]); }
+    }
+}
+
 // march n_step samples for every alive ray and append them compactly to the sample batch
 __global__ void __launch_bounds__(kMarchBlock) k_march_compact(
         const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ r_images,
         const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
-        const float* __restrict__ noises, RenderBuffers B) {
+        const float* __restrict__ noises, int fast, RenderBuffers B) {
     __shared__ float stage[kMarchBlock][kMaxNStep][5];
     Counters* ctr = B.ctr;
     const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
@@ -114,14 +142,29 @@ __global__ void __launch_bounds__(kMarchBlock) k_march_compact(
             const float noise = (first && noises) ? noises[n] : 0.0f;
             t += s.step_size(t) * noise;
             float x, y, z, dt;
-            while (t < far && count < n_step) {
-                if (s.probe(t, x, y, z, dt)) {
-                    float* q = stage[threadIdx.x][count];
-                    q[0] = x; q[1] = y; q[2] = z;
-                    t += dt;
-                    q[3] = dt; q[4] = t - last_t;
-                    last_t = t;
-                    count++;
+            if (fast) {
+                s.init_fast(B.occ_box);
+                if (first && s.misses_box()) t = far;
+                while (t < far && count < n_step) {
+                    if (s.probe_fast(t, x, y, z, dt, far)) {
+                        float* q = stage[threadIdx.x][count];
+                        q[0] = x; q[1] = y; q[2] = z;
+                        t += dt;
+                        q[3] = dt; q[4] = t - last_t;
+                        last_t = t;
+                        count++;
+                    }
+                }
+            } else {
+                while (t < far && count < n_step) {
+                    if (s.probe(t, x, y, z, dt)) {
+                        float* q = stage[threadIdx.x][count];
+                        q[0] = x; q[1] = y; q[2] = z;
+                        t += dt;
+                        q[3] = dt; q[4] = t - last_t;
+                        last_t = t;
+                        count++;
+                    }
                 }
             }
         }
@@ -268,7 +311,7 @@ __global__ void __launch_bounds__(256) k_render_finish(uint32_t N, float bg0, fl
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, scratch, total;
+    uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, occ_box, scratch, total;
 };
 static WsLayout ws_layout(uint32_t N) {
     WsLayout L{};
@@ -281,6 +324,7 @@ static WsLayout ws_layout(uint32_t N) {
     L.s_sigma = take(4 * n); L.s_rgb = take(12 * n); L.s_normal = take(12 * n); L.s_cd = take(12 * n); L.s_cs = take(12 * n);
     L.s_rough = take(4 * n);
     L.ctr = take(sizeof(Counters));
+    L.occ_box = take(8 * sizeof(int));
     L.scratch = take(256 * n);             // tensor-core path: per-sample record + env features (2 x 32 floats)
     L.total = off;
     return L;
@@ -335,11 +379,20 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     B.s_sigma = (float*)(w + L.s_sigma); B.s_rgb = (float*)(w + L.s_rgb); B.s_normal = (float*)(w + L.s_normal);
     B.s_cd = (float*)(w + L.s_cd); B.s_cs = (float*)(w + L.s_cs); B.s_rough = (float*)(w + L.s_rough);
     B.ctr = (Counters*)(w + L.ctr);
+    B.occ_box = (int*)(w + L.occ_box);
     RenderOutDev O{out->image, out->depth, out->weights_sum, out->normal_image, out->diffuse_image, out->specular_image,
                    out->roughness_image};
     if (opts->geometry_only) { O.image = out->normal_image; O.diffuse_image = nullptr; O.specular_image = nullptr; O.roughness_image = nullptr; }
     const float* a = opts->aabb;
     k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);
+    // single-cascade, constant-step scenes take the specialised march (same samples, see Dda::probe_fast)
+    const int fast = opts->cascade == 1 && opts->dt_gamma == 0.0f && opts->grid_size <= 256 && opts->grid_size % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(bitfield) & 3) == 0;
+    if (fast) {
+        const uint32_t H = opts->grid_size;
+        k_occ_box<<<kSMs, 256, 0, st>>>(bitfield, H * H * H / 32, B.occ_box);
+        g_launches += 1;
+    }
     int rc = check_launch("render_init");
     if (rc) return rc;
 
@@ -361,7 +414,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     while (!done && it < max_iters) {
         for (uint32_t b = 0; b < batch && it < max_iters; b++, it++) {
             k_march_compact<<<march_grid, kMarchBlock, 0, st>>>(rays_o, rays_d, r_images, bitfield, opts->bound, opts->dt_gamma,
-                                                               opts->max_steps, opts->cascade, opts->grid_size, noises, B);
+                                                               opts->max_steps, opts->cascade, opts->grid_size, noises, fast, B);
             const bool timed = g_timing && g_tev_used < kMaxTimed;
             int recorded = 0;
             if (timed) while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
