@@ -59,14 +59,15 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kTcMaxLayers * 256);
     uint64_t* full = bars;                           // [3]  producer -> issuer (TMA bytes landed)
     uint64_t* empty = bars + kTcStages;              // [3]  issuer -> producer (MMAs reading the stage retired)
-    uint64_t* acc_ready = bars + 2 * kTcStages;      // issuer -> epilogue warps (accumulator of a layer complete)
-    uint64_t* a_ready = acc_ready + 1;               // epilogue warps -> issuer (next layer's A operand in smem; 256 arrivals)
-    uint64_t* d_free = acc_ready + 2;                // epilogue warps -> issuer (last accumulator of the tile drained; 256 arrivals)
-    uint64_t* ide_full = acc_ready + 3;              // IDE warps -> issuer (256 arrivals)
-    uint64_t* ide_empty = acc_ready + 4;             // issuer -> IDE warps (layer-0 MMAs retired)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 5);
+    uint64_t* acc_ready = bars + 2 * kTcStages;      // [2] issuer -> epilogue warps (accumulator buffer b of a layer complete)
+    uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (256 arrivals)
+    uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
+    uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
+                                                     //     shared memory (128 arrivals: the 4 warps that own chunk parity c & 1)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 8);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
     const int nl = (int)E.n_layers;
@@ -74,14 +75,14 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
 
     if (tid == 0) {
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(acc_ready, 1);
-        tc::mbar_init(a_ready, 256);
-        tc::mbar_init(d_free, 256);
+        tc::mbar_init(&acc_ready[0], 1);
+        tc::mbar_init(&acc_ready[1], 1);
+        for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128);
         tc::mbar_init(ide_full, 256);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
     for (uint32_t i = tid; i < (uint32_t)nl * 256; i += kTcThreads) {
         const uint32_t l = i >> 8, c = i & 255;
         s_bias[i] = (c < E.L[l].Np) ? __ldg(E.bias + E.L[l].bias_off + c) : 0.0f;
@@ -111,42 +112,50 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        uint32_t stage = 0, phase = 0, a_par = 0, ide_par = 0, dfree_par = 1;    // dfree_par = 1: the first wait passes
+        // All 32 lanes run this code with warp-uniform values; one elected lane issues (tc::*_w helpers).
+        // Accumulators ping-pong between TMEM columns [0,256) and [256,512) from layer to layer, so the epilogue of layer g
+        // (which produces the next A operand chunk by chunk) overlaps the MMAs of layer g + 1, which start as soon as
+        // chunk 0 is in shared memory.  Hazards: MMA(g+2) reuses the accumulator of layer g; it is issued after the last
+        // K step of MMA(g+1), which waited for every chunk of epilogue(g) (or, across tiles, behind chunk 0 of
+        // epilogue(g+1), which the same warps run after epilogue(g)).
+        uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0, gl = 0;
+        const uint32_t ring0 = tc::smem_u32(ring);
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int l = 0; l < nl; l++) {
                 const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np;
                 const uint32_t idesc = tc::make_idesc_f16(128, Np);
-                uint32_t base_hi, base_lo;
+                const uint32_t buf = gl & 1u;
+                const uint32_t d_tmem = tmem + buf * 256u;
+                gl++;
+                uint64_t da_hi, da_lo;
                 if (l == 0) {
                     tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;          // IDE operand of this tile is in smem
-                    tc::mbar_wait(d_free, dfree_par); dfree_par ^= 1;        // previous tile's last accumulator has been read
-                    base_hi = tc::smem_u32(sI_hi); base_lo = tc::smem_u32(sI_lo);
+                    da_hi = tc::make_smem_desc(tc::smem_u32(sI_hi), 2048, 128);
+                    da_lo = tc::make_smem_desc(tc::smem_u32(sI_lo), 2048, 128);
                 } else {
-                    tc::mbar_wait(a_ready, a_par); a_par ^= 1;
-                    base_hi = tc::smem_u32(sA_hi); base_lo = tc::smem_u32(sA_lo);
+                    da_hi = tc::make_smem_desc(tc::smem_u32(sA_hi), 2048, 128);
+                    da_lo = tc::make_smem_desc(tc::smem_u32(sA_lo), 2048, 128);
                 }
-                tc::tc_fence_after();
+                const uint64_t db0 = tc::make_smem_desc(ring0, Np * 16, 128);
+                const uint32_t lo_off = Np * 32;
                 for (uint32_t s = 0; s < ksteps; s++) {
+                    if (l > 0 && (s & 1u) == 0) {                            // K steps 2c, 2c+1 read chunk c of the A operand
+                        const uint32_t c = s >> 1;
+                        tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
+                    }
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_hi = base_hi + s * 4096, a_lo = base_lo + s * 4096;
-                        const uint32_t b_hi = tc::smem_u32(ring + stage * kTcStageBytes), b_lo = b_hi + Np * 32;
-                        const uint64_t da_hi = tc::make_smem_desc(a_hi, 2048, 128), da_lo = tc::make_smem_desc(a_lo, 2048, 128);
-                        const uint64_t db_hi = tc::make_smem_desc(b_hi, Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, Np * 16, 128);
-                        tc::mma_f16_ss(tmem, da_hi, db_hi, idesc, s > 0);
-                        tc::mma_f16_ss(tmem, da_lo, db_hi, idesc, 1);
-                        tc::mma_f16_ss(tmem, da_hi, db_lo, idesc, 1);
-                        tc::mma_commit(&empty[stage]);            // frees the ring slot when these MMAs retire
-                    }
                     __syncwarp();
+                    const uint64_t db_hi = tc::desc_advance(db0, stage * kTcStageBytes), db_lo = tc::desc_advance(db_hi, lo_off);
+                    tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
+                    tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
+                    tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                    tc::mma_commit_w(&empty[stage]);              // frees the ring slot when these MMAs retire
+                    da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
-                if (lane == 0) {
-                    if (l == 0) tc::mma_commit(ide_empty);        // IDE buffer may be refilled for the next tile
-                    tc::mma_commit(acc_ready);
-                }
-                __syncwarp();
+                if (l == 0) tc::mma_commit_w(ide_empty);          // IDE buffer may be refilled for the next tile
+                tc::mma_commit_w(&acc_ready[buf]);
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -155,19 +164,22 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         const uint32_t row = quarter * 32 + lane;
         const uint32_t branch = row >> 6;
         const uint32_t lane_addr = (quarter * 32u) << 16;
-        uint32_t acc_par = 0;
+        uint32_t acc_par = 0, gl = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             for (int l = 0; l < nl; l++) {
-                tc::mbar_wait(acc_ready, acc_par); acc_par ^= 1;
+                const uint32_t buf = gl & 1u;
+                gl++;
+                tc::mbar_wait(&acc_ready[buf], (acc_par >> buf) & 1u); acc_par ^= 1u << buf;
                 tc::tc_fence_after();
+                const uint32_t acc = tmem + lane_addr + buf * 256u;
                 const float* bias = s_bias + l * 256;
                 if (l < nl - 1) {
                     const uint32_t nchunks = E.L[l].N / 32;
                     for (uint32_t cb = g; cb < nchunks; cb += 2) {
                         uint32_t r[32];
-                        tc::tmem_ld32(tmem + lane_addr + cb * 32, r);
+                        tc::tmem_ld32(acc + cb * 32, r);
                         tc::tmem_ld_wait();
                         const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
                         #pragma unroll
@@ -182,33 +194,30 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                             *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                             *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                         }
+                        tc::tc_fence_before();
+                        tc::fence_proxy_async_smem();
+                        tc::mbar_arrive(&a_rdy[cb]);             // chunk cb of the next layer's A operand is ready
+                    }
+                } else if (g == 0) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(acc, r);
+                    tc::tmem_ld_wait();
+                    const int Ef = (int)E.E;
+                    float f[16], ss = 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
+                        ss += f[i] * f[i];
+                    }
+                    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * kTcRecFloats + 16 * branch);
+                        dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+                        dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+                        dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
+                        dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
                     }
                     tc::tc_fence_before();
-                    tc::fence_proxy_async_smem();
-                    tc::mbar_arrive(a_ready);
-                } else {
-                    if (g == 0) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem + lane_addr, r);
-                        tc::tmem_ld_wait();
-                        const int Ef = (int)E.E;
-                        float f[16], ss = 0.f;
-                        #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
-                            ss += f[i] * f[i];
-                        }
-                        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
-                        if (valid) {
-                            float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * kTcRecFloats + 16 * branch);
-                            dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-                            dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
-                            dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
-                            dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
-                        }
-                    }
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(d_free);
                 }
             }
         }
@@ -257,7 +266,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem, 256);
+    if (warp == 2) tc::tmem_dealloc(tmem, 512);
 }
 
 // weight image of one layer: for every K step s: [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1], chunk = [Np][8] halfs
@@ -291,7 +300,7 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
     for (uint32_t i = 0; i < f->n_env; i++) {
         const bool last = (i == f->n_env - 1);
         const uint32_t K = f->env[i].in_dim, N = f->env[i].out_dim;
-        if (!last && (N % 32 != 0 || N > 256 || N < 32)) return false;
+        if (!last && (N % 32 != 0 || N > 256 || N < 64)) return false;      // >= 64: both epilogue groups own a chunk (see k_env_tc)
         if (last && N > 16) return false;
         if (i > 0 && K != f->env[i - 1].out_dim) return false;
         TcLayer& L = t.L[i];

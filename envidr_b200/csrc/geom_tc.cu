@@ -24,7 +24,7 @@ constexpr uint32_t kGHid = 32768, kGHidHalf = 16384;   // hidden operand:   128 
 constexpr uint32_t kGJacBase = 128, kGJacCols = 96;    // TMEM columns: 2 accumulators x 64, then 4 jacobian slots x 96
 
 struct GeomOutDev { float *sigma, *normal, *sdf, *roughness, *grad_x; };
-struct GLevel { uint32_t off2, size, res, hashed, pow2, on; float scale; uint32_t pad; };
+struct GLevel { uint32_t off2, size, res, hashed, magic, on; float scale; uint32_t res2; };
 
 __device__ __forceinline__ float g_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float g_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
@@ -38,17 +38,12 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// hash-grid cell index with the level's indexing mode decided once per level (same value as cell_index<3>, gridenc.cuh)
-__device__ __forceinline__ uint32_t g_index(const GLevel& lv, uint32_t x, uint32_t y, uint32_t z) {
-    uint32_t idx;
-    if (lv.hashed) {
-        idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
-        idx = lv.pow2 ? (idx & (lv.size - 1)) : (idx % lv.size);
-    } else {
-        idx = x + lv.res * (y + lv.res * z);
-        if (idx >= lv.size) idx %= lv.size;
-    }
-    return idx;
+// raw % size with magic = floor(2^32 / size): the estimated quotient is exact or one short, so one conditional
+// subtraction completes it (same value as the reference's `index % hashmap_size`, hashencoder.cu:71).
+__device__ __forceinline__ uint32_t g_mod(uint32_t raw, uint32_t size, uint32_t magic) {
+    uint32_t r = raw - __umulhi(raw, magic) * size;
+    if (r >= size) r -= size;
+    return r;
 }
 
 // write `vals` (32 columns col0..col0+31 of row `row`) into a 128-row hidden operand as fp16 hi / lo
@@ -81,7 +76,8 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
     uint64_t* jac_free = bars + 9;        // [4] chain group -> gather (128 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (M + 127) / 128;
     if (blockIdx.x >= n_tiles) return;             // nothing to do for this CTA (tail iterations of the render loop)
@@ -111,9 +107,9 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
         uint32_t stride = 1;
         for (int d = 0; d < 3; d++) if (stride <= lv.size) stride *= lv.res;
         lv.hashed = stride > lv.size ? 1u : 0u;
-        lv.pow2 = (lv.size & (lv.size - 1)) == 0 ? 1u : 0u;
+        lv.magic = lv.size > 1 ? (uint32_t)(0x100000000ull / lv.size) : 0xFFFFFFFFu;
         lv.on = !(G.enabled_levels > 0 && (int)l >= G.enabled_levels) ? 1u : 0u;
-        lv.pad = 0;
+        lv.res2 = lv.res * lv.res;
         s_lvl[l] = lv;
     }
     if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
@@ -145,22 +141,24 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
                         tc::mbar_wait(a_ready + u, (a_par >> u) & 1u); a_par ^= 1u << u;
                     }
                     tc::tc_fence_after();
-                    if (lane == 0) {
+                    __syncwarp();
+                    {
                         const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
                         const uint32_t a_hi0 = tc::smem_u32(st == 0 ? s_enc + u * kGEnc : s_hid + u * kGHid);
                         const uint32_t a_lo0 = a_hi0 + (st == 0 ? kGEncHalf : kGHidHalf);
-                        const uint32_t b0 = tc::smem_u32(s_w + I.off);
                         const uint32_t d = tmem + u * 64;
+                        uint64_t da_hi = tc::make_smem_desc(a_hi0, 2048, 128), da_lo = tc::make_smem_desc(a_lo0, 2048, 128);
+                        uint64_t db_hi = tc::make_smem_desc(tc::smem_u32(s_w + I.off), I.Np * 16, 128);
                         for (uint32_t s = 0; s < I.Kp / 16; s++) {
-                            const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
-                            const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
-                            const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
-                            tc::mma_f16_ss(d, da_hi, db_hi, idesc, s > 0);
-                            tc::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
-                            tc::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
+                            const uint64_t db_lo = tc::desc_advance(db_hi, I.Np * 32);
+                            tc::mma_f16_ss_w(d, da_hi, db_hi, idesc, s > 0);
+                            tc::mma_f16_ss_w(d, da_lo, db_hi, idesc, 1);
+                            tc::mma_f16_ss_w(d, da_hi, db_lo, idesc, 1);
+                            da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
+                            db_hi = tc::desc_advance(db_hi, I.Np * 64);
                         }
-                        tc::mma_commit(acc_ready + u);
-                        if (st == 0) tc::mma_commit(enc_free + u);
+                        tc::mma_commit_w(acc_ready + u);
+                        if (st == 0) tc::mma_commit_w(enc_free + u);
                     }
                     __syncwarp();
                 }
@@ -225,9 +223,23 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
                             }
                             sc[u] = lv.scale;
                             const float2* grid = reinterpret_cast<const float2*>(G.table + lv.off2);
+                            // corner c = (x bit 0, y bit 1, z bit 2); hashencoder.cu:54-72 with the y / z products shared
+                            uint32_t raw[8];
+                            if (lv.hashed) {
+                                const uint32_t y0 = pg[1] * 2654435761u, y1 = y0 + 2654435761u;
+                                const uint32_t z0 = pg[2] * 805459861u, z1 = z0 + 805459861u;
+                                const uint32_t yz[4] = {y0 ^ z0, y1 ^ z0, y0 ^ z1, y1 ^ z1};
+                                #pragma unroll
+                                for (uint32_t c = 0; c < 8; c++) raw[c] = (pg[0] + (c & 1u)) ^ yz[c >> 1];
+                            } else {
+                                const uint32_t y0 = pg[1] * lv.res, z0 = pg[2] * lv.res2;
+                                const uint32_t yz[4] = {y0 + z0, y0 + lv.res + z0, y0 + z0 + lv.res2, y0 + lv.res + z0 + lv.res2};
+                                #pragma unroll
+                                for (uint32_t c = 0; c < 8; c++) raw[c] = pg[0] + (c & 1u) + yz[c >> 1];
+                            }
                             #pragma unroll
                             for (uint32_t c = 0; c < 8; c++) {
-                                const float2 t = __ldg(grid + g_index(lv, pg[0] + (c & 1u), pg[1] + ((c >> 1) & 1u), pg[2] + ((c >> 2) & 1u)));
+                                const float2 t = __ldg(grid + g_mod(raw[c], lv.size, lv.magic));
                                 rows[u][c][0] = t.x; rows[u][c][1] = t.y;
                             }
                         }
@@ -237,31 +249,31 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
                 for (int u = 0; u < 2; u++) {
                     const uint32_t l = l0 + 2 * u;
                     if (l < G.L) {
-                        float e0 = 0.f, e1 = 0.f, jv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        // tri-"linear" interpolation with smoothstep weights, factored x -> y -> z; the x / y / z differences
+                        // that fall out are exactly the terms of d enc / d x (hashencoder.cu:210-253)
+                        float ev[2], jv[6];
                         #pragma unroll
-                        for (uint32_t c = 0; c < 8; c++) {
-                            float wt_ = 1;
+                        for (int ch = 0; ch < 2; ch++) {
+                            float a[4], dx[4];
                             #pragma unroll
-                            for (int d = 0; d < 3; d++) wt_ *= ((c >> d) & 1u) ? w[u][d] : 1 - w[u][d];
-                            e0 += wt_ * rows[u][c][0];
-                            e1 += wt_ * rows[u][c][1];
-                        }
-                        #pragma unroll
-                        for (int gd = 0; gd < 3; gd++) {
-                            #pragma unroll
-                            for (uint32_t sub = 0; sub < 4; sub++) {
-                                float wt_ = sc[u];
-                                uint32_t c = 0;
-                                #pragma unroll
-                                for (int nd = 0; nd < 2; nd++) {
-                                    const int d = nd >= gd ? nd + 1 : nd;
-                                    if ((sub >> nd) & 1u) { wt_ *= w[u][d]; c |= 1u << d; }
-                                    else                  { wt_ *= 1 - w[u][d]; }
-                                }
-                                jv[gd * 2 + 0] += wt_ * (rows[u][c | (1u << gd)][0] - rows[u][c][0]) * dw[u][gd];
-                                jv[gd * 2 + 1] += wt_ * (rows[u][c | (1u << gd)][1] - rows[u][c][1]) * dw[u][gd];
+                            for (int j = 0; j < 4; j++) {
+                                dx[j] = rows[u][2 * j + 1][ch] - rows[u][2 * j][ch];
+                                a[j] = fmaf(w[u][0], dx[j], rows[u][2 * j][ch]);
                             }
+                            float b[2], bx[2], by[2];
+                            #pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                by[k] = a[2 * k + 1] - a[2 * k];
+                                b[k] = fmaf(w[u][1], by[k], a[2 * k]);
+                                bx[k] = fmaf(w[u][1], dx[2 * k + 1] - dx[2 * k], dx[2 * k]);
+                            }
+                            const float ez = b[1] - b[0];
+                            ev[ch] = fmaf(w[u][2], ez, b[0]);
+                            jv[0 + ch] = fmaf(w[u][2], bx[1] - bx[0], bx[0]) * (dw[u][0] * sc[u]);
+                            jv[2 + ch] = fmaf(w[u][2], by[1] - by[0], by[0]) * (dw[u][1] * sc[u]);
+                            jv[4 + ch] = ez * (dw[u][2] * sc[u]);
                         }
+                        const float e0 = ev[0], e1 = ev[1];
                         uint32_t hi, lo;
                         tc::split2(e0, e1, hi, lo);
                         const uint32_t off = tc::op_off(128, s, 2 * l);

@@ -39,7 +39,8 @@ k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restri
     uint64_t* a_ready = bars + 1 + kSGroups;       // [4] chain group -> issuer (128 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kSGroups);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (M + 127) / 128;
     if (blockIdx.x >= n_tiles) return;             // nothing to do for this CTA (tail iterations of the render loop)
@@ -76,20 +77,22 @@ k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restri
                     for (uint32_t u = 0; u < ntp; u++) {
                         tc::mbar_wait(a_ready + u, (a_par >> u) & 1u); a_par ^= 1u << u;
                         tc::tc_fence_after();
-                        if (lane == 0) {
+                        __syncwarp();
+                        {
                             const uint32_t idesc = tc::make_idesc_f16(128, I.Np);
                             const uint32_t a_hi0 = tc::smem_u32(s_op + u * kSOperand), a_lo0 = a_hi0 + kSOperandHalf;
-                            const uint32_t b0 = tc::smem_u32(s_w + I.off);
                             const uint32_t d = tmem + u * 64;
+                            uint64_t da_hi = tc::make_smem_desc(a_hi0, 2048, 128), da_lo = tc::make_smem_desc(a_lo0, 2048, 128);
+                            uint64_t db_hi = tc::make_smem_desc(tc::smem_u32(s_w + I.off), I.Np * 16, 128);
                             for (uint32_t s = 0; s < I.Kp / 16; s++) {
-                                const uint32_t b_hi = b0 + s * I.Np * 64, b_lo = b_hi + I.Np * 32;
-                                const uint64_t da_hi = tc::make_smem_desc(a_hi0 + s * 4096, 2048, 128), da_lo = tc::make_smem_desc(a_lo0 + s * 4096, 2048, 128);
-                                const uint64_t db_hi = tc::make_smem_desc(b_hi, I.Np * 16, 128), db_lo = tc::make_smem_desc(b_lo, I.Np * 16, 128);
-                                tc::mma_f16_ss(d, da_hi, db_hi, idesc, s > 0);
-                                tc::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
-                                tc::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
+                                const uint64_t db_lo = tc::desc_advance(db_hi, I.Np * 32);
+                                tc::mma_f16_ss_w(d, da_hi, db_hi, idesc, s > 0);
+                                tc::mma_f16_ss_w(d, da_lo, db_hi, idesc, 1);
+                                tc::mma_f16_ss_w(d, da_hi, db_lo, idesc, 1);
+                                da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
+                                db_hi = tc::desc_advance(db_hi, I.Np * 64);
                             }
-                            tc::mma_commit(acc_ready + u);
+                            tc::mma_commit_w(acc_ready + u);
                         }
                         __syncwarp();
                     }

@@ -99,6 +99,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- warp-uniform issue helpers -----------------------------------------------------------------------------
+// Called by ALL lanes of a converged warp with warp-uniform operands; one elected lane issues.  Keeping the call
+// site free of `if (lane == 0)` lets the compiler hold descriptors in uniform registers instead of wrapping every
+// operand in an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence (measured: ~90 SASS instructions per K step before).
+__device__ __forceinline__ void mma_f16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+                 " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+    asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+                 " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+// descriptor of the same operand `bytes` further in shared memory (address field is in 16-byte units)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // fp32 -> (hi, lo) fp16 pair with hi + lo ~= x to ~2^-22 relative (lo may be subnormal: absolute error <= 3e-8)
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
