@@ -30,13 +30,21 @@
 
 namespace envidr {
 
-constexpr int kTcThreads = 640;                    // 4 control warps + 8 epilogue warps + 8 IDE warps
+constexpr int kTcIdeSplit = 4;                    // threads per row in the IDE role (orders m = k mod 4)
+constexpr int kTcThreads = (4 + 8 + 4 * kTcIdeSplit) * 32;   // 4 control warps + 8 epilogue warps + 16 IDE warps
 constexpr int kTcStages = 3;
 constexpr uint32_t kTcStageBytes = 16384;          // one K step (16) of a 256-wide layer: 2 (hi,lo) x 2 chunks x 256 x 16 B
 constexpr uint32_t kTcARegion = 65536;             // 128 rows x 256 K x 2 B
 constexpr uint32_t kTcIdeRegion = 20480;           // 128 rows x 80 K x 2 B (IDE features, deg_view <= 5, K padded to 16)
 __constant__ IdeTables c_ide_tc;
 static int g_ide_tc_deg = 0;
+// clock64() timeline of CTA 0 (envidr_debug_env_tc_timeline): slot 0 = number of tiles recorded, then per tile kProfPerTile slots:
+//   issuer : 0 wait(ide_full) start, 1 end, 2 layer-0 issued, 3 last layer issued, 4 cycles spent in wait(a_rdy), 5 in wait(full)
+//   IDE w12: 8 wait(ide_empty) start, 9 end, 10 operand written
+//   epilogue w4: 12 + 2*l wait(acc_ready) end, 13 + 2*l layer epilogue done (l < 4)
+constexpr uint32_t kProfPerTile = 24;
+static unsigned long long* g_prof = nullptr;
+static uint32_t g_prof_cap = 0;
 
 // fp32 pair -> packed fp16 (hi) pair and packed fp16 (lo = x - hi) pair
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -48,7 +56,8 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host) {
+k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
+         unsigned long long* __restrict__ prof, uint32_t prof_cap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA_hi = smem;                                   // hidden-layer A operand (written by the epilogues)
     uint8_t* sA_lo = smem + kTcARegion;
@@ -60,7 +69,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint64_t* full = bars;                           // [3]  producer -> issuer (TMA bytes landed)
     uint64_t* empty = bars + kTcStages;              // [3]  issuer -> producer (MMAs reading the stage retired)
     uint64_t* acc_ready = bars + 2 * kTcStages;      // [2] issuer -> epilogue warps (accumulator buffer b of a layer complete)
-    uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (256 arrivals)
+    uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (128 * kTcIdeSplit arrivals)
     uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
     uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
                                                      //     shared memory (128 arrivals: the 4 warps that own chunk parity c & 1)
@@ -72,13 +81,18 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
     const int nl = (int)E.n_layers;
     if (blockIdx.x >= n_tiles) return;                // nothing to do for this CTA (tail iterations of the render loop)
+    if (blockIdx.x != 0) prof = nullptr;
+    auto stamp = [&](uint32_t tile_i, uint32_t slot, unsigned long long v) {
+        const uint32_t idx = 1 + tile_i * kProfPerTile + slot;
+        if (prof && idx < prof_cap) prof[idx] = v;
+    };
 
     if (tid == 0) {
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&acc_ready[0], 1);
         tc::mbar_init(&acc_ready[1], 1);
         for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128);
-        tc::mbar_init(ide_full, 256);
+        tc::mbar_init(ide_full, 128 * kTcIdeSplit);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
@@ -97,13 +111,17 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         uint32_t stage = 0, phase = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int l = 0; l < nl; l++) {
-                const uint32_t ksteps = E.L[l].Kp / 16, bytes = E.L[l].Np * 64;
+                // a ring stage carries as many K steps as fit in kTcStageBytes (1 for a 256-wide layer, all 16 for the 16-wide
+                // last layer: otherwise that layer is bound by 16 ring round trips of 1 KB each)
+                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64;
+                const uint32_t kper = max(1u, kTcStageBytes / kbytes);
                 const uint8_t* src = E.blob + E.L[l].img_off;
-                for (uint32_t s = 0; s < ksteps; s++) {
+                for (uint32_t s = 0; s < ksteps; s += kper) {
+                    const uint32_t bytes = min(kper, ksteps - s) * kbytes;
                     tc::mbar_wait(&empty[stage], phase ^ 1);
                     if (lane == 0) {
                         tc::mbar_arrive_expect_tx(&full[stage], bytes);
-                        tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * bytes, bytes, &full[stage]);
+                        tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * kbytes, bytes, &full[stage]);
                     }
                     __syncwarp();
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
@@ -118,9 +136,10 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         // chunk 0 is in shared memory.  Hazards: MMA(g+2) reuses the accumulator of layer g; it is issued after the last
         // K step of MMA(g+1), which waited for every chunk of epilogue(g) (or, across tiles, behind chunk 0 of
         // epilogue(g+1), which the same warps run after epilogue(g)).
-        uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0, gl = 0;
+        uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0, gl = 0, ti = 0;
         const uint32_t ring0 = tc::smem_u32(ring);
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+            unsigned long long w_a = 0, w_f = 0;
             for (int l = 0; l < nl; l++) {
                 const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np;
                 const uint32_t idesc = tc::make_idesc_f16(128, Np);
@@ -129,7 +148,9 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 gl++;
                 uint64_t da_hi, da_lo;
                 if (l == 0) {
+                    if (prof && lane == 0) stamp(ti, 0, clock64());
                     tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;          // IDE operand of this tile is in smem
+                    if (prof && lane == 0) stamp(ti, 1, clock64());
                     da_hi = tc::make_smem_desc(tc::smem_u32(sI_hi), 2048, 128);
                     da_lo = tc::make_smem_desc(tc::smem_u32(sI_lo), 2048, 128);
                 } else {
@@ -137,25 +158,39 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     da_lo = tc::make_smem_desc(tc::smem_u32(sA_lo), 2048, 128);
                 }
                 const uint64_t db0 = tc::make_smem_desc(ring0, Np * 16, 128);
-                const uint32_t lo_off = Np * 32;
-                for (uint32_t s = 0; s < ksteps; s++) {
-                    if (l > 0 && (s & 1u) == 0) {                            // K steps 2c, 2c+1 read chunk c of the A operand
-                        const uint32_t c = s >> 1;
-                        tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
-                    }
+                const uint32_t lo_off = Np * 32, kbytes = Np * 64;
+                const uint32_t kper = max(1u, kTcStageBytes / kbytes);
+                for (uint32_t s0 = 0; s0 < ksteps; s0 += kper) {
+                    const unsigned long long t1 = prof ? clock64() : 0;
                     tc::mbar_wait(&full[stage], phase);
-                    tc::tc_fence_after();
-                    __syncwarp();
-                    const uint64_t db_hi = tc::desc_advance(db0, stage * kTcStageBytes), db_lo = tc::desc_advance(db_hi, lo_off);
-                    tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
-                    tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
-                    tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                    if (prof) w_f += clock64() - t1;
+                    const uint32_t kend = min(ksteps, s0 + kper);
+                    uint64_t db_hi = tc::desc_advance(db0, stage * kTcStageBytes);
+                    for (uint32_t s = s0; s < kend; s++) {
+                        if (l > 0 && (s & 1u) == 0) {                        // K steps 2c, 2c+1 read chunk c of the A operand
+                            const uint32_t c = s >> 1;
+                            const unsigned long long t0 = prof ? clock64() : 0;
+                            tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
+                            if (prof) w_a += clock64() - t0;
+                        }
+                        tc::tc_fence_after();
+                        __syncwarp();
+                        const uint64_t db_lo = tc::desc_advance(db_hi, lo_off);
+                        tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
+                        tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
+                        tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                        da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
+                        db_hi = tc::desc_advance(db_hi, kbytes);
+                    }
                     tc::mma_commit_w(&empty[stage]);              // frees the ring slot when these MMAs retire
-                    da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
                 if (l == 0) tc::mma_commit_w(ide_empty);          // IDE buffer may be refilled for the next tile
                 tc::mma_commit_w(&acc_ready[buf]);
+                if (prof && lane == 0) {
+                    if (l == 0) stamp(ti, 2, clock64());
+                    if (l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; }
+                }
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -164,14 +199,16 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         const uint32_t row = quarter * 32 + lane;
         const uint32_t branch = row >> 6;
         const uint32_t lane_addr = (quarter * 32u) << 16;
-        uint32_t acc_par = 0, gl = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t acc_par = 0, gl = 0, ti = 0;
+        const bool pw = prof && tid == 4 * 32;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             for (int l = 0; l < nl; l++) {
                 const uint32_t buf = gl & 1u;
                 gl++;
                 tc::mbar_wait(&acc_ready[buf], (acc_par >> buf) & 1u); acc_par ^= 1u << buf;
+                if (pw && l < 4) stamp(ti, 12 + 2 * l, clock64());
                 tc::tc_fence_after();
                 const uint32_t acc = tmem + lane_addr + buf * 256u;
                 const float* bias = s_bias + l * 256;
@@ -219,16 +256,18 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     }
                     tc::tc_fence_before();
                 }
+                if (pw && l < 4) stamp(ti, 13 + 2 * l, clock64());
             }
         }
     } else if (warp >= 12) {
         // ===================== IDE warps: directional encoding of the NEXT tile while the current one is in the MMA pipe ====
-        const uint32_t t2 = tid - 12 * 32;               // 0..255
-        const uint32_t row = t2 & 127, mpar = t2 >> 7;   // two threads per row: even / odd orders m
+        const uint32_t t2 = tid - 12 * 32;               // 0 .. 128 * kTcIdeSplit - 1
+        const uint32_t row = t2 & 127, mpar = t2 >> 7;   // kTcIdeSplit threads per row: orders m = mpar (mod kTcIdeSplit)
         const uint32_t branch = row >> 6;
         const uint32_t Kp0 = E.L[0].Kp, P = E.P;
-        uint32_t empty_par = 1;                          // first wait passes
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t empty_par = 1, ti = 0;                  // first wait passes
+        const bool pw = prof && tid == 12 * 32;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             float dx = 0.f, dy = 0.f, dz = 1.f, kap = 0.f;
@@ -237,9 +276,11 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 dx = q[22 + 3 * branch]; dy = q[23 + 3 * branch]; dz = q[24 + 3 * branch];
                 kap = branch ? q[20] : E.kappa_diffuse;
             }
+            if (pw) stamp(ti, 8, clock64());
             tc::mbar_wait(ide_empty, empty_par); empty_par ^= 1;
+            if (pw) stamp(ti, 9, clock64());
             if (valid) {
-                ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, [&](int i, float re, float im) {
+                auto emit = [&](int i, float re, float im) {
                     __half h, lo;
                     tc::split_f16(re, h, lo);
                     *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, i)) = h;
@@ -247,7 +288,21 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     tc::split_f16(im, h, lo);
                     *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, P + i)) = h;
                     *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, P + i)) = lo;
-                }, (int)mpar, 2);
+                };
+                // mpar is warp-uniform (4 warps per residue class of m)
+                if (c_ide_tc.deg == 5) {
+                    if (mpar == 0)      ide_eval_emit_static<5, 0, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else if (mpar == 1) ide_eval_emit_static<5, 1, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else if (mpar == 2) ide_eval_emit_static<5, 2, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else                ide_eval_emit_static<5, 3, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                } else if (c_ide_tc.deg == 4) {
+                    if (mpar == 0)      ide_eval_emit_static<4, 0, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else if (mpar == 1) ide_eval_emit_static<4, 1, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else if (mpar == 2) ide_eval_emit_static<4, 2, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                    else                ide_eval_emit_static<4, 3, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
+                } else {
+                    ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit, (int)mpar, kTcIdeSplit);
+                }
                 if (mpar == 0) {
                     for (uint32_t k = 2 * P; k < Kp0; k++) {
                         *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, k)) = __float2half_rn(0.f);
@@ -262,6 +317,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(ide_full);
+            if (pw) stamp(ti, 10, clock64());
         }
     }
     tc::tc_fence_before();
@@ -354,8 +410,14 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
     uint32_t grid = kSMs;
     if (!M_dev) grid = min((uint32_t)kSMs, (2 * M_host + 127) / 128);
     if (grid == 0) return 0;
-    k_env_tc<<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host);
+    k_env_tc<<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
     return check_launch("env_tc");
 }
 
 }  // namespace envidr
+
+extern "C" int envidr_debug_env_tc_timeline(uint64_t* buf, uint32_t capacity) {
+    envidr::g_prof = reinterpret_cast<unsigned long long*>(buf);
+    envidr::g_prof_cap = buf ? capacity : 0;
+    return 0;
+}

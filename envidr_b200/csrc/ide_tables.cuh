@@ -127,6 +127,48 @@ __device__ __forceinline__ void ide_eval_emit(const IdeTables& T, float x, float
         }
     }
 }
+// Compile-time-unrolled variant for the tensor-core kernel: DEG fixes every loop bound, so after unrolling all table indices are
+// immediates (ra / rb / qmm become constant-bank operands of the FMULs, no index arithmetic, no band tests at run time) and
+// the feature index handed to `emit` is a constant.  Same recurrence, same operation order as ide_eval_emit.
+__host__ __device__ constexpr bool ide_is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+__host__ __device__ constexpr int ide_ilog2(int v) { return v <= 1 ? 0 : 1 + ide_ilog2(v >> 1); }
+__host__ __device__ constexpr int ide_band_base(int b) { return (1 << b) - 1 + b; }
+
+template <int DEG, int MSTART, int MSTEP, class Emit>
+__device__ __forceinline__ void ide_eval_emit_static(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale, Emit&& emit) {
+    constexpr int LMAX = 1 << (DEG - 1);
+    if (x == 0.0f && y == 0.0f) y += 1.0f;
+    float att[DEG];
+    #pragma unroll
+    for (int b = 0; b < DEG; b++) att[b] = expf(-T.band_sigma[b] * kappa_inv) * scale;
+    float re = 1.0f, im = 0.0f, sr = 1.0f, si = 0.0f;
+    #pragma unroll
+    for (int k = 0; k < MSTART; k++) { const float nr = re * x - im * y; im = re * y + im * x; re = nr; }
+    #pragma unroll
+    for (int k = 0; k < MSTEP; k++) { const float nr = sr * x - si * y; si = sr * y + si * x; sr = nr; }
+    #pragma unroll
+    for (int m = MSTART; m <= LMAX; m += MSTEP) {
+        if (m > MSTART) {
+            const float nr = re * sr - im * si;
+            im = re * si + im * sr;
+            re = nr;
+        }
+        float p2 = 0.0f, p1 = T.qmm[m];
+        if (ide_is_pow2(m)) {
+            const float a = att[ide_ilog2(m)];
+            emit(ide_band_base(ide_ilog2(m)) + m, re * p1 * a, im * p1 * a);
+        }
+        #pragma unroll
+        for (int l = m + 1; l <= LMAX; l++) {
+            const float q = T.ra[l][m] * z * p1 - T.rb[l][m] * p2;
+            p2 = p1; p1 = q;
+            if (ide_is_pow2(l)) {
+                const float a = att[ide_ilog2(l)];
+                emit(ide_band_base(ide_ilog2(l)) + m, re * q * a, im * q * a);
+            }
+        }
+    }
+}
 // out_re[i*sr], out_im[i*si], i < P
 __device__ __forceinline__ void ide_eval(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale,
                                          float* out_re, int sr, float* out_im, int si) {

@@ -275,6 +275,9 @@ int envidr_tc_probe(const float* A, const float* B, float* D, uint32_t N, uint32
 uint64_t envidr_launch_count(void);
 int envidr_render_timing(int enable);
 int envidr_render_field_time(float* total_ms, uint32_t* launches);
+/* Profiling hook: when `buf` (device, `capacity` uint64 slots) is non-NULL, CTA 0 of every following tensor-core env_net launch
+ * records a clock64() timeline of its roles into it (layout in csrc/field_tc.cu, kProf*); NULL switches it off. */
+int envidr_debug_env_tc_timeline(uint64_t* buf, uint32_t capacity);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

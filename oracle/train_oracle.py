@@ -236,6 +236,7 @@ def render_train(th, P, rays_o, rays_d, bitfield, *, cascade=1, grid_size=128, m
                                                            noises=noises, dt_gamma=dt_gamma, max_steps=max_steps,
                                                            early_stop_steps=early_stop_steps)
     M = int(counter[0])
+    M += 128 - M % 128            # raymarching.py:235-241 with align = 128 (cuda_ray.py:79): zero-padded samples ride along
     xyzs, dirs, deltas = xyzs[:M], dirs[:M], deltas[:M]
     x = torch.from_numpy(xyzs).to(dtype).requires_grad_(True)
     d = torch.from_numpy(dirs).to(dtype)
