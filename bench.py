@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-indir", action="store_true", help="single pass (BASELINE config 2 style)")
     ap.add_argument("--cpu-sample", type=int, default=12288, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the auxiliary train-step (BASELINE config 3) measurement")
+    ap.add_argument("--train-rays", type=int, default=4096)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="env_net arithmetic: tc = tcgen05 tensor cores with fp16 hi/lo split operands (default), fp32 = FFMA path")
     return ap.parse_args()
@@ -111,6 +113,58 @@ def cpu_baseline(fp, bf, ro, rd, args, indir, n_rays, rot=None):
     O.render(P, ro.numpy()[sel], rd.numpy()[sel], bf, indir_ref=indir, bg_color=1.0, env_rot_radian=rot, dtype=torch.float32, stats=st)
     dt = time.perf_counter() - t0
     return len(sel) / dt, dt, sum(s["samples"] for s in st), len(sel)
+
+
+def train_step_bench(fp_cpu, bf, ro, rd, dev, n_rays, steps=10, warmup=3):
+    """BASELINE config 3 (auxiliary, not the headline): one training step forward + backward over `n_rays` random pixels of the
+    frame through the run_cuda training branch on the library's CUDA operators (march_rays_train, hash_encode incl. second-order
+    backward, composite_rays_train) with the toaster.ini loss terms; dense layers through cuBLAS fp32.  No optimizer step."""
+    import torch
+    from envidr_b200 import render, train
+    g = torch.Generator().manual_seed(0)
+    sel = torch.randperm(ro.shape[0], generator=g)[:n_rays]
+    o, d = ro[sel].to(dev), rd[sel].to(dev)
+    gt_rgb = torch.rand(n_rays, 3, generator=g).to(dev)
+    gt_mask = (torch.rand(n_rays, generator=g) > 0.5).float().to(dev)
+    r_img = torch.rand(n_rays, 4, generator=g).to(dev)
+    field = train.TrainableField(fp_cpu.to(dev))
+    bft = torch.from_numpy(bf).to(dev)
+    cfg = render.RenderConfig()
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def step(mean_count):
+        for p in field.parameters():
+            p.grad = None
+        counter.zero_()
+        out = train.render_train(field, bft, o, d, cfg, r_images=r_img, perturb=True, force_all_rays=mean_count <= 0,
+                                 mean_count=mean_count, step_counter=counter)
+        train.loss_epilogue(field, out, gt_rgb, gt_mask).backward()
+        return out
+
+    out = step(-1)                                   # first step sizes the static sample buffer, as the reference's mean_count does
+    torch.cuda.synchronize()
+    mean_count = int(out["xyzs"].shape[0]) - 128     # march_rays_train re-adds the alignment slack (raymarching.py:213-216)
+    del out
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for a, b in ev:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in ev)[steps // 2]
+
+    ms_eager = timed(lambda: step(mean_count))
+    eager_samples = int(counter[0].item())
+    graphed = train.GraphedTrainStep(field, bft, cfg, n_rays, mean_count)
+    ms = timed(lambda: graphed(o, d, gt_rgb, gt_mask, r_img))
+    counter = graphed.counter
+    assert abs(int(counter[0].item()) - eager_samples) < 0.05 * eager_samples
+    return {"rays": n_rays, "samples": int(counter[0].item()), "ms_per_step_fwd_bwd": ms, "rays_per_sec": n_rays / (ms * 1e-3),
+            "ms_per_step_fwd_bwd_eager": ms_eager, "mode": "CUDA graph replay of the captured step (train.GraphedTrainStep); host copies the step's inputs in",
+            "what": "run_cuda train branch fwd+bwd (use_renv, r_images; colour L1 + mask BCE + Cauchy + eikonal), fp32, no optimizer"}
 
 
 def run_reference(args):
@@ -262,6 +316,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
                 "traffic": None, "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
                 "kernel_share_of_step": field_ms_per_step / ms_per_step, "algorithmic_flop_per_step": flop_step,
+                "executed_frac": (3.0 if tcp else 1.0) * achieved_tf / peak_tf,
                 "arithmetic": ("tcgen05.mma kind::f16, 3 MMAs per K step (hi*hi + lo*hi + hi*lo): the tensor pipe executes 3x the "
                                "algorithmic FLOPs counted here") if tcp else "fp32 FFMA (exact path)"}
     if rank == 0:
@@ -271,6 +326,12 @@ def main():
             cpu = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{n} rays (stride sample of the {W}x{H} frame, {s} samples) in {dt:.1f} s; oracle CPU port "
                              f"(C march/hash/composite + torch-CPU fp32 MLPs, all host threads)"}
+        trn = None
+        if world == 1 and not args.no_train:
+            try:
+                trn = train_step_bench(fp_cpu, bf, ro, rd, dev, args.train_rays)
+            except Exception as e:                      # auxiliary: never take the headline line down with it
+                trn = {"error": repr(e)[:200]}
         line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (env_net: fp16 hi+lo split operands on tensor cores, fp32 accumulate)" if tcp else "f32",
@@ -279,7 +340,7 @@ def main():
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,6 +174,63 @@ __global__ void __launch_bounds__(128) k_ide_fwd(const float* __restrict__ dirs,
     for (uint32_t k = threadIdx.x; k < rows * 2 * P; k += 128) dst[k] = s_out[k];
 }
 
+// Backward of the encoding w.r.t. the direction and kappa_inv (the reference gets it from autograd over ~20 torch ops,
+// ide_encoder.py:98-130).  With P_m = (x+iy)^m, q = K_l^m Q_l^m(z), a_l = exp(-sigma_l kappa) * scale:
+//   out_re = Re(P_m) q a,  out_im = Im(P_m) q a
+//   d/dx: m Re(P_{m-1}) q a | m Im(P_{m-1}) q a      d/dy: -m Im(P_{m-1}) q a | m Re(P_{m-1}) q a
+//   d/dz: q' from the differentiated recurrence q'_l = ra (q_{l-1} + z q'_{l-1}) - rb q'_{l-2}, q'_m = 0
+//   d/dkappa: -sigma_l * out
+// One thread per direction; the gradient row [2P] is read through shared memory (coalesced).
+__global__ void __launch_bounds__(128) k_ide_bwd(const float* __restrict__ dirs, const float* __restrict__ kappa_arr, float kappa_scalar,
+                                                uint32_t B, float scale, const float* __restrict__ grad, float* __restrict__ grad_dirs,
+                                                float* __restrict__ grad_kappa) {
+    extern __shared__ float s_g[];                   // [128][2P + 1] (padded: conflict-free row access)
+    const IdeTables& T = c_ide;
+    const uint32_t P = T.P, W = 2 * P + 1;
+    const uint32_t rows = min(128u, B - blockIdx.x * 128);
+    const float* src = grad + (size_t)blockIdx.x * 128 * 2 * P;
+    for (uint32_t k = threadIdx.x; k < rows * 2 * P; k += 128) s_g[(k / (2 * P)) * W + k % (2 * P)] = src[k];
+    __syncthreads();
+    const uint32_t b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= B) return;
+    const float* g = s_g + threadIdx.x * W;
+    float x = dirs[3 * (size_t)b], y = dirs[3 * (size_t)b + 1];
+    const float z = dirs[3 * (size_t)b + 2];
+    const float kap = kappa_arr ? kappa_arr[b] : kappa_scalar;
+    if (x == 0.0f && y == 0.0f) y += 1.0f;
+    float att[5];
+    #pragma unroll
+    for (int d = 0; d < 5; d++) att[d] = d < (int)T.deg ? expf(-T.band_sigma[d] * kap) * scale : 0.f;
+    const int l_max = (int)T.l_max;
+    float gx = 0.f, gy = 0.f, gz = 0.f, gk = 0.f;
+    float re = 1.0f, im = 0.0f, pre = 0.0f, pim = 0.0f;          // P_m and P_{m-1}
+    for (int m = 0; m <= l_max; m++) {
+        if (m > 0) { pre = re; pim = im; const float nr = re * x - im * y; im = re * y + im * x; re = nr; }
+        float q2 = 0.0f, q1 = T.qmm[m], d2 = 0.0f, d1 = 0.0f;      // q_{l-2}, q_{l-1} and their z-derivatives
+        for (int l = m; l <= l_max; l++) {
+            float q = q1, dq = d1;
+            if (l > m) {
+                const float ra = T.ra[l][m], rb = T.rb[l][m];
+                q = ra * z * q1 - rb * q2;
+                dq = ra * (q1 + z * d1) - rb * d2;
+                q2 = q1; q1 = q; d2 = d1; d1 = dq;
+            }
+            if (l > 0 && (l & (l - 1)) == 0) {
+                const int band = 31 - __clz(l);
+                const int i = T.band_base[band] + m;
+                const float a = att[band], gr = g[i], gi = g[P + i];
+                const float qa = q * a;
+                gx += (float)m * (pre * gr + pim * gi) * qa;
+                gy += (float)m * (pre * gi - pim * gr) * qa;
+                gz += (re * gr + im * gi) * dq * a;
+                gk -= T.band_sigma[band] * (re * gr + im * gi) * qa;
+            }
+        }
+    }
+    grad_dirs[3 * (size_t)b] = gx; grad_dirs[3 * (size_t)b + 1] = gy; grad_dirs[3 * (size_t)b + 2] = gz;
+    if (grad_kappa) grad_kappa[b] = gk;
+}
+
 }  // namespace envidr
 
 using namespace envidr;
@@ -235,6 +292,21 @@ int envidr_ide_encode_forward(const float* dirs, const float* kappa_inv_arr, flo
     if (!attr) { cudaFuncSetAttribute(k_ide_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 2 * 36 * 4); attr = true; }
     k_ide_fwd<<<ceil_div(B, 128), 128, smem, as_stream(stream)>>>(dirs, kappa_inv_arr, kappa_inv_scalar, B, scale, out);
     return check_launch("ide_encode_forward");
+}
+
+int envidr_ide_encode_backward(const float* dirs, const float* kappa_inv_arr, float kappa_inv_scalar, uint32_t B, uint32_t deg_view,
+                               float scale, const float* grad, float* grad_dirs, float* grad_kappa, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(dirs && grad && grad_dirs, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(deg_view >= 1 && deg_view <= 5, ENVIDR_E_UNSUPPORTED, "Only deg_view of at most 5 is numerically stable.");
+    if (B == 0) return 0;
+    int rc = ensure_ide_tables(deg_view);
+    if (rc) return rc;
+    const uint32_t P = (1u << deg_view) - 1 + deg_view;
+    const size_t smem = (size_t)128 * (2 * P + 1) * sizeof(float);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_ide_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (2 * 36 + 1) * 4); attr = true; }
+    k_ide_bwd<<<ceil_div(B, 128), 128, smem, as_stream(stream)>>>(dirs, kappa_inv_arr, kappa_inv_scalar, B, scale, grad, grad_dirs, grad_kappa);
+    return check_launch("ide_encode_backward");
 }
 
 // host-only helper (no GPU needed): the IDE coefficient tables, for tests against ide_encoder.py:84-96

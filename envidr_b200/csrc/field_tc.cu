@@ -55,6 +55,15 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// CTAS = 1: one CTA per tile, tcgen05 cta_group::1.
+// CTAS = 2: thread-block cluster of two CTAs (one TPC) working as a CTA pair: every MMA is M = 256 (128 rows = one tile per
+//   CTA), each CTA streams only ITS half of every weight stage (N/2 rows of B) and the tensor cores read the other half from the
+//   peer -- halves the weight bytes each SM pulls from L2 and the B-operand shared-memory reads per MMA.  Measured before
+//   this change (profiles/r01_run8_9.md): shared-memory bandwidth was the wall (MMA operand reads + TMA writes + epilogue
+//   writes ~ 2.6 MB per tile at 128 B/clk = 20 k cycles vs 14.6 k of tensor-pipe time).  The leader (rank 0) issues; the peer's
+//   operand-ready signals go to the leader's mbarriers through shared::cluster arrives, completions come back by multicast
+//   commit.
+template <int CTAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
          unsigned long long* __restrict__ prof, uint32_t prof_cap) {
@@ -72,15 +81,21 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (128 * kTcIdeSplit arrivals)
     uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
     uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
-                                                     //     shared memory (128 arrivals: the 4 warps that own chunk parity c & 1)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 8);
+                                                     //     shared memory (128 arrivals per CTA: the 4 warps that own chunk parity c & 1)
+    uint64_t* pfull = a_rdy + 8;                     // [3] CTAS = 2: peer's relay warp -> leader's issuer (peer's half of the stage landed)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + kTcStages);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
     const int nl = (int)E.n_layers;
-    if (blockIdx.x >= n_tiles) return;                // nothing to do for this CTA (tail iterations of the render loop)
+    // work units: tiles (CTAS = 1) or tile pairs (CTAS = 2: CTA `rank` of cluster u takes tile 2 * unit + rank; a tile past
+    // n_tiles is all-invalid rows, computed as zeros and never stored)
+    const uint32_t rank = CTAS == 2 ? tc::cluster_ctarank() : 0u;
+    const uint32_t unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
+    const uint32_t n_units = (n_tiles + CTAS - 1) / CTAS;
+    if (unit0 >= n_units) return;                     // nothing to do for this CTA / cluster (tail iterations of the render loop)
     if (blockIdx.x != 0) prof = nullptr;
     auto stamp = [&](uint32_t tile_i, uint32_t slot, unsigned long long v) {
         const uint32_t idx = 1 + tile_i * kProfPerTile + slot;
@@ -91,31 +106,39 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&acc_ready[0], 1);
         tc::mbar_init(&acc_ready[1], 1);
-        for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128);
-        tc::mbar_init(ide_full, 128 * kTcIdeSplit);
+        for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 * CTAS);
+        for (int i = 0; i < kTcStages; i++) tc::mbar_init(&pfull[i], 1);
+        tc::mbar_init(ide_full, 128 * kTcIdeSplit * CTAS);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 2) { if (CTAS == 2) tc::tmem_alloc2(tmem_slot, 512); else tc::tmem_alloc(tmem_slot, 512); }
     for (uint32_t i = tid; i < (uint32_t)nl * 256; i += kTcThreads) {
         const uint32_t l = i >> 8, c = i & 255;
         s_bias[i] = (c < E.L[l].Np) ? __ldg(E.bias + E.L[l].bias_off + c) : 0.0f;
     }
     tc::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) tc::cluster_sync_all(); else __syncthreads();       // barriers of BOTH CTAs initialised before any remote arrive
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // where operand-ready signals go: the issuing CTA's copy of the barrier (rank 0 of the pair)
+    auto to_issuer = [&](uint64_t* bar) { return CTAS == 2 ? tc::map_to_rank(tc::smem_u32(bar), 0) : tc::smem_u32(bar); };
+    auto arrive_issuer = [&](uint32_t addr) {
+        if (CTAS == 2) tc::mbar_arrive_cluster(addr);
+        else asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
+    };
 
     if (warp == 0) {
         // ===================== producer =====================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
             for (int l = 0; l < nl; l++) {
                 // a ring stage carries as many K steps as fit in kTcStageBytes (1 for a 256-wide layer, all 16 for the 16-wide
-                // last layer: otherwise that layer is bound by 16 ring round trips of 1 KB each)
-                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64;
+                // last layer: otherwise that layer is bound by 16 ring round trips of 1 KB each).  CTAS = 2: this CTA's half
+                // of B (rows rank * N/2 ...) is a contiguous image of its own, so a stage holds twice the K steps.
+                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64 / CTAS;
                 const uint32_t kper = max(1u, kTcStageBytes / kbytes);
-                const uint8_t* src = E.blob + E.L[l].img_off;
+                const uint8_t* src = E.blob + (CTAS == 2 ? E.L[l].img2_off + rank * ksteps * kbytes : E.L[l].img_off);
                 for (uint32_t s = 0; s < ksteps; s += kper) {
                     const uint32_t bytes = min(kper, ksteps - s) * kbytes;
                     tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -128,8 +151,23 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 3 && CTAS == 2 && rank == 1) {
+        // ===================== peer relay: "my half of the stage landed" -> leader's issuer =====================
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
+            for (int l = 0; l < nl; l++) {
+                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64 / CTAS;
+                const uint32_t kper = max(1u, kTcStageBytes / kbytes);
+                for (uint32_t s = 0; s < ksteps; s += kper) {
+                    tc::mbar_wait(&full[stage], phase);
+                    if (lane == 0) tc::mbar_arrive_cluster(tc::map_to_rank(tc::smem_u32(&pfull[stage]), 0));
+                    __syncwarp();
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
         // All 32 lanes run this code with warp-uniform values; one elected lane issues (tc::*_w helpers).
         // Accumulators ping-pong between TMEM columns [0,256) and [256,512) from layer to layer, so the epilogue of layer g
         // (which produces the next A operand chunk by chunk) overlaps the MMAs of layer g + 1, which start as soon as
@@ -138,18 +176,19 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         // epilogue(g+1), which the same warps run after epilogue(g)).
         uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0, gl = 0, ti = 0;
         const uint32_t ring0 = tc::smem_u32(ring);
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
             unsigned long long w_a = 0, w_f = 0;
             for (int l = 0; l < nl; l++) {
-                const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np;
-                const uint32_t idesc = tc::make_idesc_f16(128, Np);
+                const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np, Nb = Np / CTAS;     // Nb: rows of B held by one CTA
+                const uint32_t idesc = tc::make_idesc_f16(128 * CTAS, Np);
                 const uint32_t buf = gl & 1u;
                 const uint32_t d_tmem = tmem + buf * 256u;
                 gl++;
                 uint64_t da_hi, da_lo;
                 if (l == 0) {
                     if (prof && lane == 0) stamp(ti, 0, clock64());
-                    tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;          // IDE operand of this tile is in smem
+                    if (CTAS == 2) tc::mbar_wait_cluster(ide_full, ide_par); else tc::mbar_wait(ide_full, ide_par);
+                    ide_par ^= 1;                                            // IDE operand of this tile (pair) is in smem
                     if (prof && lane == 0) stamp(ti, 1, clock64());
                     da_hi = tc::make_smem_desc(tc::smem_u32(sI_hi), 2048, 128);
                     da_lo = tc::make_smem_desc(tc::smem_u32(sI_lo), 2048, 128);
@@ -157,12 +196,13 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     da_hi = tc::make_smem_desc(tc::smem_u32(sA_hi), 2048, 128);
                     da_lo = tc::make_smem_desc(tc::smem_u32(sA_lo), 2048, 128);
                 }
-                const uint64_t db0 = tc::make_smem_desc(ring0, Np * 16, 128);
-                const uint32_t lo_off = Np * 32, kbytes = Np * 64;
+                const uint64_t db0 = tc::make_smem_desc(ring0, Nb * 16, 128);
+                const uint32_t lo_off = Nb * 32, kbytes = Nb * 64;
                 const uint32_t kper = max(1u, kTcStageBytes / kbytes);
                 for (uint32_t s0 = 0; s0 < ksteps; s0 += kper) {
                     const unsigned long long t1 = prof ? clock64() : 0;
                     tc::mbar_wait(&full[stage], phase);
+                    if (CTAS == 2) tc::mbar_wait_cluster(&pfull[stage], phase);
                     if (prof) w_f += clock64() - t1;
                     const uint32_t kend = min(ksteps, s0 + kper);
                     uint64_t db_hi = tc::desc_advance(db0, stage * kTcStageBytes);
@@ -170,23 +210,37 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         if (l > 0 && (s & 1u) == 0) {                        // K steps 2c, 2c+1 read chunk c of the A operand
                             const uint32_t c = s >> 1;
                             const unsigned long long t0 = prof ? clock64() : 0;
-                            tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
+                            if (CTAS == 2) tc::mbar_wait_cluster(&a_rdy[c], (chunk_par >> c) & 1u);
+                            else tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u);
+                            chunk_par ^= 1u << c;
                             if (prof) w_a += clock64() - t0;
                         }
                         tc::tc_fence_after();
                         __syncwarp();
                         const uint64_t db_lo = tc::desc_advance(db_hi, lo_off);
-                        tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
-                        tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
-                        tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                        if (CTAS == 2) {
+                            tc::mma2_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
+                            tc::mma2_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
+                            tc::mma2_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                        } else {
+                            tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
+                            tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
+                            tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                        }
                         da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
                         db_hi = tc::desc_advance(db_hi, kbytes);
                     }
-                    tc::mma_commit_w(&empty[stage]);              // frees the ring slot when these MMAs retire
+                    // frees the ring slot (in both CTAs) when these MMAs retire
+                    if (CTAS == 2) tc::mma2_commit_w(&empty[stage]); else tc::mma_commit_w(&empty[stage]);
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
-                if (l == 0) tc::mma_commit_w(ide_empty);          // IDE buffer may be refilled for the next tile
-                tc::mma_commit_w(&acc_ready[buf]);
+                if (CTAS == 2) {
+                    if (l == 0) tc::mma2_commit_w(ide_empty);
+                    tc::mma2_commit_w(&acc_ready[buf]);
+                } else {
+                    if (l == 0) tc::mma_commit_w(ide_empty);      // IDE buffer may be refilled for the next tile
+                    tc::mma_commit_w(&acc_ready[buf]);
+                }
                 if (prof && lane == 0) {
                     if (l == 0) stamp(ti, 2, clock64());
                     if (l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; }
@@ -201,7 +255,9 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         const uint32_t lane_addr = (quarter * 32u) << 16;
         uint32_t acc_par = 0, gl = 0, ti = 0;
         const bool pw = prof && tid == 4 * 32;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+        const uint32_t a_rdy_addr = to_issuer(&a_rdy[0]);
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
+            const uint32_t tile = unit * CTAS + rank;
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             for (int l = 0; l < nl; l++) {
@@ -233,7 +289,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         }
                         tc::tc_fence_before();
                         tc::fence_proxy_async_smem();
-                        tc::mbar_arrive(&a_rdy[cb]);             // chunk cb of the next layer's A operand is ready
+                        arrive_issuer(a_rdy_addr + cb * 8);         // chunk cb of the next layer's A operand is ready
                     }
                 } else if (g == 0) {
                     uint32_t r[16];
@@ -267,7 +323,9 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         const uint32_t Kp0 = E.L[0].Kp, P = E.P;
         uint32_t empty_par = 1, ti = 0;                  // first wait passes
         const bool pw = prof && tid == 12 * 32;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+        const uint32_t ide_full_addr = to_issuer(ide_full);
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
+            const uint32_t tile = unit * CTAS + rank;
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             float dx = 0.f, dy = 0.f, dz = 1.f, kap = 0.f;
@@ -316,13 +374,13 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 }
             }
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(ide_full);
+            arrive_issuer(ide_full_addr);
             if (pw) stamp(ti, 10, clock64());
         }
     }
     tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem, 512);
+    if (CTAS == 2) tc::cluster_sync_all(); else __syncthreads();       // peer may still read this CTA's B half / signal its barriers
+    if (warp == 2) { if (CTAS == 2) tc::tmem_dealloc2(tmem, 512); else tc::tmem_dealloc(tmem, 512); }
 }
 
 // weight image of one layer: for every K step s: [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1], chunk = [Np][8] halfs
@@ -340,6 +398,22 @@ __global__ void k_pack_tc(const float* __restrict__ W, const float* __restrict__
         *reinterpret_cast<__half*>(img + base + (size_t)Np * 32) = lo;
     }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x) bias[i] = (b && i < N) ? b[i] : 0.0f;
+}
+
+// CTA-pair image of one layer: rank r (rows n in [r * Nb, (r + 1) * Nb), Nb = Np / 2) is a contiguous run of K steps, each
+// [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1] with chunk = [Nb][8] halfs
+__global__ void k_pack_tc2(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+    const uint32_t total = Kp * Np, Nb = Np / 2, ksteps = Kp / 16;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t n = i / Kp, k = i - n * Kp;
+        const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+        __half h, lo;
+        tc::split_f16(v, h, lo);
+        const uint32_t r = n / Nb, j = n - r * Nb, s = k >> 4, kk = k & 15;
+        const size_t base = (size_t)r * ksteps * Nb * 64 + (size_t)s * Nb * 64 + (kk >> 3) * (Nb * 16) + j * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(img + base) = h;
+        *reinterpret_cast<__half*>(img + base + (size_t)Nb * 32) = lo;
+    }
 }
 
 static uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -364,6 +438,8 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
         if (L.Kp > 256 || (i == 0 && L.Kp > 80)) return false;
         L.img_off = (uint32_t)off;
         off += (uint64_t)(L.Kp / 16) * L.Np * 64;
+        L.img2_off = (uint32_t)off;                    // CTA-pair image (same size, rows split by rank)
+        off += (uint64_t)(L.Kp / 16) * L.Np * 64;
         L.bias_off = boff;
         boff += L.Np;
     }
@@ -387,11 +463,21 @@ int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st
     for (uint32_t i = 0; i < t.n_layers; i++) {
         const TcLayer& L = t.L[i];
         k_pack_tc<<<128, 256, 0, st>>>(f->env[i].weight, f->env[i].bias, blob + L.img_off, bias + L.bias_off, L.K, L.N, L.Kp, L.Np);
+        k_pack_tc2<<<128, 256, 0, st>>>(f->env[i].weight, blob + L.img2_off, L.K, L.N, L.Kp, L.Np);
     }
     return check_launch("field_pack_tc");
 }
 
 constexpr size_t kTcSmem = 2 * kTcARegion + 2 * kTcIdeRegion + kTcStages * kTcStageBytes + kTcMaxLayers * 256 * sizeof(float) + 256;
+
+// ENVIDR_ENV_TC_CTAS=2 selects the CTA-pair kernel.  Default is the single-CTA kernel: measured on B200 (profiles/r01_run12.md) the
+// pair kernel is correct but not faster yet -- the per-tile critical path is the epilogue / operand hand-off chain, not the
+// shared-memory bandwidth the pair relieves, and the remote (cluster-scope) arrives lengthen that chain.
+static int env_tc_ctas() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("ENVIDR_ENV_TC_CTAS"); v = (e && e[0] == '2') ? 2 : 1; }
+    return v;
+}
 
 int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
     if ((int)ide_degree != g_ide_tc_deg) {
@@ -403,14 +489,30 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
     }
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_env_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_error("env_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
+    const uint32_t n_tiles_host = (2 * M_host + 127) / 128;
+    if (env_tc_ctas() == 2) {
+        uint32_t grid = kSMs & ~1u;                    // whole CTA pairs
+        if (!M_dev) grid = min(grid, 2 * ((n_tiles_host + 1) / 2));
+        if (grid == 0) return 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+        if (e != cudaSuccess) { set_error("env_tc (CTA pair) launch: %s", cudaGetErrorString(e)); return (int)e; }
+        return check_launch("env_tc2");
+    }
     uint32_t grid = kSMs;
-    if (!M_dev) grid = min((uint32_t)kSMs, (2 * M_host + 127) / 128);
+    if (!M_dev) grid = min((uint32_t)kSMs, n_tiles_host);
     if (grid == 0) return 0;
-    k_env_tc<<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+    k_env_tc<1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
     return check_launch("env_tc");
 }
 

@@ -10,6 +10,7 @@ constexpr int kTcRecFloats = 32;
 struct TcLayer {
     uint32_t K, Kp, N, Np;        // Kp multiple of 16; Np = N (hidden, multiple of 32) or N rounded up to 16 (last layer)
     uint32_t img_off;             // byte offset of the layer image in the blob; stage s at img_off + s * Np * 64
+    uint32_t img2_off;            // CTA-pair image: rank r at img2_off + r * (Kp/16) * (Np/2) * 64, K step s at + s * (Np/2) * 64
     uint32_t bias_off;            // float offset in the bias region
 };
 struct TcEnv {

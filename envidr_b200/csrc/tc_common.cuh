@@ -116,6 +116,46 @@ __device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
 // descriptor of the same operand `bytes` further in shared memory (address field is in 16-byte units)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
+// ---- thread-block cluster / CTA-pair (cta_group::2) helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_u32, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_u32), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {     // release at cluster scope, possibly remote
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {  // same warp id in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMA over the CTA pair: each CTA supplies its 128 rows of A and its half (N/2 rows) of B from the same shared-memory
+// offsets; each CTA's tensor memory receives the accumulator rows of its own A tile.  Issued by the leader CTA only.
+__device__ __forceinline__ void mma2_f16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+                 " @e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (when all prior MMAs of this thread retire) on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void mma2_commit_w(uint64_t* bar) {
+    asm volatile("{\n .reg .pred e;\n .reg .b16 m;\n mov.b16 m, 3;\n elect.sync _|e, 0xffffffff;\n"
+                 " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
 // fp32 -> (hi, lo) fp16 pair with hi + lo ~= x to ~2^-22 relative (lo may be subnormal: absolute error <= 3e-8)
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);

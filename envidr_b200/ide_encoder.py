@@ -2,9 +2,10 @@
 
 Same module interface: buffers mat / ml_array / pow_level / sigma (non-persistent), output_dim,
 forward(xyz, roughness=0).  The reference has no native code for IDE (about 20 small torch kernels and an
-`isnan().any()` host sync per call); here the no-grad CUDA forward is one kernel
-(envidr_ide_encode_forward).  When autograd needs the encoding (training), the torch formulation below is
-used so gradients reach the normals and the roughness exactly as in the reference.
+`isnan().any()` host sync per call, ~60 more in the backward); here forward and backward are one CUDA kernel
+each (envidr_ide_encode_forward / _backward) behind an autograd.Function, so gradients reach the normals and
+the roughness exactly as in the reference.  The torch formulation is kept for CPU tensors (it is what the
+tests compare the kernels with) and for double backward through the encoding, which no shipped loss needs.
 """
 from __future__ import annotations
 
@@ -32,6 +33,43 @@ def get_ml_array(deg_view):
     return np.array(ml_list).T
 
 
+class _ide_encode(torch.autograd.Function):
+    """out [B, 2P] = IDE(dirs [B,3], kappa_inv [B] or scalar); once differentiable w.r.t. dirs and the kappa array."""
+
+    @staticmethod
+    def forward(ctx, dirs, kappa, deg_view, out_dim):
+        d = dirs.detach().float().contiguous()
+        B = d.shape[0]
+        out = torch.empty(B, out_dim, dtype=torch.float32, device=d.device)
+        if torch.is_tensor(kappa):
+            k = kappa.detach().float().reshape(-1).contiguous()
+            assert k.numel() == B, "roughness must be [..., 1] matching xyz"
+            check(lib().envidr_ide_encode_forward(ptr(d), ptr(k), 0.0, B, deg_view, 1.0, ptr(out), stream()), "ide_encode_forward")
+            ctx.save_for_backward(d, k)
+            ctx.kappa_scalar = 0.0
+        else:
+            check(lib().envidr_ide_encode_forward(ptr(d), None, float(kappa), B, deg_view, 1.0, ptr(out), stream()), "ide_encode_forward")
+            ctx.save_for_backward(d)
+            ctx.kappa_scalar = float(kappa)
+        ctx.deg_view = deg_view
+        ctx.kappa_shape = tuple(kappa.shape) if torch.is_tensor(kappa) else None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        saved = ctx.saved_tensors
+        d = saved[0]
+        k = saved[1] if len(saved) > 1 else None
+        B = d.shape[0]
+        grad = grad.float().contiguous()
+        gd = torch.empty_like(d)
+        gk = torch.empty(B, dtype=torch.float32, device=d.device) if k is not None else None
+        check(lib().envidr_ide_encode_backward(ptr(d), ptr(k), ctx.kappa_scalar, B, ctx.deg_view, 1.0, ptr(grad), ptr(gd), ptr(gk), stream()),
+              "ide_encode_backward")
+        return gd, (gk.view(ctx.kappa_shape) if gk is not None else None), None, None
+
+
 class IntegratedDirEncoder(nn.Module):
     def __init__(self, input_dim=3, deg_view=4):
         super().__init__()
@@ -52,10 +90,17 @@ class IntegratedDirEncoder(nn.Module):
         self.output_dim = (2 ** deg_view - 1 + deg_view) * 2
 
     def forward(self, xyz, roughness=0, **kwargs):
+        if not xyz.is_cuda:
+            return self._forward_torch(xyz, roughness)
         needs_grad = torch.is_grad_enabled() and (xyz.requires_grad or (torch.is_tensor(roughness) and roughness.requires_grad))
-        if xyz.is_cuda and not needs_grad:
+        if not needs_grad:
             return self._forward_kernel(xyz, roughness)
-        return self._forward_torch(xyz, roughness)
+        prefix = xyz.shape[:-1]
+        kap = roughness
+        if torch.is_tensor(kap):
+            kap = kap.reshape(-1) if kap.numel() > 1 else float(kap)
+        out = _ide_encode.apply(xyz.reshape(-1, 3), kap, self.deg_view, self.output_dim)
+        return out.reshape(*prefix, self.output_dim)
 
     def _forward_kernel(self, xyz, roughness):
         prefix = xyz.shape[:-1]

@@ -152,6 +152,11 @@ int envidr_sh_encode_backward(const float* grad, const float* inputs, uint32_t B
  * out [B, 2*P], P = 2^deg_view - 1 + deg_view ([Re | Im] halves), deg_view in 1..5; out *= scale. */
 int envidr_ide_encode_forward(const float* dirs, const float* kappa_inv_arr, float kappa_inv_scalar,
                               uint32_t B, uint32_t deg_view, float scale, float* out, envidr_stream_t stream);
+/* Backward of envidr_ide_encode_forward (the reference differentiates ide_encoder.py:98-130 with autograd): grad [B, 2*P] ->
+ * grad_dirs [B,3] and, when grad_kappa != NULL, grad_kappa [B] (d/d kappa_inv; meaningful with a per-sample kappa array). */
+int envidr_ide_encode_backward(const float* dirs, const float* kappa_inv_arr, float kappa_inv_scalar,
+                               uint32_t B, uint32_t deg_view, float scale, const float* grad,
+                               float* grad_dirs, float* grad_kappa, envidr_stream_t stream);
 /* Host-only: the coefficient tables the kernel uses (ide_encoder.py:84-96): mat [(l_max+1), P] row-major,
  * sigma [P], ml [2, P] (row 0 = m, row 1 = l).  l_max = 2^(deg_view-1). */
 int envidr_ide_tables(uint32_t deg_view, float* mat, float* sigma, int32_t* ml);

@@ -104,3 +104,66 @@ def test_train_step_mean_count_static_buffers(dev):
     for p in field.parameters():
         if p.grad is not None:
             assert torch.isfinite(p.grad).all()
+
+
+@pytest.mark.parametrize("deg", [4, 5])
+def test_ide_encode_backward_kernel(dev, deg):
+    """envidr_ide_encode_backward (one kernel) against autograd over the oracle's float64, exact-table formulation of
+    ide_encoder.py:98-130: gradients w.r.t. the direction (not normalised: all three components free) and the per-sample
+    kappa_inv.  Tolerance 2e-5 of the gradient's max (fp32 kernel vs float64)."""
+    from envidr_b200.ide_encoder import IntegratedDirEncoder
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(deg)
+    B = 777
+    x = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1) * (0.9 + 0.2 * torch.rand(B, 1, generator=g))
+    x[0] = torch.tensor([0.0, 0.0, 1.0])                       # the (x == 0 & y == 0) guard
+    kap = torch.rand(B, 1, generator=g) * 0.3
+    w = torch.randn(B, 2 * (2 ** deg - 1 + deg), generator=g)
+    xr, kr = x.double().requires_grad_(True), kap.double().requires_grad_(True)
+    ref = O.ide_encode(xr, kr, deg, exact_tables=True)
+    (ref * w.double()).sum().backward()
+    enc = IntegratedDirEncoder(deg_view=deg).to(dev)
+    xg, kg = x.to(dev).requires_grad_(True), kap.to(dev).requires_grad_(True)
+    out = enc(xg, kg)
+    (out * w.to(dev)).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=2e-5)
+    for a, b, name in ((xg.grad, xr.grad, "dirs"), (kg.grad, kr.grad, "kappa")):
+        scale = float(b.abs().max())
+        err = float((a.cpu().double() - b).abs().max()) / scale
+        assert err <= 2e-5, (name, err)
+    # scalar kappa (the diffuse branch: IDE(n, diffuse_kappa_inv))
+    xr2 = x.double().requires_grad_(True)
+    (O.ide_encode(xr2, 0.64, deg, exact_tables=True) * w.double()).sum().backward()
+    xg2 = x.to(dev).requires_grad_(True)
+    (enc(xg2, 0.64) * w.to(dev)).sum().backward()
+    assert float((xg2.grad.cpu().double() - xr2.grad).abs().max()) / float(xr2.grad.abs().max()) <= 2e-5
+
+
+def test_graphed_train_step_equals_eager(dev):
+    """train.GraphedTrainStep (whole forward + backward replayed from one CUDA graph) leaves the same loss and gradients as
+    the eager step on the same inputs (perturb off: the march is then deterministic)."""
+    from envidr_b200 import train
+    from envidr_b200.render import RenderConfig
+    fp, bf, ro, rd, gt_rgb, gt_mask, ri = _setup(32, 64, 4)
+    cfg = RenderConfig(max_steps=512)
+    bft = torch.from_numpy(bf).to(dev)
+    field = train.TrainableField(fp.to(dev))
+    N = ro.shape[0]
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    out = train.render_train(field, bft, ro.to(dev), rd.to(dev), cfg, force_all_rays=False, mean_count=8192, step_counter=counter,
+                             perturb=False, r_images=ri.to(dev))
+    loss = train.loss_epilogue(field, out, gt_rgb.to(dev), gt_mask.to(dev))
+    loss.backward()
+    eager = {n: p.grad.clone() for n, p in field.named_parameters() if p.grad is not None}
+    loss_eager, n_eager = float(loss.detach()), int(counter[0])
+    del out, loss                                              # drop the eager autograd graph (its AccumulateGrad nodes live on the default stream)
+    g = train.GraphedTrainStep(field, bft, cfg, N, 8192, perturb=False)
+    for _ in range(2):                                         # replay twice: static buffers must not accumulate
+        lg = g(ro.to(dev), rd.to(dev), gt_rgb.to(dev), gt_mask.to(dev), ri.to(dev))
+    torch.cuda.synchronize()
+    assert abs(float(lg) - loss_eager) <= 1e-6 * max(1.0, abs(loss_eager))
+    assert int(g.counter[0]) == n_eager
+    for n, p in field.named_parameters():
+        if n in eager:
+            scale = float(eager[n].abs().max()) + 1e-20
+            assert float((p.grad - eager[n]).abs().max()) <= 1e-4 * scale, n      # float atomics reorder between runs
