@@ -311,10 +311,16 @@ def main():
     achieved_tf = flop_step / (field_ms_per_step * 1e-3) / 1e12 if field_ms_per_step > 0 else 0.0
     kname = ("k_env_tc (IDE + env_net x2 on tcgen05, fp16 hi/lo split operands: 3 MMAs per K step, fp32 accumulate in TMEM)" if tcp else
              "k_field (fused per-sample field: hash gather + SDF + normal + IDE + env/diffuse/colour MLPs, fp32 FFMA)")
+    traffic = None                                   # dram bytes of one captured launch of the dominant kernel (ncu --set full)
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_env_tc" if tcp else "k_field"]
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
-                "traffic": None, "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
+                "traffic": traffic, "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
                 "kernel_share_of_step": field_ms_per_step / ms_per_step, "algorithmic_flop_per_step": flop_step,
                 "executed_frac": (3.0 if tcp else 1.0) * achieved_tf / peak_tf,
                 "arithmetic": ("tcgen05.mma kind::f16, 3 MMAs per K step (hi*hi + lo*hi + hi*lo): the tensor pipe executes 3x the "
