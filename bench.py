@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-indir", action="store_true", help="single pass (BASELINE config 2 style)")
     ap.add_argument("--cpu-sample", type=int, default=12288, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA path (oracle/ref_cuda.py)")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary train-step (BASELINE config 3) measurement")
     ap.add_argument("--train-rays", type=int, default=4096)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
@@ -165,6 +166,31 @@ def train_step_bench(fp_cpu, bf, ro, rd, dev, n_rays, steps=10, warmup=3):
     return {"rays": n_rays, "samples": int(counter[0].item()), "ms_per_step_fwd_bwd": ms, "rays_per_sec": n_rays / (ms * 1e-3),
             "ms_per_step_fwd_bwd_eager": ms_eager, "mode": "CUDA graph replay of the captured step (train.GraphedTrainStep); host copies the step's inputs in",
             "what": "run_cuda train branch fwd+bwd (use_renv, r_images; colour L1 + mask BCE + Cauchy + eikonal), fp32, no optimizer"}
+
+
+def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2):
+    """The reference's own CUDA path on this GPU (oracle/ref_cuda.py: unmodified reference kernels rebuilt for sm_100a + the
+    reference's host loop + torch fp32 MLPs with autograd normals) on the same frame: the "reference rays/sec on the same
+    B200" of the north star.  Reported next to the contract's figures; the driver's reference arm stays `--impl reference`."""
+    import torch
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/*.so not present"}
+    F_ = ref_cuda.RefField(fp_cpu.to_oracle(), dev)
+    bft = torch.from_numpy(bf).to(dev)
+    ref_cuda.render(F_, bft, ro_d, rd_d, indir_ref=indir, bg_color=1.0)          # warm-up (cuBLAS handles, allocator)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(frames):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = ref_cuda.render(F_, bft, ro_d, rd_d, indir_ref=indir, bg_color=1.0)
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = sorted(ms)[len(ms) // 2]
+    return {"value": ro_d.shape[0] / (t * 1e-3), "unit": "rays/s", "ms_per_frame": t, "image": out["image"],
+            "what": "reference CUDA kernels (oracle/_ref, unmodified sources, sm_100a) + reference host loop + torch fp32 MLPs, same frame"}
 
 
 def run_reference(args):
@@ -332,6 +358,17 @@ def main():
             cpu = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{n} rays (stride sample of the {W}x{H} frame, {s} samples) in {dt:.1f} s; oracle CPU port "
                              f"(C march/hash/composite + torch-CPU fp32 MLPs, all host threads)"}
+        gref = None
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                gref = gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir)
+                if "image" in gref:
+                    e = (gref.pop("image") - out["image"]).abs().max(-1).values
+                    gref["rgb_linf_vs_ours_p99999"] = float(torch.quantile(e[e > 0], 0.99999)) if int((e > 0).sum()) else 0.0
+                    gref["pixels_over_1e-4"] = int((e > 1e-4).sum())
+                    gref["speedup_ours_over_gpu_reference"] = value / gref["value"]
+            except Exception as e:                      # auxiliary: never take the headline line down with it
+                gref = {"error": repr(e)[:200]}
         trn = None
         if world == 1 and not args.no_train:
             try:
@@ -346,7 +383,7 @@ def main():
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -385,10 +385,10 @@ def ide_encode(xyz: torch.Tensor, kappa_inv, deg_view: int, exact_tables: bool =
         re, im = re + [re[-1] * x - im[-1] * y], im + [re[-1] * y + im[-1] * x]
     re = torch.cat([re[m] for m in ml[0]], dim=-1)
     im = torch.cat([im[m] for m in ml[0]], dim=-1)
-    zc = vmz @ torch.from_numpy(mat).to(dt)
+    zc = vmz @ torch.from_numpy(mat).to(device=xyz.device, dtype=dt)
     if not torch.is_tensor(kappa_inv):
-        kappa_inv = torch.tensor(float(kappa_inv), dtype=dt)
-    att = torch.exp(-torch.from_numpy(sigma).to(dt) * kappa_inv.to(dt))
+        kappa_inv = torch.tensor(float(kappa_inv), dtype=dt, device=xyz.device)
+    att = torch.exp(-torch.from_numpy(sigma).to(device=xyz.device, dtype=dt) * kappa_inv.to(dt))
     return torch.cat([re * zc * att, im * zc * att], dim=-1)
 
 

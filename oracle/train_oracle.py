@@ -116,18 +116,18 @@ def composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh=1e-4, ret_weights=
 STACKS = ("sdf", "env", "diffuse", "color", "renv")
 
 
-def params_from_dict(P: Dict, dtype=torch.float64, frozen=("diffuse", "color")) -> Dict[str, torch.Tensor]:
+def params_from_dict(P: Dict, dtype=torch.float64, frozen=("diffuse", "color"), device="cpu") -> Dict[str, torch.Tensor]:
     """Leaf tensors {embeddings, beta, <stack>.<i>.weight/bias}; toaster.ini freezes the colour and diffuse MLPs
     (frozen_mlps = [specular, diffuse], network.py:785-796)."""
     th: Dict[str, torch.Tensor] = {}
-    th["embeddings"] = torch.from_numpy(P["embeddings"]).to(dtype).requires_grad_(True)
-    th["beta"] = torch.tensor(float(P["beta"]), dtype=dtype, requires_grad=True)
+    th["embeddings"] = torch.from_numpy(P["embeddings"]).to(device=device, dtype=dtype).requires_grad_(True)
+    th["beta"] = torch.tensor(float(P["beta"]), dtype=dtype, device=device, requires_grad=True)
     for name in STACKS:
         if P.get(name) is None:
             continue
         for i, (W, b) in enumerate(P[name]):
-            th[f"{name}.{i}.weight"] = torch.from_numpy(W).to(dtype).requires_grad_(name not in frozen)
-            th[f"{name}.{i}.bias"] = torch.from_numpy(b).to(dtype).requires_grad_(name not in frozen)
+            th[f"{name}.{i}.weight"] = torch.from_numpy(W).to(device=device, dtype=dtype).requires_grad_(name not in frozen)
+            th[f"{name}.{i}.bias"] = torch.from_numpy(b).to(device=device, dtype=dtype).requires_grad_(name not in frozen)
     return th
 
 
@@ -162,14 +162,15 @@ def laplace_density(sdf, beta, alpha=None):
     return alpha * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))              # network.py:32-37
 
 
-def forward_sigma(th, P, xyzs, eikonal=True):
-    """forward_geometry + compute_normal + LaplaceDensity.  xyzs must require grad."""
+def forward_sigma(th, P, xyzs, eikonal=True, encode=None):
+    """forward_geometry + compute_normal + LaplaceDensity.  xyzs must require grad.  `encode` replaces the C-oracle hash
+    encoder (oracle/ref_cuda.py passes the reference's own CUDA kernel)."""
     bound = float(P["bound"])
     x01 = (xyzs + bound) / (2 * bound)                                                    # hashgrid.py:161
-    enc = hash_encode(x01, th["embeddings"], P["offsets"], P["per_level_scale"], P["base_resolution"], True)
+    enc = (encode or hash_encode)(x01, th["embeddings"], P["offsets"], P["per_level_scale"], P["base_resolution"], True)
     L = P["offsets"].shape[0] - 1
     if P.get("enabled_levels", -1) > 0:                                                   # network.py:390-393
-        mask = torch.zeros(L, 2, dtype=enc.dtype)
+        mask = torch.zeros(L, 2, dtype=enc.dtype, device=enc.device)
         mask[: P["enabled_levels"]] = 1
         enc = enc * mask.reshape(-1)
     h = _mlp(enc, _stack(th, "sdf"))
