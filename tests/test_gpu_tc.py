@@ -101,3 +101,34 @@ def test_render_with_tensor_cores(dev):
     err = (out["image"] - ref["image"]).abs().max().item()
     assert err <= 1e-4, f"image L-inf tensor-core vs fp32 path {err}"
     assert (out["image"] - ref["image"]).abs().mean().item() <= 2e-6
+
+
+def test_cta_pair_env_kernel_in_subprocess(dev):
+    """The CTA-pair env_net kernel (tcgen05 cta_group::2, ENVIDR_ENV_TC_CTAS=2 -- read once per process, hence the subprocess):
+    same RGB as the fp32 FFMA path within 2e-5 per sample, odd and even tile counts, a tail tile, and a batch smaller than one pair."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+from envidr_b200 import scene
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+worst = 0.0
+for env, deg, M in ((256, 5, 64 * 148 * 3 + 17), (160, 4, 64 * 5 + 1), (64, 4, 40)):
+    fp_cpu = scene.make_synthetic_field(3, hidden_dim_env=env, ide_degree=deg)
+    x = torch.from_numpy(rng.uniform(-0.6, 0.6, (M, 3)).astype(np.float32)).to(dev)
+    d = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((M, 3)).astype(np.float32)), dim=-1).to(dev)
+    ri = torch.from_numpy(rng.uniform(0, 1, (M, 4)).astype(np.float32)).to(dev)
+    fp_cpu.precision = "tc"; a = fp_cpu.to(dev).pack().forward(x, d, ri, want=("rgb", "sigma"))
+    fp_cpu.precision = "fp32"; b = fp_cpu.to(dev).pack().forward(x, d, ri, want=("rgb", "sigma"))
+    worst = max(worst, float((a["rgb"] - b["rgb"]).abs().max()))
+print("WORST", worst)
+assert worst <= 2e-5, worst
+'''
+    env = dict(os.environ, ENVIDR_ENV_TC_CTAS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "WORST" in r.stdout
