@@ -30,8 +30,12 @@
 
 namespace envidr {
 
-constexpr int kTcIdeSplit = 4;                    // threads per row in the IDE role (orders m = k mod 4)
-constexpr int kTcThreads = (4 + 8 + 4 * kTcIdeSplit) * 32;   // 4 control warps + 8 epilogue warps + 16 IDE warps
+// IDE role: 16 warps.  Rows 64-127 of a tile (reflected direction, per-sample kappa = roughness) get 6 threads each (orders
+// m = part mod 6, warps 0-11); rows 0-63 (normal direction, constant kappa = diffuse_kappa_inv) get 2 threads each (warps 12-15):
+// with the shipped kappa = 0.64 their bands l >= 8 are attenuated by exp(-36 * 0.64) = 1e-10 and below, so only l <= 4 is
+// evaluated there (see ide_nb0 in env_tc_launch) and the rest of those rows stays zero.
+constexpr int kTcIdeThreads = 512;
+constexpr int kTcThreads = (4 + 8) * 32 + kTcIdeThreads;   // 4 control warps + 8 epilogue warps + 16 IDE warps
 constexpr int kTcStages = 3;
 constexpr uint32_t kTcStageBytes = 16384;          // one K step (16) of a 256-wide layer: 2 (hi,lo) x 2 chunks x 256 x 16 B
 constexpr uint32_t kTcARegion = 65536;             // 128 rows x 256 K x 2 B
@@ -78,7 +82,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint64_t* full = bars;                           // [3]  producer -> issuer (TMA bytes landed)
     uint64_t* empty = bars + kTcStages;              // [3]  issuer -> producer (MMAs reading the stage retired)
     uint64_t* acc_ready = bars + 2 * kTcStages;      // [2] issuer -> epilogue warps (accumulator buffer b of a layer complete)
-    uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (128 * kTcIdeSplit arrivals)
+    uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (kTcIdeThreads arrivals per CTA)
     uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
     uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
                                                      //     shared memory (128 arrivals per CTA: the 4 warps that own chunk parity c & 1)
@@ -108,11 +112,14 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         tc::mbar_init(&acc_ready[1], 1);
         for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 * CTAS);
         for (int i = 0; i < kTcStages; i++) tc::mbar_init(&pfull[i], 1);
-        tc::mbar_init(ide_full, 128 * kTcIdeSplit * CTAS);
+        tc::mbar_init(ide_full, kTcIdeThreads * CTAS);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
     if (warp == 2) { if (CTAS == 2) tc::tmem_alloc2(tmem_slot, 512); else tc::tmem_alloc(tmem_slot, 512); }
+    for (uint32_t i = tid; i < 2 * kTcIdeRegion / 16; i += kTcThreads)       // layer-0 operand starts as zeros: K padding and skipped bands
+        reinterpret_cast<uint4*>(sI_hi)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async_smem();
     for (uint32_t i = tid; i < (uint32_t)nl * 256; i += kTcThreads) {
         const uint32_t l = i >> 8, c = i & 255;
         s_bias[i] = (c < E.L[l].Np) ? __ldg(E.bias + E.L[l].bias_off + c) : 0.0f;
@@ -317,9 +324,10 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         }
     } else if (warp >= 12) {
         // ===================== IDE warps: directional encoding of the NEXT tile while the current one is in the MMA pipe ====
-        const uint32_t t2 = tid - 12 * 32;               // 0 .. 128 * kTcIdeSplit - 1
-        const uint32_t row = t2 & 127, mpar = t2 >> 7;   // kTcIdeSplit threads per row: orders m = mpar (mod kTcIdeSplit)
-        const uint32_t branch = row >> 6;
+        const uint32_t t2 = tid - 12 * 32;               // 0 .. 511
+        const uint32_t branch = t2 < 384 ? 1u : 0u;      // warp-uniform
+        const uint32_t part = branch ? t2 >> 6 : (t2 - 384) >> 6;                // 0..5 (reflected) / 0..1 (normal), warp-uniform
+        const uint32_t row = branch ? 64 + (t2 & 63) : (t2 - 384) & 63;
         const uint32_t Kp0 = E.L[0].Kp, P = E.P;
         uint32_t empty_par = 1, ti = 0;                  // first wait passes
         const bool pw = prof && tid == 12 * 32;
@@ -338,36 +346,51 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
             tc::mbar_wait(ide_empty, empty_par); empty_par ^= 1;
             if (pw) stamp(ti, 9, clock64());
             if (valid) {
+                // layer-0 K order is interleaved (column 2i = Re_i, 2i+1 = Im_i; the weight image is packed with the same
+                // permutation, k_pack_tc `interleave`): one packed fp16x2 store per (hi, lo) instead of four 2-byte stores,
+                // and the packed conversion instead of scalar ones
                 auto emit = [&](int i, float re, float im) {
-                    __half h, lo;
-                    tc::split_f16(re, h, lo);
-                    *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, i)) = h;
-                    *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, i)) = lo;
-                    tc::split_f16(im, h, lo);
-                    *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, P + i)) = h;
-                    *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, P + i)) = lo;
+                    uint32_t hi, lo;
+                    split2(re, im, hi, lo);
+                    *reinterpret_cast<uint32_t*>(sI_hi + tc::op_off(128, row, 2 * i)) = hi;
+                    *reinterpret_cast<uint32_t*>(sI_lo + tc::op_off(128, row, 2 * i)) = lo;
                 };
-                // mpar is warp-uniform (4 warps per residue class of m)
-                if (c_ide_tc.deg == 5) {
-                    if (mpar == 0)      ide_eval_emit_static<5, 0, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else if (mpar == 1) ide_eval_emit_static<5, 1, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else if (mpar == 2) ide_eval_emit_static<5, 2, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else                ide_eval_emit_static<5, 3, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                } else if (c_ide_tc.deg == 4) {
-                    if (mpar == 0)      ide_eval_emit_static<4, 0, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else if (mpar == 1) ide_eval_emit_static<4, 1, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else if (mpar == 2) ide_eval_emit_static<4, 2, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                    else                ide_eval_emit_static<4, 3, 4>(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit);
-                } else {
-                    ide_eval_emit(c_ide_tc, dx, dy, dz, kap, E.light_scale, emit, (int)mpar, kTcIdeSplit);
-                }
-                if (mpar == 0) {
-                    for (uint32_t k = 2 * P; k < Kp0; k++) {
-                        *reinterpret_cast<__half*>(sI_hi + tc::op_off(128, row, k)) = __float2half_rn(0.f);
-                        *reinterpret_cast<__half*>(sI_lo + tc::op_off(128, row, k)) = __float2half_rn(0.f);
+                const float ls = E.light_scale;
+                const uint32_t deg = c_ide_tc.deg;
+                if (branch) {                              // reflected direction: all bands, 6 threads per row
+                    if (deg == 5) {
+                        switch (part) {
+                            case 0: ide_eval_emit_static<5, 0, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 1: ide_eval_emit_static<5, 1, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 2: ide_eval_emit_static<5, 2, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 3: ide_eval_emit_static<5, 3, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 4: ide_eval_emit_static<5, 4, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            default: ide_eval_emit_static<5, 5, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                        }
+                    } else if (deg == 4) {
+                        switch (part) {
+                            case 0: ide_eval_emit_static<4, 0, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 1: ide_eval_emit_static<4, 1, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 2: ide_eval_emit_static<4, 2, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 3: ide_eval_emit_static<4, 3, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            case 4: ide_eval_emit_static<4, 4, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                            default: ide_eval_emit_static<4, 5, 6>(c_ide_tc, dx, dy, dz, kap, ls, emit); break;
+                        }
+                    } else {
+                        ide_eval_emit(c_ide_tc, dx, dy, dz, kap, ls, emit, (int)part, 6);
+                    }
+                } else {                                   // normal direction: constant kappa, 2 threads per row
+                    if (deg == 5 && E.ide_nb0 == 3) {
+                        if (part == 0) ide_eval_emit_static<5, 0, 2, 3>(c_ide_tc, dx, dy, dz, kap, ls, emit);
+                        else           ide_eval_emit_static<5, 1, 2, 3>(c_ide_tc, dx, dy, dz, kap, ls, emit);
+                    } else if (deg == 4 && E.ide_nb0 == 3) {
+                        if (part == 0) ide_eval_emit_static<4, 0, 2, 3>(c_ide_tc, dx, dy, dz, kap, ls, emit);
+                        else           ide_eval_emit_static<4, 1, 2, 3>(c_ide_tc, dx, dy, dz, kap, ls, emit);
+                    } else {
+                        ide_eval_emit(c_ide_tc, dx, dy, dz, kap, ls, emit, (int)part, 2);
                     }
                 }
-            } else if (mpar == 0) {
+            } else if (part == 0) {
                 for (uint32_t k = 0; k < Kp0; k += 8) {
                     *reinterpret_cast<uint4*>(sI_hi + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
                     *reinterpret_cast<uint4*>(sI_lo + tc::op_off(128, row, k)) = make_uint4(0, 0, 0, 0);
@@ -384,12 +407,14 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
 }
 
 // weight image of one layer: for every K step s: [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1], chunk = [Np][8] halfs
+// `interleave` = P > 0 (layer 0 only): packed K index k < 2P reads source column (k & 1) * P + (k >> 1), i.e. [Re_0, Im_0, Re_1, ...]
 __global__ void k_pack_tc(const float* __restrict__ W, const float* __restrict__ b, uint8_t* __restrict__ img, float* __restrict__ bias,
-                          uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+                          uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np, uint32_t interleave) {
     const uint32_t total = Kp * Np;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t n = i / Kp, k = i - n * Kp;
-        const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+        const uint32_t ks = (interleave && k < 2 * interleave) ? (k & 1u) * interleave + (k >> 1) : k;
+        const float v = (n < N && k < K) ? W[(size_t)n * K + ks] : 0.0f;
         __half h, lo;
         tc::split_f16(v, h, lo);
         const uint32_t s = k >> 4, kk = k & 15;
@@ -402,11 +427,13 @@ __global__ void k_pack_tc(const float* __restrict__ W, const float* __restrict__
 
 // CTA-pair image of one layer: rank r (rows n in [r * Nb, (r + 1) * Nb), Nb = Np / 2) is a contiguous run of K steps, each
 // [hi: chunk 0 | chunk 1][lo: chunk 0 | chunk 1] with chunk = [Nb][8] halfs
-__global__ void k_pack_tc2(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+__global__ void k_pack_tc2(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np,
+                           uint32_t interleave) {
     const uint32_t total = Kp * Np, Nb = Np / 2, ksteps = Kp / 16;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t n = i / Kp, k = i - n * Kp;
-        const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+        const uint32_t ks = (interleave && k < 2 * interleave) ? (k & 1u) * interleave + (k >> 1) : k;
+        const float v = (n < N && k < K) ? W[(size_t)n * K + ks] : 0.0f;
         __half h, lo;
         tc::split_f16(v, h, lo);
         const uint32_t r = n / Nb, j = n - r * Nb, s = k >> 4, kk = k & 15;
@@ -449,6 +476,10 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
     off += (uint64_t)boff * 4;
     t.n_layers = f->n_env; t.P = P; t.E = f->env[f->n_env - 1].out_dim;
     t.kappa_diffuse = f->diffuse_kappa_inv; t.light_scale = f->light_intensity_scale;
+    // bands of the normal-direction encoding whose attenuation exp(-sigma_l * kappa) is below e^-21 = 7.6e-10 are not evaluated
+    // (their features stay exactly zero; the reference computes values of that magnitude, 5 orders below the parity bar):
+    // sigma_l = l(l+1)/2 = 1, 3, 10, 36, 136 -> with kappa >= 21/36 only l <= 4 (3 bands) remains
+    t.ide_nb0 = (f->diffuse_kappa_inv * 36.0f > 21.0f && f->ide_degree >= 4) ? 3u : f->ide_degree;
     if (f->packed) {
         t.blob = reinterpret_cast<const uint8_t*>(f->packed);
         t.bias = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(f->packed) + bias_bytes_off);
@@ -462,8 +493,9 @@ int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st
     float* bias = const_cast<float*>(reinterpret_cast<const float*>(blob + (reinterpret_cast<const uint8_t*>(t.bias) - t.blob)));
     for (uint32_t i = 0; i < t.n_layers; i++) {
         const TcLayer& L = t.L[i];
-        k_pack_tc<<<128, 256, 0, st>>>(f->env[i].weight, f->env[i].bias, blob + L.img_off, bias + L.bias_off, L.K, L.N, L.Kp, L.Np);
-        k_pack_tc2<<<128, 256, 0, st>>>(f->env[i].weight, blob + L.img2_off, L.K, L.N, L.Kp, L.Np);
+        const uint32_t il = (i == 0) ? t.P : 0u;
+        k_pack_tc<<<128, 256, 0, st>>>(f->env[i].weight, f->env[i].bias, blob + L.img_off, bias + L.bias_off, L.K, L.N, L.Kp, L.Np, il);
+        k_pack_tc2<<<128, 256, 0, st>>>(f->env[i].weight, blob + L.img2_off, L.K, L.N, L.Kp, L.Np, il);
     }
     return check_launch("field_pack_tc");
 }

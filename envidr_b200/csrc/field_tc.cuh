@@ -17,6 +17,7 @@ struct TcEnv {
     const uint8_t* blob;          // weight images
     const float* bias;            // [sum Np] floats
     uint32_t n_layers, P, E;
+    uint32_t ide_nb0;             // bands evaluated for the normal-direction (constant kappa) encoding, see tc_layout
     float kappa_diffuse, light_scale;
     TcLayer L[kTcMaxLayers];
 };

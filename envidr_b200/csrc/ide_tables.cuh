@@ -134,13 +134,16 @@ __host__ __device__ constexpr bool ide_is_pow2(int v) { return v > 0 && (v & (v 
 __host__ __device__ constexpr int ide_ilog2(int v) { return v <= 1 ? 0 : 1 + ide_ilog2(v >> 1); }
 __host__ __device__ constexpr int ide_band_base(int b) { return (1 << b) - 1 + b; }
 
-template <int DEG, int MSTART, int MSTEP, class Emit>
+// NB <= DEG: only the first NB bands (l = 1 .. 2^(NB-1)) are evaluated; the caller guarantees the others are negligible
+// (exp(-sigma_l kappa) below its threshold) and keeps their outputs at zero.
+template <int DEG, int MSTART, int MSTEP, int NB = DEG, class Emit>
 __device__ __forceinline__ void ide_eval_emit_static(const IdeTables& T, float x, float y, float z, float kappa_inv, float scale, Emit&& emit) {
-    constexpr int LMAX = 1 << (DEG - 1);
+    static_assert(NB >= 1 && NB <= DEG, "band count");
+    constexpr int LMAX = 1 << (NB - 1);
     if (x == 0.0f && y == 0.0f) y += 1.0f;
-    float att[DEG];
+    float att[NB];
     #pragma unroll
-    for (int b = 0; b < DEG; b++) att[b] = expf(-T.band_sigma[b] * kappa_inv) * scale;
+    for (int b = 0; b < NB; b++) att[b] = expf(-T.band_sigma[b] * kappa_inv) * scale;
     float re = 1.0f, im = 0.0f, sr = 1.0f, si = 0.0f;
     #pragma unroll
     for (int k = 0; k < MSTART; k++) { const float nr = re * x - im * y; im = re * y + im * x; re = nr; }

@@ -1,1 +1,5 @@
-timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -m gpu -k pair 2>&1 | tail -12
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_tc.py tests/test_gpu_field.py tests/test_gpu_refpath.py -x -q -m gpu 2>&1 | tail -4
+timeout 100 python profiles/env_timeline.py > gpurun_out/r15_env_timeline.txt 2>&1; cut -c1-330 gpurun_out/r15_env_timeline.txt | sed -n 2,5p
+timeout 400 python bench.py --steps 10 --warmup 3 --no-train --no-gpu-reference > gpurun_out/r15_bench.json 2>gpurun_out/r15_bench.err; python -c "
+import json;d=json.load(open('gpurun_out/r15_bench.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel_ms_per_step'],d['roofline']['frac'])"
