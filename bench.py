@@ -220,7 +220,10 @@ def config_dict(args, W, H, indir):
     return {"workload": f"synthetic toaster-dims scene {W}x{H} inference, " + ("use_renv + indir_ref (3 passes)" if indir else "1 pass"),
             "rays_per_step_per_gpu": W * H, "hash": "L16 C2 base16 res2048 T2^19 (48.8 MB fp32)",
             "mlps": "sdf 32-64-64-15, env IDE72-256-256-256-12 x2, diffuse 24-32-3, color 28-64-64-3, renv 4-64-64-64-12",
-            "max_steps": 1024, "T_thresh": 1e-4, "parallelism": f"ray/frame sharding x{args.gpus} + all_gather",
+            "max_steps": 1024, "T_thresh": 1e-4,
+            "schedule": "passes 1-2: the reference's iterative schedule (n_step = N // n_alive <= 8); main pass: one batch over the per-ray "
+                        "sample counts found by the geometry pass (RenderConfig.replay_main_pass)" if indir else "reference iterative schedule",
+            "parallelism": f"ray/frame sharding x{args.gpus} + all_gather",
             "cache": "inputs larger than L2 are not needed: 48.8 MB table + per-iteration sample buffers are re-written each step; "
                      "L2 is flushed between timed steps by writing a 256 MB buffer"}
 

@@ -54,7 +54,7 @@ class RenderOpts(ctypes.Structure):
 
 class RenderOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("image", "depth", "weights_sum", "normal_image", "diffuse_image", "specular_image",
-                                              "roughness_image")]
+                                              "roughness_image", "sample_count")]
 
 
 _SCALARS = {"uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "int32_t": ctypes.c_int32, "int": ctypes.c_int,

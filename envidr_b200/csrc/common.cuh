@@ -10,6 +10,10 @@
 #endif
 
 namespace envidr {
+extern uint64_t g_launches;                 // kernels launched through the library (bench.py gpu_launches), render.cu
+cudaEvent_t* timing_acquire();              // render.cu: CUDA-event timing of the dominant field kernel
+void timing_commit();
+
 
 void set_error(const char* fmt, ...);
 

@@ -751,7 +751,12 @@ int envidr_field_pack(const envidr_field* field, void* packed, uint64_t packed_b
 
 int envidr_field_forward(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images, uint32_t M, int mode,
                          const envidr_field_out* out, envidr_stream_t stream) {
-    return field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), nullptr, nullptr);
+    cudaEvent_t* ev = (mode != 1 && field && field->precision == 1) ? timing_acquire() : nullptr;
+    int recorded = 0;
+    const int rc = field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), ev, &recorded);
+    if (ev && recorded) timing_commit();
+    if (rc == 0 && M > 0) g_launches += (field->precision == 1 && mode != 1) ? 3 : 1;
+    return rc;
 }
 
 }  // extern "C"

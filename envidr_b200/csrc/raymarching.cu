@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kRayBlock) k_march_train_write(
     if (count == 0 || offset + count > M) return;
     Dda s; s.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, grid);
     const float far = fars[n], near = nears[n];
-    float t = perturbed_start(s, near, noises[n]);
+    float t = perturbed_start(s, near, noises ? noises[n] : 0.0f);
     float last_t = near;
     float* px = xyzs + 3 * (size_t)offset;
     float* pd = dirs + 3 * (size_t)offset;
@@ -206,6 +206,72 @@ __global__ void __launch_bounds__(kRayBlock) k_march_train_write(
             px += 3; pd += 3; pl += 2; step++;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// replay of a pass with known per-ray sample counts (see envidr_march_rays_replay in the header)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_replay_counts(const int32_t* __restrict__ counts, uint32_t N, int32_t* __restrict__ rays) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    rays[3 * n] = (int32_t)n;
+    rays[3 * n + 2] = counts[n] > 0 ? counts[n] : 0;
+}
+
+// dst[off + s, :] = src[n, :] for every sample s of ray n (per-ray rows -> per-sample rows; one warp per ray, float4 rows)
+__global__ void __launch_bounds__(256) k_scatter_rows4(const int32_t* __restrict__ rays, uint32_t N, uint32_t M, const float4* __restrict__ src,
+                                                      float4* __restrict__ dst) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= N) return;
+    const uint32_t id = rays[3 * w], off = rays[3 * w + 1], cnt = rays[3 * w + 2];
+    if (off + cnt > M) return;
+    const float4 v = src[id];
+    for (uint32_t s = lane; s < cnt; s += 32) dst[off + s] = v;
+}
+
+// Inference compositor (reference kernel_composite_rays, raymarching.cu:957-1046) over ray-contiguous samples: the pre-sample
+// transmittance T = 1 - sum w, w = alpha T, every image accumulated sample by sample in the same order.  One thread per ray.
+__global__ void __launch_bounds__(128) k_composite_replay(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                         const float* __restrict__ normals, const float* __restrict__ cds,
+                                                         const float* __restrict__ css, const float* __restrict__ roughs,
+                                                         const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                                                         const float* __restrict__ nears, uint32_t M,
+                                                         uint32_t N, float T_thresh, uint32_t input_alpha, float* __restrict__ weights_sum,
+                                                         float* __restrict__ depth, float* __restrict__ image, float* __restrict__ normal_image,
+                                                         float* __restrict__ diffuse_image, float* __restrict__ specular_image,
+                                                         float* __restrict__ roughness_image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * n], off = (uint32_t)rays[3 * n + 1];
+    uint32_t cnt = (uint32_t)rays[3 * n + 2];
+    if (off + cnt > M) cnt = 0;                                    // dropped ray (capacity), as in march_rays_train
+    float ws = 0, d = 0, t = nears ? nears[index] : 0.0f, acc[3] = {0, 0, 0}, nrm[3] = {0, 0, 0}, cd[3] = {0, 0, 0}, cs[3] = {0, 0, 0}, rgh = 0;
+    for (uint32_t s = 0; s < cnt; s++) {
+        const size_t m = (size_t)off + s;
+        const float2 dl = *reinterpret_cast<const float2*>(deltas + 2 * m);
+        if (dl.x == 0) break;
+        const float sg = sigmas[m];
+        const float alpha = input_alpha ? 0.0f + sg : 1.0f - __expf(-sg * dl.x);
+        const float T = 1 - ws;
+        const float w = alpha * T;
+        ws += w;
+        t = t + dl.y;
+        d += w * t;
+        const float* c = rgbs + 3 * m;
+        acc[0] += w * c[0]; acc[1] += w * c[1]; acc[2] += w * c[2];
+        if (normal_image) { const float* q = normals + 3 * m; nrm[0] += w * q[0]; nrm[1] += w * q[1]; nrm[2] += w * q[2]; }
+        if (diffuse_image) { const float* q = cds + 3 * m; cd[0] += w * q[0]; cd[1] += w * q[1]; cd[2] += w * q[2]; }
+        if (specular_image) { const float* q = css + 3 * m; cs[0] += w * q[0]; cs[1] += w * q[1]; cs[2] += w * q[2]; }
+        if (roughness_image) rgh += w * roughs[m];
+        if (T < T_thresh) break;
+    }
+    weights_sum[index] = ws;
+    if (depth) depth[index] = d;
+    image[3 * index] = acc[0]; image[3 * index + 1] = acc[1]; image[3 * index + 2] = acc[2];
+    if (normal_image) { float* q = normal_image + 3 * index; q[0] = nrm[0]; q[1] = nrm[1]; q[2] = nrm[2]; }
+    if (diffuse_image) { float* q = diffuse_image + 3 * index; q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; }
+    if (specular_image) { float* q = specular_image + 3 * index; q[0] = cs[0]; q[1] = cs[1]; q[2] = cs[2]; }
+    if (roughness_image) roughness_image[index] = rgh;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,6 +566,48 @@ int envidr_march_rays_train(const float* rays_o, const float* rays_d, const uint
     k_march_train_write<<<ceil_div(N, kRayBlock), kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                                       nears, fars, noises, rays, xyzs, dirs, deltas);
     return check_launch("march_rays_train");
+}
+
+int envidr_march_rays_replay(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                             const float* fars, const int32_t* counts, float* xyzs, float* dirs, float* deltas,
+                             int32_t* rays, int32_t* counter, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(rays_o && rays_d && grid && nears && fars && counts && xyzs && dirs && deltas && rays && counter,
+                   ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024, ENVIDR_E_UNSUPPORTED, "cascades must be 1..8, grid size <= 1024");
+    if (N == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    k_replay_counts<<<ceil_div(N, 256), 256, 0, st>>>(counts, N, rays);
+    k_march_train_scan<<<1, 1024, 0, st>>>(rays, N, counter);
+    k_march_train_write<<<ceil_div(N, kRayBlock), kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                      nears, fars, nullptr, rays, xyzs, dirs, deltas);
+    g_launches += 3;
+    return check_launch("march_rays_replay");
+}
+
+int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const float* src, float* dst, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(rays && src && dst, ENVIDR_E_BADARG, "null pointer");
+    if (N == 0) return 0;
+    k_scatter_rows4<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(rays, N, M, reinterpret_cast<const float4*>(src),
+                                                                   reinterpret_cast<float4*>(dst));
+    g_launches += 1;
+    return check_launch("scatter_ray_rows4");
+}
+
+int envidr_composite_rays_replay(const float* sigmas, const float* rgbs, const float* normals, const float* c_diffuse,
+                                 const float* c_specular, const float* roughness, const float* deltas, const int32_t* rays,
+                                 const float* nears, uint32_t M, uint32_t N, float T_thresh, uint32_t input_alpha, float* weights_sum,
+                                 float* depth, float* image, float* normal_image, float* diffuse_image,
+                                 float* specular_image, float* roughness_image, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && image, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE((!normal_image || normals) && (!diffuse_image || c_diffuse) && (!specular_image || c_specular) &&
+                   (!roughness_image || roughness), ENVIDR_E_BADARG, "an output image needs its per-sample input");
+    if (N == 0) return 0;
+    k_composite_replay<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(sigmas, rgbs, normals, c_diffuse, c_specular, roughness, deltas,
+                                                                        rays, nears, M, N, T_thresh, input_alpha, weights_sum, depth, image,
+                                                                        normal_image, diffuse_image, specular_image, roughness_image);
+    g_launches += 1;
+    return check_launch("composite_rays_replay");
 }
 
 int envidr_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,

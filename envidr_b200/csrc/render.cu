@@ -46,6 +46,7 @@ struct RenderBuffers {
 
 struct RenderOutDev {
     float *image, *depth, *weights_sum, *normal_image, *diffuse_image, *specular_image, *roughness_image;
+    int32_t* sample_count;
 };
 
 __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N,
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ r
     if (O.diffuse_image) { O.diffuse_image[3 * n] = 0; O.diffuse_image[3 * n + 1] = 0; O.diffuse_image[3 * n + 2] = 0; }
     if (O.specular_image) { O.specular_image[3 * n] = 0; O.specular_image[3 * n + 1] = 0; O.specular_image[3 * n + 2] = 0; }
     if (O.roughness_image) O.roughness_image[n] = 0;
+    if (O.sample_count) O.sample_count[n] = 0;
 }
 
 // bounding box of the occupied cells of cascade level 0 (bit = Morton(x, y, z), reference raymarching.cu:56-81)
@@ -227,9 +229,10 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
                 if (O.diffuse_image) { const float* q = O.diffuse_image + 3 * index; cd[0] = q[0]; cd[1] = q[1]; cd[2] = q[2]; }
                 if (O.specular_image) { const float* q = O.specular_image + 3 * index; cs[0] = q[0]; cs[1] = q[1]; cs[2] = q[2]; }
                 if (O.roughness_image) rgh = O.roughness_image[index];
-                uint32_t step = 0;
+                uint32_t step = 0, used = 0;
                 while (step < n_step) {
                     if (step >= cnt) break;                       // zero-delta slot in the reference layout
+                    used++;
                     const size_t m = (size_t)sl.x + step;
                     const float2 dl = *reinterpret_cast<const float2*>(B.s_delta + 2 * m);
                     const float sg = B.s_sigma[m];
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
                 if (O.diffuse_image) { float* q = O.diffuse_image + 3 * index; q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; }
                 if (O.specular_image) { float* q = O.specular_image + 3 * index; q[0] = cs[0]; q[1] = cs[1]; q[2] = cs[2]; }
                 if (O.roughness_image) O.roughness_image[index] = rgh;
+                if (O.sample_count) O.sample_count[index] += (int32_t)used;
             }
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
             uint32_t wbase = 0;
@@ -335,11 +339,19 @@ static cudaEvent_t g_events[2];
 static bool g_events_ok = false;
 
 // instrumentation (bench.py): kernel launch counter and per-launch CUDA-event timing of the field kernel
-static uint64_t g_launches = 0;
+uint64_t g_launches = 0;           // also bumped by the operator entry points the replay path uses (common.cuh)
 static int g_timing = 0;
 constexpr int kMaxTimed = 4096;
 static cudaEvent_t g_tev[2 * kMaxTimed];
 static int g_tev_created = 0, g_tev_used = 0;
+
+// event pair for timing one field launch outside the fused loop (envidr_field_forward); nullptr when timing is off
+cudaEvent_t* timing_acquire() {
+    if (!g_timing || g_tev_used >= kMaxTimed) return nullptr;
+    while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
+    return &g_tev[2 * g_tev_used];
+}
+void timing_commit() { g_tev_used++; }
 
 }  // namespace envidr
 
@@ -381,7 +393,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     B.ctr = (Counters*)(w + L.ctr);
     B.occ_box = (int*)(w + L.occ_box);
     RenderOutDev O{out->image, out->depth, out->weights_sum, out->normal_image, out->diffuse_image, out->specular_image,
-                   out->roughness_image};
+                   out->roughness_image, out->sample_count};
     if (opts->geometry_only) { O.image = out->normal_image; O.diffuse_image = nullptr; O.specular_image = nullptr; O.roughness_image = nullptr; }
     const float* a = opts->aabb;
     k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);

@@ -37,6 +37,9 @@ class RenderConfig:
     indir_ref: bool = False
     indir_max_steps: int = 1024
     obj_aabb: Optional[Sequence[float]] = None
+    # main pass of the indirect-reflection scheme as ONE batch over the sample counts the geometry pass found (render_rays_replay)
+    # instead of re-discovering ray termination iteration by iteration; False = the reference's iterative schedule
+    replay_main_pass: bool = True
 
     def aabb6(self):
         return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3
@@ -59,7 +62,8 @@ def _workspace(N: int, device) -> torch.Tensor:
 def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, cfg: RenderConfig, *,
                 bg_color=1.0, r_images: Optional[torch.Tensor] = None, geometry_only: bool = False,
                 env_rot_radian: Optional[float] = None, get_normal_image: bool = True, visual_items: Sequence[str] = (),
-                perturb: bool = False, max_steps: Optional[int] = None, min_near: Optional[float] = None) -> Dict[str, torch.Tensor]:
+                perturb: bool = False, max_steps: Optional[int] = None, min_near: Optional[float] = None,
+                sample_count: bool = False) -> Dict[str, torch.Tensor]:
     """One run_cuda inference pass over N rays.  Returns image [N,3], depth [N], weights_sum [N] and
     (optionally) normal_image / diffuse_image / specular_image / roughness_image, all on the device."""
     if field._packed is None:
@@ -83,6 +87,8 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
             res["specular_image"] = torch.empty(N, 3, **f32)
         if "roughness" in visual_items or "specular" in visual_items:
             res["roughness_image"] = torch.empty(N, **f32)
+    if sample_count:
+        res["sample_count"] = torch.empty(N, dtype=torch.int32, device=dev)
     for k, t in res.items():
         setattr(out, k, t.data_ptr())
     opts = _lib.RenderOpts()
@@ -124,6 +130,78 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
     return res
 
 
+_aabb_cache: Dict[tuple, torch.Tensor] = {}
+REPLAY_CHUNK = 1 << 20          # samples per field launch in render_rays_replay (bounds the tensor-core scratch: 256 B / sample)
+
+
+def render_rays_replay(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, counts: torch.Tensor,
+                       cfg: RenderConfig, *, bg_color=1.0, r_images: Optional[torch.Tensor] = None,
+                       env_rot_radian: Optional[float] = None, visual_items: Sequence[str] = (), max_steps: Optional[int] = None,
+                       min_near: Optional[float] = None) -> Dict[str, torch.Tensor]:
+    """One inference pass over rays whose per-ray sample counts are known (`counts`, from an earlier pass over the same
+    rays with `sample_count=True`): march all samples in one launch, evaluate the field on the whole batch, composite with
+    the inference compositor's arithmetic.  Same samples and the same per-sample math as the iterative loop; what changes is
+    the batching (one pass over ~3 M samples instead of ~60 iterations of <= 81 k), so sample positions can differ from the
+    iterative schedule by the ulp-level re-synchronisation of rays_t at iteration boundaries."""
+    from . import raymarching as rm
+    if field._packed is None:
+        field.pack()
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N, dev = rays_o.shape[0], rays_o.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    key = (tuple(float(v) for v in cfg.aabb6()), str(dev))
+    if key not in _aabb_cache:
+        _aabb_cache[key] = torch.tensor(key[0], **f32)
+    nears, fars = rm.near_far_from_aabb(rays_o, rays_d, _aabb_cache[key], cfg.min_near if min_near is None else min_near)
+    counts = counts.to(torch.int32).contiguous()
+    M = int(counts.sum().item()) if N else 0
+    xyzs, dirs, deltas = torch.empty(M, 3, **f32), torch.empty(M, 3, **f32), torch.empty(M, 2, **f32)
+    rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    check(lib().envidr_march_rays_replay(ptr(rays_o), ptr(rays_d), ptr(bitfield), cfg.bound, cfg.dt_gamma,
+                                         cfg.max_steps if max_steps is None else max_steps, N, cfg.cascade, cfg.grid_size, M, ptr(nears),
+                                         ptr(fars), ptr(counts), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), stream()),
+          "march_rays_replay")
+    r_s = None
+    if r_images is not None:
+        r_s = torch.empty(M, 4, **f32)
+        check(lib().envidr_scatter_ray_rows4(ptr(rays), N, M, ptr(r_images.float().contiguous().view(-1, 4)), ptr(r_s), stream()),
+              "scatter_ray_rows4")
+    want = ["sigma", "rgb"]
+    if "diffuse" in visual_items:
+        want.append("c_diffuse")
+    if "specular" in visual_items:
+        want.append("c_specular")
+    if "roughness" in visual_items or "specular" in visual_items:
+        want.append("roughness")
+    parts = []
+    for a in range(0, M, REPLAY_CHUNK):
+        b = min(M, a + REPLAY_CHUNK)
+        parts.append(field.forward(xyzs[a:b], dirs[a:b], None if r_s is None else r_s[a:b], env_rot_radian=env_rot_radian, want=tuple(want)))
+    so = {k: (torch.cat([p[k] for p in parts]) if len(parts) != 1 else parts[0][k]) for k in want} if parts else \
+        {k: torch.empty((0, 3) if k in ("rgb", "c_diffuse", "c_specular") else (0,), **f32) for k in want}
+    res = {"image": torch.empty(N, 3, **f32), "depth": torch.empty(N, **f32), "weights_sum": torch.empty(N, **f32)}
+    if "c_diffuse" in so:
+        res["diffuse_image"] = torch.empty(N, 3, **f32)
+    if "c_specular" in so:
+        res["specular_image"] = torch.empty(N, 3, **f32)
+    if "roughness" in so:
+        res["roughness_image"] = torch.empty(N, **f32)
+    check(lib().envidr_composite_rays_replay(ptr(so["sigma"]), ptr(so["rgb"]), None, ptr(so.get("c_diffuse")), ptr(so.get("c_specular")),
+                                             ptr(so.get("roughness")), ptr(deltas), ptr(rays), ptr(nears), M, N, cfg.T_thresh,
+                                             int(cfg.input_alpha), ptr(res["weights_sum"]), ptr(res["depth"]), ptr(res["image"]), None,
+                                             ptr(res.get("diffuse_image")), ptr(res.get("specular_image")), ptr(res.get("roughness_image")),
+                                             stream()), "composite_rays_replay")
+    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32) if not isinstance(bg_color, (list, tuple)) \
+        else torch.tensor([float(v) for v in bg_color], **f32)
+    res["image"] = res["image"] + (1 - res["weights_sum"]).unsqueeze(-1) * bg
+    if "roughness_image" in res:
+        res["roughness_image"] = res["roughness_image"][..., None]
+    res["_samples"] = M
+    return res
+
+
 def last_stats() -> Dict[str, int]:
     """Blocks until the last render_rays finished; {'iterations', 'samples'} of that pass."""
     st = (ctypes.c_uint32 * 4)()
@@ -152,7 +230,8 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             stats.append(last_stats())
     else:
         dt = 2 * SQRT3 / cfg.indir_max_steps
-        geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian)
+        geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
+                          sample_count=cfg.replay_main_pass)
         if stats is not None:
             stats.append(last_stats())
         normals = geo["normal_image"]
@@ -173,10 +252,17 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         ref2ray = ref_mask[ray_mask]
         r_img = ref_image.new_zeros(ref2ray.shape[0], 4)
         r_img[ref2ray] = ref_image
-        main = render_rays(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], cfg, bg_color=0.0, r_images=r_img,
-                           env_rot_radian=env_rot_radian, get_normal_image=get_normal_image, visual_items=visual_items)
-        if stats is not None:
-            stats.append(last_stats())
+        if cfg.replay_main_pass:
+            # the main pass visits the rays of the geometry pass again (same origins, same density): replay its sample counts
+            main = render_rays_replay(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], geo["sample_count"][ray_mask], cfg, bg_color=0.0,
+                                      r_images=r_img, env_rot_radian=env_rot_radian, visual_items=visual_items)
+            if stats is not None:
+                stats.append(dict(iterations=1, samples=int(main.pop("_samples"))))
+        else:
+            main = render_rays(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], cfg, bg_color=0.0, r_images=r_img,
+                               env_rot_radian=env_rot_radian, get_normal_image=get_normal_image, visual_items=visual_items)
+            if stats is not None:
+                stats.append(last_stats())
         results = {"normal_image": normals, "depth": depth}
         for k in ("image", "specular_image", "diffuse_image", "roughness_image"):
             if k in main:

@@ -259,6 +259,7 @@ typedef struct envidr_render_out {
     float* diffuse_image;   /* [N,3]  optional ('diffuse' in visual_items)  */
     float* specular_image;  /* [N,3]  optional ('specular' in visual_items) */
     float* roughness_image; /* [N]    optional (composited roughness)       */
+    int32_t* sample_count;  /* [N]    optional: samples composited per ray (consumed by envidr_march_rays_replay) */
 } envidr_render_out;
 
 uint64_t envidr_render_workspace_bytes(uint32_t N);
@@ -268,6 +269,27 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
                        const float* r_images, const float* noises, const float* bg_per_ray, uint32_t N,
                        const envidr_render_opts* opts, const envidr_render_out* out, void* workspace,
                        uint64_t workspace_bytes, envidr_stream_t stream);
+/* Replay of a pass whose per-ray sample counts are already known (the main pass of the indirect-reflection scheme,
+ * renderer.py:439-513, visits the rays of the geometry pass again): instead of re-discovering ray termination iteration by
+ * iteration, march counts[n] samples of every ray in one launch (same DDA as envidr_march_rays / _train; ray-contiguous
+ * output like march_rays_train: rays[n] = (n, offset, counts[n]), counter[0] += sum), evaluate the field on the whole batch,
+ * and composite with the inference compositor's arithmetic (raymarching.cu:996-1039: T = 1 - sum w before the sample).
+ * Samples past capacity M are dropped ray-wise as in march_rays_train. */
+int envidr_march_rays_replay(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                             const float* fars, const int32_t* counts, float* xyzs, float* dirs, float* deltas,
+                             int32_t* rays, int32_t* counter, envidr_stream_t stream);
+/* dst[offset_n + s, 0:4] = src[ray_n, 0:4] for every sample of every ray in `rays` [N,3] (per-ray r_images -> per-sample rows). */
+int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const float* src /* [N,4] */, float* dst /* [M,4] */,
+                             envidr_stream_t stream);
+/* images may be NULL except weights_sum / image; sigmas [M], rgbs / normals / c_diffuse / c_specular [M,3], roughness [M];
+ * nears [N] (start of the depth accumulation, may be NULL = 0). */
+int envidr_composite_rays_replay(const float* sigmas, const float* rgbs, const float* normals, const float* c_diffuse,
+                                 const float* c_specular, const float* roughness, const float* deltas, const int32_t* rays,
+                                 const float* nears, uint32_t M, uint32_t N, float T_thresh, uint32_t input_alpha, float* weights_sum,
+                                 float* depth, float* image, float* normal_image, float* diffuse_image,
+                                 float* specular_image, float* roughness_image, envidr_stream_t stream);
+
 /* Waits for the most recent envidr_render_rays of this process; stats = {iterations, samples_lo, samples_hi, 0}. */
 int envidr_render_last_stats(uint32_t stats[4]);
 

@@ -20,8 +20,9 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("W,env,deg,indir,prec", [(96, 64, 4, False, "fp32"), (96, 64, 4, True, "tc"), (128, 256, 5, True, "tc")])
-def test_fused_render_matches_reference_cuda_path(dev, W, env, deg, indir, prec):
+@pytest.mark.parametrize("W,env,deg,indir,prec,replay", [(96, 64, 4, False, "fp32", False), (96, 64, 4, True, "tc", False),
+                                                         (128, 256, 5, True, "tc", False), (128, 256, 5, True, "tc", True)])
+def test_fused_render_matches_reference_cuda_path(dev, W, env, deg, indir, prec, replay):
     from envidr_b200 import render, scene
     from oracle import ref_cuda
     fp_cpu = scene.make_synthetic_field(0, hidden_dim_env=env, ide_degree=deg)
@@ -30,13 +31,18 @@ def test_fused_render_matches_reference_cuda_path(dev, W, env, deg, indir, prec)
     ro, rd = ro.to(dev), rd.to(dev)
     fp_cpu.precision = prec
     fp = fp_cpu.to(dev).pack()
-    cfg = render.RenderConfig(indir_ref=indir)
+    cfg = render.RenderConfig(indir_ref=indir, replay_main_pass=replay)
     st = []
     ours = render.render(fp, bf, ro, rd, cfg, bg_color=1.0, stats=st)
     rst = []
     ref = ref_cuda.render(ref_cuda.RefField(fp_cpu.to_oracle(), dev), bf, ro, rd, indir_ref=indir, bg_color=1.0, stats=rst)
-    assert [s["samples"] for s in st] == [s["samples"] for s in rst]          # march + termination: same samples in every pass
-    assert [s["iterations"] for s in st] == [s["iterations"] for s in rst]
+    if replay:      # main pass as one batch: it evaluates only the samples that get composited (the iterative loop also shades
+        # the <= n_step - 1 samples that follow a ray's termination inside its last iteration)
+        assert [s["samples"] for s in st[:2]] == [s["samples"] for s in rst[:2]]
+        assert st[2]["iterations"] == 1 and 0.97 * rst[2]["samples"] <= st[2]["samples"] <= rst[2]["samples"]
+    else:
+        assert [s["samples"] for s in st] == [s["samples"] for s in rst]      # march + termination: same samples in every pass
+        assert [s["iterations"] for s in st] == [s["iterations"] for s in rst]
     e = (ours["image"] - ref["image"]).abs().max(-1).values
     n_bad = int((e > 1e-4).sum())
     assert n_bad <= 2, (n_bad, float(e.max()))

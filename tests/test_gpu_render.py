@@ -168,3 +168,31 @@ def test_three_pass_indirect_reflection(dev):
     assert torch.equal(out["image"], img)
     single = render.render(fp, bft, ro, rd, one, bg_color=1.0)
     assert (single["image"] - out["image"]).abs().max() > 1e-3, "inter-reflection must change some pixels"
+
+
+@pytest.mark.parametrize("W,env_width,deg", [(128, 64, 4), (160, 256, 5)])
+def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
+    """RenderConfig.replay_main_pass: the main pass of the 3-pass scheme as one batch over the sample counts found by the
+    geometry pass (envidr_march_rays_replay + one field launch chain + envidr_composite_rays_replay) against the reference's
+    iterative schedule: same number of samples, RGB within 1e-4 on all but <= 2 pixels (kink sensitivity, test_gpu_fullsize.py),
+    visual items included."""
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=env_width, ide_degree=deg)
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    bf = torch.from_numpy(scene.make_bitfield()).to(dev)
+    ro, rd = scene.camera_rays(W, W)
+    ro, rd = ro.to(dev), rd.to(dev)
+    items = ("diffuse", "specular", "roughness")
+    st_a, st_b = [], []
+    a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True), bg_color=1.0, visual_items=items, stats=st_a)
+    b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False), bg_color=1.0, visual_items=items, stats=st_b)
+    assert st_a[0] == st_b[0] and st_a[1] == st_b[1]                        # geometry and secondary passes are untouched
+    # the replay evaluates only the samples that were composited; the iterative loop also marches / shades the samples that
+    # follow a ray's termination inside its last iteration (up to n_step - 1 per ray)
+    assert st_a[2]["iterations"] == 1 and 0.97 * st_b[2]["samples"] <= st_a[2]["samples"] <= st_b[2]["samples"]
+    for k in ("image", "diffuse_image", "specular_image", "roughness_image"):
+        e = (a[k] - b[k]).abs().reshape(a[k].shape[0], -1).max(-1).values
+        assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
+    assert float((a["weights_sum"] - b["weights_sum"]).abs().max()) <= 1e-5
+    assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["normal_image"], b["normal_image"])
