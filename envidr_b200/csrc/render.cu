@@ -50,12 +50,12 @@ struct RenderOutDev {
 };
 
 __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N,
-                                                    float min_near, float a0, float a1, float a2, float a3, float a4, float a5,
+                                                    uint32_t n_step_floor, float min_near, float a0, float a1, float a2, float a3, float a4, float a5,
                                                     RenderBuffers B, RenderOutDev O) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) {
         Counters c{};
-        c.n_alive = N; c.n_step = 1;
+        c.n_alive = N; c.n_step = n_step_floor;
         *B.ctr = c;
         for (int a = 0; a < 3; a++) { B.occ_box[2 * a] = 0x7fffffff; B.occ_box[2 * a + 1] = -1; }
     }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_march_compact(
 // composite this iteration's samples into the per-ray accumulators, decide which rays stay alive, compact
 // the alive list, and (last block) advance the iteration counters.
 __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, float T_thresh, uint32_t max_steps, int geometry_only,
-                                                                  int input_alpha, RenderBuffers B, RenderOutDev O) {
+                                                                  int input_alpha, uint32_t n_step_floor, RenderBuffers B, RenderOutDev O) {
     Counters* ctr = B.ctr;
     const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
     const bool active = !(n_alive == 0 || ctr->step_total >= max_steps);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
             ctr->M = 0;
             uint32_t ns = next ? N / next : 1;
             ns = ns > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : ns;
-            ctr->n_step = ns < 1 ? 1 : ns;
+            ctr->n_step = ns < n_step_floor ? n_step_floor : ns;
         }
         ctr->done_blocks = 0;
     }
@@ -317,19 +317,20 @@ static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 struct WsLayout {
     uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, occ_box, scratch, total;
 };
-static WsLayout ws_layout(uint32_t N) {
+static uint32_t clamp_floor(uint32_t f) { return f < 1 ? 1u : (f > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : f); }
+static WsLayout ws_layout(uint32_t N, uint32_t n_step_floor = 1) {
     WsLayout L{};
     uint64_t off = 0;
     auto take = [&](uint64_t bytes) { const uint64_t o = off; off = align_up(off + bytes, 256); return o; };
-    const uint64_t n = N;
+    const uint64_t n = N, m = (uint64_t)N * clamp_floor(n_step_floor);     // m: samples of one iteration (n_alive * n_step <= N * floor)
     L.nears = take(4 * n); L.fars = take(4 * n); L.rays_t = take(4 * n);
     L.alive0 = take(4 * n); L.alive1 = take(4 * n); L.slot = take(8 * n);
-    L.s_xyz = take(12 * n); L.s_dir = take(12 * n); L.s_delta = take(8 * n); L.s_rimg = take(16 * n);
-    L.s_sigma = take(4 * n); L.s_rgb = take(12 * n); L.s_normal = take(12 * n); L.s_cd = take(12 * n); L.s_cs = take(12 * n);
-    L.s_rough = take(4 * n);
+    L.s_xyz = take(12 * m); L.s_dir = take(12 * m); L.s_delta = take(8 * m); L.s_rimg = take(16 * m);
+    L.s_sigma = take(4 * m); L.s_rgb = take(12 * m); L.s_normal = take(12 * m); L.s_cd = take(12 * m); L.s_cs = take(12 * m);
+    L.s_rough = take(4 * m);
     L.ctr = take(sizeof(Counters));
     L.occ_box = take(8 * sizeof(int));
-    L.scratch = take(256 * n);             // tensor-core path: per-sample record + env features (2 x 32 floats)
+    L.scratch = take(256 * m);             // tensor-core path: per-sample record + env features (2 x 32 floats)
     L.total = off;
     return L;
 }
@@ -360,6 +361,7 @@ using namespace envidr;
 extern "C" {
 
 uint64_t envidr_render_workspace_bytes(uint32_t N) { return ws_layout(N).total; }
+uint64_t envidr_render_workspace_bytes_ex(uint32_t N, uint32_t n_step_floor) { return ws_layout(N, n_step_floor).total; }
 
 int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const float* rays_o, const float* rays_d,
                        const float* r_images, const float* noises, const float* bg_per_ray, uint32_t N,
@@ -371,7 +373,8 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     ENVIDR_REQUIRE(opts->cascade >= 1 && opts->cascade <= 8 && opts->grid_size >= 1 && opts->grid_size <= 1024, ENVIDR_E_UNSUPPORTED,
                    "cascades must be 1..8, grid size <= 1024");
     if (N == 0) return 0;
-    const WsLayout L = ws_layout(N);
+    const uint32_t nsf = clamp_floor(opts->n_step_floor);
+    const WsLayout L = ws_layout(N, nsf);
     ENVIDR_REQUIRE(workspace_bytes >= L.total, ENVIDR_E_WORKSPACE, "workspace too small (envidr_render_workspace_bytes)");
     ENVIDR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ENVIDR_E_BADARG, "workspace must be 256-byte aligned");
     cudaStream_t st = as_stream(stream);
@@ -396,7 +399,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
                    out->roughness_image, out->sample_count};
     if (opts->geometry_only) { O.image = out->normal_image; O.diffuse_image = nullptr; O.specular_image = nullptr; O.roughness_image = nullptr; }
     const float* a = opts->aabb;
-    k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);
+    k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, nsf, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);
     // single-cascade, constant-step scenes take the specialised march (same samples, see Dda::probe_fast)
     const int fast = opts->cascade == 1 && opts->dt_gamma == 0.0f && opts->grid_size <= 256 && opts->grid_size % 4 == 0 &&
                      (reinterpret_cast<uintptr_t>(bitfield) & 3) == 0;
@@ -409,7 +412,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     if (rc) return rc;
 
     envidr_field fld = *field;                       // per-iteration sample count is bounded by N
-    fld.scratch = w + L.scratch; fld.scratch_samples = N;
+    fld.scratch = w + L.scratch; fld.scratch_samples = (uint64_t)N * nsf;
     envidr_field_out fo{};
     fo.sigma = B.s_sigma; fo.normal = B.s_normal;
     if (!opts->geometry_only) {
@@ -436,7 +439,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
             if (timed && recorded) g_tev_used++;
             g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;      // march, [geom, env, shade | field], composite
             k_composite_compact<<<march_grid, kMarchBlock, 0, st>>>(N, opts->T_thresh, opts->max_steps, opts->geometry_only,
-                                                                   opts->input_alpha, B, O);
+                                                                   opts->input_alpha, nsf, B, O);
         }
         rc = check_launch("render_loop");
         if (rc) return rc;

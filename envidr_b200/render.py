@@ -40,6 +40,9 @@ class RenderConfig:
     # main pass of the indirect-reflection scheme as ONE batch over the sample counts the geometry pass found (render_rays_replay)
     # instead of re-discovering ray termination iteration by iteration; False = the reference's iterative schedule
     replay_main_pass: bool = True
+    # n_step floor of the secondary (reflected-ray) pass: it runs over few rays, so the reference schedule n_step = N // n_alive
+    # starts at 1 and issues ~50 launches of <= 71 k samples; a floor only changes the batching (same composited samples).  1 = reference
+    secondary_n_step_floor: int = 4
 
     def aabb6(self):
         return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3
@@ -48,13 +51,14 @@ class RenderConfig:
 _workspaces: Dict[tuple, torch.Tensor] = {}
 
 
-def _workspace(N: int, device) -> torch.Tensor:
-    key = (str(device), int(N))
+def _workspace(N: int, device, n_step_floor: int = 1) -> torch.Tensor:
+    key = (str(device), int(N), int(n_step_floor))
     ws = _workspaces.get(key)
     if ws is None:
-        nbytes = lib().envidr_render_workspace_bytes(N)
+        nbytes = lib().envidr_render_workspace_bytes_ex(N, n_step_floor)
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
-        _workspaces.clear()          # keep one workspace alive (render sizes rarely alternate)
+        if len(_workspaces) >= 4:    # the three passes of a frame alternate between a few sizes: keep those alive
+            _workspaces.pop(next(iter(_workspaces)))
         _workspaces[key] = ws
     return ws
 
@@ -63,7 +67,7 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
                 bg_color=1.0, r_images: Optional[torch.Tensor] = None, geometry_only: bool = False,
                 env_rot_radian: Optional[float] = None, get_normal_image: bool = True, visual_items: Sequence[str] = (),
                 perturb: bool = False, max_steps: Optional[int] = None, min_near: Optional[float] = None,
-                sample_count: bool = False) -> Dict[str, torch.Tensor]:
+                sample_count: bool = False, n_step_floor: int = 1) -> Dict[str, torch.Tensor]:
     """One run_cuda inference pass over N rays.  Returns image [N,3], depth [N], weights_sum [N] and
     (optionally) normal_image / diffuse_image / specular_image / roughness_image, all on the device."""
     if field._packed is None:
@@ -114,11 +118,12 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
         opts.bg_color[i] = bgc[i]
     opts.geometry_only = int(geometry_only)
     opts.input_alpha = int(cfg.input_alpha)
+    opts.n_step_floor = max(1, min(8, int(n_step_floor)))
     if r_images is not None:
         r_images = r_images.float().contiguous().view(-1, 4)
         assert r_images.shape[0] == N
     noises = torch.rand(N, **f32) if perturb else None
-    ws = _workspace(N, dev)
+    ws = _workspace(N, dev, opts.n_step_floor)
     base = ws.data_ptr()
     aligned = (base + 255) // 256 * 256
     f = field.cstruct(env_rot_radian)
@@ -131,7 +136,7 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
 
 
 _aabb_cache: Dict[tuple, torch.Tensor] = {}
-REPLAY_CHUNK = 1 << 20          # samples per field launch in render_rays_replay (bounds the tensor-core scratch: 256 B / sample)
+REPLAY_CHUNK = 1 << 22          # samples per field launch in render_rays_replay (bounds the tensor-core scratch: 256 B / sample = 1 GB)
 
 
 def render_rays_replay(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, counts: torch.Tensor,
@@ -245,7 +250,8 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             ob = torch.tensor(cfg.obj_aabb, dtype=torch.float32, device=rays_o.device)
             ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
         ref = render_rays(field, bitfield, ref_o[ref_mask], ref_d[ref_mask], cfg, bg_color=0.0, env_rot_radian=env_rot_radian,
-                          get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2)
+                          get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2,
+                          n_step_floor=cfg.secondary_n_step_floor)
         if stats is not None:
             stats.append(last_stats())
         ref_image = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)

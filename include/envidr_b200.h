@@ -249,6 +249,10 @@ typedef struct envidr_render_opts {
     float bg_color[3];      /* constant background (ignored when bg_per_ray is given) */
     int32_t geometry_only;  /* composite normals instead of colours (pass 1 of indir_ref) */
     int32_t input_alpha;    /* NeuS-style alpha input (use_neus_sdf)        */
+    uint32_t n_step_floor;  /* 0 / 1: the reference schedule n_step = clamp(N / n_alive, 1, 8) (cuda_ray.py:287); f in 2..8: n_step >= f.
+                             * Only the batching changes: every ray still composites the same samples (positions to the ulp-level
+                             * re-synchronisation of rays_t), but a pass over few rays no longer starts with N / n_alive = 1, i.e. with
+                             * launches of at most N samples.  The workspace must be sized with envidr_render_workspace_bytes_ex. */
 } envidr_render_opts;
 
 typedef struct envidr_render_out {
@@ -263,6 +267,7 @@ typedef struct envidr_render_out {
 } envidr_render_out;
 
 uint64_t envidr_render_workspace_bytes(uint32_t N);
+uint64_t envidr_render_workspace_bytes_ex(uint32_t N, uint32_t n_step_floor);
 /* r_images [N,4] (reflected radiance + visibility per ray), noises [N] (perturb), bg_per_ray [N,3] may be NULL.
  * workspace: 256-byte aligned device memory of at least envidr_render_workspace_bytes(N). */
 int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const float* rays_o, const float* rays_d,

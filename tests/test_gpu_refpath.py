@@ -31,14 +31,15 @@ def test_fused_render_matches_reference_cuda_path(dev, W, env, deg, indir, prec,
     ro, rd = ro.to(dev), rd.to(dev)
     fp_cpu.precision = prec
     fp = fp_cpu.to(dev).pack()
-    cfg = render.RenderConfig(indir_ref=indir, replay_main_pass=replay)
+    cfg = render.RenderConfig(indir_ref=indir, replay_main_pass=replay, secondary_n_step_floor=4 if replay else 1)
     st = []
     ours = render.render(fp, bf, ro, rd, cfg, bg_color=1.0, stats=st)
     rst = []
     ref = ref_cuda.render(ref_cuda.RefField(fp_cpu.to_oracle(), dev), bf, ro, rd, indir_ref=indir, bg_color=1.0, stats=rst)
     if replay:      # main pass as one batch: it evaluates only the samples that get composited (the iterative loop also shades
         # the <= n_step - 1 samples that follow a ray's termination inside its last iteration)
-        assert [s["samples"] for s in st[:2]] == [s["samples"] for s in rst[:2]]
+        # (and the secondary pass runs with n_step >= 4: it marches a few more samples past ray termination, same composited set)
+        assert st[0] == rst[0] and rst[1]["samples"] <= st[1]["samples"] <= 1.3 * rst[1]["samples"]
         assert st[2]["iterations"] == 1 and 0.97 * rst[2]["samples"] <= st[2]["samples"] <= rst[2]["samples"]
     else:
         assert [s["samples"] for s in st] == [s["samples"] for s in rst]      # march + termination: same samples in every pass

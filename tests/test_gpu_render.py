@@ -185,9 +185,12 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
     ro, rd = ro.to(dev), rd.to(dev)
     items = ("diffuse", "specular", "roughness")
     st_a, st_b = [], []
-    a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True), bg_color=1.0, visual_items=items, stats=st_a)
-    b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False), bg_color=1.0, visual_items=items, stats=st_b)
-    assert st_a[0] == st_b[0] and st_a[1] == st_b[1]                        # geometry and secondary passes are untouched
+    a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, secondary_n_step_floor=4), bg_color=1.0,
+                      visual_items=items, stats=st_a)
+    b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False, secondary_n_step_floor=1), bg_color=1.0,
+                      visual_items=items, stats=st_b)
+    assert st_a[0] == st_b[0]                                               # the geometry pass is untouched
+    assert st_a[1]["iterations"] < st_b[1]["iterations"] and st_b[1]["samples"] <= st_a[1]["samples"] <= 1.3 * st_b[1]["samples"]
     # the replay evaluates only the samples that were composited; the iterative loop also marches / shades the samples that
     # follow a ray's termination inside its last iteration (up to n_step - 1 per ray)
     assert st_a[2]["iterations"] == 1 and 0.97 * st_b[2]["samples"] <= st_a[2]["samples"] <= st_b[2]["samples"]
