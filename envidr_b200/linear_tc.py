@@ -1,0 +1,86 @@
+"""Dense layer of the training branch on tensor cores (csrc/linear_tc.cu).
+
+`linear_tc(x, W, b, relu)` = relu?(x @ W.T + b) with fp32 tensors and fp32-level accuracy (fp16 hi/lo split operands, three
+tcgen05.mma per K step, fp32 accumulation); the reference runs these layers as cuBLAS fp32 GEMMs behind nn.Linear
+(nerf/network.py:527-698).  Backward: the data gradient is the same kernel on the image of W^T, the weight gradient stays a
+cuBLAS GEMM (dY^T X) and the bias gradient a column sum.  Once differentiable: used for the env / colour / diffuse / renv MLPs;
+sdf_net keeps torch layers because the normals need a double backward through it (nerf/renderer.py:182-198).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from ._lib import check, lib, ptr, stream
+
+
+def _image(W: torch.Tensor) -> torch.Tensor:
+    """Packed fp16 hi/lo operand image of W [N, K] (device uint8 tensor, 16-byte aligned)."""
+    N, K = W.shape
+    nbytes = lib().envidr_linear_tc_image_bytes(N, K)
+    if nbytes == 0:
+        raise ValueError(f"linear_tc supports 1 <= N, K <= 256 (got N={N}, K={K})")
+    img = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    check(lib().envidr_linear_tc_pack(ptr(W), N, K, ptr(img), stream()), "linear_tc_pack")
+    return img
+
+
+def _run(x: torch.Tensor, img: torch.Tensor, bias, N: int, relu: bool) -> torch.Tensor:
+    M, K = x.shape
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(lib().envidr_linear_tc(ptr(x), M, K, ptr(img), ptr(bias), N, int(relu), ptr(y), stream()), "linear_tc")
+    return y
+
+
+def _pow2_scales(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Device tensor {s_gy, s_x, 1 / (s_gy s_x)}: powers of two that bring each operand's largest magnitude into [2^13, 2^14)."""
+    m = torch.stack([gy.abs().amax(), x.abs().amax()]).clamp_min(1e-30)
+    s = torch.exp2(13.0 - torch.floor(torch.log2(m)))
+    return torch.cat([s, (1.0 / (s[0] * s[1])).reshape(1)]).contiguous()
+
+
+WGRAD_TC = True      # weight gradients through csrc/linear_tc.cu::k_wgrad_tc (False: cuBLAS fp32 dY^T X)
+
+
+def wgrad_tc(gy: torch.Tensor, x: torch.Tensor, variant: int = 0) -> torch.Tensor:
+    """dW [N, K] = gy^T x on tensor cores (gy [M, N], x [M, K], CUDA fp32 contiguous)."""
+    M, N = gy.shape
+    K = x.shape[1]
+    P = lib().envidr_wgrad_tc_partials(M)
+    partial = torch.empty(P, N, K, dtype=torch.float32, device=gy.device)
+    sc = _pow2_scales(gy, x)
+    check(lib().envidr_wgrad_tc(ptr(gy), ptr(x), M, N, K, ptr(sc), ptr(partial), variant, stream()), "wgrad_tc")
+    return partial.sum(0)
+
+
+class _linear_tc(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        x2 = x.detach().float().contiguous()
+        Wc = W.detach().float().contiguous()
+        bc = None if b is None else b.detach().float().contiguous()
+        y = _run(x2, _image(Wc), bc, Wc.shape[0], relu)
+        ctx.save_for_backward(x2, Wc, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, b is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x2, Wc, y = ctx.saved_tensors
+        gy = gy.float().contiguous()
+        if ctx.relu:
+            gy = gy * (y > 0)
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _run(gy, _image(Wc.t().contiguous()), None, Wc.shape[1], False)       # dY W = dY (W^T)^T
+        if ctx.needs_input_grad[1]:
+            gW = wgrad_tc(gy, x2) if WGRAD_TC else gy.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gW, gb, None
+
+
+def linear_tc(x: torch.Tensor, W: torch.Tensor, b=None, relu: bool = False) -> torch.Tensor:
+    """x [M, K] (CUDA fp32), W [N, K], b [N] or None -> [M, N]."""
+    return _linear_tc.apply(x, W, b, relu)

@@ -9,8 +9,9 @@ The operators underneath are the library's own kernels, all differentiable the w
 `raymarching.march_rays_train` (count -> scan -> write, deterministic slots), `hashencoder.hash_encode` (forward with
 dy_dx, backward, second-order backward -- the normals feed the colour MLPs and the eikonal term),
 `raymarching.composite_rays_train` (warp-scan forward / backward), `raymarching.get_scatter_idx`, and the
-IDE encoder.  The dense layers run through torch (cuBLAS) here; the inference path has them fused on tcgen05
-(csrc/field_tc.cu, geom_tc.cu, shade_tc.cu) -- a fused forward+backward is the next step for this branch.
+IDE encoder (forward / backward kernels).  The dense layers of the env / colour / diffuse / renv MLPs run on tensor cores
+(`linear_tc`: forward and data gradient, csrc/linear_tc.cu, same fp16 hi/lo split as the inference kernels); their weight
+gradients and sdf_net (double backward for the normals) stay cuBLAS fp32.
 
 `TrainOps` exists so that tests can drive the same glue on the CPU with the oracle's operators; the default is the CUDA
 library and there is no fallback: without it every call raises.
@@ -83,8 +84,15 @@ class TrainableField(nn.Module):
     def stack(self, name: str) -> List:
         return [(getattr(self, f"{name}_w{i}"), getattr(self, f"{name}_b{i}")) for i in range(self.n_layers[name])]
 
+    tc_linear: bool = True      # env / colour / diffuse / renv layers through csrc/linear_tc.cu on CUDA tensors (sdf_net: torch, double backward)
+
     def mlp(self, name: str, x: torch.Tensor) -> torch.Tensor:
         layers = self.stack(name)
+        if self.tc_linear and name != "sdf" and x.is_cuda and x.dtype == torch.float32:
+            from .linear_tc import linear_tc
+            for i, (W, b) in enumerate(layers):
+                x = linear_tc(x, W, b, relu=(i != len(layers) - 1))
+            return x
         for i, (W, b) in enumerate(layers):
             x = F.linear(x, W, b)
             if i != len(layers) - 1:

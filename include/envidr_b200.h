@@ -302,6 +302,25 @@ int envidr_render_last_stats(uint32_t stats[4]);
  * tcgen05.mma chain (pins the UMMA descriptor / operand layout conventions of the tensor-core path on hardware). */
 int envidr_tc_probe(const float* A, const float* B, float* D, uint32_t N, uint32_t K, uint32_t variant, envidr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense layer on tensor cores for the TRAINING branch (the reference: nn.Linear -> cuBLAS fp32, nerf/network.py:527-698).
+ * Y[M,N] = act(X[M,K] W^T + bias), fp32 in / out, operands split into fp16 hi + lo (three tcgen05.mma per K step, fp32
+ * accumulate): fp32-level accuracy.  N, K <= 256.  The weight image is built once per weight value by envidr_linear_tc_pack
+ * (W [N,K] row-major, the torch layout); the data gradient dY W uses the same kernel on the image of W^T.
+ * ---------------------------------------------------------------------------------------------- */
+uint64_t envidr_linear_tc_image_bytes(uint32_t N, uint32_t K);
+int envidr_linear_tc_pack(const float* W, uint32_t N, uint32_t K, void* img, envidr_stream_t stream);
+int envidr_linear_tc(const float* X, uint32_t M, uint32_t K, const void* img, const float* bias /* [N] or NULL */, uint32_t N,
+                     int relu, float* Y, envidr_stream_t stream);
+
+/* Weight gradient dW [N,K] = dY^T X of the layer above (dY [M,N], X [M,K] fp32 row-major), same split precision; both operands
+ * are fed MN-major, i.e. as they lie in memory.  partial: [envidr_wgrad_tc_partials(M), N, K] floats, one partial sum per CTA
+ * (the caller adds them up); scales (device, 3 floats): power-of-two pre-scales of dY and X and the inverse of their product
+ * (a loss gradient sits around 1e-7, below fp16's normal range).  variant: 0 (1 swaps the descriptor's LBO / SBO; test hook). */
+uint32_t envidr_wgrad_tc_partials(uint32_t M);
+int envidr_wgrad_tc(const float* dY, const float* X, uint32_t M, uint32_t N, uint32_t K, const float* scales, float* partial,
+                    int variant, envidr_stream_t stream);
+
 /* Instrumentation (bench.py): launches issued by envidr_render_rays in this process; CUDA-event timing of the
  * field kernel (the dominant kernel) on its launch stream. */
 uint64_t envidr_launch_count(void);

@@ -167,3 +167,35 @@ def test_graphed_train_step_equals_eager(dev):
         if n in eager:
             scale = float(eager[n].abs().max()) + 1e-20
             assert float((p.grad - eager[n]).abs().max()) <= 1e-4 * scale, n      # float atomics reorder between runs
+
+
+@pytest.mark.parametrize("M,K,N,relu,bias", [(1000, 72, 256, True, True), (140000, 256, 256, True, True), (777, 256, 12, False, True),
+                                             (513, 28, 64, True, True), (300, 64, 3, False, False), (128, 4, 64, True, True),
+                                             (1, 24, 32, True, True)])
+def test_linear_tc_forward_backward(dev, M, K, N, relu, bias):
+    """csrc/linear_tc.cu (tcgen05, fp16 hi/lo split operands) against float64 torch: forward, data gradient (same kernel on W^T),
+    weight / bias gradients.  Tolerance: 5e-6 of the output scale (fp32-level accuracy: 22-bit operands, fp32 accumulation)."""
+    from envidr_b200.linear_tc import linear_tc
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) if bias else None
+    gy = torch.randn(M, N, generator=g)
+    xd, Wd = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    bd = None if b is None else b.double().requires_grad_(True)
+    yd = torch.nn.functional.linear(xd, Wd, bd)
+    if relu:
+        yd = torch.relu(yd)
+    yd.backward(gy.double())
+    xg, Wg = x.to(dev).requires_grad_(True), W.to(dev).requires_grad_(True)
+    bg = None if b is None else b.to(dev).requires_grad_(True)
+    y = linear_tc(xg, Wg, bg, relu)
+    y.backward(gy.to(dev))
+    scale = float(yd.abs().max())
+    assert float((y.detach().cpu().double() - yd.detach()).abs().max()) <= 5e-6 * scale
+    kink = (yd.detach().abs() < 1e-5 * scale) if relu else torch.zeros_like(yd, dtype=torch.bool)     # ReLU mask may flip at 0
+    if not bool(kink.any()):
+        assert float((xg.grad.cpu().double() - xd.grad).abs().max()) <= 5e-6 * float(xd.grad.abs().max() + 1e-30)
+        assert float((Wg.grad.cpu().double() - Wd.grad).abs().max()) <= 2e-5 * float(Wd.grad.abs().max() + 1e-30)
+        if bias:
+            assert float((bg.grad.cpu().double() - bd.grad).abs().max()) <= 2e-5 * float(bd.grad.abs().max() + 1e-30)
