@@ -52,9 +52,14 @@ class RenderOpts(ctypes.Structure):
                 ("geometry_only", ctypes.c_int32), ("input_alpha", ctypes.c_int32), ("n_step_floor", ctypes.c_uint32)]
 
 
+class SampleLog(ctypes.Structure):
+    _fields_ = [("rec", ctypes.c_void_p), ("sigma", ctypes.c_void_p), ("delta", ctypes.c_void_p), ("ray", ctypes.c_void_p),
+                ("seq", ctypes.c_void_p), ("capacity", ctypes.c_uint64)]
+
+
 class RenderOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("image", "depth", "weights_sum", "normal_image", "diffuse_image", "specular_image",
-                                              "roughness_image", "sample_count")]
+                                              "roughness_image", "sample_count", "log")]
 
 
 _SCALARS = {"uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "int32_t": ctypes.c_int32, "int": ctypes.c_int,

@@ -622,10 +622,12 @@ static int ensure_ide_field(uint32_t deg) {
 constexpr size_t kFieldSmem = (size_t)(kTile * kLd + 2 * kWbuf + S_COUNT * kTile) * sizeof(float);
 
 // timing hook (bench.py): when non-null, ev[0]/ev[1] are recorded around the dominant kernel of this call
+// mode 0: full field; 1: geometry only (sigma, normal); 2: geometry only + geometry records captured through `cap`
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
                          const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
-                         cudaEvent_t* ev, int* ev_recorded) {
+                         cudaEvent_t* ev, int* ev_recorded, const RecCapture* cap) {
     if (ev_recorded) *ev_recorded = 0;
+    if (mode == 2) ENVIDR_REQUIRE(cap && cap->rec && field->precision == 1, ENVIDR_E_BADARG, "record capture needs the tensor-core field");
     Layout lay;
     int rc = build_layout(field, &lay);
     if (rc) return rc;
@@ -665,6 +667,10 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
                    "field->packed too small for the tensor-core images (envidr_field_pack_bytes)");
     float* rec = nullptr;
     float* feat = nullptr;
+    if (mode == 2) {
+        ENVIDR_REQUIRE(geom_tc, ENVIDR_E_UNSUPPORTED, "record capture needs the tensor-core geometry kernel");
+        return geom_tc_launch(tcgeom, xyzs, dirs, M_dev, M_host, 0, cap->rec, out, st, cap->base_dev, cap->cap);
+    }
     if (mode != 1) {
         const uint64_t cap = M_dev ? field->scratch_samples : M_host;
         ENVIDR_REQUIRE(field->scratch && field->scratch_samples >= cap && cap > 0, ENVIDR_E_WORKSPACE,
@@ -753,10 +759,38 @@ int envidr_field_forward(const envidr_field* field, const float* xyzs, const flo
                          const envidr_field_out* out, envidr_stream_t stream) {
     cudaEvent_t* ev = (mode != 1 && field && field->precision == 1) ? timing_acquire() : nullptr;
     int recorded = 0;
-    const int rc = field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), ev, &recorded);
+    ENVIDR_REQUIRE(mode == 0 || mode == 1, ENVIDR_E_BADARG, "mode must be 0 or 1");
+    const int rc = field_forward_launch(field, xyzs, dirs, r_images, nullptr, M, mode, out, as_stream(stream), ev, &recorded, nullptr);
     if (ev && recorded) timing_commit();
     if (rc == 0 && M > 0) g_launches += (field->precision == 1 && mode != 1) ? 3 : 1;
     return rc;
+}
+
+int envidr_field_forward_records(const envidr_field* field, const float* rec, const float* r_images, uint32_t M,
+                                 const envidr_field_out* out, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(field && out, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(field->precision == 1, ENVIDR_E_UNSUPPORTED, "field_forward_records: tensor-core field only (precision = 1)");
+    if (M == 0) return 0;
+    ENVIDR_REQUIRE(rec && out->rgb, ENVIDR_E_BADARG, "null pointer");
+    Layout lay;
+    int rc = build_layout(field, &lay);
+    if (rc) return rc;
+    TcEnv tcenv; TcGeom tcgeom; TcShade tcshade;
+    uint64_t total = 0, total2 = 0, total3 = 0;
+    ENVIDR_REQUIRE(tc_layout(field, lay.floats * sizeof(float), &tcenv, &total), ENVIDR_E_UNSUPPORTED, "env_net outside the tensor-core kernel");
+    if (!geom_tc_layout(field, total, &tcgeom, &total2)) total2 = total;
+    ENVIDR_REQUIRE(shade_tc_layout(field, total2, &tcshade, &total3), ENVIDR_E_UNSUPPORTED, "shading heads outside the tensor-core kernel");
+    ENVIDR_REQUIRE(field->packed && field->packed_bytes >= total3, ENVIDR_E_WORKSPACE, "field->packed too small");
+    ENVIDR_REQUIRE(field->scratch && field->scratch_samples * 2 >= M, ENVIDR_E_WORKSPACE, "field->scratch: 128 B per sample needed");
+    cudaStream_t st = as_stream(stream);
+    float* feat = reinterpret_cast<float*>(field->scratch);
+    cudaEvent_t* ev = timing_acquire();
+    if (ev) cudaEventRecord(ev[0], st);
+    rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, nullptr, M, st);
+    if (ev) { cudaEventRecord(ev[1], st); timing_commit(); }
+    if (rc) return rc;
+    g_launches += 2;
+    return shade_tc_launch(tcshade, rec, feat, r_images, nullptr, M, out, st);
 }
 
 }  // extern "C"

@@ -38,7 +38,9 @@ struct TcGeom {
 bool geom_tc_layout(const envidr_field* f, uint64_t base_bytes, TcGeom* out, uint64_t* total_bytes);
 int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStream_t st);
 int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
-                   const envidr_field_out* out, cudaStream_t st);
+                   const envidr_field_out* out, cudaStream_t st, const uint32_t* rec_base_dev = nullptr, uint32_t rec_cap = 0xFFFFFFFFu);
+// capture of the geometry records of a geometry-only pass (envidr_sample_log): external record buffer + running base index
+struct RecCapture { float* rec; const uint32_t* base_dev; uint32_t cap; };
 
 // ---- shading heads on tensor cores (shade_tc.cu) -----------------------------------------------------------
 struct TcShade {

@@ -61,7 +61,8 @@ __device__ __forceinline__ void g_store32(uint8_t* hid, uint32_t row, uint32_t c
 
 __global__ void __launch_bounds__(kGThreads, 1)
 k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restrict__ dirs, const uint32_t* __restrict__ M_dev,
-          uint32_t M_host, int mode, float* __restrict__ rec, const GeomOutDev O) {
+          uint32_t M_host, int mode, float* __restrict__ rec, const GeomOutDev O, const uint32_t* __restrict__ rec_base_dev,
+          uint32_t rec_cap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem;                                           // resident weight images + float region
     uint8_t* s_enc = smem + G.res_bytes_al;                        // two encoding operands (gather -> stage 0)
@@ -414,16 +415,20 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
                                             b2 = nx * R[2] + ny * R[5] + nz * R[8];
                                 nex = b0; ney = b1; nez = b2;
                             }
-                            float4* q4 = reinterpret_cast<float4*>(rec + (size_t)m * kTcRecFloats);
-                            float gq[16];
-                            #pragma unroll
-                            for (int i = 0; i < 15; i++) gq[i] = (i < Gd) ? outv[1 + i] * ginv : 0.f;
-                            gq[15] = 0.f;
-                            #pragma unroll
-                            for (int i = 0; i < 4; i++) q4[i] = make_float4(gq[4 * i], gq[4 * i + 1], gq[4 * i + 2], gq[4 * i + 3]);
-                            q4[4] = make_float4(nx, ny, nz, ndot);
-                            q4[5] = make_float4(rough, blend, nex, ney);
-                            q4[6] = make_float4(nez, wrx, wry, wrz);
+                            // record slot: batch-local index, or (capture of a geometry pass) offset by the running sample total
+                            const size_t ri = (size_t)(rec_base_dev ? *rec_base_dev : 0u) + m;
+                            if (ri < rec_cap) {
+                                float4* q4 = reinterpret_cast<float4*>(rec + ri * kTcRecFloats);
+                                float gq[16];
+                                #pragma unroll
+                                for (int i = 0; i < 15; i++) gq[i] = (i < Gd) ? outv[1 + i] * ginv : 0.f;
+                                gq[15] = 0.f;
+                                #pragma unroll
+                                for (int i = 0; i < 4; i++) q4[i] = make_float4(gq[4 * i], gq[4 * i + 1], gq[4 * i + 2], gq[4 * i + 3]);
+                                q4[4] = make_float4(nx, ny, nz, ndot);
+                                q4[5] = make_float4(rough, blend, nex, ney);
+                                q4[6] = make_float4(nez, wrx, wry, wrz);
+                            }
                         }
                     }
                 }
@@ -509,7 +514,7 @@ int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStrea
 }
 
 int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
-                   const envidr_field_out* out, cudaStream_t st) {
+                   const envidr_field_out* out, cudaStream_t st, const uint32_t* rec_base_dev, uint32_t rec_cap) {
     const size_t smem = (size_t)g.res_bytes_al + 2 * kGEnc + 2 * kGHid + 16 * sizeof(GLevel) + 16 * 8;
     static size_t attr_set = 0;
     if (attr_set < smem) {
@@ -521,7 +526,7 @@ int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const 
     if (!M_dev) grid = min((uint32_t)kSMs, (M_host + 127) / 128);
     if (grid == 0) return 0;
     GeomOutDev O{out->sigma, out->normal, out->sdf, out->roughness, out->grad_x};
-    k_geom_tc<<<grid, kGThreads, smem, st>>>(g, xyzs, dirs, M_dev, M_host, mode, rec, O);
+    k_geom_tc<<<grid, kGThreads, smem, st>>>(g, xyzs, dirs, M_dev, M_host, mode, rec, O, rec_base_dev, rec_cap);
     return check_launch("geom_tc");
 }
 

@@ -15,9 +15,10 @@
 
 namespace envidr {
 
+struct RecCapture { float* rec; const uint32_t* base_dev; uint32_t cap; };        // same as field_tc.cuh
 int field_forward_launch(const envidr_field* field, const float* xyzs, const float* dirs, const float* r_images,
                          const uint32_t* M_dev, uint32_t M_host, int mode, const envidr_field_out* out, cudaStream_t st,
-                         cudaEvent_t* ev, int* ev_recorded);
+                         cudaEvent_t* ev, int* ev_recorded, const RecCapture* cap);
 
 constexpr int kMarchBlock = 128;
 constexpr int kMaxNStep = 8;
@@ -47,6 +48,10 @@ struct RenderBuffers {
 struct RenderOutDev {
     float *image, *depth, *weights_sum, *normal_image, *diffuse_image, *specular_image, *roughness_image;
     int32_t* sample_count;
+    // sample log (envidr_sample_log): per marched sample, at index total_samples_before_this_iteration + batch slot
+    float *log_sigma, *log_delta;
+    int32_t *log_ray, *log_seq;
+    uint32_t log_cap;
 };
 
 __global__ void __launch_bounds__(256) k_render_init(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N,
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
     const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
     const bool active = !(n_alive == 0 || ctr->step_total >= max_steps);
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t log_base = ctr->total_samples_lo;       // samples of the earlier iterations (advanced by the last block, below)
     if (active) {
         const int32_t* __restrict__ alive = B.alive[ctr->iters & 1];
         int32_t* __restrict__ alive_next = B.alive[(ctr->iters & 1) ^ 1];
@@ -230,12 +236,20 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
                 if (O.specular_image) { const float* q = O.specular_image + 3 * index; cs[0] = q[0]; cs[1] = q[1]; cs[2] = q[2]; }
                 if (O.roughness_image) rgh = O.roughness_image[index];
                 uint32_t step = 0, used = 0;
+                const uint32_t seq0 = (O.log_ray && O.sample_count) ? (uint32_t)O.sample_count[index] : 0u;
                 while (step < n_step) {
                     if (step >= cnt) break;                       // zero-delta slot in the reference layout
                     used++;
                     const size_t m = (size_t)sl.x + step;
                     const float2 dl = *reinterpret_cast<const float2*>(B.s_delta + 2 * m);
                     const float sg = B.s_sigma[m];
+                    if (O.log_ray) {
+                        const size_t gi = (size_t)log_base + m;
+                        if (gi < O.log_cap) {
+                            O.log_ray[gi] = index; O.log_seq[gi] = (int32_t)(seq0 + used - 1);
+                            O.log_sigma[gi] = sg; *reinterpret_cast<float2*>(O.log_delta + 2 * gi) = dl;
+                        }
+                    }
                     const float alpha = input_alpha ? 0.0f + sg : 1.0f - __expf(-sg * dl.x);
                     const float T = 1 - ws;
                     const float w = alpha * T;
@@ -250,6 +264,12 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
                     if (O.roughness_image) rgh += w * B.s_rough[m];
                     if (T < T_thresh) break;
                     step++;
+                }
+                if (O.log_ray) {                                  // marched but not composited: not part of any replay
+                    for (uint32_t s2 = used; s2 < cnt; s2++) {
+                        const size_t gi = (size_t)log_base + (size_t)sl.x + s2;
+                        if (gi < O.log_cap) O.log_ray[gi] = -1;
+                    }
                 }
                 keep = !(step < n_step);
                 if (keep) B.rays_t[index] = t;
@@ -292,6 +312,25 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
         }
         ctr->done_blocks = 0;
     }
+}
+
+// sample log (iteration-major, one entry per marched sample) -> ray-contiguous arrays of the samples a later pass composites.
+// One warp per log entry group: 8 lanes move the 128-byte record of one sample (float4 each), 4 samples per warp.
+__global__ void __launch_bounds__(256) k_permute_log(const float4* __restrict__ rec, const float* __restrict__ sigma, const float2* __restrict__ delta,
+                                                    const int32_t* __restrict__ ray, const int32_t* __restrict__ seq, uint64_t total,
+                                                    const int32_t* __restrict__ ray_offset, float4* __restrict__ rec_out,
+                                                    float* __restrict__ sigma_out, float2* __restrict__ delta_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t g = t >> 3;
+    const uint32_t part = (uint32_t)t & 7u;
+    if (g >= total) return;
+    const int32_t r = ray[g];
+    if (r < 0) return;
+    const int32_t off = ray_offset[r];
+    if (off < 0) return;
+    const uint64_t dst = (uint64_t)off + (uint32_t)seq[g];
+    rec_out[dst * 8 + part] = rec[g * 8 + part];
+    if (part == 0) { sigma_out[dst] = sigma[g]; delta_out[dst] = delta[g]; }
 }
 
 // image += (1 - ws) * bg ; normal_image <- F.normalize(normal_image, eps=1e-10)   (cuda_ray.py:348-359)
@@ -396,7 +435,16 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     B.ctr = (Counters*)(w + L.ctr);
     B.occ_box = (int*)(w + L.occ_box);
     RenderOutDev O{out->image, out->depth, out->weights_sum, out->normal_image, out->diffuse_image, out->specular_image,
-                   out->roughness_image, out->sample_count};
+                   out->roughness_image, out->sample_count, nullptr, nullptr, nullptr, nullptr, 0u};
+    RecCapture capture{nullptr, nullptr, 0u};
+    if (out->log) {
+        const envidr_sample_log* lg = out->log;
+        ENVIDR_REQUIRE(opts->geometry_only && field->precision == 1, ENVIDR_E_BADARG, "sample log: geometry_only passes of the tensor-core field");
+        ENVIDR_REQUIRE(lg->rec && lg->sigma && lg->delta && lg->ray && lg->seq && out->sample_count, ENVIDR_E_BADARG, "sample log: null buffer");
+        O.log_sigma = lg->sigma; O.log_delta = lg->delta; O.log_ray = lg->ray; O.log_seq = lg->seq;
+        O.log_cap = (uint32_t)(lg->capacity > 0xFFFFFFFFull ? 0xFFFFFFFFull : lg->capacity);
+        capture = RecCapture{lg->rec, &B.ctr->total_samples_lo, O.log_cap};
+    }
     if (opts->geometry_only) { O.image = out->normal_image; O.diffuse_image = nullptr; O.specular_image = nullptr; O.roughness_image = nullptr; }
     const float* a = opts->aabb;
     k_render_init<<<ceil_div(N, 256), 256, 0, st>>>(rays_o, rays_d, N, nsf, opts->min_near, a[0], a[1], a[2], a[3], a[4], a[5], B, O);
@@ -434,7 +482,8 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
             int recorded = 0;
             if (timed) while (g_tev_created < 2 * (g_tev_used + 1)) cudaEventCreate(&g_tev[g_tev_created++]);
             rc = field_forward_launch(&fld, B.s_xyz, B.s_dir, r_images ? B.s_rimg : nullptr, &B.ctr->M, 0,
-                                      opts->geometry_only ? 1 : 0, &fo, st, timed ? &g_tev[2 * g_tev_used] : nullptr, &recorded);
+                                      opts->geometry_only ? (capture.rec ? 2 : 1) : 0, &fo, st, timed ? &g_tev[2 * g_tev_used] : nullptr,
+                                      &recorded, capture.rec ? &capture : nullptr);
             if (rc) return rc;
             if (timed && recorded) g_tev_used++;
             g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;      // march, [geom, env, shade | field], composite
@@ -463,6 +512,20 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     cudaMemcpyAsync(g_host_flag + 9, &B.ctr->total_samples_lo, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(g_events[0], st);
     return check_launch("render_finish");
+}
+
+int envidr_permute_sample_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out,
+                              float* sigma_out, float* delta_out, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(log && ray_offset && rec_out && sigma_out && delta_out, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(log->rec && log->sigma && log->delta && log->ray && log->seq, ENVIDR_E_BADARG, "sample log: null buffer");
+    ENVIDR_REQUIRE(total <= log->capacity, ENVIDR_E_WORKSPACE, "sample log overflowed its capacity; the pass has to be marched again");
+    if (total == 0) return 0;
+    const uint64_t threads = total * 8;
+    k_permute_log<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(log->rec), log->sigma, reinterpret_cast<const float2*>(log->delta), log->ray, log->seq, total,
+        ray_offset, reinterpret_cast<float4*>(rec_out), sigma_out, reinterpret_cast<float2*>(delta_out));
+    g_launches += 1;
+    return check_launch("permute_sample_log");
 }
 
 /* blocks until the last envidr_render_rays call of this process has finished; stats = {iterations, samples_lo, samples_hi, 0} */

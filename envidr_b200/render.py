@@ -40,6 +40,9 @@ class RenderConfig:
     # main pass of the indirect-reflection scheme as ONE batch over the sample counts the geometry pass found (render_rays_replay)
     # instead of re-discovering ray termination iteration by iteration; False = the reference's iterative schedule
     replay_main_pass: bool = True
+    # with replay_main_pass and the tensor-core field: the geometry pass also logs its per-sample geometry records, and the main
+    # pass shades those (env_net + shading heads) instead of marching and evaluating the hash grid + sdf_net a second time
+    reuse_geometry: bool = True
     # n_step floor of the secondary (reflected-ray) pass: it runs over few rays, so the reference schedule n_step = N // n_alive
     # starts at 1 and issues ~50 launches of <= 71 k samples; a floor only changes the batching (same composited samples).  1 = reference
     secondary_n_step_floor: int = 4
@@ -49,6 +52,7 @@ class RenderConfig:
 
 
 _workspaces: Dict[tuple, torch.Tensor] = {}
+_log_need: Dict[int, int] = {}        # rays of a frame -> samples its geometry pass marched last time (sizes the sample log)
 
 
 def _workspace(N: int, device, n_step_floor: int = 1) -> torch.Tensor:
@@ -67,7 +71,7 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
                 bg_color=1.0, r_images: Optional[torch.Tensor] = None, geometry_only: bool = False,
                 env_rot_radian: Optional[float] = None, get_normal_image: bool = True, visual_items: Sequence[str] = (),
                 perturb: bool = False, max_steps: Optional[int] = None, min_near: Optional[float] = None,
-                sample_count: bool = False, n_step_floor: int = 1) -> Dict[str, torch.Tensor]:
+                sample_count: bool = False, n_step_floor: int = 1, log: Optional["SampleLogBuffers"] = None) -> Dict[str, torch.Tensor]:
     """One run_cuda inference pass over N rays.  Returns image [N,3], depth [N], weights_sum [N] and
     (optionally) normal_image / diffuse_image / specular_image / roughness_image, all on the device."""
     if field._packed is None:
@@ -91,10 +95,14 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
             res["specular_image"] = torch.empty(N, 3, **f32)
         if "roughness" in visual_items or "specular" in visual_items:
             res["roughness_image"] = torch.empty(N, **f32)
-    if sample_count:
+    if sample_count or log is not None:
         res["sample_count"] = torch.empty(N, dtype=torch.int32, device=dev)
     for k, t in res.items():
         setattr(out, k, t.data_ptr())
+    if log is not None:
+        assert geometry_only and field.precision == "tc", "sample log: geometry-only passes of the tensor-core field"
+        log_struct = log.cstruct()
+        out.log = ctypes.addressof(log_struct)
     opts = _lib.RenderOpts()
     opts.bound, opts.dt_gamma, opts.T_thresh = cfg.bound, cfg.dt_gamma, cfg.T_thresh
     opts.min_near = cfg.min_near if min_near is None else min_near
@@ -132,6 +140,94 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
                                    stream()), "render_rays")
     if "roughness_image" in res:
         res["roughness_image"] = res["roughness_image"][..., None]
+    return res
+
+
+class SampleLogBuffers:
+    """Device buffers of an envidr_sample_log (one entry per marched sample of a geometry-only pass)."""
+
+    def __init__(self, capacity: int, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.capacity = int(capacity)
+        self.rec = torch.empty(self.capacity, 32, **f32)
+        self.sigma = torch.empty(self.capacity, **f32)
+        self.delta = torch.empty(self.capacity, 2, **f32)
+        self.ray = torch.empty(self.capacity, dtype=torch.int32, device=device)
+        self.seq = torch.empty(self.capacity, dtype=torch.int32, device=device)
+
+    def cstruct(self) -> _lib.SampleLog:
+        s = _lib.SampleLog()
+        s.rec, s.sigma, s.delta, s.ray, s.seq = (t.data_ptr() for t in (self.rec, self.sigma, self.delta, self.ray, self.seq))
+        s.capacity = self.capacity
+        return s
+
+
+_logs: Dict[str, SampleLogBuffers] = {}
+
+
+def _sample_log(device, need: int) -> SampleLogBuffers:
+    """One log per device, grown geometrically (a frame's geometry pass marches a few million samples: 140 B each)."""
+    lg = _logs.get(str(device))
+    if lg is None or lg.capacity < need:
+        lg = SampleLogBuffers(max(need, 1 << 20), device)
+        _logs[str(device)] = lg
+    return lg
+
+
+def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_mask: torch.Tensor, cfg: RenderConfig, *,
+                         bg_color=0.0, r_images: Optional[torch.Tensor] = None, visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+    """Main pass from the geometry pass's sample log: the samples of the rays in `ray_mask` are gathered ray by ray
+    (envidr_permute_sample_log), shaded from their geometry records (envidr_field_forward_records: env_net + shading heads
+    only) and composited (envidr_composite_rays_replay).  counts [N_all] = samples composited per ray of the geometry pass;
+    r_images [n_masked, 4] in the order of the masked rays.  Returns per-masked-ray images."""
+    dev = counts.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    cm = torch.where(ray_mask, counts, torch.zeros_like(counts)).to(torch.int64)
+    incl = torch.cumsum(cm, 0)
+    M = int(incl[-1].item()) if cm.numel() else 0
+    ray_off = torch.where(ray_mask, incl - cm, torch.full_like(cm, -1)).to(torch.int32)
+    n_r = int(ray_mask.sum().item())
+    rec = torch.empty(M, 32, **f32)
+    sigma, delta = torch.empty(M, **f32), torch.empty(M, 2, **f32)
+    lstruct = log.cstruct()
+    check(lib().envidr_permute_sample_log(ctypes.byref(lstruct), total, ptr(ray_off), ptr(rec), ptr(sigma), ptr(delta), stream()),
+          "permute_sample_log")
+    # rays of the pass in masked order: (ray id = position among the masked rays, offset, count)
+    rays = torch.stack([torch.arange(n_r, dtype=torch.int32, device=dev), ray_off[ray_mask], counts[ray_mask].to(torch.int32)], -1).contiguous()
+    r_s = None
+    if r_images is not None:
+        r_s = torch.empty(M, 4, **f32)
+        check(lib().envidr_scatter_ray_rows4(ptr(rays), n_r, M, ptr(r_images.float().contiguous().view(-1, 4)), ptr(r_s), stream()),
+              "scatter_ray_rows4")
+    want = {"rgb": torch.empty(M, 3, **f32)}
+    if "diffuse" in visual_items:
+        want["c_diffuse"] = torch.empty(M, 3, **f32)
+    if "specular" in visual_items:
+        want["c_specular"] = torch.empty(M, 3, **f32)
+    rough = rec[:, 20].contiguous() if ("roughness" in visual_items or "specular" in visual_items) else None
+    if field._scratch is None or field._scratch.numel() < 32 * (M + 2):
+        field._scratch = torch.empty(32 * (M + 2), **f32)
+    fo = _lib.FieldOut()
+    for k, t in want.items():
+        setattr(fo, k, t.data_ptr())
+    f = field.cstruct()
+    check(lib().envidr_field_forward_records(ctypes.byref(f), ptr(rec), ptr(r_s), M, ctypes.byref(fo), stream()), "field_forward_records")
+    res = {"image": torch.empty(n_r, 3, **f32), "depth": torch.empty(n_r, **f32), "weights_sum": torch.empty(n_r, **f32)}
+    if "c_diffuse" in want:
+        res["diffuse_image"] = torch.empty(n_r, 3, **f32)
+    if "c_specular" in want:
+        res["specular_image"] = torch.empty(n_r, 3, **f32)
+    if rough is not None:
+        res["roughness_image"] = torch.empty(n_r, **f32)
+    check(lib().envidr_composite_rays_replay(ptr(sigma), ptr(want["rgb"]), None, ptr(want.get("c_diffuse")), ptr(want.get("c_specular")),
+                                             ptr(rough), ptr(delta), ptr(rays), None, M, n_r, cfg.T_thresh, int(cfg.input_alpha),
+                                             ptr(res["weights_sum"]), ptr(res["depth"]), ptr(res["image"]), None, ptr(res.get("diffuse_image")),
+                                             ptr(res.get("specular_image")), ptr(res.get("roughness_image")), stream()), "composite_rays_replay")
+    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32)
+    res["image"] = res["image"] + (1 - res["weights_sum"]).unsqueeze(-1) * bg
+    if "roughness_image" in res:
+        res["roughness_image"] = res["roughness_image"][..., None]
+    res["_samples"] = M
     return res
 
 
@@ -235,10 +331,17 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             stats.append(last_stats())
     else:
         dt = 2 * SQRT3 / cfg.indir_max_steps
+        reuse = cfg.replay_main_pass and cfg.reuse_geometry and field.precision == "tc"
+        log = _sample_log(rays_o.device, _log_need.get(N, 8 * 1 << 20)) if reuse else None
         geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
-                          sample_count=cfg.replay_main_pass)
+                          sample_count=cfg.replay_main_pass, log=log)
+        geo_stats = last_stats() if (stats is not None or reuse) else None
         if stats is not None:
-            stats.append(last_stats())
+            stats.append(geo_stats)
+        if reuse:
+            _log_need[N] = int(geo_stats["samples"] * 1.25) + 4096          # size the log for the next frame of this shape
+            if geo_stats["samples"] > log.capacity:                          # overflowed: this frame marches the main pass again
+                reuse = False
         normals = geo["normal_image"]
         depth = geo["depth"] - dt
         weights_sum = geo["weights_sum"]
@@ -258,7 +361,14 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         ref2ray = ref_mask[ray_mask]
         r_img = ref_image.new_zeros(ref2ray.shape[0], 4)
         r_img[ref2ray] = ref_image
-        if cfg.replay_main_pass:
+        if reuse:
+            main = render_rays_from_log(field, log, geo_stats["samples"], geo["sample_count"], ray_mask, cfg, bg_color=0.0, r_images=r_img,
+                                        visual_items=visual_items)
+            if stats is not None:
+                stats.append(dict(iterations=1, samples=int(main.pop("_samples"))))
+            else:
+                main.pop("_samples")
+        elif cfg.replay_main_pass:
             # the main pass visits the rays of the geometry pass again (same origins, same density): replay its sample counts
             main = render_rays_replay(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], geo["sample_count"][ray_mask], cfg, bg_color=0.0,
                                       r_images=r_img, env_rot_radian=env_rot_radian, visual_items=visual_items)

@@ -255,6 +255,20 @@ typedef struct envidr_render_opts {
                              * launches of at most N samples.  The workspace must be sized with envidr_render_workspace_bytes_ex. */
 } envidr_render_opts;
 
+/* Optional capture of a geometry-only pass (tensor-core field): one entry per MARCHED sample, in iteration-major order.
+ * The main pass of the indirect-reflection scheme shades the same samples, so it can reuse the geometry records instead of
+ * marching and evaluating the hash grid + sdf_net again: envidr_permute_sample_log orders them ray by ray,
+ * envidr_field_forward_records runs env_net + the shading heads on them, envidr_composite_rays_replay composites. */
+typedef struct envidr_sample_log {
+    float* rec;             /* [capacity, 32] per-sample geometry record of the tensor-core path (geo feature, normal, n.w_o,
+                             *                roughness, blend weight, rotated normal, reflected direction)                   */
+    float* sigma;           /* [capacity]                                                                                     */
+    float* delta;           /* [capacity, 2]                                                                                  */
+    int32_t* ray;           /* [capacity] ray index of the sample; -1 = marched past the ray's termination (not composited)  */
+    int32_t* seq;           /* [capacity] position of the sample among the composited samples of its ray                      */
+    uint64_t capacity;      /* samples; entries past it are dropped (compare envidr_render_last_stats with it)                */
+} envidr_sample_log;
+
 typedef struct envidr_render_out {
     float* image;           /* [N,3]  (unused when geometry_only)           */
     float* depth;           /* [N]                                          */
@@ -264,6 +278,7 @@ typedef struct envidr_render_out {
     float* specular_image;  /* [N,3]  optional ('specular' in visual_items) */
     float* roughness_image; /* [N]    optional (composited roughness)       */
     int32_t* sample_count;  /* [N]    optional: samples composited per ray (consumed by envidr_march_rays_replay) */
+    const envidr_sample_log* log;   /* optional (geometry_only passes of the tensor-core field): see envidr_sample_log */
 } envidr_render_out;
 
 uint64_t envidr_render_workspace_bytes(uint32_t N);
@@ -284,6 +299,15 @@ int envidr_march_rays_replay(const float* rays_o, const float* rays_d, const uin
                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                              const float* fars, const int32_t* counts, float* xyzs, float* dirs, float* deltas,
                              int32_t* rays, int32_t* counter, envidr_stream_t stream);
+/* Ray-contiguous copy of a sample log: entry g (g < total) with ray r = log->ray[g] >= 0 and ray_offset[r] >= 0 goes to
+ * slot ray_offset[r] + log->seq[g] of rec_out [*,32] / sigma_out / delta_out [*,2].  ray_offset [N]: exclusive scan of the
+ * sample counts over the rays of the next pass, -1 for rays that are not part of it. */
+int envidr_permute_sample_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out,
+                              float* sigma_out, float* delta_out, envidr_stream_t stream);
+/* env_net + shading heads on precomputed geometry records (tensor-core field only): rec [M,32], r_images [M,4] or NULL;
+ * writes out->rgb (and c_diffuse / c_specular when set).  field->scratch needs 128 B per sample. */
+int envidr_field_forward_records(const envidr_field* field, const float* rec, const float* r_images, uint32_t M,
+                                 const envidr_field_out* out, envidr_stream_t stream);
 /* dst[offset_n + s, 0:4] = src[ray_n, 0:4] for every sample of every ray in `rays` [N,3] (per-ray r_images -> per-sample rows). */
 int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const float* src /* [N,4] */, float* dst /* [M,4] */,
                              envidr_stream_t stream);

@@ -199,3 +199,11 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
         assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
     assert float((a["weights_sum"] - b["weights_sum"]).abs().max()) <= 1e-5
     assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["normal_image"], b["normal_image"])
+    # the same with the geometry recomputed (march replay + hash grid + sdf_net) instead of reused from the geometry pass's log
+    st_c = []
+    c = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, reuse_geometry=False, secondary_n_step_floor=4),
+                      bg_color=1.0, visual_items=items, stats=st_c)
+    assert st_c[2]["samples"] == st_a[2]["samples"]
+    for k in ("image", "diffuse_image", "specular_image", "roughness_image"):
+        e = (a[k] - c[k]).abs().reshape(a[k].shape[0], -1).max(-1).values
+        assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
