@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA path (oracle/ref_cuda.py)")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary train-step (BASELINE config 3) measurement")
+    ap.add_argument("--no-extra-warmup", action="store_true", help="profiling runs (ncu --launch-skip counts on exactly W warm-up frames)")
+    ap.add_argument("--no-density", action="store_true", help="skip the auxiliary occupancy-grid update measurement (SURVEY 8 f-1)")
     ap.add_argument("--train-rays", type=int, default=4096)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="env_net arithmetic: tc = tcgen05 tensor cores with fp16 hi/lo split operands (default), fp32 = FFMA path")
@@ -279,6 +281,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = []
+
     def timed(fn, steps, instrument=False):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
@@ -288,7 +292,10 @@ def main():
             fn()
             b.record()
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
+        each = [a.elapsed_time(b) for a, b in ev]
+        if instrument:
+            step_ms.extend(each)
+        ms = sum(each)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,6 +303,14 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # A fresh box needs more than 3 frames (~50 ms) to reach its steady SM clock: keep warming up (untimed) until 1.5 s of
+    # frames have run, so that the resident-input region below is measured in the same state as the e2e region after it.
+    barrier()
+    warm_extra, t_warm = 0, time.time()
+    while not args.no_extra_warmup and time.time() - t_warm < 1.5 and warm_extra < 200:
+        step_resident()
+        torch.cuda.synchronize()
+        warm_extra += 1
     barrier()
     stats = []
     out, _ = step_resident(stats)
@@ -307,7 +322,7 @@ def main():
         sampler.start()
     l0 = lib.envidr_launch_count()
     lib.envidr_render_timing(1)
-    total_ms = timed(step_resident, args.steps)
+    total_ms = timed(step_resident, args.steps, instrument=True)
     fms, fl = __import__("ctypes").c_float(), __import__("ctypes").c_uint32()
     lib.envidr_render_field_time(__import__("ctypes").byref(fms), __import__("ctypes").byref(fl))
     lib.envidr_render_timing(0)
@@ -380,15 +395,30 @@ def main():
                 trn = train_step_bench(fp_cpu, bf, ro, rd, dev, args.train_rays)
             except Exception as e:                      # auxiliary: never take the headline line down with it
                 trn = {"error": repr(e)[:200]}
+        dens = None
+        if world == 1 and not args.no_density:
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("density_bench", os.path.join(ROOT, "profiles", "density_bench.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                prec = fp_cpu.precision
+                dens = mod.measure(dev, fp_cpu, with_reference=not args.no_gpu_reference)
+                fp_cpu.precision = prec
+                dens["what"] = ("NeRFRenderer.update_extra_state (renderer.py:264-352) on the 128^3 grid: ours = envidr_density_grid_update; "
+                                "reference = its own kernels + torch ops + mean().item() (oracle/ref_cuda.update_extra_state)")
+            except Exception as e:                      # auxiliary: never take the headline line down with it
+                dens = {"error": repr(e)[:200]}
         line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "warmup_extra_steps": warm_extra, "ms_each_step": [round(x, 3) for x in step_ms],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (env_net: fp16 hi+lo split operands on tensor cores, fp32 accumulate)" if tcp else "f32",
                 "data": "synthetic", "config": config_dict(args, W, H, indir),
                 "samples_per_sec": world * samples_per_step / (ms_per_step * 1e-3), "samples_per_step_per_gpu": samples_per_step,
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

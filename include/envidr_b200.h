@@ -345,6 +345,41 @@ uint32_t envidr_wgrad_tc_partials(uint32_t M);
 int envidr_wgrad_tc(const float* dY, const float* X, uint32_t M, uint32_t N, uint32_t K, const float* scales, float* partial,
                     int variant, envidr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy-grid maintenance: the caller either side of the march.
+ * Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:264-352) and NeRFRenderer.mark_untrained_grid
+ * (nerf/renderer.py:200-262); the reference has no operator boundary here (torch ops + self.density() + morton3D + packbits
+ * driven from Python, with a .item() sync for mean_density).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct envidr_density_opts {
+    float bound;            /* model.bound                                                     */
+    uint32_t cascade;       /* model.cascade                                                   */
+    uint32_t grid_size;     /* model.grid_size (128)                                           */
+    float decay;            /* update_extra_state(decay=0.95)                                  */
+    float density_thresh;   /* model.density_thresh; the bit field uses min(mean_density, it)  */
+} envidr_density_opts;
+
+uint64_t envidr_density_workspace_bytes(uint32_t cascade, uint32_t grid_size, uint32_t n);
+/* One update_extra_state: query the density (hash grid + sdf_net + Laplace density, x density_scale) at one jittered point per
+ * visited cell, density_grid = max(density_grid * decay, tmp) where both are >= 0, mean_density = mean(clamp(density_grid, 0)),
+ * bitfield = packbits(density_grid, min(mean_density, density_thresh)).  No host synchronisation.
+ *   density_grid [cascade * H^3] in/out (Morton order within a cascade, as the reference), 16-byte aligned
+ *   coords  NULL: full update (renderer.py:279-306), n must be H^3; else int32 [cascade, n, 3] cells to visit
+ *           (partial update, renderer.py:310-336: the caller draws them as the reference does)
+ *   noise   [cascade, n, 3] U[0,1) jitter, indexed like the reference's torch.rand_like(cas_xyzs): for the full update row
+ *           (x * H + y) * H + z (meshgrid order), for the partial update row j of coords; NULL = cell centres (no jitter)
+ *   bitfield [cascade * H^3 / 8] out;  stats: device float[2] out = {mean_density, threshold used}
+ *   workspace: 256-byte aligned, envidr_density_workspace_bytes(cascade, grid_size, n) */
+int envidr_density_grid_update(const envidr_field* field, float* density_grid, const int32_t* coords, const float* noise, uint32_t n,
+                               const envidr_density_opts* opts, uint8_t* bitfield, float* stats, void* workspace,
+                               uint64_t workspace_bytes, envidr_stream_t stream);
+/* mark_untrained_grid: poses [B,4,4] camera-to-world (row-major, device), B <= 1024 per call.  count == NULL:
+ * density_grid[cells seen by none of the B cameras] = -1.  count != NULL (int32 [cascade * H^3], zeroed by the caller): the
+ * per-cell camera counts are accumulated into it instead (several calls for > 1024 poses), then envidr_mark_untrained_apply. */
+int envidr_mark_untrained_grid(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, float bound, uint32_t cascade,
+                               uint32_t grid_size, float* density_grid, int32_t* count, envidr_stream_t stream);
+int envidr_mark_untrained_apply(const int32_t* count, uint32_t n, float* density_grid, envidr_stream_t stream);
+
 /* Instrumentation (bench.py): launches issued by envidr_render_rays in this process; CUDA-event timing of the
  * field kernel (the dominant kernel) on its launch stream. */
 uint64_t envidr_launch_count(void);

@@ -616,3 +616,114 @@ def render(P: Dict, rays_o, rays_d, bitfield, *, indir_ref=False, indir_max_step
     w = res["weights_sum"][:, None]
     res["normal_image"] = res["normal_image"] * w + (1 - w)
     return res
+
+
+# --------------------------------------------------------------------------------------
+# occupancy-grid maintenance (nerf/renderer.py:200-352), restated on the CPU  
+# --------------------------------------------------------------------------------------
+
+def forward_sigma(P: Dict, xyzs: np.ndarray, dtype=torch.float32, enc_fn=None) -> np.ndarray:
+    """NeRFNetwork.density(x)['sigma'] for the shipped scene family (network.py:381-448, 497-522, 32-44): hash encoding ->
+    sdf_net -> Laplace density.  fp32 by default (what the reference computes).  enc_fn(xyz tensor) -> [M, F] replaces the hash
+    encoder (stand-in encoder of tests/golden/make_golden.py).  Returns sigma [M] float32, NOT yet times density_scale."""
+    M = xyzs.shape[0]
+    bound = float(P["bound"])
+    if enc_fn is None:
+        x01 = (np.asarray(xyzs, np.float32) + np.float32(bound)) / np.float32(2 * bound)      # hashgrid.py:161
+        enc, _ = hash_encode_forward(x01, P["embeddings"], P["offsets"], P["per_level_scale"], P["base_resolution"], False)
+        L, C = enc.shape[0], enc.shape[2]
+        enc = torch.from_numpy(np.ascontiguousarray(enc.transpose(1, 0, 2).reshape(M, L * C))).to(dtype)
+        if P.get("enabled_levels", -1) > 0:                                                 # network.py:390-393
+            m = torch.zeros(L, C, dtype=dtype)
+            m[: P["enabled_levels"]] = 1
+            enc = enc * m.reshape(-1)
+    else:
+        enc = enc_fn(torch.from_numpy(np.asarray(xyzs, np.float32))).to(dtype)
+    sdf = _mlp(enc, P["sdf"])[:, 0]
+    beta = min(max(float(P["beta"]), float(P["beta_min"])), float(P["beta_max"]))         # network.py:39-44
+    sigma = (1.0 / beta) * (0.5 + 0.5 * torch.sign(sdf) * torch.expm1(-sdf.abs() / beta))   # network.py:32-37
+    return sigma.to(torch.float32).numpy()
+
+
+CUDA_SCALAR_DIV = False      # True: x / s evaluated as x * fp32(1 / s), torch's CUDA kernel for division by a Python scalar
+
+
+def _div_scalar(x: torch.Tensor, s: float) -> torch.Tensor:
+    """torch `tensor / python_scalar`: an IEEE division on the CPU (what the golden vectors were made with), a multiplication by
+    the fp32 reciprocal on CUDA (ATen BinaryDivTrueKernel.cu) -- where the reference actually runs these lines.  GPU parity
+    tests set CUDA_SCALAR_DIV."""
+    if CUDA_SCALAR_DIV:
+        return x * float(np.float32(1.0) / np.float32(s))
+    return x / s
+
+
+def density_cell_positions(coords: np.ndarray, noise: Optional[np.ndarray], bound_c: float, H: int) -> np.ndarray:
+    """renderer.py:290-301 / 320-331 in fp32, one rounding per torch op: xyzs = 2 * coords.float() / (H - 1) - 1;
+    cas_xyzs = xyzs * (bound - half_grid_size); cas_xyzs += (rand * 2 - 1) * half_grid_size."""
+    hgs = bound_c / H
+    x = torch.from_numpy(np.asarray(coords)).float()
+    x = _div_scalar(2 * x, H - 1) - 1
+    x = x * (bound_c - hgs)
+    if noise is not None:
+        x = x + (torch.from_numpy(np.asarray(noise, np.float32)) * 2 - 1) * hgs
+    return x.numpy()
+
+
+def update_extra_state(P: Dict, density_grid: np.ndarray, *, cascade: int = 1, grid_size: int = 128, decay: float = 0.95,
+                       density_thresh: float = 0.01, density_scale: float = 1.0, noise: Optional[np.ndarray] = None,
+                       coords: Optional[np.ndarray] = None, enc_fn=None, dtype=torch.float32):
+    """NeRFRenderer.update_extra_state (renderer.py:264-352), density-grid half.
+    density_grid [C, H^3] fp32 (Morton order), returned updated (copy).
+    coords None: full update -- every cell, meshgrid (ij) order as the reference's custom_meshgrid(xs, ys, zs) with S = 128;
+    noise [C, H^3, 3] in that order (None: no jitter).  coords [C, n, 3] int: partial update with noise [C, n, 3].
+    Returns (density_grid, mean_density, density_thresh_used, bitfield uint8 [C*H^3/8], tmp_grid)."""
+    H = grid_size
+    grid = np.array(density_grid, np.float32).reshape(cascade, H ** 3).copy()
+    tmp = -np.ones_like(grid)
+    if coords is None:
+        r = np.arange(H, dtype=np.int32)
+        cc = np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3)
+    for cas in range(cascade):
+        bound_c = min(2 ** cas, float(P["bound"]))
+        c = cc if coords is None else np.asarray(coords[cas], np.int32)
+        idx = morton3D(c).astype(np.int64)
+        xyz = density_cell_positions(c, None if noise is None else noise[cas], bound_c, H)
+        sig = forward_sigma(P, xyz, dtype=dtype, enc_fn=enc_fn) * np.float32(density_scale)
+        tmp[cas, idx] = sig                                                          # duplicates: last writer wins (numpy)
+    valid = (grid >= 0) & (tmp >= 0)                                                 # renderer.py:343-345
+    grid[valid] = np.maximum(grid[valid] * np.float32(decay), tmp[valid])
+    mean = float(torch.mean(torch.from_numpy(grid).clamp(min=0)).item())
+    th = min(mean, density_thresh)
+    return grid, mean, th, packbits(grid.reshape(-1), th), tmp
+
+
+def mark_untrained_grid(poses: np.ndarray, intrinsic, *, bound: float = 1.0, cascade: int = 1, grid_size: int = 128,
+                        dtype=np.float64):
+    """NeRFRenderer.mark_untrained_grid (renderer.py:200-262): per-cell count of the cameras that see the cell, Morton order
+    [C, H^3] int32, plus the smallest margin of any of the three comparisons per cell (cells whose margin is at rounding
+    level are ambiguous between two correct fp32 evaluations)."""
+    H = grid_size
+    fx, fy, cx, cy = [float(v) for v in intrinsic]
+    r = np.arange(H, dtype=np.int32)
+    cc = np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3)
+    idx = morton3D(cc).astype(np.int64)
+    world = (_div_scalar(2 * torch.from_numpy(cc).float(), H - 1) - 1).numpy()
+    count = np.zeros((cascade, H ** 3), np.int32)
+    margin = np.full((cascade, H ** 3), np.inf)
+    poses = np.asarray(poses, np.float32)
+    for cas in range(cascade):
+        bound_c = min(2 ** cas, bound)
+        hgs = bound_c / H
+        w = (world * np.float32(bound_c - hgs)).astype(dtype)
+        cnt = np.zeros(H ** 3, np.int32)
+        mg = np.full(H ** 3, np.inf)
+        for b in range(poses.shape[0]):
+            cam = (w - poses[b, :3, 3].astype(dtype)) @ poses[b, :3, :3].astype(dtype)
+            lim_x = cx / fx * cam[:, 2] + hgs * 2
+            lim_y = cy / fy * cam[:, 2] + hgs * 2
+            m = (cam[:, 2] > 0) & (np.abs(cam[:, 0]) < lim_x) & (np.abs(cam[:, 1]) < lim_y)
+            cnt += m
+            mg = np.minimum(mg, np.minimum(np.abs(cam[:, 2]), np.minimum(np.abs(np.abs(cam[:, 0]) - lim_x), np.abs(np.abs(cam[:, 1]) - lim_y))))
+        count[cas, idx] = cnt
+        margin[cas, idx] = mg
+    return count, margin

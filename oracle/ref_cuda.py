@@ -183,3 +183,85 @@ def render(F_: RefField, bitfield, rays_o, rays_d, *, indir_ref=False, indir_max
     w = res["weights_sum"][:, None]
     res["normal_image"] = res["normal_image"] * w + (1 - w)
     return res
+
+
+@torch.no_grad()
+def update_extra_state(F_: RefField, density_grid, density_bitfield, *, cascade=1, grid_size=128, decay=0.95, density_thresh=0.01,
+                       S=128, noise=None, iter_density=0, full_update=False):
+    """NeRFRenderer.update_extra_state (renderer.py:264-352) as the reference executes it: torch ops + its own morton3D /
+    packbits kernels + its hash encoder kernel + torch fp32 MLPs, including the mean().item() round trip.
+    density_grid [C, H^3] is updated in place; returns (mean_density, density_bitfield).
+    noise: list (one per cascade) of [H^3, 3] tensors in meshgrid order replacing torch.rand_like (full update only)."""
+    R = ref_module("_raymarching")
+    P, th, dev = F_.P, F_.th, F_.device
+    H = grid_size
+    bound_model = float(P["bound"])
+
+    def morton3D(coords):
+        coords = coords.int().contiguous()
+        idx = torch.empty(coords.shape[0], dtype=torch.int32, device=dev)
+        R.morton3D(coords, coords.shape[0], idx)
+        return idx
+
+    def morton3D_invert(indices):
+        indices = indices.int().contiguous()
+        c = torch.empty(indices.shape[0], 3, dtype=torch.int32, device=dev)
+        R.morton3D_invert(indices, indices.shape[0], c)
+        return c
+
+    def density(x):                                                                      # network.py:713-716 under no_grad
+        x01 = (x + bound_model) / (2 * bound_model)
+        enc = _encode(x01, th["embeddings"], P["offsets"], P["per_level_scale"], P["base_resolution"], False)
+        if P.get("enabled_levels", -1) > 0:
+            L = P["offsets"].shape[0] - 1
+            mask = torch.zeros(L, 2, dtype=enc.dtype, device=dev)
+            mask[: P["enabled_levels"]] = 1
+            enc = enc * mask.reshape(-1)
+        sdf = TO._mlp(enc, TO._stack(th, "sdf"))[:, 0]
+        return TO.laplace_density(sdf, TO.get_beta(th, P))
+
+    tmp_grid = -torch.ones_like(density_grid)
+    if iter_density < 16 or full_update:
+        X = torch.arange(H, dtype=torch.int32, device=dev).split(S)
+        for xs in X:
+            for ys in X:
+                for zs in X:
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    indices = morton3D(coords).long()
+                    xyzs = 2 * coords.float() / (H - 1) - 1
+                    for cas in range(cascade):
+                        bound = min(2 ** cas, bound_model)
+                        half_grid_size = bound / H
+                        cas_xyzs = xyzs * (bound - half_grid_size)
+                        u = torch.rand_like(cas_xyzs) if noise is None else noise[cas]
+                        cas_xyzs += (u * 2 - 1) * half_grid_size
+                        sigmas = density(cas_xyzs).reshape(-1).detach()
+                        sigmas *= P.get("density_scale", 1.0)
+                        tmp_grid[cas, indices] = sigmas
+    else:
+        N = H ** 3 // 4
+        for cas in range(cascade):
+            coords = torch.randint(0, H, (N, 3), device=dev)
+            indices = morton3D(coords).long()
+            occ_indices = torch.nonzero(density_grid[cas] > 0).squeeze(-1)
+            rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
+            occ_indices = occ_indices[rand_mask]
+            occ_coords = morton3D_invert(occ_indices)
+            indices = torch.cat([indices, occ_indices], dim=0)
+            coords = torch.cat([coords, occ_coords], dim=0)
+            xyzs = 2 * coords.float() / (H - 1) - 1
+            bound = min(2 ** cas, bound_model)
+            half_grid_size = bound / H
+            cas_xyzs = xyzs * (bound - half_grid_size)
+            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
+            sigmas = density(cas_xyzs).reshape(-1).detach()
+            sigmas *= P.get("density_scale", 1.0)
+            tmp_grid[cas, indices] = sigmas
+    valid_mask = (density_grid >= 0) & (tmp_grid >= 0)
+    density_grid[valid_mask] = torch.maximum(density_grid[valid_mask] * decay, tmp_grid[valid_mask])
+    mean_density = torch.mean(density_grid.clamp(min=0)).item()
+    thresh = min(mean_density, density_thresh)
+    N8 = density_grid.numel() // 8
+    R.packbits(density_grid.contiguous(), N8, thresh, density_bitfield)
+    return mean_density, density_bitfield

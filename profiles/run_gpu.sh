@@ -25,14 +25,14 @@ fi
 if [[ "$WHAT" == *" launches "* ]]; then
   # launch list of one timed frame (warm-up 3 frames + 1 stats frame are skipped by the summary script's frame split)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2400 -c 1000 --csv \
-      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train > $OUT/${TAG}_launches.log 2>&1
+      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-extra-warmup > $OUT/${TAG}_launches.log 2>&1
   python profiles/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches.md 2>&1
   cat $OUT/${TAG}_launches.md
 fi
 if [[ "$WHAT" == *" full "* ]]; then
   for K in k_env_tc k_geom_tc k_shade_tc k_march_compact; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 140 --launch-count 1 -f \
-        -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train > $OUT/${TAG}_full_$K.log 2>&1
+        -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-extra-warmup > $OUT/${TAG}_full_$K.log 2>&1
     echo "ncu full $K exit $?"
   done
 fi

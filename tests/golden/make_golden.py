@@ -204,16 +204,16 @@ class StandInEncoder(torch.nn.Module):
         return torch.sin(xyz @ self.A + self.b)
 
 
-def build_model(extra_args):
+def build_model(extra_args, cuda_ray=False):
     from nerf.options import config_parser
     argv = sys.argv
     sys.argv = ["x", "--config", os.path.join(REF, "configs/scenes/toaster.ini")] + extra_args
     opt = config_parser()
     sys.argv = argv
-    opt.cuda_ray = False                    # no density-grid buffers needed for the per-sample field
+    opt.cuda_ray = cuda_ray                 # density-grid buffers only for gen_density_grid
     from nerf.network import NeRFNetwork
     torch.manual_seed(0)
-    model = NeRFNetwork(encoding="hashgrid", encoding_dir=opt.encoding_dir, bound=opt.bound, cuda_ray=False,
+    model = NeRFNetwork(encoding="hashgrid", encoding_dir=opt.encoding_dir, bound=opt.bound, cuda_ray=cuda_ray,
                         density_scale=1, min_near=opt.min_near, density_thresh=opt.density_thresh, bg_radius=opt.bg_radius,
                         use_sdf=opt.use_sdf, hidden_dim=opt.hidden_dim, num_layers=opt.num_layers,
                         num_layers_color=opt.num_layers_color, hidden_dim_color=opt.hidden_dim_color,
@@ -306,8 +306,69 @@ def gen_relight():
     print("relight_mlps.npz written")
 
 
+def gen_density_grid():
+    """NeRFRenderer.update_extra_state / mark_untrained_grid of the reference (nerf/renderer.py:200-352) on the CPU.
+    The three CUDA-only helpers it calls (raymarching.morton3D / morton3D_invert / packbits) are bound to the oracle's C
+    restatements (pinned bit-exact against the reference kernels on the GPU by tests/test_gpu_ops.py); the hash encoder is the
+    stand-in encoder.  Sequence: 2 full updates (iter_density 0, 1), then one partial update (iter_density forced to 16), all from
+    torch.manual_seed(3) -- the test replays the same torch-CPU random calls.  Stored: the grid at every 16th cell after each
+    stage, mean_density, the full bit fields; the partial update's coords and noise (they depend on the grid values)."""
+    sys.path.insert(0, REPO)
+    from oracle import oracle as O
+    import nerf.renderer as R
+    model, opt = build_model(["--hidden_dim_env", "64"], cuda_ray=True)
+    g = torch.Generator().manual_seed(4)
+    A = torch.randn(3, model.in_dim, generator=g) * 1.5
+    b = torch.rand(model.in_dim, generator=g) * 6.28
+    model.encoder = StandInEncoder(A, b)
+    with torch.no_grad():
+        model.sdf_net[-1].weight[0] *= 0.2
+        model.sdf_net[-1].bias[0] += 0.05
+        model.sdf_density.beta.fill_(0.05)
+    R.raymarching.morton3D = lambda c: torch.from_numpy(O.morton3D(c.numpy()))
+    R.raymarching.morton3D_invert = lambda i: torch.from_numpy(O.morton3D_invert(i.numpy().astype(np.int32)))
+
+    def packbits(grid, thresh, bitfield=None):
+        return torch.from_numpy(O.packbits(grid.detach().numpy().reshape(-1), float(thresh)))
+    R.raymarching.packbits = packbits
+    out = dict(A=A.numpy(), b=b.numpy(), seed=np.int32(3), cascade=np.int32(model.cascade), bound=np.float32(model.bound),
+               density_thresh=np.float32(model.density_thresh), density_scale=np.float32(model.density_scale))
+    out.update(model_weights(model))
+    out["opt_beta_min"] = np.float32(opt.beta_min); out["opt_beta_max"] = np.float32(opt.beta_max)
+    # mark_untrained_grid with 6 cameras on a ring
+    sys.path.insert(0, REPO)
+    from envidr_b200 import scene
+    poses = np.stack([scene.nerf_matrix_to_ngp(scene.pose_spherical(th, -30.0, 4.0), scale=0.65) for th in range(0, 360, 60)])
+    intr = scene.intrinsics_from_fov(800, 800, 0.35)                # narrow field of view: part of the grid is never seen
+    model.mark_untrained_grid(poses, intr)
+    out["poses"] = poses.astype(np.float32); out["intrinsic"] = np.asarray(intr, np.float64)
+    out["marked"] = np.packbits((model.density_grid.numpy().reshape(-1) < 0))
+    torch.manual_seed(3)
+    sub = slice(None, None, 16)
+    for stage in range(2):
+        model.update_extra_state()
+        out[f"full{stage}_grid_sub"] = model.density_grid.numpy().reshape(-1)[sub].copy()
+        out[f"full{stage}_mean"] = np.float64(model.mean_density)
+        out[f"full{stage}_bits"] = model.density_bitfield.numpy().copy()
+    model.iter_density = 16
+    # record the random draws of the partial update by replaying them from the same generator state afterwards
+    st = torch.get_rng_state()
+    model.update_extra_state()
+    out["part_grid_sub"] = model.density_grid.numpy().reshape(-1)[sub].copy()
+    out["part_mean"] = np.float64(model.mean_density)
+    out["part_bits"] = model.density_bitfield.numpy().copy()
+    out["part_rng_state"] = st.numpy()
+    np.savez_compressed(os.path.join(HERE, "density_grid.npz"), **out)
+    print("density_grid.npz: marked", int((model.density_grid < 0).sum()), "means", out["full0_mean"], out["full1_mean"], out["part_mean"],
+          "occupied", int(np.unpackbits(out["part_bits"]).sum()))
+
+
 if __name__ == "__main__":
     install_shims()
+    if "density" in sys.argv[1:]:
+        torch.set_num_threads(8)
+        gen_density_grid()
+        sys.exit(0)
     torch.set_num_threads(1)
     gen_ide()
     gen_demo()

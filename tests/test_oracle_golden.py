@@ -108,3 +108,67 @@ def test_demo_sphere_config1(golden_dir):
     c_s = torch.sigmoid(O._mlp(torch.cat([geo, n, f_r, ndv], -1), spe)).float().numpy()
     np.testing.assert_allclose(c_d, z["diffuse"], atol=2e-5)
     np.testing.assert_allclose(c_s, z["specular"], atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# occupancy-grid maintenance: oracle vs the reference's own update_extra_state / mark_untrained_grid
+# (tests/golden/make_golden.py::gen_density_grid, run on the CPU with the reference's Python code)
+# ---------------------------------------------------------------------------------------------
+
+def _density_P(z):
+    n = sorted({int(k.split("_")[2]) for k in z.files if k.startswith("sdf_net_")})
+    return dict(bound=float(z["bound"]), beta=float(z["beta"]), beta_min=float(z["opt_beta_min"]), beta_max=float(z["opt_beta_max"]),
+                sdf=_layers(z, "sdf_net", n))
+
+
+def _bits_equal_except_near_threshold(bits, ref_bits, grid, th, rtol=1e-4):
+    a, b = np.unpackbits(bits, bitorder="little"), np.unpackbits(ref_bits, bitorder="little")
+    bad = np.nonzero(a != b)[0]
+    assert all(abs(grid.reshape(-1)[i] - th) <= rtol * max(th, 1e-6) for i in bad), (len(bad), bad[:8])
+    return len(bad)
+
+
+def test_density_grid_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "density_grid.npz"))
+    P = _density_P(z)
+    C, H = int(z["cascade"]), 128
+    A, b = torch.from_numpy(z["A"]), torch.from_numpy(z["b"])
+    enc_fn = lambda x: torch.sin(x @ A + b)
+    kw = dict(cascade=C, grid_size=H, density_thresh=float(z["density_thresh"]), density_scale=float(z["density_scale"]), enc_fn=enc_fn)
+    # mark_untrained_grid: exact except where a comparison is decided at rounding level
+    count, margin = O.mark_untrained_grid(z["poses"], z["intrinsic"], bound=P["bound"], cascade=C, grid_size=H)
+    marked_ref = np.unpackbits(z["marked"]).astype(bool)[: C * H ** 3]
+    sure = margin.reshape(-1) > 1e-5
+    assert sure.mean() > 0.999
+    np.testing.assert_array_equal((count.reshape(-1) == 0)[sure], marked_ref[sure])
+    grid = np.zeros((C, H ** 3), np.float32)
+    grid[marked_ref.reshape(C, -1)] = -1
+    torch.manual_seed(int(z["seed"]))
+    sub = slice(None, None, 16)
+    for stage in range(2):                                             # iter_density 0, 1: full updates
+        noise = np.stack([torch.rand(H ** 3, 3).numpy() for _ in range(C)])
+        grid, mean, th, bits, _ = O.update_extra_state(P, grid, noise=noise, **kw)
+        np.testing.assert_allclose(grid.reshape(-1)[sub], z[f"full{stage}_grid_sub"], rtol=2e-5, atol=1e-6)
+        assert abs(mean - float(z[f"full{stage}_mean"])) <= 1e-5 * abs(mean)
+        _bits_equal_except_near_threshold(bits, z[f"full{stage}_bits"], grid, th)
+    assert (grid.reshape(-1)[marked_ref] == -1).all()                 # untrained cells never come back
+    # partial update: replay the reference's random draws (renderer.py:310-331) from the recorded generator state
+    torch.set_rng_state(torch.from_numpy(z["part_rng_state"]))
+    N = H ** 3 // 4
+    coords, noise = [], []
+    for cas in range(C):
+        c = torch.randint(0, H, (N, 3))
+        occ = torch.nonzero(torch.from_numpy(grid[cas]) > 0).squeeze(-1)
+        rm = torch.randint(0, occ.shape[0], [N], dtype=torch.long)
+        oc = torch.from_numpy(O.morton3D_invert(occ[rm].numpy().astype(np.int32)))
+        coords.append(torch.cat([c.int(), oc.int()], 0).numpy())
+        noise.append(torch.rand(2 * N, 3).numpy())
+    grid_p, mean, th, bits, tmp = O.update_extra_state(P, grid, noise=np.stack(noise), coords=np.stack(coords), **kw)
+    # duplicated cells: index_put keeps one of the candidates (which one is unspecified); compare the cells visited once
+    idx = O.morton3D(np.stack(coords)[0])
+    uniq, cnt = np.unique(idx, return_counts=True)
+    once = np.zeros(H ** 3, bool); once[uniq[cnt == 1]] = True
+    untouched = np.ones(H ** 3, bool); untouched[uniq] = False
+    cmp_mask = (once | untouched)[sub]
+    np.testing.assert_allclose(grid_p.reshape(-1)[sub][cmp_mask], z["part_grid_sub"][cmp_mask], rtol=2e-5, atol=1e-6)
+    assert abs(mean - float(z["part_mean"])) <= 1e-4 * abs(mean)
