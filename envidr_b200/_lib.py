@@ -62,8 +62,8 @@ class RenderOut(ctypes.Structure):
                                               "roughness_image", "sample_count", "log")]
 
 
-_SCALARS = {"uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "int32_t": ctypes.c_int32, "int": ctypes.c_int,
-            "float": ctypes.c_float, "envidr_stream_t": ctypes.c_void_p}
+_SCALARS = {"uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "int": ctypes.c_int,
+            "float": ctypes.c_float, "double": ctypes.c_double, "envidr_stream_t": ctypes.c_void_p}
 _RET = {"int": ctypes.c_int, "uint64_t": ctypes.c_uint64, "const char*": ctypes.c_char_p}
 
 

@@ -380,6 +380,72 @@ int envidr_mark_untrained_grid(const float* poses, uint32_t B, float fx, float f
                                uint32_t grid_size, float* density_grid, int32_t* count, envidr_stream_t stream);
 int envidr_mark_untrained_apply(const int32_t* count, uint32_t n, float* density_grid, envidr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step for the trainable state of the path.
+ * Replaces optimizer.zero_grad() + torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15).step() of the reference's training loop
+ * (main_nerf.py:150, nerf/utils.py:1079-1087; torch/optim/adam.py, no weight decay / amsgrad / maximize) by one launch over
+ * all parameter tensors.  step_size = lr / (1 - beta1^step) and bias_correction2_sqrt = sqrt(1 - beta2^step) are computed by
+ * the caller (torch computes them as Python doubles on the host), per tensor because lr is per parameter group.
+ * ---------------------------------------------------------------------------------------------- */
+#define ENVIDR_ADAM_MAX_TENSORS 64 /* per launch; longer lists are split */
+typedef struct envidr_adam_tensor {
+    float* param;                 /* [n] updated in place        */
+    float* grad;                  /* [n] (cleared when zero_grad) */
+    float* exp_avg;               /* [n] first moment            */
+    float* exp_avg_sq;            /* [n] second moment           */
+    uint64_t n;
+    float step_size;              /* lr / bias_correction1       */
+    float bias_correction2_sqrt;
+} envidr_adam_tensor;
+/* tensors: HOST array of n_tensors descriptors (device pointers inside).  div_mode: 0 = sqrt(v) / bc2 as an IEEE division
+ * (torch's foreach implementation, the CUDA default), 1 = sqrt(v) * fp32(1 / bc2) (torch's single-tensor implementation).
+ * beta1 / beta2 / eps are doubles because torch derives the fp32 kernel constants from Python doubles: fp32(1 - beta1), not 1.0f - fp32(beta1). */
+int envidr_adam_step(const envidr_adam_tensor* tensors, uint32_t n_tensors, double beta1, double beta2, double eps, int zero_grad,
+                     int div_mode, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray generation and loss epilogue: the steps either side of the training branch.
+ * ---------------------------------------------------------------------------------------------- */
+/* get_rays (nerf/utils.py:110-209).  poses [B,4,4] camera-to-world (device, row-major); intrinsics4 = HOST {fx, fy, cx, cy};
+ * inds: device int64 [N] flat pixel indices h * W + w shared by all B poses (the reference's `inds.expand([B, N])`), or NULL for
+ * all H * W pixels (N must be H * W).  rays_o, rays_d [B, N, 3] out.  The random choice of `inds` stays with the caller
+ * (torch.randint / multinomial, utils.py:132-186), as does the gather of the ground-truth pixels. */
+int envidr_get_rays(const float* poses, uint32_t B, const float* intrinsics4, uint32_t H, uint32_t W, const int64_t* inds, uint32_t N,
+                    float* rays_o, float* rays_d, envidr_stream_t stream);
+
+/* Loss terms of Trainer.train_step (nerf/utils.py:661-662 colour, :712-717 mask BCE, :735-747 back-sdf, :762-776 Cauchy,
+ * :793-798 eikonal) over the outputs of run_cuda's training branch, including the auxiliary block that prepares them
+ * (nerf/render_func/cuda_ray.py:173-211).  A term whose weight is 0 is skipped, as in the reference; backsdf_w > 0 switches the
+ * auxiliary block on (point mask; the Cauchy term then averages over the masked samples, cuda_ray.py:209). */
+typedef struct envidr_loss_in {
+    const float* image;          /* [N,3] outputs['image']                                   */
+    const float* weights_sum;    /* [N]   outputs['weights_sum'] (mask term)                 */
+    const float* gt_rgb;         /* [N,3]                                                    */
+    const float* gt_mask;        /* [N] alpha_mask, or NULL (no mask term)                   */
+    const float* sdfs;           /* [M]                                                      */
+    const float* sdf_gradients;  /* [M,3] or NULL (no eikonal term)                          */
+    const float* weights;        /* [M] compositing weights (back-sdf; carry no gradient, raymarching.py:291) */
+    const float* deltas;         /* [M,2]                                                    */
+    const int32_t* rays;         /* [n_rays,3] (ray, offset, count) of march_rays_train      */
+    const float* beta;           /* device scalar: sdf_density.get_beta()                    */
+} envidr_loss_in;
+typedef struct envidr_loss_opts {
+    uint32_t N, M, n_rays;
+    int32_t color_l1;            /* 1: L1Loss (color_l1_loss), 0: MSELoss (main_nerf.py:84-86) */
+    int32_t backsdf_mean;        /* backsdf_mode != 'sum': divide by 1 + sum of the masked weights */
+    float color_w, mask_w, cauchy_w, eikonal_w, backsdf_w, backsdf_thresh;
+} envidr_loss_opts;
+uint64_t envidr_train_loss_workspace_bytes(uint32_t M);
+/* terms: device float[8] = {total, colour, mask, Cauchy, eikonal, back-sdf, #samples in the point mask, back-sdf denominator}. */
+int envidr_train_loss_forward(const envidr_loss_in* in, const envidr_loss_opts* opts, float* terms, void* workspace, uint64_t workspace_bytes,
+                              envidr_stream_t stream);
+/* Gradients of grad_loss * total (grad_loss: device scalar or NULL = 1).  Needs `terms` and the SAME workspace as the forward
+ * call (it holds the point-mask flags).  Any output pointer may be NULL.  d_image [N,3], d_weights_sum [N], d_sdfs [M],
+ * d_sdf_gradients [M,3] are overwritten. */
+int envidr_train_loss_backward(const envidr_loss_in* in, const envidr_loss_opts* opts, const float* terms, const float* grad_loss,
+                               float* d_image, float* d_weights_sum, float* d_sdfs, float* d_sdf_gradients, void* workspace,
+                               uint64_t workspace_bytes, envidr_stream_t stream);
+
 /* Instrumentation (bench.py): launches issued by envidr_render_rays in this process; CUDA-event timing of the
  * field kernel (the dominant kernel) on its launch stream. */
 uint64_t envidr_launch_count(void);

@@ -727,3 +727,28 @@ def mark_untrained_grid(poses: np.ndarray, intrinsic, *, bound: float = 1.0, cas
         count[cas, idx] = cnt
         margin[cas, idx] = mg
     return count, margin
+
+
+# --------------------------------------------------------------------------------------
+# optimizer step: torch.optim.Adam as the reference configures it (main_nerf.py:150)
+# --------------------------------------------------------------------------------------
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add emulated through fp64 (the product of two fp32 values is exact in fp64)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.99, eps: float = 1e-15):
+    """One torch.optim.Adam step (torch/optim/adam.py::_single_tensor_adam, no weight decay / amsgrad / maximize; the third-party
+    arithmetic of the reference's training loop, nerf/utils.py:1079-1087) on fp32 numpy arrays, with the fused multiply-adds the
+    CUDA kernels of torch contract to.  step: 1-based.  Returns (param, exp_avg, exp_avg_sq)."""
+    f = np.float32
+    p, g, m, v = [np.asarray(a, np.float32) for a in (param, grad, exp_avg, exp_avg_sq)]
+    m = _fma32(np.full_like(g, f(1 - beta1)), g - m, m)                                  # exp_avg.lerp_(grad, 1 - beta1)
+    v = _fma32(np.full_like(g, f(1 - beta2)), g * g, v * f(beta2))                      # mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    bias_correction1 = 1 - beta1 ** step
+    bias_correction2 = 1 - beta2 ** step
+    step_size = lr / bias_correction1
+    denom = np.sqrt(v) / f(bias_correction2 ** 0.5) + f(eps)
+    p = _fma32(np.full_like(g, f(-step_size)), m / denom, p)                            # addcdiv_(exp_avg, denom, value=-step_size)
+    return p, m, v

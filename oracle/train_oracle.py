@@ -283,3 +283,89 @@ def train_step(P: Dict, rays_o, rays_d, bitfield, gt_rgb, gt_mask, *, dtype=torc
     grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
     g = {k: (None if gr is None else gr.detach().to(torch.float32).numpy()) for k, gr in zip(leaves.keys(), grads)}
     return float(loss.detach()), g, out
+
+
+# --------------------------------------------------------------------------------------
+# ray generation + loss epilogue: the steps either side of the training branch
+# --------------------------------------------------------------------------------------
+
+def get_rays(poses, intrinsics, H: int, W: int, inds=None, dtype=torch.float64):
+    """nerf/utils.py:110-209 for given pixel indices (`inds` [N] flat h * W + w, None = all pixels): pixel centres + 0.5,
+    normalised directions rotated by the camera-to-world matrix.  poses [B,4,4].  -> rays_o, rays_d [B,N,3]."""
+    poses = torch.as_tensor(np.asarray(poses), dtype=dtype)
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    inds = torch.arange(H * W) if inds is None else torch.as_tensor(np.asarray(inds)).long()
+    i = (inds % W).to(dtype) + 0.5
+    j = (inds // W).to(dtype) + 0.5
+    zs = torch.ones_like(i)
+    directions = torch.stack(((i - cx) / fx * zs, (j - cy) / fy * zs, zs), dim=-1)
+    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
+    rays_d = directions[None] @ poses[:, :3, :3].transpose(-1, -2)
+    rays_o = poses[:, None, :3, 3].expand_as(rays_d)
+    return rays_o.contiguous(), rays_d.contiguous()
+
+
+def aux_point_mask(deltas, rays, M: int):
+    """The point mask of run_cuda's auxiliary block (cuda_ray.py:173-190): every sample but the last of each valid ray, whose
+    successor in the buffer is a real, contiguous continuation of the same ray.  deltas [M,2], rays [N,3] torch tensors."""
+    point_mask = torch.ones(M, dtype=torch.bool)
+    ray_valid = (rays[:, 2] > 0) * (rays[:, 1] + rays[:, 2] < M)
+    end = rays[ray_valid, 1] + rays[ray_valid, 2] - 1
+    point_mask[end.long()] = False
+    ds = torch.roll(deltas, -1, 0)
+    delta_mask = (ds[:, 0] > 0) * (ds[:, 1] > 0)
+    cont_mask = ds[:, 1] < 1.2 * ds[:, 0]
+    return point_mask * delta_mask * cont_mask, ds
+
+
+def train_loss(image, weights_sum, gt_rgb, gt_mask, sdfs, sdf_gradients, weights, deltas, rays, beta: float, *, color_l1=True,
+               color_w=1.0, mask_w=1.0, cauchy_w=0.1, eikonal_w=0.001, backsdf_w=5e-3, backsdf_thresh=0.01, backsdf_mean=False,
+               dtype=torch.float64):
+    """Trainer.train_step's loss terms for the shipped scene configs (nerf/utils.py:661-662 colour, :712-717 mask BCE, :735-747
+    back-sdf, :762-776 Cauchy, :793-798 eikonal) on the outputs of run_cuda's training branch including its auxiliary block
+    (cuda_ray.py:173-211: relsdf / sdf_weights / sdf_dist and the MASKED sdfs the Cauchy term then sees).  A term with weight 0
+    is skipped as in the reference; backsdf_w == 0 also switches the auxiliary block off (Cauchy then runs over all M samples).
+    The compositing weights carry no gradient (the reference's composite backward ignores grad_weights, raymarching.py:291).
+    Returns (terms dict of floats incl. 'total', grads dict: image, weights_sum, sdfs, sdf_gradients as float32 numpy)."""
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype)
+    image, weights_sum, sdfs, sdf_gradients = [t(a).clone().requires_grad_(True) for a in (image, weights_sum, sdfs, sdf_gradients)]
+    gt_rgb, gt_mask, weights, deltas = t(gt_rgb), t(gt_mask), t(weights), t(deltas)
+    rays = torch.as_tensor(np.asarray(rays)).long()
+    M = sdfs.shape[0]
+    terms = {}
+    diff = image - gt_rgb
+    color = (diff.abs() if color_l1 else diff ** 2).mean(-1).mean()
+    loss = color_w * color
+    terms["color"] = color
+    if mask_w > 0:
+        lm = torch.nn.functional.binary_cross_entropy(weights_sum.clip(1e-3, 1.0 - 1e-3), gt_mask)
+        loss = loss + mask_w * lm
+        terms["mask"] = lm
+    sd = sdfs
+    if backsdf_w > 0:
+        pm, ds = aux_point_mask(deltas, rays, M)
+        relsdf = (torch.roll(sdfs, -1, dims=0) - sdfs)[pm]
+        w, dist, sd = weights[pm], ds[pm, 1], sdfs[pm]
+        mask = (w > backsdf_thresh) * (relsdf > 0)
+        s_sq = relsdf[mask] ** 2
+        mw = w[mask]
+        r_cos_sq = s_sq / (dist[mask].clamp(min=5e-4) ** 2 + s_sq)
+        denom = (1 + mw.sum()) if backsdf_mean else 1
+        lb = (mw * r_cos_sq).sum() / denom
+        loss = loss + backsdf_w * lb
+        terms["backsdf"] = lb
+    if cauchy_w > 0:
+        reg = laplace_density(sd, torch.tensor(float(beta), dtype=dtype), 1)
+        lc = 1.0 / 4.0 * torch.log1p((1 - reg) ** 2 * 16.0).mean()
+        loss = loss + cauchy_w * lc
+        terms["cauchy"] = lc
+    if eikonal_w > 0:
+        le = ((sdf_gradients.norm(p=2, dim=-1) - 1) ** 2).mean()
+        loss = loss + eikonal_w * le
+        terms["eikonal"] = le
+    terms["total"] = loss
+    leaves = [image, weights_sum, sdfs, sdf_gradients]
+    g = torch.autograd.grad(loss, leaves, allow_unused=True)
+    f32 = lambda x, like: (torch.zeros_like(like) if x is None else x).detach().to(torch.float32).numpy()
+    grads = dict(image=f32(g[0], image), weights_sum=f32(g[1], weights_sum), sdfs=f32(g[2], sdfs), sdf_gradients=f32(g[3], sdf_gradients))
+    return {k: float(v.detach()) for k, v in terms.items()}, grads

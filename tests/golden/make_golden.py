@@ -363,8 +363,122 @@ def gen_density_grid():
           "occupied", int(np.unpackbits(out["part_bits"]).sum()))
 
 
+def gen_train_epilogue():
+    """SURVEY 8 f-2 -- the reference's own code for the steps either side of the training branch, run on the CPU:
+      * nerf.utils.get_rays (utils.py:110-209) for random pixel indices and for the full image;
+      * the auxiliary block of run_cuda (cuda_ray.py:173-211), executed from the reference's source lines where they lie
+        (the block has no function boundary) on a seeded sample buffer;
+      * Trainer.train_step's loss terms (utils.py:560-808) with `self` stubbed: model.render returns the prepared outputs, so
+        the reference computes colour L1 + mask BCE + back-sdf + Cauchy + eikonal and autograd gives the gradients.
+    -> tests/golden/train_epilogue.npz"""
+    import textwrap
+    import nerf.utils as U
+    from nerf.options import config_parser
+    out = {}
+    # ---- get_rays -------------------------------------------------------------------------------------------
+    sys.path.insert(0, REPO)
+    from envidr_b200 import scene
+    poses = np.stack([scene.nerf_matrix_to_ngp(scene.pose_spherical(th, -30.0, 4.0), scale=0.65) for th in (10.0, 200.0)])
+    H, W = 37, 53
+    intr = scene.intrinsics_from_fov(W, H, 0.69)
+    torch.manual_seed(7)
+    r = U.get_rays(torch.from_numpy(poses), intr, H, W, N=300)
+    out.update(rays_poses=poses.astype(np.float32), rays_intrinsics=np.asarray(intr, np.float64), rays_HW=np.array([H, W]),
+               rays_inds=r["inds"][0].numpy(), rays_o=r["rays_o"].numpy(), rays_d=r["rays_d"].numpy())
+    r = U.get_rays(torch.from_numpy(poses[:1]), intr, H, W, N=-1)
+    out.update(rays_full_o=r["rays_o"].numpy(), rays_full_d=r["rays_d"].numpy())
+    # ---- auxiliary block + losses -----------------------------------------------------------------------------
+    argv = sys.argv
+    sys.argv = ["x", "--config", os.path.join(REF, "configs/scenes/toaster.ini")]
+    opt = config_parser()
+    sys.argv = argv
+    g = torch.Generator().manual_seed(8)
+    N, M = 96, 1200
+    cnt = torch.randint(0, 24, (N,), generator=g); cnt[5] = 0
+    off = torch.cumsum(cnt, 0) - cnt
+    total = int(cnt.sum())
+    assert total < M
+    rays = torch.stack([torch.arange(N), off, cnt], -1).int()
+    deltas = torch.zeros(M, 2)
+    deltas[:total, 0] = 2 * 3 ** 0.5 / 1024
+    deltas[:total, 1] = deltas[:total, 0] * (1 + (torch.rand(total, generator=g) < 0.15).float() * 3)     # some gaps (empty cells skipped)
+    sdfs = (torch.randn(M, generator=g) * 0.03).requires_grad_(True)
+    sigmas = torch.rand(M, generator=g)
+    weights = torch.rand(M, generator=g) * 0.04
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    normals = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    xyzs = torch.rand(M, 3, generator=g) * 2 - 1
+    src = open(os.path.join(REF, "nerf/render_func/cuda_ray.py")).read().splitlines()
+    assert src[172].strip().startswith("if main_pass and (use_relsdf_loss or use_backsdf_loss or use_orientation_loss):"), src[172]
+    block = textwrap.dedent("\n".join(src[172:212]))
+
+    class _S:
+        obj_aabb = None
+        use_sdf = True
+    results = {"sdfs": sdfs}
+    ns = dict(torch=torch, self=_S(), main_pass=True, use_relsdf_loss=False, use_backsdf_loss=True, use_orientation_loss=False,
+              sigmas=sigmas, rays=rays, deltas=deltas, xyzs=xyzs, sdfs=sdfs, dirs=dirs, normals=normals, weights=weights, results=results)
+    exec(compile(block, "cuda_ray.py[173:212]", "exec"), ns)
+    image = torch.rand(1, N, 3, generator=g).requires_grad_(True)
+    weights_sum = torch.rand(1, N, generator=g)
+    weights_sum[0, :4] = torch.tensor([0.0, 1.0, 5e-4, 0.9995])                                            # outside the BCE clip
+    weights_sum.requires_grad_(True)
+    sdf_gradients = (torch.randn(M, 3, generator=g) * 0.7).requires_grad_(True)
+    with torch.no_grad():
+        sdf_gradients[3] = 0                                                                              # norm at the origin
+    results.update(image=image, weights_sum=weights_sum, sdf_gradients=sdf_gradients, sigmas=sigmas)
+    images = torch.rand(1, N, 4, generator=g)
+    images[..., 3] = (images[..., 3] > 0.4).float()
+    beta = 0.02
+
+    class _Density:
+        def get_beta(self):
+            return torch.tensor(beta)
+
+        def density_func(self, sdf, beta=None, alpha=None):
+            a = 1 / beta if alpha is None else alpha
+            return a * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))                           # network.py:32-37
+
+    class _Model:
+        bg_radius = -1
+        sdf_density = _Density()
+
+        def render(self, rays_o, rays_d, **kw):
+            return results
+
+    class _Self:
+        pass
+    fake = _Self()
+    opt.color_space = "srgb"                      # keep gt as given (the srgb->linear conversion is data preparation)
+    opt.alpha_bg_mode = "white"
+    opt.eikonal_loss = True; opt.cauchy_loss = True; opt.backsdf_loss = True; opt.mask_loss = True
+    opt.relsdf_loss = False; opt.orientation_loss = False; opt.dist_bound = False; opt.diffuse_loss = False
+    opt.entropy_loss_weight = 0; opt.env_sph_mode = False; opt.cauchy_roughness_weighted = False
+    fake.opt, fake.model, fake.device, fake.error_map = opt, _Model(), torch.device("cpu"), None
+    fake.criterion = torch.nn.L1Loss(reduction="none")
+    fake.epoch, fake.global_step = 500, 500
+    data = dict(rays_o=torch.zeros(1, N, 3), rays_d=torch.zeros(1, N, 3), images=images.clone())
+    pred, gt_rgb, loss, ld = U.Trainer.train_step(fake, data)
+    gi, gw, gs, gg = torch.autograd.grad(loss, [image, weights_sum, sdfs, sdf_gradients])
+    f = lambda t: t.detach().numpy().astype(np.float32)
+    out.update(loss_rays=rays.numpy(), loss_deltas=f(deltas), loss_sdfs=f(sdfs), loss_weights=f(weights), loss_image=f(image[0]),
+               loss_weights_sum=f(weights_sum[0]), loss_sdf_gradients=f(sdf_gradients), loss_gt_rgb=f(gt_rgb[0]), loss_gt_mask=f(images[0, :, 3]),
+               loss_beta=np.float32(beta), loss_total=np.float64(loss.item()),
+               loss_w=np.array([opt.color_loss_weight, opt.mask_loss_weight, opt.cauchy_loss_weight, opt.eikonal_loss_weight,
+                                opt.backsdf_loss_weight, opt.backsdf_thresh], np.float64),
+               loss_backsdf_mean=np.int32(opt.backsdf_mode != "sum"),
+               **{f"loss_term_{k}": np.float64(v.item()) for k, v in ld.items()},
+               grad_image=f(gi[0]), grad_weights_sum=f(gw[0]), grad_sdfs=f(gs), grad_sdf_gradients=f(gg),
+               aux_point_count=np.int32(results["sdfs"].shape[0]), aux_relsdf=f(results["relsdf"]), aux_sdf_dist=f(results["sdf_dist"]))
+    np.savez_compressed(os.path.join(HERE, "train_epilogue.npz"), **out)
+    print("train_epilogue.npz:", {k: float(v) for k, v in ld.items()}, "total", loss.item(), "aux points", int(results["sdfs"].shape[0]), "of", M)
+
+
 if __name__ == "__main__":
     install_shims()
+    if "epilogue" in sys.argv[1:]:
+        gen_train_epilogue()
+        sys.exit(0)
     if "density" in sys.argv[1:]:
         torch.set_num_threads(8)
         gen_density_grid()

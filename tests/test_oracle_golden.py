@@ -172,3 +172,47 @@ def test_density_grid_matches_reference(golden_dir):
     cmp_mask = (once | untouched)[sub]
     np.testing.assert_allclose(grid_p.reshape(-1)[sub][cmp_mask], z["part_grid_sub"][cmp_mask], rtol=2e-5, atol=1e-6)
     assert abs(mean - float(z["part_mean"])) <= 1e-4 * abs(mean)
+
+
+# ---------------------------------------------------------------------------------------------
+# ray generation + loss epilogue: oracle vs the reference's own get_rays, auxiliary block and
+# Trainer.train_step (tests/golden/make_golden.py::gen_train_epilogue)
+# ---------------------------------------------------------------------------------------------
+
+def test_get_rays_matches_reference(golden_dir):
+    from oracle import train_oracle as TO
+    z = np.load(os.path.join(golden_dir, "train_epilogue.npz"))
+    H, W = [int(v) for v in z["rays_HW"]]
+    ro, rd = TO.get_rays(z["rays_poses"], z["rays_intrinsics"], H, W, z["rays_inds"])
+    np.testing.assert_allclose(ro.numpy(), z["rays_o"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(rd.numpy(), z["rays_d"], rtol=0, atol=1e-6)
+    ro, rd = TO.get_rays(z["rays_poses"][:1], z["rays_intrinsics"], H, W, None)
+    np.testing.assert_allclose(rd.numpy(), z["rays_full_d"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ro.numpy(), z["rays_full_o"], rtol=0, atol=1e-6)
+
+
+def loss_case_from_golden(z):
+    w = z["loss_w"]
+    kw = dict(color_l1=True, color_w=float(w[0]), mask_w=float(w[1]), cauchy_w=float(w[2]), eikonal_w=float(w[3]), backsdf_w=float(w[4]),
+              backsdf_thresh=float(w[5]), backsdf_mean=bool(z["loss_backsdf_mean"]))
+    args = (z["loss_image"], z["loss_weights_sum"], z["loss_gt_rgb"], z["loss_gt_mask"], z["loss_sdfs"], z["loss_sdf_gradients"],
+            z["loss_weights"], z["loss_deltas"], z["loss_rays"], float(z["loss_beta"]))
+    return args, kw
+
+
+def test_train_loss_matches_reference(golden_dir):
+    from oracle import train_oracle as TO
+    z = np.load(os.path.join(golden_dir, "train_epilogue.npz"))
+    args, kw = loss_case_from_golden(z)
+    pm, ds = TO.aux_point_mask(torch.from_numpy(z["loss_deltas"]), torch.from_numpy(z["loss_rays"]).long(), z["loss_sdfs"].shape[0])
+    assert int(pm.sum()) == int(z["aux_point_count"])
+    sd = torch.from_numpy(z["loss_sdfs"])
+    np.testing.assert_array_equal((torch.roll(sd, -1, 0) - sd)[pm].numpy(), z["aux_relsdf"])
+    np.testing.assert_array_equal(ds[pm, 1].numpy(), z["aux_sdf_dist"])
+    terms, grads = TO.train_loss(*args, **kw)
+    assert abs(terms["total"] - float(z["loss_total"])) <= 2e-6 * abs(terms["total"])
+    for k in ("color", "mask", "backsdf", "cauchy", "eikonal"):
+        assert abs(terms[k] - float(z[f"loss_term_{k}"])) <= 3e-6 * abs(terms[k]), k
+    for k in ("image", "weights_sum", "sdfs", "sdf_gradients"):
+        ref = z[f"grad_{k}"]
+        np.testing.assert_allclose(grads[k], ref, rtol=2e-4, atol=2e-6 * float(np.abs(ref).max()), err_msg=k)
