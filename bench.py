@@ -165,9 +165,27 @@ def train_step_bench(fp_cpu, bf, ro, rd, dev, n_rays, steps=10, warmup=3):
     ms = timed(lambda: graphed(o, d, gt_rgb, gt_mask, r_img))
     counter = graphed.counter
     assert abs(int(counter[0].item()) - eager_samples) < 0.05 * eager_samples
-    return {"rays": n_rays, "samples": int(counter[0].item()), "ms_per_step_fwd_bwd": ms, "rays_per_sec": n_rays / (ms * 1e-3),
-            "ms_per_step_fwd_bwd_eager": ms_eager, "mode": "CUDA graph replay of the captured step (train.GraphedTrainStep); host copies the step's inputs in",
-            "what": "run_cuda train branch fwd+bwd (use_renv, r_images; colour L1 + mask BCE + Cauchy + eikonal), fp32, no optimizer"}
+    n_samples = int(counter[0].item())
+    # the whole optimisation step: graph replay + Adam over the trainable tensors (hash table 12.2 M floats + sdf / env / renv MLPs),
+    # fused (envidr_b200.optim.FusedAdam, one launch) and with torch.optim.Adam as the reference configures it (main_nerf.py:150)
+    from envidr_b200.optim import FusedAdam
+    params = [p for p in field.parameters() if p.requires_grad]
+    res = {}
+    for name, cls in (("fused_adam", FusedAdam), ("torch_adam", torch.optim.Adam)):
+        try:
+            opt = cls(params, lr=1e-4, betas=(0.9, 0.99), eps=1e-15)
+
+            def full():
+                graphed(o, d, gt_rgb, gt_mask, r_img)
+                opt.step()
+            res[f"ms_per_step_with_{name}"] = timed(full)
+        except Exception as e:
+            res[f"{name}_error"] = repr(e)[:160]
+    return {"rays": n_rays, "samples": n_samples, "ms_per_step_fwd_bwd": ms, "rays_per_sec": n_rays / (ms * 1e-3),
+            "ms_per_step_fwd_bwd_eager": ms_eager, **res,
+            "mode": "CUDA graph replay of the captured step (train.GraphedTrainStep); host copies the step's inputs in",
+            "what": "run_cuda train branch fwd+bwd (use_renv, r_images; colour L1 + mask BCE + Cauchy + eikonal through the fused loss "
+                    "epilogue), fp32; ms_per_step_with_*: + optimizer step over all trainable tensors"}
 
 
 def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2):

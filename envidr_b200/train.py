@@ -186,7 +186,7 @@ def _aabb_tensor(cfg: RenderConfig, device) -> torch.Tensor:
 def render_train(field: TrainableField, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, cfg: RenderConfig, *,
                  bg_color=1.0, perturb: bool = False, force_all_rays: bool = True, mean_count: int = -1,
                  step_counter: Optional[torch.Tensor] = None, early_stop_steps: int = -1, r_images: Optional[torch.Tensor] = None,
-                 geometry_only: bool = False, ops: Optional[TrainOps] = None) -> Dict[str, torch.Tensor]:
+                 geometry_only: bool = False, ops: Optional[TrainOps] = None, ret_weights: bool = False) -> Dict[str, torch.Tensor]:
     """run_cuda, training branch (cuda_ray.py:64-168): march (no grad) -> field -> composite; everything returned is
     differentiable w.r.t. the field parameters exactly as in the reference (image, weights_sum, sdfs, sdf_gradients, ...)."""
     ops = ops or default_ops()
@@ -210,7 +210,9 @@ def render_train(field: TrainableField, bitfield: torch.Tensor, rays_o: torch.Te
         image = None
     else:
         rgbs = field.forward_color(ops, geo, dirs, normals, roughness, blend, r_images)
-        ws, depth, image, _ = ops.composite_rays_train(sigma, rgbs, deltas, rays, cfg.T_thresh, False, cfg.input_alpha)
+        ws, depth, image, weights = ops.composite_rays_train(sigma, rgbs, deltas, rays, cfg.T_thresh, ret_weights, cfg.input_alpha)
+        if ret_weights:
+            out["weights"] = weights.detach()             # no gradient path: the composite backward ignores grad_weights (raymarching.py:291)
         image = image + (1 - ws).unsqueeze(-1) * bg_color
     depth = (depth + nears) * (depth != 0)
     out.update(image=image, depth=depth, weights_sum=ws, sigmas=sigma, sdfs=sdf, roughness=roughness, sdf_gradients=sdf_grad,
@@ -219,10 +221,23 @@ def render_train(field: TrainableField, bitfield: torch.Tensor, rays_o: torch.Te
 
 
 def loss_epilogue(field: TrainableField, out: Dict[str, torch.Tensor], gt_rgb: torch.Tensor, gt_mask: torch.Tensor, *, color_w=1.0,
-                  mask_w=1.0, cauchy_w=0.1, eikonal_w=0.01) -> torch.Tensor:
+                  mask_w=1.0, cauchy_w=0.1, eikonal_w=0.01, backsdf_w=0.0, backsdf_thresh=0.01, fused: Optional[bool] = None) -> torch.Tensor:
     """The Trainer.train_step terms (nerf/utils.py:661-808) that reach every output of the branch under toaster.ini:
-    colour L1 (:661-662), mask BCE (:712-717), Cauchy (:762-776), eikonal (:793-798).  Used by bench / tests to drive a
-    full backward; the trainer itself is outside the hot path."""
+    colour L1 (:661-662), mask BCE (:712-717), Cauchy (:762-776), eikonal (:793-798), and with backsdf_w > 0 the back-sdf term
+    (:735-747) over run_cuda's auxiliary block (cuda_ray.py:173-211; render_train(..., ret_weights=True) supplies the weights).
+    On CUDA tensors this is the fused epilogue kernel (envidr_b200.epilogue.train_loss: 2 launches forward, 1 backward); the
+    torch formulation below serves the CPU checks that run this module's glue on the oracle's operators (tests/test_train_cpu.py)."""
+    if fused is None:
+        fused = out["image"].is_cuda
+    if fused:
+        from . import epilogue
+        cfg = epilogue.LossConfig(color_l1=True, color_w=color_w, mask_w=mask_w, cauchy_w=cauchy_w, eikonal_w=eikonal_w, backsdf_w=backsdf_w,
+                                  backsdf_thresh=backsdf_thresh)
+        total, _ = epilogue.train_loss(out["image"], out["weights_sum"], out["sdfs"], out["sdf_gradients"], gt_rgb, gt_mask, out.get("weights"),
+                                       out["deltas"], out["rays"], field.get_beta().detach(), cfg)
+        return total
+    if backsdf_w > 0:
+        raise NotImplementedError("the back-sdf term exists in the fused epilogue only")
     loss = color_w * (out["image"] - gt_rgb).abs().mean(-1).mean()
     loss = loss + mask_w * F.binary_cross_entropy(out["weights_sum"].clip(1e-3, 1.0 - 1e-3), gt_mask)
     reg = field.laplace_density(out["sdfs"], field.get_beta().detach(), 1)
@@ -257,7 +272,8 @@ class GraphedTrainStep:
                 p.grad = None
             self.counter.zero_()
             out = render_train(field, bitfield, self.rays_o, self.rays_d, cfg, bg_color=bg_color, perturb=perturb, force_all_rays=False,
-                               mean_count=mean_count, step_counter=self.counter, r_images=self.r_images)
+                               mean_count=mean_count, step_counter=self.counter, r_images=self.r_images,
+                               ret_weights=lk.get("backsdf_w", 0.0) > 0)
             loss = loss_epilogue(field, out, self.gt_rgb, self.gt_mask, **lk)
             loss.backward()
             return loss.detach(), out["image"].detach(), out["weights_sum"].detach()
