@@ -46,6 +46,11 @@ class RenderConfig:
     # n_step floor of the secondary (reflected-ray) pass: it runs over few rays, so the reference schedule n_step = N // n_alive
     # starts at 1 and issues ~50 launches of <= 71 k samples; a floor only changes the batching (same composited samples).  1 = reference
     secondary_n_step_floor: int = 4
+    # secondary pass with deferred shading (tensor-core field): its iterative loop runs geometry-only (ray termination depends on
+    # the density alone) while logging the per-sample records, then env_net + the shading heads run ONCE over all composited
+    # samples (envidr_field_forward_records) and envidr_composite_rays_replay composites -- the main pass's scheme, applied to
+    # the reflected rays.  Same composited samples and per-sample math as the iterative loop; False = shade inside the loop
+    defer_secondary_shading: bool = True
 
     def aabb6(self):
         return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3
@@ -165,12 +170,13 @@ class SampleLogBuffers:
 _logs: Dict[str, SampleLogBuffers] = {}
 
 
-def _sample_log(device, need: int) -> SampleLogBuffers:
-    """One log per device, grown geometrically (a frame's geometry pass marches a few million samples: 140 B each)."""
-    lg = _logs.get(str(device))
+def _sample_log(device, need: int, slot: str = "primary") -> SampleLogBuffers:
+    """One log per device and pass, grown geometrically (a frame's geometry pass marches a few million samples: 140 B each)."""
+    key = f"{device}/{slot}"
+    lg = _logs.get(key)
     if lg is None or lg.capacity < need:
         lg = SampleLogBuffers(max(need, 1 << 20), device)
-        _logs[str(device)] = lg
+        _logs[key] = lg
     return lg
 
 
@@ -352,11 +358,28 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         if cfg.obj_aabb is not None:
             ob = torch.tensor(cfg.obj_aabb, dtype=torch.float32, device=rays_o.device)
             ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
-        ref = render_rays(field, bitfield, ref_o[ref_mask], ref_d[ref_mask], cfg, bg_color=0.0, env_rot_radian=env_rot_radian,
-                          get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2,
-                          n_step_floor=cfg.secondary_n_step_floor)
-        if stats is not None:
-            stats.append(last_stats())
+        sec_o, sec_d = ref_o[ref_mask], ref_d[ref_mask]
+        n_sec = sec_o.shape[0]
+        ref = None
+        if cfg.defer_secondary_shading and field.precision == "tc" and n_sec > 0:
+            log2 = _sample_log(rays_o.device, _log_need.get(("sec", N), 4 * 1 << 20), "secondary")
+            geo2 = render_rays(field, bitfield, sec_o, sec_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
+                               max_steps=cfg.indir_max_steps, min_near=dt * 2, n_step_floor=cfg.secondary_n_step_floor,
+                               sample_count=True, log=log2)
+            st2 = last_stats()
+            _log_need[("sec", N)] = int(st2["samples"] * 1.25) + 4096
+            if st2["samples"] <= log2.capacity:
+                ref = render_rays_from_log(field, log2, st2["samples"], geo2["sample_count"],
+                                           torch.ones(n_sec, dtype=torch.bool, device=rays_o.device), cfg, bg_color=0.0)
+                st2 = dict(st2, shaded=int(ref.pop("_samples")))
+            if stats is not None and ref is not None:
+                stats.append(st2)
+        if ref is None:                                                     # shading inside the loop (reference-shaped)
+            ref = render_rays(field, bitfield, sec_o, sec_d, cfg, bg_color=0.0, env_rot_radian=env_rot_radian,
+                              get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2,
+                              n_step_floor=cfg.secondary_n_step_floor)
+            if stats is not None:
+                stats.append(last_stats())
         ref_image = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)
         ref2ray = ref_mask[ray_mask]
         r_img = ref_image.new_zeros(ref2ray.shape[0], 4)

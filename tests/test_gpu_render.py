@@ -187,8 +187,10 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
     st_a, st_b = [], []
     a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, secondary_n_step_floor=4), bg_color=1.0,
                       visual_items=items, stats=st_a)
-    b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False, secondary_n_step_floor=1), bg_color=1.0,
-                      visual_items=items, stats=st_b)
+    b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False, secondary_n_step_floor=1,
+                                                          defer_secondary_shading=False), bg_color=1.0, visual_items=items, stats=st_b)
+    # deferred shading of the secondary pass: the composited samples only, never more than were marched
+    assert "shaded" in st_a[1] and 0.7 * st_b[1]["samples"] <= st_a[1]["shaded"] <= st_b[1]["samples"]
     assert st_a[0] == st_b[0]                                               # the geometry pass is untouched
     assert st_a[1]["iterations"] < st_b[1]["iterations"] and st_b[1]["samples"] <= st_a[1]["samples"] <= 1.3 * st_b[1]["samples"]
     # the replay evaluates only the samples that were composited; the iterative loop also marches / shades the samples that
@@ -201,8 +203,9 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
     assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["normal_image"], b["normal_image"])
     # the same with the geometry recomputed (march replay + hash grid + sdf_net) instead of reused from the geometry pass's log
     st_c = []
-    c = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, reuse_geometry=False, secondary_n_step_floor=4),
-                      bg_color=1.0, visual_items=items, stats=st_c)
+    c = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, reuse_geometry=False, secondary_n_step_floor=4,
+                                                          defer_secondary_shading=False), bg_color=1.0, visual_items=items, stats=st_c)
+    assert "shaded" not in st_c[1]
     assert st_c[2]["samples"] == st_a[2]["samples"]
     for k in ("image", "diffuse_image", "specular_image", "roughness_image"):
         e = (a[k] - c[k]).abs().reshape(a[k].shape[0], -1).max(-1).values
