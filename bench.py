@@ -321,14 +321,12 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # A fresh box needs more than 3 frames (~50 ms) to reach its steady SM clock: keep warming up (untimed) until 1.5 s of
-    # frames have run, so that the resident-input region below is measured in the same state as the e2e region after it.
+    # A fresh box needs more than 3 frames (~50 ms) to reach its steady state: 60 more untimed frames (~1 s), so that the
+    # resident-input region below is measured in the same state as the e2e region after it.
     barrier()
-    warm_extra, t_warm = 0, time.time()
-    while not args.no_extra_warmup and time.time() - t_warm < 1.5 and warm_extra < 200:
+    warm_extra = 0 if args.no_extra_warmup else 60    # a fixed count: every rank must issue the same number of all-gathers
+    for _ in range(warm_extra):
         step_resident()
-        torch.cuda.synchronize()
-        warm_extra += 1
     barrier()
     stats = []
     out, _ = step_resident(stats)
@@ -396,7 +394,7 @@ def main():
                                "algorithmic FLOPs counted here") if tcp else "fp32 FFMA (exact path)"}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             v, dt, s, n = cpu_baseline(fp_cpu, bf, ro, rd, args, indir, args.cpu_sample, rot)
             cpu = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{n} rays (stride sample of the {W}x{H} frame, {s} samples) in {dt:.1f} s; oracle CPU port "

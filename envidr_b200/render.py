@@ -180,26 +180,34 @@ def _sample_log(device, need: int, slot: str = "primary") -> SampleLogBuffers:
     return lg
 
 
-def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_mask: torch.Tensor, cfg: RenderConfig, *,
-                         bg_color=0.0, r_images: Optional[torch.Tensor] = None, visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
-    """Main pass from the geometry pass's sample log: the samples of the rays in `ray_mask` are gathered ray by ray
-    (envidr_permute_sample_log), shaded from their geometry records (envidr_field_forward_records: env_net + shading heads
-    only) and composited (envidr_composite_rays_replay).  counts [N_all] = samples composited per ray of the geometry pass;
-    r_images [n_masked, 4] in the order of the masked rays.  Returns per-masked-ray images."""
+def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor],
+                         cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
+                         visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+    """A pass shaded from a geometry-only pass's sample log: the samples of the rays `ray_idx` (int64 indices into the logged
+    pass's rays, ascending; None = all of them) are gathered ray by ray (envidr_permute_sample_log), shaded from their geometry
+    records (envidr_field_forward_records: env_net + shading heads only) and composited (envidr_composite_rays_replay).
+    counts [N_all] = samples composited per ray of the logged pass; r_images [n_selected, 4] in the order of ray_idx.
+    Returns per-selected-ray images.  One host synchronisation (the batch size M sizes the buffers)."""
     dev = counts.device
     f32 = dict(dtype=torch.float32, device=dev)
-    cm = torch.where(ray_mask, counts, torch.zeros_like(counts)).to(torch.int64)
-    incl = torch.cumsum(cm, 0)
-    M = int(incl[-1].item()) if cm.numel() else 0
-    ray_off = torch.where(ray_mask, incl - cm, torch.full_like(cm, -1)).to(torch.int32)
-    n_r = int(ray_mask.sum().item())
+    n_all = counts.shape[0]
+    cs = (counts if ray_idx is None else counts[ray_idx]).to(torch.int64)
+    n_r = int(cs.shape[0])
+    incl = torch.cumsum(cs, 0)
+    M = int(incl[-1].item()) if n_r else 0
+    off = (incl - cs).to(torch.int32)
+    if ray_idx is None:
+        ray_off = off
+    else:
+        ray_off = torch.full((n_all,), -1, dtype=torch.int32, device=dev)
+        ray_off[ray_idx] = off
     rec = torch.empty(M, 32, **f32)
     sigma, delta = torch.empty(M, **f32), torch.empty(M, 2, **f32)
     lstruct = log.cstruct()
     check(lib().envidr_permute_sample_log(ctypes.byref(lstruct), total, ptr(ray_off), ptr(rec), ptr(sigma), ptr(delta), stream()),
           "permute_sample_log")
-    # rays of the pass in masked order: (ray id = position among the masked rays, offset, count)
-    rays = torch.stack([torch.arange(n_r, dtype=torch.int32, device=dev), ray_off[ray_mask], counts[ray_mask].to(torch.int32)], -1).contiguous()
+    # rays of the pass in selected order: (ray id = position among the selected rays, offset, count)
+    rays = torch.stack([torch.arange(n_r, dtype=torch.int32, device=dev), off, cs.to(torch.int32)], -1).contiguous()
     r_s = None
     if r_images is not None:
         r_s = torch.empty(M, 4, **f32)
@@ -358,7 +366,12 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         if cfg.obj_aabb is not None:
             ob = torch.tensor(cfg.obj_aabb, dtype=torch.float32, device=rays_o.device)
             ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
-        sec_o, sec_d = ref_o[ref_mask], ref_d[ref_mask]
+        # The reference indexes with the boolean masks at every use (each one a host synchronisation); here the two index lists are
+        # built once and every later gather / scatter uses them.  ref_mask is a subset of ray_mask (ws > 0.9 vs > 0.3).
+        ref_idx = ref_mask.nonzero().squeeze(-1)
+        ray_idx = ray_mask.nonzero().squeeze(-1)
+        pos_in_ray = torch.cumsum(ray_mask, 0) - 1                       # position of a ray among the main-pass rays
+        sec_o, sec_d = ref_o[ref_idx], ref_d[ref_idx]
         n_sec = sec_o.shape[0]
         ref = None
         if cfg.defer_secondary_shading and field.precision == "tc" and n_sec > 0:
@@ -369,8 +382,7 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             st2 = last_stats()
             _log_need[("sec", N)] = int(st2["samples"] * 1.25) + 4096
             if st2["samples"] <= log2.capacity:
-                ref = render_rays_from_log(field, log2, st2["samples"], geo2["sample_count"],
-                                           torch.ones(n_sec, dtype=torch.bool, device=rays_o.device), cfg, bg_color=0.0)
+                ref = render_rays_from_log(field, log2, st2["samples"], geo2["sample_count"], None, cfg, bg_color=0.0)
                 st2 = dict(st2, shaded=int(ref.pop("_samples")))
             if stats is not None and ref is not None:
                 stats.append(st2)
@@ -381,11 +393,10 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             if stats is not None:
                 stats.append(last_stats())
         ref_image = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)
-        ref2ray = ref_mask[ray_mask]
-        r_img = ref_image.new_zeros(ref2ray.shape[0], 4)
-        r_img[ref2ray] = ref_image
+        r_img = ref_image.new_zeros(ray_idx.shape[0], 4)
+        r_img[pos_in_ray[ref_idx]] = ref_image                              # == r_img[ref_mask[ray_mask]] = ref_image (renderer.py:484-486)
         if reuse:
-            main = render_rays_from_log(field, log, geo_stats["samples"], geo["sample_count"], ray_mask, cfg, bg_color=0.0, r_images=r_img,
+            main = render_rays_from_log(field, log, geo_stats["samples"], geo["sample_count"], ray_idx, cfg, bg_color=0.0, r_images=r_img,
                                         visual_items=visual_items)
             if stats is not None:
                 stats.append(dict(iterations=1, samples=int(main.pop("_samples"))))
@@ -393,12 +404,12 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
                 main.pop("_samples")
         elif cfg.replay_main_pass:
             # the main pass visits the rays of the geometry pass again (same origins, same density): replay its sample counts
-            main = render_rays_replay(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], geo["sample_count"][ray_mask], cfg, bg_color=0.0,
+            main = render_rays_replay(field, bitfield, rays_o[ray_idx], rays_d[ray_idx], geo["sample_count"][ray_idx], cfg, bg_color=0.0,
                                       r_images=r_img, env_rot_radian=env_rot_radian, visual_items=visual_items)
             if stats is not None:
                 stats.append(dict(iterations=1, samples=int(main.pop("_samples"))))
         else:
-            main = render_rays(field, bitfield, rays_o[ray_mask], rays_d[ray_mask], cfg, bg_color=0.0, r_images=r_img,
+            main = render_rays(field, bitfield, rays_o[ray_idx], rays_d[ray_idx], cfg, bg_color=0.0, r_images=r_img,
                                env_rot_radian=env_rot_radian, get_normal_image=get_normal_image, visual_items=visual_items)
             if stats is not None:
                 stats.append(last_stats())
@@ -406,10 +417,10 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         for k in ("image", "specular_image", "diffuse_image", "roughness_image"):
             if k in main:
                 v = normals.new_zeros(N, main[k].shape[-1])
-                v[ray_mask] = main[k]
+                v[ray_idx] = main[k]
                 results[k] = v
         ws_full = normals.new_zeros(N)
-        ws_full[ray_mask] = main["weights_sum"]
+        ws_full[ray_idx] = main["weights_sum"]
         bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(bg_color, dtype=torch.float32, device=rays_o.device)
         results["image"] = (torch.zeros_like(normals) + bg) * (1 - ws_full[:, None]) + results["image"]
         results["weights_sum"] = ws_full
