@@ -320,9 +320,11 @@ k_wgrad_tc(const float* __restrict__ G, const float* __restrict__ X, uint32_t M,
     const uint32_t n_st_total = (M + kWgSamples - 1) / kWgSamples;
     const uint32_t per = (n_st_total + gridDim.x - 1) / gridDim.x;
     const uint32_t st0 = min(n_st_total, blockIdx.x * per), st1 = min(n_st_total, st0 + per);
-    float* out = partial + (size_t)blockIdx.x * N * K;
+    const bool accumulate = (variant & 2) != 0;  // partial is dW [N, K] itself (zeroed by the caller): CTAs add their sums atomically
+    float* out = accumulate ? partial : partial + (size_t)blockIdx.x * N * K;
     if (st0 >= st1) {                            // no samples: the partial is zero
-        for (uint32_t i = tid; i < N * K; i += kWgThreads) out[i] = 0.0f;
+        if (!accumulate)
+            for (uint32_t i = tid; i < N * K; i += kWgThreads) out[i] = 0.0f;
         return;
     }
     if (tid == 0) {
@@ -350,12 +352,12 @@ k_wgrad_tc(const float* __restrict__ G, const float* __restrict__ X, uint32_t M,
             for (uint32_t j = 0; j < kWgSamples / 16; j++) {
                 // B operand (X): hi block then lo block, each Kp rows x 32 samples
                 const uint32_t b_hi = sbase + kWgABytes + j * 2 * lboB, b_lo = b_hi + Kp * kWgSamples * 2;
-                const uint64_t db_hi = variant ? tc::make_smem_desc(b_hi, 128, lboB) : tc::make_smem_desc(b_hi, lboB, 128);
-                const uint64_t db_lo = variant ? tc::make_smem_desc(b_lo, 128, lboB) : tc::make_smem_desc(b_lo, lboB, 128);
+                const uint64_t db_hi = (variant & 1) ? tc::make_smem_desc(b_hi, 128, lboB) : tc::make_smem_desc(b_hi, lboB, 128);
+                const uint64_t db_lo = (variant & 1) ? tc::make_smem_desc(b_lo, 128, lboB) : tc::make_smem_desc(b_lo, lboB, 128);
                 for (uint32_t h = 0; h < n_halves; h++) {
                     const uint32_t a_hi = sbase + h * (2 * 128 * kWgSamples * 2) + j * 2 * lboA, a_lo = a_hi + 128 * kWgSamples * 2;
-                    const uint64_t da_hi = variant ? tc::make_smem_desc(a_hi, 128, lboA) : tc::make_smem_desc(a_hi, lboA, 128);
-                    const uint64_t da_lo = variant ? tc::make_smem_desc(a_lo, 128, lboA) : tc::make_smem_desc(a_lo, lboA, 128);
+                    const uint64_t da_hi = (variant & 1) ? tc::make_smem_desc(a_hi, 128, lboA) : tc::make_smem_desc(a_hi, lboA, 128);
+                    const uint64_t da_lo = (variant & 1) ? tc::make_smem_desc(a_lo, 128, lboA) : tc::make_smem_desc(a_lo, lboA, 128);
                     const uint32_t d = tmem + h * 256u;
                     const uint32_t acc = (it > 0 || j > 0) ? 1u : 0u;
                     tc::mma_f16_ss_w(d, da_hi, db_hi, idesc, acc);
@@ -439,8 +441,19 @@ k_wgrad_tc(const float* __restrict__ G, const float* __restrict__ X, uint32_t M,
                 tc::tmem_ld16(acc + c0, r);
                 tc::tmem_ld_wait();
                 if (n < N) {
-                    #pragma unroll
-                    for (int e = 0; e < 16; e++) if (c0 + e < K) out[(size_t)n * K + c0 + e] = __uint_as_float(r[e]) * inv;
+                    if (!accumulate) {
+                        #pragma unroll
+                        for (int e = 0; e < 16; e++) if (c0 + e < K) out[(size_t)n * K + c0 + e] = __uint_as_float(r[e]) * inv;
+                    } else if ((K & 3) == 0 && c0 + 16 <= K) {       // 16-byte aligned rows: four vector reductions (red.global.add.v4.f32)
+                        #pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            atomicAdd(reinterpret_cast<float4*>(out + (size_t)n * K + c0 + e),
+                                      make_float4(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv, __uint_as_float(r[e + 2]) * inv,
+                                                  __uint_as_float(r[e + 3]) * inv));
+                    } else {
+                        #pragma unroll
+                        for (int e = 0; e < 16; e++) if (c0 + e < K) atomicAdd(out + (size_t)n * K + c0 + e, __uint_as_float(r[e]) * inv);
+                    }
                 }
             }
         }
@@ -452,9 +465,117 @@ k_wgrad_tc(const float* __restrict__ G, const float* __restrict__ X, uint32_t M,
 
 constexpr size_t kWgSmem = 2 * kWgStage + 256;
 
+// Per-tensor power-of-two scales of the two wgrad operands in one launch (the torch formulation is ~14 tiny kernels):
+// scales[0] = s_a, [1] = s_b with s = 2^(13 - floor(log2(max|.|))) (largest magnitude into [2^13, 2^14)), [2] = 1 / (s_a s_b).
+// scales[4..6] are scratch (bit patterns of the two maxima, ticket) and must be zero on entry; the last block restores that.
+// The pass over `a` (= dY [M, N]) can also produce its column sums (the bias gradient), added into colsum [N] (zeroed by the
+// caller): with 16-byte loads and a grid stride that is a multiple of N every thread keeps seeing the same four columns, so
+// the sums stay in registers; one shared-memory and one global atomic per column and block at the end.
+constexpr int kPsBlock = 256;
+__global__ void __launch_bounds__(kPsBlock) k_pow2_scales(const float* __restrict__ a, uint64_t na, const float* __restrict__ b, uint64_t nb,
+                                                          float* __restrict__ scales, uint32_t N, float* __restrict__ colsum, int vec) {
+    __shared__ float s_col[256];
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(scales + 4);
+    float ma = 0.0f, mb = 0.0f;
+    const uint64_t T = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (colsum) {
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s_col[i] = 0.0f;
+        __syncthreads();
+    }
+    if (vec) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        const uint64_t na4 = na / 4, nb4 = nb / 4;
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint64_t i = t0;
+        for (; i + 3 * T < na4; i += 4 * T) {                // four independent 16-byte loads in flight
+            const float4 v0 = __ldg(a4 + i), v1 = __ldg(a4 + i + T), v2 = __ldg(a4 + i + 2 * T), v3 = __ldg(a4 + i + 3 * T);
+            ma = fmaxf(ma, fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                                 fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)))));
+            ma = fmaxf(ma, fmaxf(fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))),
+                                 fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)))));
+            cs.x += (v0.x + v1.x) + (v2.x + v3.x); cs.y += (v0.y + v1.y) + (v2.y + v3.y);
+            cs.z += (v0.z + v1.z) + (v2.z + v3.z); cs.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; i < na4; i += T) {
+            const float4 v = __ldg(a4 + i);
+            ma = fmaxf(ma, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+        }
+        if (colsum) {                                        // (4 * T) % N == 0 and N % 4 == 0 (checked by the host): fixed columns
+            const uint32_t c0 = (uint32_t)((4 * t0) % N);
+            atomicAdd(&s_col[c0], cs.x); atomicAdd(&s_col[c0 + 1], cs.y); atomicAdd(&s_col[c0 + 2], cs.z); atomicAdd(&s_col[c0 + 3], cs.w);
+        }
+        if (t0 == 0)
+            for (uint64_t k = na4 * 4; k < na; k++) ma = fmaxf(ma, fabsf(a[k]));      // (no column sums here: na % 4 == 0 when colsum is set)
+        i = t0;
+        for (; i + 3 * T < nb4; i += 4 * T) {
+            const float4 v0 = __ldg(b4 + i), v1 = __ldg(b4 + i + T), v2 = __ldg(b4 + i + 2 * T), v3 = __ldg(b4 + i + 3 * T);
+            mb = fmaxf(mb, fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                                 fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)))));
+            mb = fmaxf(mb, fmaxf(fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))),
+                                 fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)))));
+        }
+        for (; i < nb4; i += T) {
+            const float4 v = __ldg(b4 + i);
+            mb = fmaxf(mb, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        if (t0 == 0)
+            for (uint64_t k = nb4 * 4; k < nb; k++) mb = fmaxf(mb, fabsf(b[k]));
+    } else {
+        for (uint64_t i = t0; i < na; i += T) ma = fmaxf(ma, fabsf(__ldg(a + i)));
+        for (uint64_t i = t0; i < nb; i += T) mb = fmaxf(mb, fabsf(__ldg(b + i)));
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {                       // non-negative floats order like their bit patterns
+        atomicMax(scratch + 0, __float_as_uint(ma));
+        atomicMax(scratch + 1, __float_as_uint(mb));
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (colsum)
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(colsum + i, s_col[i]);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(scratch + 2, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        float s[2];
+        for (int k = 0; k < 2; k++) {
+            float m = __uint_as_float(atomicAdd(scratch + k, 0u));
+            m = fminf(fmaxf(m, 1e-30f), 1e30f);          // clamp_min(1e-30); inf / nan gradients keep a finite scale
+            s[k] = exp2f(13.0f - floorf(log2f(m)));
+        }
+        scales[0] = s[0]; scales[1] = s[1]; scales[2] = 1.0f / (s[0] * s[1]);
+        scratch[0] = 0; scratch[1] = 0; scratch[2] = 0;
+    }
+}
+
 }  // namespace envidr
 
 extern "C" {
+
+int envidr_pow2_scales(const float* a, uint64_t na, const float* b, uint64_t nb, float* scales8, uint32_t N, float* colsum,
+                       envidr_stream_t stream) {
+    ENVIDR_REQUIRE(a && b && scales8, ENVIDR_E_BADARG, "null pointer");
+    const uint64_t n = na > nb ? na : nb;
+    uint32_t blocks = (uint32_t)(n / 4096 < 1 ? 1 : (n / 4096 > 8u * envidr::kSMs ? 8u * envidr::kSMs : n / 4096));
+    const int vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+    if (colsum) {
+        // fixed columns per thread need 16-byte loads, N | row length, and a grid stride (4 * blocks * 256 elements) divisible by N
+        ENVIDR_REQUIRE(vec && N >= 4 && N <= 256 && (N & (N - 1)) == 0 && na % N == 0, ENVIDR_E_UNSUPPORTED,
+                       "pow2_scales: column sums need 16-byte aligned operands and N a power of two in 4..256");
+    }
+    envidr::k_pow2_scales<<<blocks, envidr::kPsBlock, 0, envidr::as_stream(stream)>>>(a, na, b, nb, scales8, N, colsum, vec);
+    envidr::g_launches += 1;
+    return envidr::check_launch("pow2_scales");
+}
 
 /* partial: [grid, N, K] floats with grid = envidr_wgrad_tc_partials(M); scales (device): {s_dY, s_X, 1 / (s_dY * s_X)}, powers of two. */
 uint32_t envidr_wgrad_tc_partials(uint32_t M) {

@@ -42,15 +42,31 @@ def _pow2_scales(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 WGRAD_TC = True      # weight gradients through csrc/linear_tc.cu::k_wgrad_tc (False: cuBLAS fp32 dY^T X)
 
 
-def wgrad_tc(gy: torch.Tensor, x: torch.Tensor, variant: int = 0) -> torch.Tensor:
-    """dW [N, K] = gy^T x on tensor cores (gy [M, N], x [M, K], CUDA fp32 contiguous)."""
+WGRAD_ATOMIC = True  # CTAs add their partial dW into one [N, K] tensor with vector atomics (False: [grid, N, K] partials + torch sum)
+
+
+def wgrad_tc(gy: torch.Tensor, x: torch.Tensor, variant: int = 0, with_bias: bool = False):
+    """dW [N, K] = gy^T x on tensor cores (gy [M, N], x [M, K], CUDA fp32 contiguous).
+    with_bias: also return the bias gradient gy.sum(0) -> (dW, db); it comes out of the same pass over gy that finds the operand
+    scales when N is a power of two in 4..256 (otherwise a torch column sum)."""
     M, N = gy.shape
     K = x.shape[1]
-    P = lib().envidr_wgrad_tc_partials(M)
-    partial = torch.empty(P, N, K, dtype=torch.float32, device=gy.device)
-    sc = _pow2_scales(gy, x)
-    check(lib().envidr_wgrad_tc(ptr(gy), ptr(x), M, N, K, ptr(sc), ptr(partial), variant, stream()), "wgrad_tc")
-    return partial.sum(0)
+    if not WGRAD_ATOMIC:
+        P = lib().envidr_wgrad_tc_partials(M)
+        partial = torch.empty(P, N, K, dtype=torch.float32, device=gy.device)
+        sc = _pow2_scales(gy, x)
+        check(lib().envidr_wgrad_tc(ptr(gy), ptr(x), M, N, K, ptr(sc), ptr(partial), variant, stream()), "wgrad_tc")
+        dW = partial.sum(0)
+        return (dW, gy.sum(0)) if with_bias else dW
+    fused_bias = with_bias and 4 <= N <= 256 and (N & (N - 1)) == 0 and gy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0
+    buf = torch.zeros(8 + N * K + (N if fused_bias else 0), dtype=torch.float32, device=gy.device)     # scales8 + dW (+ db): one zero-fill
+    sc, dW = buf[:8], buf[8:8 + N * K].view(N, K)
+    db = buf[8 + N * K:] if fused_bias else None
+    check(lib().envidr_pow2_scales(ptr(gy), gy.numel(), ptr(x), x.numel(), ptr(sc), N, ptr(db), stream()), "pow2_scales")
+    check(lib().envidr_wgrad_tc(ptr(gy), ptr(x), M, N, K, ptr(sc), ptr(dW), variant | 2, stream()), "wgrad_tc")
+    if with_bias:
+        return dW, (db if fused_bias else gy.sum(0))
+    return dW
 
 
 class _linear_tc(Function):
@@ -74,9 +90,14 @@ class _linear_tc(Function):
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
             gx = _run(gy, _image(Wc.t().contiguous()), None, Wc.shape[1], False)       # dY W = dY (W^T)^T
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gW = wgrad_tc(gy, x2) if WGRAD_TC else gy.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if WGRAD_TC:
+                r = wgrad_tc(gy, x2, with_bias=want_b)
+                gW, gb = r if want_b else (r, None)
+            else:
+                gW = gy.t() @ x2
+        if want_b and gb is None:
             gb = gy.sum(0)
         return gx, gW, gb, None
 

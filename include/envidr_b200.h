@@ -342,6 +342,14 @@ int envidr_linear_tc(const float* X, uint32_t M, uint32_t K, const void* img, co
  * (the caller adds them up); scales (device, 3 floats): power-of-two pre-scales of dY and X and the inverse of their product
  * (a loss gradient sits around 1e-7, below fp16's normal range).  variant: 0 (1 swaps the descriptor's LBO / SBO; test hook). */
 uint32_t envidr_wgrad_tc_partials(uint32_t M);
+/* The per-tensor scales envidr_wgrad_tc expects, in one launch: scales8 = device float[8], ZERO on first use (entries 4..6 are
+ * scratch that the kernel leaves zeroed again); on return scales8[0..2] = {s_a, s_b, 1 / (s_a s_b)}, s = 2^(13 - floor(log2 max|.|)).
+ * colsum != NULL: a is [na / N, N] and its column sums (the bias gradient when a = dY) are ADDED into colsum [N] in the same pass
+ * (N a power of two in 4..256, 16-byte aligned operands; otherwise ENVIDR_E_UNSUPPORTED). */
+int envidr_pow2_scales(const float* a, uint64_t na, const float* b, uint64_t nb, float* scales8, uint32_t N, float* colsum,
+                       envidr_stream_t stream);
+/* variant bit 1 (value 2): `partial` is dW [N, K] itself, zeroed by the caller; every CTA adds its partial sum with vector atomics
+ * (no [grid, N, K] round trip through HBM; the summation order, hence the last bit, is not deterministic). */
 int envidr_wgrad_tc(const float* dY, const float* X, uint32_t M, uint32_t N, uint32_t K, const float* scales, float* partial,
                     int variant, envidr_stream_t stream);
 

@@ -36,3 +36,10 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, to
     step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=35, max_name_column_width=60))
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+busy = sum(e.time_range.elapsed_us() for e in ev)
+span = ev[-1].time_range.end - ev[0].time_range.start
+small = [e for e in ev if e.time_range.elapsed_us() < 10]
+print(f"eager step: {len(ev)} GPU kernels/copies, busy {busy / 1e3:.2f} ms, span {span / 1e3:.2f} ms; {len(small)} of them < 10 us "
+      f"({sum(e.time_range.elapsed_us() for e in small) / 1e3:.2f} ms)")

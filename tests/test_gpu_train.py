@@ -199,3 +199,25 @@ def test_linear_tc_forward_backward(dev, M, K, N, relu, bias):
         assert float((Wg.grad.cpu().double() - Wd.grad).abs().max()) <= 2e-5 * float(Wd.grad.abs().max() + 1e-30)
         if bias:
             assert float((bg.grad.cpu().double() - bd.grad).abs().max()) <= 2e-5 * float(bd.grad.abs().max() + 1e-30)
+
+
+@pytest.mark.parametrize("M,N,K", [(70_000, 256, 256), (4097, 64, 28), (300, 32, 24), (513, 12, 256), (2, 4, 4)])
+def test_wgrad_tc_atomic_accumulate_and_fused_bias(dev, M, N, K):
+    """envidr_pow2_scales (operand scales + bias column sums in one pass) and k_wgrad_tc's atomic accumulation (variant bit 1)
+    against float64 torch; N = 12 takes the torch column-sum path.  Also against the partials + torch.sum formulation."""
+    from envidr_b200 import linear_tc as L
+    g = torch.Generator().manual_seed(M + N + K)
+    gy = (torch.randn(M, N, generator=g) * 1e-7).to(dev)                     # loss-gradient magnitudes
+    x = torch.randn(M, K, generator=g).to(dev)
+    dW, db = L.wgrad_tc(gy, x, with_bias=True)
+    dW_ref = gy.double().t() @ x.double()
+    db_ref = gy.double().sum(0)
+    assert float((dW.double() - dW_ref).abs().max()) <= 2e-5 * float(dW_ref.abs().max())
+    assert float((db.double() - db_ref).abs().max()) <= 2e-5 * float(db_ref.abs().max()) + 1e-6 * float(gy.abs().max()) * M ** 0.5
+    L.WGRAD_ATOMIC = False
+    try:
+        dW2, db2 = L.wgrad_tc(gy, x, with_bias=True)
+    finally:
+        L.WGRAD_ATOMIC = True
+    assert float((dW - dW2).abs().max()) <= 2e-5 * float(dW_ref.abs().max())
+    assert float((db - db2).abs().max()) <= 2e-5 * float(db_ref.abs().max()) + 1e-6 * float(gy.abs().max()) * M ** 0.5
