@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA path (oracle/ref_cuda.py)")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary train-step (BASELINE config 3) measurement")
+    ap.add_argument("--no-defer", action="store_true", help="shade inside the iterative loops (RenderConfig.defer_shading / defer_secondary_shading off)")
     ap.add_argument("--no-extra-warmup", action="store_true", help="profiling runs (ncu --launch-skip counts on exactly W warm-up frames)")
     ap.add_argument("--no-density", action="store_true", help="skip the auxiliary occupancy-grid update measurement (SURVEY 8 f-1)")
     ap.add_argument("--train-rays", type=int, default=4096)
@@ -237,12 +238,13 @@ def run_reference(args):
 
 
 def config_dict(args, W, H, indir):
-    return {"workload": f"synthetic toaster-dims scene {W}x{H} inference, " + ("use_renv + indir_ref (3 passes)" if indir else "1 pass"),
+    return {"workload": f"synthetic toaster-dims scene {W}x{H} inference, " + ("use_renv + indir_ref (3 passes)" if indir else "1 pass (BASELINE config 2 shape)"),
             "rays_per_step_per_gpu": W * H, "hash": "L16 C2 base16 res2048 T2^19 (48.8 MB fp32)",
             "mlps": "sdf 32-64-64-15, env IDE72-256-256-256-12 x2, diffuse 24-32-3, color 28-64-64-3, renv 4-64-64-64-12",
             "max_steps": 1024, "T_thresh": 1e-4,
             "schedule": "passes 1-2: the reference's iterative schedule (n_step = N // n_alive <= 8); main pass: one batch over the per-ray "
-                        "sample counts found by the geometry pass (RenderConfig.replay_main_pass)" if indir else "reference iterative schedule",
+                        "sample counts found by the geometry pass (RenderConfig.replay_main_pass)" if indir else "geometry-only iterative loop (reference schedule), then one shading batch over the composited samples "
+                        "(RenderConfig.defer_shading)",
             "parallelism": f"ray/frame sharding x{args.gpus} + all_gather",
             "cache": "inputs larger than L2 are not needed: 48.8 MB table + per-iteration sample buffers are re-written each step; "
                      "L2 is flushed between timed steps by writing a 256 MB buffer"}
@@ -274,7 +276,7 @@ def main():
     fp = fp_cpu.to(dev).pack()
     bft = torch.from_numpy(bf).to(dev)
     rot = (2 * np.pi * rank / world) if world > 1 else None
-    cfg = render.RenderConfig(indir_ref=indir)
+    cfg = render.RenderConfig(indir_ref=indir, defer_shading=not args.no_defer, defer_secondary_shading=not args.no_defer)
     ro_d, rd_d = ro.to(dev), rd.to(dev)
     ro_h, rd_h = ro.pin_memory(), rd.pin_memory()
     img_h = torch.empty(N, 3).pin_memory()
@@ -367,7 +369,7 @@ def main():
             flop_step = (stats[0]["samples"] * FLOP_GEOMETRY + stats[1]["samples"] * FLOP_PER_SAMPLE
                          + stats[2]["samples"] * (FLOP_PER_SAMPLE + FLOP_RENV_EXTRA))
     else:
-        flop_step = stats[0]["samples"] * (FLOP_ENV if tcp else FLOP_PER_SAMPLE)
+        flop_step = stats[0].get("shaded", stats[0]["samples"]) * (FLOP_ENV if tcp else FLOP_PER_SAMPLE)
     field_ms_per_step = fms.value / args.steps
     peaks = {}
     try:

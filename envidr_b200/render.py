@@ -51,6 +51,8 @@ class RenderConfig:
     # samples (envidr_field_forward_records) and envidr_composite_rays_replay composites -- the main pass's scheme, applied to
     # the reflected rays.  Same composited samples and per-sample math as the iterative loop; False = shade inside the loop
     defer_secondary_shading: bool = True
+    # the same scheme for the single-pass render (indir_ref = False): geometry-only loop, then one shading batch + one compositing launch
+    defer_shading: bool = True
 
     def aabb6(self):
         return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3
@@ -237,7 +239,8 @@ def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, 
                                              ptr(rough), ptr(delta), ptr(rays), None, M, n_r, cfg.T_thresh, int(cfg.input_alpha),
                                              ptr(res["weights_sum"]), ptr(res["depth"]), ptr(res["image"]), None, ptr(res.get("diffuse_image")),
                                              ptr(res.get("specular_image")), ptr(res.get("roughness_image")), stream()), "composite_rays_replay")
-    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32)
+    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32) if not isinstance(bg_color, (list, tuple)) \
+        else torch.tensor([float(v) for v in bg_color], **f32)
     res["image"] = res["image"] + (1 - res["weights_sum"]).unsqueeze(-1) * bg
     if "roughness_image" in res:
         res["roughness_image"] = res["roughness_image"][..., None]
@@ -339,10 +342,27 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
     rays_d = rays_d.float().contiguous().view(-1, 3)
     N = rays_o.shape[0]
     if not cfg.indir_ref:
-        results = render_rays(field, bitfield, rays_o, rays_d, cfg, bg_color=bg_color, r_images=r_images, env_rot_radian=env_rot_radian,
-                              get_normal_image=get_normal_image, visual_items=visual_items)
-        if stats is not None:
-            stats.append(last_stats())
+        results = None
+        if cfg.defer_shading and field.precision == "tc" and N > 0:
+            # single pass with deferred shading: geometry-only loop (logging the per-sample records), then ONE env_net + heads
+            # batch over the composited samples and one compositing launch -- the scheme of the 3-pass path's main pass
+            log = _sample_log(rays_o.device, _log_need.get(("one", N), 8 * 1 << 20), "primary")
+            geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
+                              sample_count=True, log=log)
+            st = last_stats()
+            _log_need[("one", N)] = int(st["samples"] * 1.25) + 4096
+            if st["samples"] <= log.capacity:
+                main = render_rays_from_log(field, log, st["samples"], geo["sample_count"], None, cfg, bg_color=bg_color, r_images=r_images,
+                                            visual_items=visual_items)
+                st = dict(st, shaded=int(main.pop("_samples")))
+                results = dict(main, depth=geo["depth"], normal_image=geo["normal_image"])
+                if stats is not None:
+                    stats.append(st)
+        if results is None:
+            results = render_rays(field, bitfield, rays_o, rays_d, cfg, bg_color=bg_color, r_images=r_images, env_rot_radian=env_rot_radian,
+                                  get_normal_image=get_normal_image, visual_items=visual_items)
+            if stats is not None:
+                stats.append(last_stats())
     else:
         dt = 2 * SQRT3 / cfg.indir_max_steps
         reuse = cfg.replay_main_pass and cfg.reuse_geometry and field.precision == "tc"

@@ -210,3 +210,32 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
     for k in ("image", "diffuse_image", "specular_image", "roughness_image"):
         e = (a[k] - c[k]).abs().reshape(a[k].shape[0], -1).max(-1).values
         assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
+
+
+@pytest.mark.parametrize("W,env_width,deg", [(64, 64, 4), (96, 256, 5)])
+def test_single_pass_deferred_shading_equals_loop(dev, W, env_width, deg):
+    """RenderConfig.defer_shading (single-pass render): geometry-only loop + one shading batch + one compositing launch against
+    shading inside the iterative loop -- same composited samples, RGB / visual items within 1e-4 on all but <= 2 pixels, depth and
+    weights_sum to rounding, per-ray r_images and a per-ray background included."""
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=env_width, ide_degree=deg)
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    bf = torch.from_numpy(scene.make_bitfield()).to(dev)
+    ro, rd = scene.camera_rays(W, W)
+    ro, rd = ro.to(dev), rd.to(dev)
+    g = torch.Generator().manual_seed(3)
+    r_img = torch.rand(W * W, 4, generator=g).to(dev)
+    bg = torch.rand(W * W, 3, generator=g).to(dev)
+    items = ("diffuse", "specular", "roughness")
+    for kw in (dict(bg_color=1.0), dict(bg_color=bg, r_images=r_img), dict(bg_color=[0.2, 0.4, 0.6], env_rot_radian=0.7)):
+        st_a, st_b = [], []
+        a = render.render(fp, bf, ro, rd, render.RenderConfig(defer_shading=True), visual_items=items, stats=st_a, **kw)
+        b = render.render(fp, bf, ro, rd, render.RenderConfig(defer_shading=False), visual_items=items, stats=st_b, **kw)
+        assert st_a[0]["samples"] == st_b[0]["samples"] and st_a[0]["iterations"] == st_b[0]["iterations"]
+        assert 0.9 * st_b[0]["samples"] <= st_a[0]["shaded"] <= st_b[0]["samples"]
+        for k in ("image", "diffuse_image", "specular_image", "roughness_image", "normal_image"):
+            e = (a[k] - b[k]).abs().reshape(a[k].shape[0], -1).max(-1).values
+            assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
+        assert float((a["weights_sum"] - b["weights_sum"]).abs().max()) <= 1e-5
+        assert float((a["depth"] - b["depth"]).abs().max()) <= 1e-5
