@@ -384,12 +384,17 @@ def main():
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_env_tc" if tcp else "k_field"]
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        if tcp and t.get("samples") and fl.value:
+            # the capture is one launch over t["samples"] samples; per launch of THIS step = bytes / sample x shaded samples / launches
+            traffic_per_sample = traffic / t["samples"]
+            traffic = traffic_per_sample * (flop_step / FLOP_ENV) / (fl.value / args.steps)
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
-                "traffic": traffic, "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
+                "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram bytes per sample of a 1 M-sample launch) scaled to this "
+                                                    "step's average launch", "kernel_ms_per_step": field_ms_per_step, "kernel_launches_per_step": fl.value / args.steps,
                 "kernel_share_of_step": field_ms_per_step / ms_per_step, "algorithmic_flop_per_step": flop_step,
                 "executed_frac": (3.0 if tcp else 1.0) * achieved_tf / peak_tf,
                 "arithmetic": ("tcgen05.mma kind::f16, 3 MMAs per K step (hi*hi + lo*hi + hi*lo): the tensor pipe executes 3x the "
@@ -406,9 +411,12 @@ def main():
             try:
                 gref = gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir)
                 if "image" in gref:
-                    e = (gref.pop("image") - out["image"]).abs().max(-1).values
+                    gimg = gref.pop("image")
+                    e = (gimg - out["image"]).abs().max(-1).values
                     gref["rgb_linf_vs_ours_p99999"] = float(torch.quantile(e[e > 0], 0.99999)) if int((e > 0).sum()) else 0.0
                     gref["pixels_over_1e-4"] = int((e > 1e-4).sum())
+                    mse = float(((gimg - out["image"]) ** 2).mean())
+                    gref["psnr_ours_vs_reference_image_db"] = float(-10.0 * np.log10(max(mse, 1e-20)))     # PSNRMeter formula (utils.py:296-306)
                     gref["speedup_ours_over_gpu_reference"] = value / gref["value"]
             except Exception as e:                      # auxiliary: never take the headline line down with it
                 gref = {"error": repr(e)[:200]}
