@@ -106,14 +106,23 @@ __global__ void __launch_bounds__(kDBlock) k_density_ema(float4* __restrict__ gr
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {                                              // block-parallel, fixed-order combination of the per-block sums
         __threadfence();
-        double tot = 0.0;
-        for (uint32_t b = 0; b < gridDim.x; b++) tot += reinterpret_cast<volatile double*>(partial)[b];
-        const float mean = (float)(tot * inv_cells);        // torch.mean(density_grid.clamp(min=0))
-        stats->mean = mean;
-        stats->thresh = fminf(mean, density_thresh);         // density_thresh = min(self.mean_density, self.density_thresh)
-        *ticket = 0;
+        __shared__ double fin[kDBlock];
+        double t = 0.0;
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += kDBlock) t += __ldcg(partial + b);
+        fin[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = kDBlock / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) fin[threadIdx.x] += fin[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const float mean = (float)(fin[0] * inv_cells);     // torch.mean(density_grid.clamp(min=0))
+            stats->mean = mean;
+            stats->thresh = fminf(mean, density_thresh);         // density_thresh = min(self.mean_density, self.density_thresh)
+            *ticket = 0;
+        }
     }
 }
 

@@ -163,11 +163,23 @@ __global__ void __launch_bounds__(kEBlock) k_loss_fwd(const LossArgs A, double* 
         is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    __shared__ double fin[S_N][kEBlock];
+    if (is_last) {                                           // block-parallel, fixed-order combination of the per-block sums
         __threadfence();
-        double tot[S_N] = {0, 0, 0, 0, 0, 0, 0};
-        for (uint32_t b = 0; b < gridDim.x; b++)
-            for (int k = 0; k < S_N; k++) tot[k] += reinterpret_cast<volatile double*>(partial)[(size_t)b * S_N + k];
+        double t[S_N] = {0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += kEBlock)
+            for (int k = 0; k < S_N; k++) t[k] += __ldcg(partial + (size_t)b * S_N + k);
+        for (int k = 0; k < S_N; k++) fin[k][threadIdx.x] = t[k];
+        __syncthreads();
+        for (int o = kEBlock / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o)
+                for (int k = 0; k < S_N; k++) fin[k][threadIdx.x] += fin[k][threadIdx.x + o];
+            __syncthreads();
+        }
+    }
+    if (is_last && threadIdx.x == 0) {
+        double tot[S_N];
+        for (int k = 0; k < S_N; k++) tot[k] = fin[k][0];
         const double color = tot[S_COLOR] / (3.0 * A.N);
         const double mask = (A.mask_w > 0.0f && A.gt_mask) ? tot[S_MASK] / A.N : 0.0;
         const double cnt = tot[S_COUNT];

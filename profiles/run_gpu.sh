@@ -23,10 +23,10 @@ if [[ "$WHAT" == *" ref "* ]]; then
   tail -c 1500 $OUT/${TAG}_bench_ref.json
 fi
 if [[ "$WHAT" == *" launches "* ]]; then
-  # launch list of one timed frame (warm-up 3 frames + 1 stats frame are skipped by the summary script's frame split)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2400 -c 1000 --csv \
+  # launch list of the whole run (8 frames of ~210 launches); the summary keeps the whole frames between the first two L2 flushes
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
       --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-extra-warmup > $OUT/${TAG}_launches.log 2>&1
-  python profiles/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches.md 2>&1
+  python profiles/summarize_launches.py $OUT/${TAG}_launches.csv --frames > $OUT/${TAG}_launches.md 2>&1
   cat $OUT/${TAG}_launches.md
 fi
 if [[ "$WHAT" == *" full "* ]]; then
