@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -72,15 +72,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (wall clock of the timed region); the sampler is started a little earlier because
+        nvidia-smi needs a few hundred ms to produce its first line.  If the region was shorter than the sampling period, the
+        samples nearest to it (taken under the same load: the untimed frames right before it) are used and counted as such."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= (t1 or t) + 0.15)]
+        inside = len(rows)
+        if not rows and self.rows:
+            rows = [r for _, r in sorted(self.rows, key=lambda x: abs(x[0] - t0))[:3]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
@@ -90,7 +97,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_inside_timed_region": inside}
 
 
 def workload(args):
@@ -338,18 +345,21 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)                               # nvidia-smi start-up; the GPU keeps no work queued meanwhile, frames follow
     lib.envidr_render_timing(1)                       # untimed pass with the kernel-timing hook on: creates its CUDA events
     for _ in range(args.steps):
         step_resident()
     barrier()
     l0 = lib.envidr_launch_count()
     lib.envidr_render_timing(1)                       # reset the hook's accumulators; the events now exist
+    t_wall0 = time.time()
     total_ms = timed(step_resident, args.steps, instrument=True)
+    t_wall1 = time.time()
     fms, fl = __import__("ctypes").c_float(), __import__("ctypes").c_uint32()
     lib.envidr_render_field_time(__import__("ctypes").byref(fms), __import__("ctypes").byref(fl))
     lib.envidr_render_timing(0)
     launches = int(lib.envidr_launch_count() - l0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
