@@ -474,8 +474,22 @@ def gen_train_epilogue():
     print("train_epilogue.npz:", {k: float(v) for k, v in ld.items()}, "total", loss.item(), "aux points", int(results["sdfs"].shape[0]), "of", M)
 
 
+def gen_state_dict_keys():
+    """Key names and shapes of the reference NeRFNetwork.state_dict() under configs/scenes/toaster.ini (cuda_ray on) -> the
+    contract envidr_b200.checkpoint.state_from_field / field_from_state must meet.  -> tests/golden/state_dict_keys.json"""
+    import json
+    model, opt = build_model([], cuda_ray=True)
+    keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+    json.dump(dict(keys=keys, per_level_scale=float(model.encoder.per_level_scale), base_resolution=int(model.encoder.base_resolution),
+                   beta_min=float(opt.beta_min), beta_max=float(opt.beta_max)), open(os.path.join(HERE, "state_dict_keys.json"), "w"), indent=1)
+    print("state_dict_keys.json:", len(keys), "keys")
+
+
 if __name__ == "__main__":
     install_shims()
+    if "keys" in sys.argv[1:]:
+        gen_state_dict_keys()
+        sys.exit(0)
     if "epilogue" in sys.argv[1:]:
         gen_train_epilogue()
         sys.exit(0)
