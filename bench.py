@@ -363,6 +363,16 @@ def main():
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    sharded = None
+    if world > 1:
+        # strong scaling of ONE frame (auxiliary): interleaved 8x8-pixel tiles per rank + one all-gather of the packed outputs
+        def step_sharded():
+            return edist.render_sharded(lambda o, d: render.render(fp, bft, o, d, cfg, bg_color=1.0, get_normal_image=True), ro_d, rd_d, H, W)
+        for _ in range(5):
+            step_sharded()
+        sh_ms = timed(step_sharded, args.steps) / args.steps
+        sharded = {"ms_per_frame": sh_ms, "rays_per_sec": N / (sh_ms * 1e-3), "what": f"one {W}x{H} frame sharded over {world} ranks "
+                   "(envidr_b200.dist.render_sharded), all-gather inside the timed region, max over ranks"}
     ms_per_step = total_ms / args.steps
     value = world * N / (ms_per_step * 1e-3)
     e2e_value = world * N / (e2e_ms / args.steps * 1e-3)
@@ -459,7 +469,7 @@ def main():
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens, "sharded_frame": sharded}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

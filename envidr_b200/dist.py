@@ -19,14 +19,38 @@ import torch.distributed as dist
 TILE = 8
 
 
+_idx_cache: Dict[tuple, torch.Tensor] = {}
+
+
 def tile_shard_indices(H: int, W: int, rank: int, world_size: int, tile: int = TILE) -> torch.Tensor:
     """Flat pixel indices (row-major, int64) of the rays owned by `rank`: tiles of tile x tile pixels are numbered
     row-major and tile t belongs to rank t % world_size.  Ragged borders are handled (partial tiles)."""
+    key = (H, W, rank, world_size, tile)
+    if key not in _idx_cache:
+        if len(_idx_cache) > 64:
+            _idx_cache.clear()
+        _idx_cache[key] = _tile_shard_indices(H, W, rank, world_size, tile)
+    return _idx_cache[key]
+
+
+def _tile_shard_indices(H: int, W: int, rank: int, world_size: int, tile: int) -> torch.Tensor:
     ty = torch.arange(H) // tile
     tx = torch.arange(W) // tile
     tiles_x = (W + tile - 1) // tile
     tid = ty[:, None] * tiles_x + tx[None, :]
     return torch.nonzero((tid % world_size == rank).reshape(-1)).flatten()
+
+
+_dev_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _dev_idx(H: int, W: int, rank: int, world_size: int, device) -> torch.Tensor:
+    key = (H, W, rank, world_size, str(device))
+    if key not in _dev_cache:
+        if len(_dev_cache) > 64:
+            _dev_cache.clear()
+        _dev_cache[key] = tile_shard_indices(H, W, rank, world_size).to(device)
+    return _dev_cache[key]
 
 
 def shard_sizes(H: int, W: int, world_size: int, tile: int = TILE):
@@ -40,7 +64,7 @@ def render_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, t
     frame on every rank.  rays_o / rays_d are the full [H*W, 3] tensors (replicated inputs)."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    idx = tile_shard_indices(H, W, rank, ws).to(rays_o.device)
+    idx = _dev_idx(H, W, rank, ws, rays_o.device)
     res = render_fn(rays_o[idx].contiguous(), rays_d[idx].contiguous())
     cols = []
     for k in keys:
@@ -60,7 +84,7 @@ def render_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, t
         gathered = [out[r * n_max: r * n_max + sizes[r]] for r in range(ws)]
     full = packed.new_empty(H * W, C)
     for r in range(ws):
-        full[tile_shard_indices(H, W, r, ws).to(full.device)] = gathered[r]
+        full[_dev_idx(H, W, r, ws, full.device)] = gathered[r]
     outd, c0 = {}, 0
     for k in keys:
         w = res[k].reshape(res[k].shape[0], -1).shape[1]
