@@ -145,6 +145,17 @@ struct Dda {
         bx0 = box[0]; bx1 = box[1]; by0 = box[2]; by1 = box[3]; bz0 = box[4]; bz1 = box[5];
     }
 
+    // the same specialisation without an occupied-cell box (no early termination): the box is the whole grid
+    __device__ __forceinline__ void init_fast_full() {
+        c_mipb = fminf(scalbnf(1.0f, 0), bound);
+        c_rmipb = 1 / c_mipb;
+        c_dt = clampf(0.0f, dt_min, dt_max);
+        hx = 0.5f + 0.5f * copysignf(1.0f, dx);
+        hy = 0.5f + 0.5f * copysignf(1.0f, dy);
+        hz = 0.5f + 0.5f * copysignf(1.0f, dz);
+        bx0 = by0 = bz0 = 0; bx1 = by1 = bz1 = (int)H - 1;
+    }
+
     // conservative slab test of the ray against the occupied box grown by one cell (sides on the grid border are open)
     __device__ __forceinline__ bool misses_box() const {
         if (bx0 > bx1) return true;                  // no occupied cell at all
@@ -194,5 +205,8 @@ struct Dda {
         return false;
     }
 };
+
+// bounding box of the occupied cells of cascade 0 (render.cu); box = {x0, x1, y0, y1, z0, z1} must hold {INT_MAX, -1, ...} on entry
+__global__ void k_occ_box(const uint8_t* __restrict__ grid, uint32_t n_words, int* __restrict__ box);
 
 }  // namespace envidr

@@ -137,45 +137,87 @@ __global__ void __launch_bounds__(kRayBlock) k_march_train_count(
     rays[3 * n + 2] = (int32_t)count;
 }
 
-// Single-block exclusive scan of rays[:,2] into rays[:,1] (offset by counter[0]); advances counter.
-__global__ void __launch_bounds__(1024) k_march_train_scan(int32_t* __restrict__ rays, uint32_t N, int32_t* __restrict__ counter) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
+// Exclusive scan of rays[:,2] into rays[:,1] (offset by counter[0]); advances counter.  Three small launches: per-block scan
+// (1,024 rays per block, block totals to a scratch array), scan of the block totals by one block, add-back.  A single block
+// walking all rays (the first version) cost 1.2 ms for the 640,000 rays of a frame; rays are few thousand in a training step.
+__device__ __forceinline__ uint32_t block_inclusive_scan_1024(uint32_t v, uint32_t* warp_sums) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = (uint32_t)counter[0];
+    uint32_t inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += u;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
-    for (uint32_t base = 0; base < N; base += 1024) {
-        const uint32_t n = base + threadIdx.x;
-        const uint32_t v = n < N ? (uint32_t)rays[3 * n + 2] : 0u;
-        uint32_t inc = v;
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane];
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += u;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= (uint32_t)o) ws += u;
         }
-        if (lane == 31) warp_sums[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane];
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= (uint32_t)o) ws += u;
-            }
-            warp_sums[lane] = ws;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t warp_excl = wid ? warp_sums[wid - 1] : 0u;
+        warp_sums[lane] = ws;  // inclusive over warps
+    }
+    __syncthreads();
+    return inc + (wid ? warp_sums[wid - 1] : 0u);
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(int32_t* __restrict__ rays, uint32_t N, uint32_t* __restrict__ block_tot) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t n = blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t v = n < N ? (uint32_t)rays[3 * n + 2] : 0u;
+    const uint32_t inc = block_inclusive_scan_1024(v, warp_sums);
+    if (n < N) rays[3 * n + 1] = (int32_t)(inc - v);             // offset inside the block
+    if (threadIdx.x == 1023) block_tot[blockIdx.x] = inc;
+}
+
+// one block: exclusive scan of the block totals in place (chunks of 1,024 with a running carry that starts at counter[0])
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t* __restrict__ block_tot, uint32_t nb, uint32_t N, int32_t* __restrict__ counter) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = (uint32_t)counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t b = base + threadIdx.x;
+        const uint32_t v = b < nb ? block_tot[b] : 0u;
+        const uint32_t inc = block_inclusive_scan_1024(v, warp_sums);
         const uint32_t c = carry;
-        if (n < N) rays[3 * n + 1] = (int32_t)(c + warp_excl + inc - v);
+        if (b < nb) block_tot[b] = c + inc - v;
         __syncthreads();
-        if (threadIdx.x == 0) carry = c + warp_sums[31];
+        if (threadIdx.x == 1023) carry = c + inc;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         counter[0] = (int32_t)carry;
         counter[1] += (int32_t)N;
     }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int32_t* __restrict__ rays, uint32_t N, const uint32_t* __restrict__ block_tot) {
+    const uint32_t n = blockIdx.x * 1024 + threadIdx.x;
+    if (n < N) rays[3 * n + 1] += (int32_t)block_tot[blockIdx.x];
+}
+
+// scratch for the block totals: grown on demand, one per process (the operator surface has no workspace argument to carry it)
+static uint32_t* g_scan_scratch = nullptr;
+static uint32_t g_scan_cap = 0;
+
+static int scan_ray_counts(int32_t* rays, uint32_t N, int32_t* counter, cudaStream_t st) {
+    const uint32_t nb = ceil_div(N, 1024);
+    if (nb > g_scan_cap) {
+        if (g_scan_scratch) cudaFree(g_scan_scratch);
+        g_scan_cap = nb < 1024 ? 1024 : nb * 2;
+        if (cudaMalloc(&g_scan_scratch, (size_t)g_scan_cap * sizeof(uint32_t)) != cudaSuccess) {
+            g_scan_scratch = nullptr; g_scan_cap = 0;
+            set_error("march: scan scratch allocation failed");
+            return (int)cudaErrorMemoryAllocation;
+        }
+    }
+    k_scan_blocks<<<nb, 1024, 0, st>>>(rays, N, g_scan_scratch);
+    k_scan_tops<<<1, 1024, 0, st>>>(g_scan_scratch, nb, N, counter);
+    k_scan_add<<<nb, 1024, 0, st>>>(rays, N, g_scan_scratch);
+    return 0;
 }
 
 __global__ void __launch_bounds__(kRayBlock) k_march_train_write(
@@ -207,6 +249,131 @@ __global__ void __launch_bounds__(kRayBlock) k_march_train_write(
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// training march in ONE launch with deterministic, ray-ordered offsets: count -> decoupled look-back scan across blocks ->
+// write.  The reference also marches every ray twice inside one kernel (raymarching.cu:340-509) but takes its offsets from
+// atomicAdd (run-to-run different sample order); the three-kernel count / scan / write formulation of this library paid the
+// bit-field lookups of the second march from L2 (cold L1, new launch) and was 0.6x the reference at 640,000 rays.  Here the
+// second march follows the first in the same thread (its occupancy bytes are L1-hot), and the block prefix comes from the
+// chained-scan protocol: blocks take a ticket (so every predecessor is resident or done), publish (flag, value) words --
+// 1 = block aggregate, 2 = inclusive prefix -- and warp 0 looks back 32 predecessors at a time.
+// ------------------------------------------------------------------------------------------------
+template <bool kFast>       // kFast: one cascade, dt_gamma == 0 -> Dda::probe_fast (same samples, a third of the instructions)
+__global__ void __launch_bounds__(kRayBlock) k_march_train_fused(
+        const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, float bound,
+        float dt_gamma, uint32_t max_steps, uint32_t early_stop_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+        const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+        int32_t* __restrict__ rays, int32_t* __restrict__ counter, unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
+        const int* __restrict__ box, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    __shared__ uint32_t s_bid, s_prefix, s_base;
+    __shared__ uint32_t warp_sums[kRayBlock / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        s_base = (uint32_t)counter[0];                 // read before any block can have finished (see the last block below)
+        s_bid = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    const uint32_t bid = s_bid, nb = gridDim.x;
+    const uint32_t n = bid * kRayBlock + tid;
+    // ---- pass 1: count ----
+    Dda s;
+    float far = 0.0f, near = 0.0f, t_start = 0.0f;
+    uint32_t count = 0;
+    if (n < N) {
+        s.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, grid);
+        far = fars[n]; near = nears[n];
+        t_start = perturbed_start(s, near, noises[n]);
+        float t = t_start, x, y, z, dt;
+        if (kFast) {
+            // box of the occupied cells: a ray that misses it emits nothing (the reference steps through empty cells up to `far`);
+            // one that has left it for good stops there -- same samples, see Dda::probe_fast
+            if (box) { s.init_fast(box); if (s.misses_box()) t = far; }
+            else s.init_fast_full();
+        }
+        while (t < far && count < early_stop_steps) {
+            if (kFast ? s.probe_fast(t, x, y, z, dt, far) : s.probe(t, x, y, z, dt)) { count++; t += dt; }
+        }
+    }
+    // ---- block scan of the counts ----
+    uint32_t inc = count;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += u;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    uint32_t warp_excl = 0, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < kRayBlock / 32; w++) {
+        if (w < wid) warp_excl += warp_sums[w];
+        total += warp_sums[w];
+    }
+    // ---- chained scan across blocks (warp 0) ----
+    if (wid == 0) {
+        volatile unsigned long long* st = status;
+        if (lane == 0 && bid > 0) { st[bid] = (1ull << 32) | total; __threadfence(); }
+        uint32_t sum = 0;
+        int j = (int)bid - 1;                          // nearest predecessor; index -1 = the virtual block holding counter[0]
+        while (true) {
+            const int idx = j - (int)lane;
+            unsigned long long v;
+            if (idx >= 0) {
+                do { v = st[idx]; } while ((v >> 32) == 0ull);
+            } else {
+                v = (2ull << 32) | (idx == -1 ? (unsigned long long)s_base : 0ull);
+            }
+            const uint32_t incl = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+            const int first = incl ? __ffs((int)incl) - 1 : 32;
+            uint32_t c = ((int)lane <= first) ? (uint32_t)(v & 0xffffffffull) : 0u;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            sum += c;
+            if (incl) break;
+            j -= 32;
+        }
+        if (lane == 0) {
+            __threadfence();
+            st[bid] = (2ull << 32) | (unsigned long long)(sum + total);
+            s_prefix = sum;
+            if (bid == nb - 1) {                       // every block has read counter[0] by now (it did so before publishing)
+                counter[0] = (int32_t)(sum + total);
+                counter[1] += (int32_t)N;
+            }
+        }
+    }
+    __syncthreads();
+    if (n >= N) return;
+    const uint32_t offset = s_prefix + warp_excl + inc - count;
+    rays[3 * n] = (int32_t)n; rays[3 * n + 1] = (int32_t)offset; rays[3 * n + 2] = (int32_t)count;
+    if (count == 0 || offset + count > M) return;
+    // ---- pass 2: write (the same march; identical arithmetic to k_march_train_write) ----
+    float t = t_start, last_t = near;
+    float* px = xyzs + 3 * (size_t)offset;
+    float* pd = dirs + 3 * (size_t)offset;
+    float* pl = deltas + 2 * (size_t)offset;
+    uint32_t step = 0;
+    float x, y, z, dt;
+    while (t < far && step < count) {
+        if (kFast ? s.probe_fast(t, x, y, z, dt, far) : s.probe(t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = s.dx; pd[1] = s.dy; pd[2] = s.dz;
+            t += dt;
+            pl[0] = dt; pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_occ_box_reset(int* __restrict__ box) {
+    if (threadIdx.x < 6) box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
+}
+
+// scratch of the chained scan: one 8-byte status word per block + the ticket + the occupied-cell box, grown on demand
+static unsigned long long* g_chain = nullptr;
+static uint32_t g_chain_cap = 0;
 
 // ------------------------------------------------------------------------------------------------
 // replay of a pass with known per-ray sample counts (see envidr_march_rays_replay in the header)
@@ -560,11 +727,33 @@ int envidr_march_rays_train(const float* rays_o, const float* rays_d, const uint
     ENVIDR_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024, ENVIDR_E_UNSUPPORTED, "cascades must be 1..8, grid size <= 1024");
     if (N == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    k_march_train_count<<<ceil_div(N, kRayBlock), kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps,
-                                                                      early_stop_steps, N, C, H, nears, fars, noises, rays);
-    k_march_train_scan<<<1, 1024, 0, st>>>(rays, N, counter);
-    k_march_train_write<<<ceil_div(N, kRayBlock), kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                      nears, fars, noises, rays, xyzs, dirs, deltas);
+    const uint32_t nb = ceil_div(N, kRayBlock);
+    if (nb + 8 > g_chain_cap) {                       // (allocated by the warm-up calls that precede a CUDA-graph capture)
+        if (g_chain) cudaFree(g_chain);
+        g_chain_cap = nb + 8 < 8192 ? 8192 : 2 * (nb + 8);
+        if (cudaMalloc(&g_chain, (size_t)g_chain_cap * sizeof(unsigned long long)) != cudaSuccess) {
+            g_chain = nullptr; g_chain_cap = 0;
+            set_error("march_rays_train: scan scratch allocation failed");
+            return (int)cudaErrorMemoryAllocation;
+        }
+    }
+    cudaMemsetAsync(g_chain, 0, (size_t)(nb + 1) * sizeof(unsigned long long), st);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(g_chain + nb);
+    int* box = reinterpret_cast<int*>(g_chain + nb + 1);
+    const bool fast = C == 1 && dt_gamma == 0.0f && H <= 256;
+    const bool with_box = fast && H % 4 == 0 && (reinterpret_cast<uintptr_t>(grid) & 3) == 0;
+    if (with_box) {
+        k_occ_box_reset<<<1, 32, 0, st>>>(box);
+        k_occ_box<<<kSMs, 256, 0, st>>>(grid, H * H * H / 32, box);
+        g_launches += 2;
+    }
+    if (fast)
+        k_march_train_fused<true><<<nb, kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, early_stop_steps, N, C, H, M, nears,
+                                                            fars, noises, rays, counter, g_chain, ticket, with_box ? box : nullptr, xyzs, dirs, deltas);
+    else
+        k_march_train_fused<false><<<nb, kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, early_stop_steps, N, C, H, M, nears,
+                                                             fars, noises, rays, counter, g_chain, ticket, nullptr, xyzs, dirs, deltas);
+    g_launches += 1;
     return check_launch("march_rays_train");
 }
 
@@ -578,7 +767,7 @@ int envidr_march_rays_replay(const float* rays_o, const float* rays_d, const uin
     if (N == 0) return 0;
     cudaStream_t st = as_stream(stream);
     k_replay_counts<<<ceil_div(N, 256), 256, 0, st>>>(counts, N, rays);
-    k_march_train_scan<<<1, 1024, 0, st>>>(rays, N, counter);
+    { const int rc = scan_ray_counts(rays, N, counter, st); if (rc) return rc; }
     k_march_train_write<<<ceil_div(N, kRayBlock), kRayBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                                       nears, fars, nullptr, rays, xyzs, dirs, deltas);
     g_launches += 3;

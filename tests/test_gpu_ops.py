@@ -146,17 +146,17 @@ def test_march_rays_train_counts_and_samples(dev, scene_data):
     nears, fars = rm.near_far_from_aabb(ro, rd, aabb, 0.2)
     g = torch.Generator().manual_seed(3)
     noises = torch.rand(N, generator=g).to(dev)
-    for early in (1024, 24):
+    for early, dtg in ((1024, 0.0), (24, 0.0), (1024, 1.0 / 128)):       # dt_gamma = 0: specialised probe; > 0: general probe
         M = N * 64
         from envidr_b200.backend import _raymarching as B
         xyzs, dirs, deltas = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         counter = torch.zeros(2, dtype=torch.int32, device=dev)
-        B.march_rays_train(ro, rd, bf, 1.0, 0.0, 1024, early, N, 1, 128, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises)
+        B.march_rays_train(ro, rd, bf, 1.0, dtg, 1024, early, N, 1, 128, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises)
         xr, dr, dlr = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
         rays_r = torch.empty(N, 3, dtype=torch.int32, device=dev)
         counter_r = torch.zeros(2, dtype=torch.int32, device=dev)
-        R.march_rays_train(ro, rd, bf, 1.0, 0.0, 1024, early, N, 1, 128, M, nears, fars, xr, dr, dlr, rays_r, counter_r, noises)
+        R.march_rays_train(ro, rd, bf, 1.0, dtg, 1024, early, N, 1, 128, M, nears, fars, xr, dr, dlr, rays_r, counter_r, noises)
         assert torch.equal(counter, counter_r)                       # total samples / rays
         # reference slot order is scheduling dependent: compare ray id -> (count, samples)
         rr = rays_r.cpu().numpy(); mine = rays.cpu().numpy()
@@ -173,7 +173,7 @@ def test_march_rays_train_counts_and_samples(dev, scene_data):
         # and the deterministic CPU oracle reproduces our layout exactly
         xo, do, dlo, rays_o_, ctr_o = O.march_rays_train(ro.cpu().numpy(), rd.cpu().numpy(), 1.0, scene_data["bitfield"], 1, 128,
                                                          nears.cpu().numpy(), fars.cpu().numpy(), M, noises=noises.cpu().numpy(),
-                                                         early_stop_steps=early)
+                                                         dt_gamma=dtg, early_stop_steps=early)
         np.testing.assert_array_equal(mine, rays_o_)
         np.testing.assert_array_equal(X, xo)
         np.testing.assert_array_equal(DL, dlo)
