@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const EncMode m, const float
     #pragma unroll
     for (int c = 0; c < C; c++) out[c] = acc[c];
     if (!jac) return;
+    float jrow[D * C];          // the (sample, level) block of dy_dx: written with the widest stores its alignment allows (below)
     #pragma unroll
     for (int gd = 0; gd < D; gd++) {
         float g[C];
@@ -85,7 +86,25 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const EncMode m, const float
             }
         }
         #pragma unroll
-        for (int c = 0; c < C; c++) jac[gd * C + c] = g[c];
+        for (int c = 0; c < C; c++) jrow[gd * C + c] = g[c];
+    }
+    // dy_dx rows of neighbouring threads lie D*L*C floats apart, so every scalar store is its own 32-byte sector write at L2: the
+    // six 4-byte stores of the D = 3, C = 2 case cost 4x the kernel's gather time.  A 24-byte block is 8-byte aligned and either
+    // its first or its last 16 bytes are 16-byte aligned: one 16-byte and one 8-byte store.
+    if constexpr (D * C == 6) {
+        if ((reinterpret_cast<uintptr_t>(jac) & 15) == 0) {
+            *reinterpret_cast<float4*>(jac) = make_float4(jrow[0], jrow[1], jrow[2], jrow[3]);
+            *reinterpret_cast<float2*>(jac + 4) = make_float2(jrow[4], jrow[5]);
+        } else if ((reinterpret_cast<uintptr_t>(jac) & 7) == 0) {
+            *reinterpret_cast<float2*>(jac) = make_float2(jrow[0], jrow[1]);
+            *reinterpret_cast<float4*>(jac + 2) = make_float4(jrow[2], jrow[3], jrow[4], jrow[5]);
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 6; i++) jac[i] = jrow[i];
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < D * C; i++) jac[i] = jrow[i];
     }
 }
 
