@@ -39,6 +39,8 @@ int envidr_version(void);
 /* sizeof {envidr_mlp_layer, envidr_field, envidr_field_out, envidr_render_opts, envidr_render_out}: lets a
  * foreign-language binding verify its struct mirrors. */
 int envidr_abi_sizes(uint32_t out[5]);
+/* sizeof {envidr_density_opts, envidr_adam_tensor, envidr_loss_in, envidr_loss_opts, envidr_sample_log} */
+int envidr_abi_sizes_aux(uint32_t out[5]);
 
 /* ------------------------------------------------------------------------------------------------
  * raymarching  (reference: raymarching/src/raymarching.h:7-18, bindings.cpp:5-20)

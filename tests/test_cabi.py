@@ -27,7 +27,9 @@ def test_header_symbols_all_exported(lib):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in protos:
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
-    assert lib.envidr_version() == 100
+    assert lib.envidr_version() == 101
+    assert {"envidr_density_grid_update", "envidr_mark_untrained_grid", "envidr_adam_step", "envidr_get_rays", "envidr_train_loss_forward",
+            "envidr_train_loss_backward", "envidr_pow2_scales"} <= set(protos)
 
 
 def test_struct_mirrors_match_c_layout(lib):
@@ -35,6 +37,11 @@ def test_struct_mirrors_match_c_layout(lib):
     assert lib.envidr_abi_sizes(sizes) == 0
     assert list(sizes) == [ctypes.sizeof(_lib.MlpLayer), ctypes.sizeof(_lib.Field), ctypes.sizeof(_lib.FieldOut),
                            ctypes.sizeof(_lib.RenderOpts), ctypes.sizeof(_lib.RenderOut)]
+    from envidr_b200 import density, epilogue, optim
+    aux = (ctypes.c_uint32 * 5)()
+    assert lib.envidr_abi_sizes_aux(aux) == 0
+    assert list(aux) == [ctypes.sizeof(density.DensityOpts), ctypes.sizeof(optim.AdamTensor), ctypes.sizeof(epilogue.LossIn),
+                         ctypes.sizeof(epilogue.LossOpts), ctypes.sizeof(_lib.SampleLog)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -48,6 +55,12 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -1 and b"C must be 1, 2, 4, or 8" in lib.envidr_last_error()
     rc = lib.envidr_ide_encode_forward(dummy, None, 0.1, 8, 6, 1.0, dummy, None)
     assert rc == -1 and b"deg_view" in lib.envidr_last_error()
+    # the round-1 "next row" entry points validate the same way
+    assert lib.envidr_adam_step(None, 3, 0.9, 0.99, 1e-15, 0, 0, None) == -2
+    assert lib.envidr_get_rays(None, 1, None, 8, 8, None, 64, None, None, None) == -2
+    assert lib.envidr_density_grid_update(None, None, None, None, 8, None, None, None, None, 0, None) == -2
+    assert lib.envidr_train_loss_forward(None, None, None, None, 0, None) == -2
+    assert lib.envidr_pow2_scales(None, 4, None, 4, None, 0, None, None) == -2
     rc = lib.envidr_sh_encode_forward(dummy, dummy, 8, 3, 9, None, None)
     assert rc == -1
     assert lib.envidr_near_far_from_aabb(dummy, dummy, dummy, 0, 0.2, dummy, dummy, None) == 0      # empty input is a no-op
