@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA path (oracle/ref_cuda.py)")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary train-step (BASELINE config 3) measurement")
+    ap.add_argument("--sec-floor", type=int, default=None, help="RenderConfig.secondary_n_step_floor override (experiments)")
     ap.add_argument("--no-defer", action="store_true", help="shade inside the iterative loops (RenderConfig.defer_shading / defer_secondary_shading off)")
     ap.add_argument("--no-extra-warmup", action="store_true", help="profiling runs (ncu --launch-skip counts on exactly W warm-up frames)")
     ap.add_argument("--no-density", action="store_true", help="skip the auxiliary occupancy-grid update measurement (SURVEY 8 f-1)")
@@ -284,6 +285,8 @@ def main():
     bft = torch.from_numpy(bf).to(dev)
     rot = (2 * np.pi * rank / world) if world > 1 else None
     cfg = render.RenderConfig(indir_ref=indir, defer_shading=not args.no_defer, defer_secondary_shading=not args.no_defer)
+    if args.sec_floor is not None:
+        cfg.secondary_n_step_floor = args.sec_floor
     ro_d, rd_d = ro.to(dev), rd.to(dev)
     ro_h, rd_h = ro.pin_memory(), rd.pin_memory()
     img_h = torch.empty(N, 3).pin_memory()
