@@ -356,6 +356,19 @@ int envidr_wgrad_tc(const float* dY, const float* X, uint32_t M, uint32_t N, uin
                     int variant, envidr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * NeuS-style opacity: NeuSDensity.forward (nerf/network.py:46-102), the density of the use_neus_sdf configs,
+ * consumed by the compositors with input_alpha = 1.  variance: device scalar (the module's parameter); dists: [M] or NULL
+ * (then dist_scalar, the module's base_dist); gradients [M,3] or NULL (the reference's gradient-free branch).
+ * Backward: gradients of sum(grad_alpha * alpha) w.r.t. sdf [M], gradients [M,3] and variance (device scalar); any may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int envidr_neus_alpha_forward(const float* sdf, const float* dirs, const float* gradients, const float* dists, float dist_scalar,
+                              const float* variance, float cos_anneal_ratio, uint32_t M, float* alpha, envidr_stream_t stream);
+uint64_t envidr_neus_workspace_bytes(void);
+int envidr_neus_alpha_backward(const float* grad_alpha, const float* sdf, const float* dirs, const float* gradients, const float* dists,
+                               float dist_scalar, const float* variance, float cos_anneal_ratio, uint32_t M, float* grad_sdf,
+                               float* grad_gradients, float* grad_variance, void* workspace, uint64_t workspace_bytes, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Occupancy-grid maintenance: the caller either side of the march.
  * Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:264-352) and NeRFRenderer.mark_untrained_grid
  * (nerf/renderer.py:200-262); the reference has no operator boundary here (torch ops + self.density() + morton3D + packbits

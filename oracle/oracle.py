@@ -752,3 +752,37 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, beta1: flo
     denom = np.sqrt(v) / f(bias_correction2 ** 0.5) + f(eps)
     p = _fma32(np.full_like(g, f(-step_size)), m / denom, p)                            # addcdiv_(exp_avg, denom, value=-step_size)
     return p, m, v
+
+
+# --------------------------------------------------------------------------------------
+# NeuS-style opacity (nerf/network.py:46-102), SURVEY.md 8 a-6
+# --------------------------------------------------------------------------------------
+
+def neus_alpha(sdf, dirs, dists, gradients, variance: float, cos_anneal_ratio: float = 1.0, grad_alpha=None, dtype=torch.float64):
+    """NeuSDensity.forward restated (float64 by default).  Returns alpha [M] float32, and with grad_alpha [M] also the gradients of
+    sum(grad_alpha * alpha) w.r.t. (sdf, gradients, variance) by autograd."""
+    t = lambda a: None if a is None else torch.as_tensor(np.asarray(a), dtype=dtype)
+    sdf_t, g_t = t(sdf).clone().requires_grad_(True), t(gradients)
+    if g_t is not None:
+        g_t = g_t.clone().requires_grad_(True)
+    var = torch.tensor(float(variance), dtype=dtype, requires_grad=True)
+    d = t(dirs)
+    dist = t(dists) if not np.isscalar(dists) else float(dists)
+    inv_s = torch.exp(var * 10.0).clip(1e-6, 1e6)
+    if g_t is not None:
+        true_cos = (d * g_t).sum(-1, keepdim=True)
+        iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio) + torch.relu(-true_cos) * cos_anneal_ratio)
+        nxt = sdf_t + iter_cos.squeeze(-1) * dist * 0.5
+        prv = sdf_t - iter_cos.squeeze(-1) * dist * 0.5
+    else:
+        nxt = sdf_t - dist * 0.5
+        prv = sdf_t + dist * 0.5
+    pc, nc = torch.sigmoid(prv * inv_s), torch.sigmoid(nxt * inv_s)
+    alpha = ((pc - nc + 1e-5) / (pc + 1e-5)).clip(0.0, 1.0)
+    out = alpha.detach().to(torch.float32).numpy()
+    if grad_alpha is None:
+        return out
+    leaves = [sdf_t, var] + ([g_t] if g_t is not None else [])
+    gr = torch.autograd.grad((alpha * t(grad_alpha)).sum(), leaves)
+    f32 = lambda x: x.detach().to(torch.float32).numpy()
+    return out, f32(gr[0]), (f32(gr[2]) if g_t is not None else None), float(gr[1])

@@ -485,8 +485,38 @@ def gen_state_dict_keys():
     print("state_dict_keys.json:", len(keys), "keys")
 
 
+def gen_neus():
+    """NeuSDensity of the reference (nerf/network.py:46-102) on seeded inputs, with autograd gradients -> tests/golden/neus.npz"""
+    from nerf.network import NeuSDensity
+    g = torch.Generator().manual_seed(5)
+    M = 512
+    out = {}
+    for tag, ratio, with_grad, tensor_dist, var in (("a", 1.0, True, False, 0.3), ("b", 0.3, True, True, 0.45), ("c", 1.0, False, False, 0.3),
+                                                    ("d", 0.0, True, True, 1.5)):
+        mod = NeuSDensity(var)
+        sdf = (torch.randn(M, generator=g) * 0.02).requires_grad_(True)
+        dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+        grads = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1) * (0.8 + 0.4 * torch.rand(M, 1, generator=g))
+        grads.requires_grad_(True)
+        dists = (torch.rand(M, generator=g) * 0.004 + 0.002) if tensor_dist else mod.base_dist
+        ga = torch.randn(M, generator=g)
+        alpha = mod(sdf, dirs, dists, grads if with_grad else None, cos_anneal_ratio=ratio)
+        leaves = [sdf, mod.variance] + ([grads] if with_grad else [])
+        gr = torch.autograd.grad((alpha * ga).sum(), leaves)
+        f = lambda t: t.detach().numpy().astype(np.float32)
+        out.update({f"{tag}_sdf": f(sdf), f"{tag}_dirs": f(dirs), f"{tag}_grads": f(grads), f"{tag}_dists": f(dists) if tensor_dist else np.float32(dists),
+                    f"{tag}_ga": f(ga), f"{tag}_alpha": f(alpha), f"{tag}_g_sdf": f(gr[0]), f"{tag}_g_var": np.float64(gr[1].item()),
+                    f"{tag}_g_grads": f(gr[2]) if with_grad else np.zeros(0, np.float32), f"{tag}_ratio": np.float32(ratio),
+                    f"{tag}_var": np.float32(var), f"{tag}_with_grad": np.int32(with_grad)})
+    np.savez_compressed(os.path.join(HERE, "neus.npz"), **out)
+    print("neus.npz: alpha ranges", {t: (float(out[f"{t}_alpha"].min()), float(out[f"{t}_alpha"].max())) for t in "abcd"})
+
+
 if __name__ == "__main__":
     install_shims()
+    if "neus" in sys.argv[1:]:
+        gen_neus()
+        sys.exit(0)
     if "keys" in sys.argv[1:]:
         gen_state_dict_keys()
         sys.exit(0)

@@ -216,3 +216,26 @@ def test_train_loss_matches_reference(golden_dir):
     for k in ("image", "weights_sum", "sdfs", "sdf_gradients"):
         ref = z[f"grad_{k}"]
         np.testing.assert_allclose(grads[k], ref, rtol=2e-4, atol=2e-6 * float(np.abs(ref).max()), err_msg=k)
+
+
+# ---------------------------------------------------------------------------------------------
+# NeuS-style opacity: oracle vs the reference's NeuSDensity (tests/golden/make_golden.py::gen_neus)
+# ---------------------------------------------------------------------------------------------
+
+def neus_case(z, tag):
+    dists = z[f"{tag}_dists"]
+    dists = float(dists) if dists.ndim == 0 else dists
+    grads = z[f"{tag}_grads"] if int(z[f"{tag}_with_grad"]) else None
+    return z[f"{tag}_sdf"], z[f"{tag}_dirs"], dists, grads, float(z[f"{tag}_var"]), float(z[f"{tag}_ratio"]), z[f"{tag}_ga"]
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_neus_alpha_matches_reference(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, "neus.npz"))
+    sdf, dirs, dists, grads, var, ratio, ga = neus_case(z, tag)
+    alpha, g_sdf, g_grads, g_var = O.neus_alpha(sdf, dirs, dists, grads, var, ratio, grad_alpha=ga)
+    np.testing.assert_allclose(alpha, z[f"{tag}_alpha"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(g_sdf, z[f"{tag}_g_sdf"], rtol=5e-4, atol=5e-5 * float(np.abs(z[f"{tag}_g_sdf"]).max()) + 1e-30)
+    assert abs(g_var - float(z[f"{tag}_g_var"])) <= 1e-3 * abs(float(z[f"{tag}_g_var"])) + 1e-6
+    if grads is not None:
+        np.testing.assert_allclose(g_grads, z[f"{tag}_g_grads"], rtol=5e-4, atol=5e-5 * float(np.abs(z[f"{tag}_g_grads"]).max()) + 1e-12)
