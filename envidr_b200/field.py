@@ -193,7 +193,8 @@ class FieldParams:
               and opt.use_diffuse and opt.diffuse_with_env and opt.wo_viewdir and opt.normal_with_mlp and opt.use_n_dot_viewdir
               and opt.use_roughness and opt.geo_feat_act == "unitNorm" and opt.env_feat_act == "unitNorm"
               and opt.encoding_ref == "integrated_dir" and opt.color_act == "sigmoid" and not opt.geometric_init
-              and not opt.skip_layers and opt.diffuse_env_fusion == "concat" and not opt.split_diffuse_env)
+              and not opt.skip_layers and opt.diffuse_env_fusion == "concat" and not opt.split_diffuse_env
+              and float(getattr(opt, "normal_anneal_ratio", 1)) >= 1)          # the fused kernels take the normal from the SDF gradient alone
         if not ok:
             raise _lib.EnvidrError("fused field: model configuration is outside the fused path (use the operator-level modules)")
         lin = lambda net: [(l.weight.detach().float().contiguous(), None if l.bias is None else l.bias.detach().float().contiguous())

@@ -65,8 +65,11 @@ class TrainableField(nn.Module):
     """Parameters of the per-sample field as leaves: `embeddings`, `beta`, `<stack>_w.<i>` / `<stack>_b.<i>`.
     `frozen` lists the stacks that do not train (toaster.ini: frozen_mlps = [specular, diffuse], network.py:785-796)."""
 
-    def __init__(self, fp: FieldParams, frozen: Sequence[str] = ("diffuse", "color")):
+    def __init__(self, fp: FieldParams, frozen: Sequence[str] = ("diffuse", "color"), *, detach_normal: bool = False,
+                 normal_anneal_ratio: float = 1.0):
         super().__init__()
+        self.detach_normal = detach_normal                     # opt.detach_normal       (renderer.py:191)
+        self.normal_anneal_ratio = normal_anneal_ratio         # opt.normal_anneal_ratio (renderer.py:193-196)
         self.cfg = {f.name: getattr(fp, f.name) for f in dataclasses.fields(fp)
                     if f.name not in ("embeddings", "offsets", "_packed", "_scratch") + STACKS}
         self.register_buffer("offsets", fp.offsets.clone().int())
@@ -136,7 +139,13 @@ class TrainableField(nn.Module):
         roughness = c["roughness_act_scale"] * F.softplus(h[:, 1 + G:2 + G] + c["roughness_bias"]) * c["roughness_scale"]
         blend = torch.sigmoid(h[:, 2 + G:3 + G])
         grad_x = torch.autograd.grad(sdf, xyzs, torch.ones_like(sdf), retain_graph=True, create_graph=True)[0]
-        normals = F.normalize(grad_x, dim=-1, eps=1e-10)
+        # compute_normal (renderer.py:182-198): opt.detach_normal, opt.normal_anneal_ratio (blend with the radial direction)
+        n_src = grad_x.detach() if getattr(self, "detach_normal", False) else grad_x
+        normals = F.normalize(n_src, dim=-1, eps=1e-10)
+        ratio = float(getattr(self, "normal_anneal_ratio", 1.0))
+        if ratio < 1:
+            normals = normals * ratio + (1 - ratio) * F.normalize(xyzs.detach(), dim=-1, eps=1e-10)
+            normals = F.normalize(normals, dim=-1, eps=1e-10)
         sigma = self.laplace_density(sdf, self.get_beta()) * c["density_scale"]
         return sdf, sigma, geo, normals, (grad_x if eikonal else None), roughness, blend
 

@@ -131,3 +131,26 @@ def test_product_train_glue_with_oracle_ops_matches_train_oracle(with_r_images):
     assert checked >= 12
     for st in ("diffuse", "color"):                                   # frozen MLPs (toaster.ini frozen_mlps)
         assert getattr(field, f"{st}_w0").grad is None
+
+
+def test_compute_normal_options_detach_and_anneal():
+    """compute_normal's two options (renderer.py:191-196) in the train-branch glue: detach_normal cuts the path from the normal to
+    the SDF network; normal_anneal_ratio blends the SDF normal with the radial direction and renormalises."""
+    import torch.nn.functional as F
+    from envidr_b200 import scene, train
+    fp = small_field()
+    ops = oracle_ops(torch.float64)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(64, 3, generator=g) * 1.0 - 0.5).double()
+    base = train.TrainableField(fp).double()
+    xa = x.clone().requires_grad_(True)
+    _, _, _, n0, gx0, _, _ = base.forward_sigma(ops, xa)
+    ann = train.TrainableField(fp, normal_anneal_ratio=0.25).double()
+    xb = x.clone().requires_grad_(True)
+    _, _, _, n1, _, _, _ = ann.forward_sigma(ops, xb)
+    want = F.normalize(n0.detach() * 0.25 + 0.75 * F.normalize(x, dim=-1, eps=1e-10), dim=-1, eps=1e-10)
+    assert float((n1.detach() - want).abs().max()) < 1e-6
+    det = train.TrainableField(fp, detach_normal=True).double()
+    xc = x.clone().requires_grad_(True)
+    _, _, _, n2, gx2, _, _ = det.forward_sigma(ops, xc)
+    assert torch.allclose(n2, n0.detach(), atol=1e-7) and not n2.requires_grad and gx2.requires_grad     # eikonal gradient keeps its graph
