@@ -175,3 +175,40 @@ def test_field_from_checkpoint_round_trip_renders_identically(dev, tmp_path):
     a = ref.to(dev).pack().forward(x, d)
     b = back.pack().forward(x, d)
     assert back.ide_degree == 5 and torch.equal(a["rgb"], b["rgb"])
+
+
+def test_config1_demo_sphere_through_the_tensor_core_shading_path(dev, golden_dir):
+    """BASELINE config 1 (demo.ipynb: sdf_net + diffuse_net + specular_net + env_net on the 64x64 sphere hits, the reference's
+    CPU-runnable path): the per-sample shading of the notebook through envidr_field_forward_records (k_env_tc + k_shade_tc) with
+    the shipped demo/ weights, against the outputs the notebook's own code produced (tests/golden/demo_sphere.npz): 2e-5."""
+    import ctypes
+    import os
+    from envidr_b200 import _lib, scene
+    from envidr_b200._lib import check, lib, ptr, stream
+    z = np.load(os.path.join(golden_dir, "demo_sphere.npz"))
+    fp = scene.make_synthetic_field(0, hidden_dim_env=160, ide_degree=4, with_renv=False)
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float32))
+    fp.env = [(t(z[f"env_{i}_weight"]), t(z[f"env_{i}_bias"])) for i in (0, 2, 4, 6)]
+    fp.diffuse = [(t(z[f"diffuse_{i}_weight"]), t(z[f"diffuse_{i}_bias"])) for i in (0, 2)]
+    fp.color = [(t(z[f"specular_{i}_weight"]), t(z[f"specular_{i}_bias"])) for i in (0, 2, 4)]
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    n, d = t(z["xyz"]), t(z["dirs"])                       # unit sphere: the normal is the hit point
+    M = n.shape[0]
+    w_o = -d
+    ndv = (n * w_o).sum(-1, keepdim=True)
+    w_r = 2 * ndv * n - w_o
+    rec = torch.zeros(M, 32)
+    rec[:, :12] = t(z["geo"])[None]
+    rec[:, 16:19], rec[:, 19:20], rec[:, 20] = n, ndv, float(z["kappa_inv"])
+    rec[:, 22:25], rec[:, 25:28] = n, w_r
+    rec = rec.to(dev).contiguous()
+    rgb, c_d, c_s = (torch.empty(M, 3, device=dev) for _ in range(3))
+    fp._scratch = torch.empty(32 * (M + 2), device=dev)
+    fo = _lib.FieldOut()
+    fo.rgb, fo.c_diffuse, fo.c_specular = rgb.data_ptr(), c_d.data_ptr(), c_s.data_ptr()
+    f = fp.cstruct()
+    check(lib().envidr_field_forward_records(ctypes.byref(f), ptr(rec), None, M, ctypes.byref(fo), stream()), "field_forward_records")
+    np.testing.assert_allclose(c_d.cpu().numpy(), z["diffuse"], atol=2e-5)
+    np.testing.assert_allclose(c_s.cpu().numpy(), z["specular"], atol=2e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), z["diffuse"] + z["specular"], atol=4e-5)
