@@ -101,3 +101,21 @@ def gather_frames(frame: torch.Tensor, group=None) -> torch.Tensor:
     out = frame.new_empty(ws, *frame.shape)
     dist.all_gather_into_tensor(out.view(ws * frame.shape[0], *frame.shape[1:]), frame.contiguous(), group=group)
     return out
+
+
+def allreduce_gradients(params, group=None, average: bool = True) -> None:
+    """Data-parallel training (optional): every rank runs the training step on its share of the ray batch, then the
+    gradients of the replicated state (hash table 48.8 MB dense + < 1 MB of MLP weights) are summed / averaged with ONE all-reduce
+    over a flat buffer -- the only exchange step of data-parallel training; the optimizer step stays local and identical on all ranks.
+    The reference has no reachable multi-GPU training path (its DDP scaffold is never activated, nerf/utils.py:360-402)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(dist.get_world_size(group))
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)

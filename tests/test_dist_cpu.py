@@ -56,3 +56,37 @@ def test_single_process_paths():
     out = edist.render_sharded(_fake_render, o, d, 24, 24)
     assert torch.equal(out["image"], o * 2 + d)
     assert edist.gather_frames(torch.ones(4, 3)).shape == (1, 4, 3)
+
+
+def _dp_worker(rank, world, port, tmp):
+    """Data-parallel step: every rank differentiates the loss of ITS half of the batch; after allreduce_gradients both hold the
+    gradient of the full-batch mean loss and an identical optimizer step keeps the replicas in sync."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    W1, b1, unused = torch.randn(5, 3, generator=g), torch.randn(5, generator=g), torch.randn(2, generator=g)
+    x, y = torch.randn(8, 3, generator=g), torch.randn(8, 5, generator=g)
+    params = [W1.clone().requires_grad_(True), b1.clone().requires_grad_(True), unused.clone().requires_grad_(True)]
+    sl = slice(rank * 4, rank * 4 + 4)
+    ((x[sl] @ params[0].T + params[1] - y[sl]) ** 2).mean().backward()
+    edist.allreduce_gradients(params)
+    full = [W1.clone().requires_grad_(True), b1.clone().requires_grad_(True)]
+    ((x @ full[0].T + full[1] - y) ** 2).mean().backward()
+    ok = all(torch.allclose(p.grad, f.grad, atol=1e-6) for p, f in zip(params, full)) and params[2].grad is None
+    opt = torch.optim.Adam(params[:2], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    opt.step()
+    gathered = [torch.zeros_like(params[0]) for _ in range(world)]
+    dist.all_gather(gathered, params[0].detach())
+    ok = ok and torch.equal(gathered[0], gathered[1])
+    torch.save(ok, os.path.join(tmp, f"dp{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(torch.load(os.path.join(tmp_path, f"dp{r}.pt")) for r in range(2))
+    p = torch.ones(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    edist.allreduce_gradients([p])                       # single process: a no-op
+    assert torch.equal(p.grad, torch.ones(3))
