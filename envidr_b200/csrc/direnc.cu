@@ -15,11 +15,14 @@ namespace envidr {
 // One thread per output element (coalesced stores); cos is sin(. + pi/2) with the fast intrinsic,
 // exactly as the reference computes it.
 // ------------------------------------------------------------------------------------------------
+// kIdx = uint32_t whenever B * C fits (always, in practice): the element -> (sample, column) split is then a 32-bit division
+// instead of a 64-bit one, which was most of the kernel's instructions.
+template <typename kIdx>
 __global__ void __launch_bounds__(256) k_freq_fwd(const float* __restrict__ inputs, uint32_t B, uint32_t D, uint32_t C,
                                                  float* __restrict__ outputs) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)B * C) return;
-    const uint32_t b = (uint32_t)(t / C), c = (uint32_t)(t - (size_t)b * C);
+    const kIdx t = (kIdx)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (kIdx)B * C) return;
+    const uint32_t b = (uint32_t)(t / C), c = (uint32_t)(t - (kIdx)b * C);
     const float* x = inputs + (size_t)b * D;
     float v;
     if (c < D) {
@@ -27,7 +30,9 @@ __global__ void __launch_bounds__(256) k_freq_fwd(const float* __restrict__ inpu
     } else {
         const uint32_t col = c / D - 1, d = c % D, freq = col / 2;
         const float phase_shift = (col % 2) * (3.141592653589793f / 2);
-        v = __sinf(scalbnf(x[d], freq) + phase_shift);
+        // scalbnf(x, f) of the reference == x * 2^f exactly (a power-of-two product rounds nowhere short of overflow); the exponent-field
+        // constant saves scalbnf's special-case code, which was half of the kernel's instructions
+        v = __sinf(x[d] * __uint_as_float((127u + freq) << 23) + phase_shift);
     }
     outputs[t] = v;
 }
@@ -59,12 +64,16 @@ __constant__ float c_sh_norm[8 * 8];   // N_l^m (incl. sqrt(2) for m > 0), [l][m
 template <bool kGrad>
 __global__ void __launch_bounds__(128) k_sh_fwd(const float* __restrict__ inputs, float* __restrict__ outputs, uint32_t B, uint32_t D,
                                                uint32_t deg, float* __restrict__ dy_dx) {
+    // outputs of a thread (its sample's row of deg^2 values) are staged in shared memory (row stride deg^2 + 1: conflict-free)
+    // and written by the whole block as one contiguous, coalesced run; the per-thread row stores of the first version were one
+    // 32-byte sector write per value.
+    __shared__ float s_out[128 * 65];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float x = inputs[(size_t)b * D], y = inputs[(size_t)b * D + 1], z = inputs[(size_t)b * D + 2];
     const uint32_t C2 = deg * deg;
-    float* out = outputs + (size_t)b * C2;
-    float* gx = kGrad ? dy_dx + (size_t)b * 3 * C2 : nullptr;
+    const uint32_t bc = min(b, B - 1);                                   // threads past the end compute a duplicate, store nothing
+    const float x = inputs[(size_t)bc * D], y = inputs[(size_t)bc * D + 1], z = inputs[(size_t)bc * D + 2];
+    float* out = s_out + threadIdx.x * (C2 + 1);
+    float* gx = kGrad ? dy_dx + (size_t)bc * 3 * C2 : nullptr;
     float* gy = kGrad ? gx + C2 : nullptr;
     float* gz = kGrad ? gy + C2 : nullptr;
     float A = 1.0f, Bi = 0.0f;           // Re / Im (x+iy)^m
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(128) k_sh_fwd(const float* __restrict__ inputs
             const uint32_t ip = l * l + l + m, in = l * l + l - m;
             out[ip] = nq * A;
             if (m) out[in] = nq * Bi;
-            if (kGrad) {
+            if (kGrad && b < B) {
                 const float ndq = -Nlm * r;                          // d/dz Q_l^m = -Q_l^{m+1}
                 gx[ip] = m ? nq * m * Ap : 0.0f;
                 gy[ip] = m ? -nq * m * Bp : 0.0f;
@@ -112,6 +121,11 @@ __global__ void __launch_bounds__(128) k_sh_fwd(const float* __restrict__ inputs
             r_prev2 = r_prev; r_prev = r;
         }
     }
+    __syncthreads();
+    const uint32_t b0 = blockIdx.x * blockDim.x;
+    const uint32_t rows = min((uint32_t)blockDim.x, B - b0);
+    float* dst = outputs + (size_t)b0 * C2;
+    for (uint32_t i = threadIdx.x; i < rows * C2; i += blockDim.x) dst[i] = s_out[(i / C2) * (C2 + 1) + i % C2];
 }
 
 // grad_inputs[b,d] += sum_k grad[b,k] * dy_dx[b,d,k]   (shencoder.cu:358-383)
@@ -242,7 +256,10 @@ int envidr_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint
     ENVIDR_REQUIRE(C == D + 2 * D * deg, ENVIDR_E_BADARG, "C must equal D + 2*D*deg");
     if (B == 0) return 0;
     const size_t total = (size_t)B * C;
-    k_freq_fwd<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(inputs, B, D, C, outputs);
+    if (total + 256 < 0xffffffffull)
+        k_freq_fwd<uint32_t><<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(inputs, B, D, C, outputs);
+    else
+        k_freq_fwd<size_t><<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(inputs, B, D, C, outputs);
     return check_launch("freq_encode_forward");
 }
 
