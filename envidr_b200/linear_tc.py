@@ -86,7 +86,7 @@ class _linear_tc(Function):
         x2, Wc, y = ctx.saved_tensors
         gy = gy.float().contiguous()
         if ctx.relu:
-            gy = gy * (y > 0)
+            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)          # gy * (y > 0) in one kernel instead of a compare and a multiply
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
             gx = _run(gy, _image(Wc.t().contiguous()), None, Wc.shape[1], False)       # dY W = dY (W^T)^T
