@@ -105,3 +105,71 @@ class _linear_tc(Function):
 def linear_tc(x: torch.Tensor, W: torch.Tensor, b=None, relu: bool = False) -> torch.Tensor:
     """x [M, K] (CUDA fp32), W [N, K], b [N] or None -> [M, N]."""
     return _linear_tc.apply(x, W, b, relu)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Differentiable-to-any-order family for sdf_net: the normals are d sdf / d x taken with create_graph=True (renderer.py:182-198), so
+# the loss differentiates THROUGH the first backward of these layers.  Three products, each one's backward written with the other
+# two (all on the tensor-core kernels above), close under differentiation:
+#     nt(a [M,K], b [N,K]) = a b^T  [M,N]      d a = nn(g, b)      d b = tn(g, a)
+#     nn(a [M,N], b [N,K]) = a b    [M,K]      d a = nt(g, b)      d b = tn(a, g)
+#     tn(a [M,N], b [M,K]) = a^T b  [N,K]      d a = nt(b, g)      d b = nn(a, g)
+# M is the sample dimension (large); the other operand of nt / nn and the result of tn are weight-sized (<= 256 x 256).
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _mm_nt(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a2, b2 = a.detach().float().contiguous(), b.detach().float().contiguous()
+        ctx.save_for_backward(a, b)
+        return _run(a2, _image(b2), None, b2.shape[0], False)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (mm_nn(g, b) if ctx.needs_input_grad[0] else None), (mm_tn(g, a) if ctx.needs_input_grad[1] else None)
+
+
+class _mm_nn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a2, b2 = a.detach().float().contiguous(), b.detach().float().contiguous()
+        ctx.save_for_backward(a, b)
+        return _run(a2, _image(b2.t().contiguous()), None, b2.shape[1], False)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (mm_nt(g, b) if ctx.needs_input_grad[0] else None), (mm_tn(a, g) if ctx.needs_input_grad[1] else None)
+
+
+class _mm_tn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a2, b2 = a.detach().float().contiguous(), b.detach().float().contiguous()
+        ctx.save_for_backward(a, b)
+        return wgrad_tc(a2, b2)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (mm_nt(b, g) if ctx.needs_input_grad[0] else None), (mm_nn(a, g) if ctx.needs_input_grad[1] else None)
+
+
+def mm_nt(a, b):
+    return _mm_nt.apply(a, b)
+
+
+def mm_nn(a, b):
+    return _mm_nn.apply(a, b)
+
+
+def mm_tn(a, b):
+    return _mm_tn.apply(a, b)
+
+
+def linear_tc_nd(x: torch.Tensor, W: torch.Tensor, b=None) -> torch.Tensor:
+    """x W^T + b on the tensor-core kernels, differentiable to any order (no fused ReLU: torch's relu supplies its own
+    double backward)."""
+    y = mm_nt(x, W)
+    return y if b is None else y + b

@@ -87,7 +87,8 @@ class TrainableField(nn.Module):
     def stack(self, name: str) -> List:
         return [(getattr(self, f"{name}_w{i}"), getattr(self, f"{name}_b{i}")) for i in range(self.n_layers[name])]
 
-    tc_linear: bool = True      # env / colour / diffuse / renv layers through csrc/linear_tc.cu on CUDA tensors (sdf_net: torch, double backward)
+    tc_linear: bool = True      # env / colour / diffuse / renv layers through csrc/linear_tc.cu on CUDA tensors
+    tc_sdf: bool = True         # sdf_net through the any-order-differentiable nt / nn / tn family of linear_tc.py (False: torch layers)
 
     def mlp(self, name: str, x: torch.Tensor) -> torch.Tensor:
         layers = self.stack(name)
@@ -95,6 +96,13 @@ class TrainableField(nn.Module):
             from .linear_tc import linear_tc
             for i, (W, b) in enumerate(layers):
                 x = linear_tc(x, W, b, relu=(i != len(layers) - 1))
+            return x
+        if self.tc_linear and self.tc_sdf and name == "sdf" and x.is_cuda and x.dtype == torch.float32:
+            from .linear_tc import linear_tc_nd                       # differentiable to any order (the normals' double backward)
+            for i, (W, b) in enumerate(layers):
+                x = linear_tc_nd(x, W, b)
+                if i != len(layers) - 1:
+                    x = F.relu(x)
             return x
         for i, (W, b) in enumerate(layers):
             x = F.linear(x, W, b)
