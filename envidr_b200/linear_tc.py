@@ -3,8 +3,9 @@
 `linear_tc(x, W, b, relu)` = relu?(x @ W.T + b) with fp32 tensors and fp32-level accuracy (fp16 hi/lo split operands, three
 tcgen05.mma per K step, fp32 accumulation); the reference runs these layers as cuBLAS fp32 GEMMs behind nn.Linear
 (nerf/network.py:527-698).  Backward: the data gradient is the same kernel on the image of W^T, the weight gradient stays a
-cuBLAS GEMM (dY^T X) and the bias gradient a column sum.  Once differentiable: used for the env / colour / diffuse / renv MLPs;
-sdf_net keeps torch layers because the normals need a double backward through it (nerf/renderer.py:182-198).
+tensor-core kernel k_wgrad_tc (dY^T X) and the bias gradient comes out of the operand-scale pass.  `linear_tc` is once differentiable: used for
+the env / colour / diffuse / renv MLPs; sdf_net, whose normals need a double backward (nerf/renderer.py:182-198), uses the any-order family
+`mm_nt / mm_nn / mm_tn` at the end of this file (same kernels).
 """
 from __future__ import annotations
 

@@ -221,3 +221,36 @@ def test_wgrad_tc_atomic_accumulate_and_fused_bias(dev, M, N, K):
         L.WGRAD_ATOMIC = True
     assert float((dW - dW2).abs().max()) <= 2e-5 * float(dW_ref.abs().max())
     assert float((db - db2).abs().max()) <= 2e-5 * float(db_ref.abs().max()) + 1e-6 * float(gy.abs().max()) * M ** 0.5
+
+
+def test_mm_family_double_backward_matches_float64(dev):
+    """linear_tc.mm_nt / mm_nn / mm_tn: a 3-layer ReLU net whose input gradient (create_graph=True) enters the loss, as the normals do
+    (renderer.py:182-198): first- and second-order gradients against float64 torch."""
+    from envidr_b200.linear_tc import linear_tc_nd
+    g = torch.Generator().manual_seed(4)
+    M = 3000
+    x0 = torch.randn(M, 32, generator=g)
+    Ws = [torch.randn(64, 32, generator=g) / 32 ** 0.5, torch.randn(64, 64, generator=g) / 8, torch.randn(15, 64, generator=g) / 8]
+    bs = [torch.randn(64, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1, torch.randn(15, generator=g) * 0.1]
+
+    def run(dtype, device, lin):
+        x = x0.to(device=device, dtype=dtype).requires_grad_(True)
+        W = [w.to(device=device, dtype=dtype).requires_grad_(True) for w in Ws]
+        b = [v.to(device=device, dtype=dtype).requires_grad_(True) for v in bs]
+        h = x
+        for i in range(3):
+            h = lin(h, W[i], b[i])
+            if i < 2:
+                h = torch.relu(h)
+        sdf = h[:, 0]
+        n = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True)[0]
+        loss = ((n.norm(dim=-1) - 1) ** 2).mean() + (h[:, 1:] ** 2).mean() + (n * x).sum(-1).mean()
+        grads = torch.autograd.grad(loss, [x] + W + b)
+        return float(loss), [t.detach().double().cpu() for t in grads], n.detach().double().cpu()
+
+    loss_r, g_r, n_r = run(torch.float64, "cpu", torch.nn.functional.linear)
+    loss_t, g_t, n_t = run(torch.float32, dev, linear_tc_nd)
+    assert abs(loss_t - loss_r) <= 1e-5 * max(1.0, abs(loss_r))
+    assert float((n_t - n_r).abs().max()) <= 2e-5 * float(n_r.abs().max())
+    for a, b in zip(g_t, g_r):
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-9
