@@ -496,9 +496,56 @@ def run_cuda(model, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, fo
     return results
 
 
-def install(render_func_module=None):
-    """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop."""
-    global _reference_run_cuda
+_reference_render = None
+
+
+def render_model(model, rays_o, rays_d, staged=False, max_ray_batch=4096, get_normal_image=False, use_specular_color=True,
+                 env_net_index=None, material=None, r_images=None, env_rot_radian=None, **kwargs):
+    """Replacement for NeRFRenderer.render (nerf/renderer.py:364-531) on a reference model.  The evaluation-time three-pass
+    indirect-reflection frame (opt.indir_ref, renderer.py:439-513) goes through `render()` of this module -- geometry pass with sample
+    log, deferred shading of the secondary pass, main pass shaded from the log -- instead of three separate run_cuda calls; every other
+    call (training, single pass, staged / chunked, sphere modes, ...) is forwarded to the reference method, whose run_cuda is ours."""
+    opt = model.opt
+    fast = (getattr(model, "cuda_ray", False) and not model.training and opt.indir_ref and not opt.debug and not opt.use_neus_sdf
+            and not opt.error_bound_sample and not opt.env_sph_mode and not opt.render_env_on_sphere and not (model.bg_radius > 0)
+            and material is None and env_net_index is None and use_specular_color and r_images is None
+            and not kwargs.get("perturb", False) and kwargs.get("ray_depth") is None and int(getattr(opt, "max_ray_batch_cuda", 0)) <= 0
+            and rays_o.shape[0] == 1)
+    if not fast:
+        if _reference_render is None:
+            raise _lib.EnvidrError("render_model: this call needs the reference NeRFRenderer.render; call install(patch_render=True) first")
+        return _reference_render(model, rays_o, rays_d, staged=staged, max_ray_batch=max_ray_batch, get_normal_image=get_normal_image,
+                                 use_specular_color=use_specular_color, env_net_index=env_net_index, material=material, r_images=r_images,
+                                 env_rot_radian=env_rot_radian, **kwargs)
+    field = getattr(model, "_envidr_field", None)
+    if field is None or getattr(model, "_envidr_field_dirty", True):
+        field = FieldParams.from_reference_model(model)
+        field.precision = "tc"
+        field = field.pack()
+        model._envidr_field, model._envidr_field_dirty = field, False
+    ob = getattr(model, "obj_aabb", None)
+    cfg = RenderConfig(bound=float(model.bound), cascade=int(model.cascade), grid_size=int(model.grid_size), min_near=float(model.min_near),
+                       dt_gamma=float(kwargs.get("dt_gamma", 0)), max_steps=int(kwargs.get("max_steps", 1024)),
+                       T_thresh=float(kwargs.get("T_thresh", 1e-4)), aabb=[float(v) for v in model.aabb_infer.tolist()], indir_ref=True,
+                       indir_max_steps=int(opt.indir_max_steps), obj_aabb=None if ob is None else [float(v) for v in ob.tolist()])
+    bg = kwargs.get("bg_color")
+    bg = 0.0 if bg is None else bg                                        # renderer.py:463-466: None means black in the three-pass frame
+    N = rays_o.shape[1]
+    res = render(field, model.density_bitfield, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), cfg, bg_color=bg, get_normal_image=get_normal_image,
+                 env_rot_radian=env_rot_radian, visual_items=tuple(opt.visual_items) if opt.use_diffuse else ())
+    out = {"image": res["image"].view(1, N, 3), "depth": res["depth"].view(1, N), "weights_sum": res["weights_sum"].view(1, N),
+           "normal_image": res["normal_image"].view(1, N, 3)}
+    for k in ("diffuse_image", "specular_image", "roughness_image"):
+        if k in res:
+            out[k] = res[k].view(1, N, -1)
+    return out
+
+
+def install(render_func_module=None, patch_render: bool = False, renderer_class=None):
+    """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop.
+    patch_render: also replace NeRFRenderer.render by `render_model` (the batched three-pass frame); renderer_class defaults to
+    nerf.renderer.NeRFRenderer."""
+    global _reference_run_cuda, _reference_render
     from .backend import install_into_sys_modules
     install_into_sys_modules()
     if render_func_module is None:
@@ -507,4 +554,11 @@ def install(render_func_module=None):
     if _reference_run_cuda is None:
         _reference_run_cuda = render_func_module.run_cuda
     render_func_module.run_cuda = run_cuda
+    if patch_render:
+        if renderer_class is None:
+            import importlib
+            renderer_class = importlib.import_module("nerf.renderer").NeRFRenderer
+        if _reference_render is None:
+            _reference_render = renderer_class.render
+        renderer_class.render = render_model
     return render_func_module

@@ -239,3 +239,45 @@ def test_single_pass_deferred_shading_equals_loop(dev, W, env_width, deg):
             assert int((e > 1e-4).sum()) <= 2, (k, int((e > 1e-4).sum()), float(e.max()))
         assert float((a["weights_sum"] - b["weights_sum"]).abs().max()) <= 1e-5
         assert float((a["depth"] - b["depth"]).abs().max()) <= 1e-5
+
+
+def test_render_model_routes_the_three_pass_frame(dev):
+    """render.render_model (the NeRFRenderer.render replacement) on an object with the reference model's attributes: the evaluation
+    three-pass frame equals render.render bit for bit with the reference's output shapes ([1, N, ...]); ineligible calls are forwarded."""
+    import types
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=64, ide_degree=4)
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    bf = torch.from_numpy(scene.make_bitfield()).to(dev)
+    W = 64
+    ro, rd = scene.camera_rays(W, W)
+    ro, rd = ro.to(dev), rd.to(dev)
+    opt = types.SimpleNamespace(indir_ref=True, debug=False, use_neus_sdf=False, error_bound_sample=False, env_sph_mode=False,
+                                render_env_on_sphere=False, max_ray_batch_cuda=-1, indir_max_steps=1024, visual_items=["specular", "roughness", "diffuse"],
+                                use_diffuse=True)
+    model = types.SimpleNamespace(opt=opt, cuda_ray=True, training=False, bg_radius=-1, bound=1.0, cascade=1, grid_size=128, min_near=0.2,
+                                  aabb_infer=torch.tensor([-1.0, -1, -1, 1, 1, 1]), obj_aabb=None, density_bitfield=bf,
+                                  _envidr_field=fp, _envidr_field_dirty=False)
+    kw = dict(bg_color=None, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=1e-4, early_stop_steps=-1)
+    out = render.render_model(model, ro[None], rd[None], staged=True, get_normal_image=True, env_rot_radian=0.4, **kw)
+    ref = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True), bg_color=0.0, get_normal_image=True, env_rot_radian=0.4,
+                        visual_items=("specular", "roughness", "diffuse"))
+    N = W * W
+    assert out["image"].shape == (1, N, 3) and out["depth"].shape == (1, N) and out["weights_sum"].shape == (1, N)
+    assert out["normal_image"].shape == (1, N, 3) and out["roughness_image"].shape == (1, N, 1) and out["diffuse_image"].shape == (1, N, 3)
+    for k in ("image", "depth", "weights_sum", "normal_image", "diffuse_image", "specular_image", "roughness_image"):
+        assert torch.equal(out[k].reshape(ref[k].shape), ref[k]), k
+    # a training call is not ours: forwarded to the reference method (here: a recorder)
+    calls = []
+    render._reference_render = lambda m, o, d, **k: calls.append(sorted(k)) or {"image": None}
+    try:
+        model.training = True
+        render.render_model(model, ro[None], rd[None], **kw)
+        assert calls and "staged" in calls[0] and "bg_color" in calls[0]
+    finally:
+        render._reference_render = None
+        model.training = False
+    with pytest.raises(Exception):
+        model.training = True
+        render.render_model(model, ro[None], rd[None], **kw)          # no reference method installed: fails loudly
