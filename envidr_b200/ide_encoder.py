@@ -33,6 +33,19 @@ def get_ml_array(deg_view):
     return np.array(ml_list).T
 
 
+# the reference module's public helper names (ide_encoder.py:5-41; demo.ipynb imports the module wholesale)
+def generalized_binomial_coeff(a, k):
+    return _gen_binom(a, k)
+
+
+def assoc_legendre_coeff(l, m, k):
+    return ((-1) ** m * 2 ** l * math.factorial(l) / math.factorial(k) / math.factorial(l - k - m) * _gen_binom(0.5 * (l + k + m - 1.0), l))
+
+
+def sph_harm_coeff(l, m, k):
+    return _sph_harm_coeff(l, m, k)
+
+
 class _ide_encode(torch.autograd.Function):
     """out [B, 2P] = IDE(dirs [B,3], kappa_inv [B] or scalar); once differentiable w.r.t. dirs and the kappa array."""
 

@@ -43,6 +43,39 @@ for name in ("update_extra_state", "mark_untrained_grid"):
     a = list(inspect.signature(getattr(m, name)).parameters.items())
     b = list(inspect.signature(getattr(R.NeRFRenderer, name)).parameters.items())[1:]
     assert [(k, v.default) for k, v in a] == [(k, v.default) for k, v in b], name
+# every public class / function of the reference's operator modules exists in its mirror with the same parameters and defaults
+import importlib
+pairs = [("raymarching.raymarching", "envidr_b200.raymarching"), ("hashencoder.hashgrid", "envidr_b200.hashencoder"),
+         ("gridencoder.grid", "envidr_b200.gridencoder"), ("freqencoder.freq", "envidr_b200.freqencoder"),
+         ("shencoder.sphere_harmonics", "envidr_b200.shencoder"), ("ide_encoder.ide_encoder", "envidr_b200.ide_encoder")]
+bad, checked = [], 0
+for rn, on in pairs:
+    r, o = importlib.import_module(rn), importlib.import_module(on)
+    for name, obj in vars(r).items():
+        if name.startswith("__") or not (inspect.isclass(obj) or inspect.isfunction(obj)) or getattr(obj, "__module__", "") != r.__name__:
+            continue
+        if not hasattr(o, name):
+            bad.append((rn, name, "missing")); continue
+        ours = getattr(o, name)
+        for meth in ("forward", "__init__") if inspect.isclass(obj) else (None,):
+            f_r = getattr(obj, meth, None) if meth else obj
+            f_o = getattr(ours, meth, None) if meth else ours
+            if f_r is None or f_o is None or f_r is object.__init__:
+                continue
+            try:
+                pr = [(k, v.default) for k, v in inspect.signature(f_r).parameters.items() if v.kind is not v.VAR_KEYWORD]
+                po = [(k, v.default) for k, v in inspect.signature(f_o).parameters.items() if v.kind is not v.VAR_KEYWORD]
+            except (TypeError, ValueError):
+                continue
+            checked += 1
+            if pr != po:
+                bad.append((rn, name, meth, pr, po))
+assert not bad and checked >= 30, (checked, bad)
+import numpy as np
+import ide_encoder.ide_encoder as IR, envidr_b200.ide_encoder as IO
+for l, m, k in ((1, 0, 1), (4, 2, 2), (8, 3, 1), (16, 5, 7)):
+    assert abs(IR.sph_harm_coeff(l, m, k) - IO.sph_harm_coeff(l, m, k)) <= 1e-12 * abs(IR.sph_harm_coeff(l, m, k)) + 1e-300
+    assert abs(IR.assoc_legendre_coeff(l, m, k) - IO.assoc_legendre_coeff(l, m, k)) <= 1e-12 * abs(IR.assoc_legendre_coeff(l, m, k)) + 1e-300
 print("INSTALL-OK")
 '''
 
