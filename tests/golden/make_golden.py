@@ -512,8 +512,100 @@ def gen_neus():
     print("neus.npz: alpha ranges", {t: (float(out[f"{t}_alpha"].min()), float(out[f"{t}_alpha"].max())) for t in "abcd"})
 
 
+def gen_train_branch():
+    """The reference's OWN run_cuda training branch (nerf/render_func/cuda_ray.py:64-168) through NeRFRenderer.render and
+    NeRFNetwork.forward_sigma / compute_normal / get_color_mlp_extra_params / forward_color, run on the CPU: the CUDA-only operators it
+    calls are bound to the oracle's restatements (raymarching.near_far_from_aabb / march_rays_train / composite_rays_train /
+    get_scatter_idx -> oracle C + its autograd wrapper; HashEncoder.forward -> the oracle's hash_encode with second-order backward, on
+    the reference module's own embeddings / offsets / per_level_scale).  Two cases: single pass, and main pass with r_images (renv
+    branch).  Stored: weights, rays, outputs and the gradients of a fixed functional of the outputs.  -> tests/golden/train_branch.npz"""
+    sys.path.insert(0, REPO)
+    from envidr_b200 import scene
+    from oracle import oracle as O
+    from oracle import train_oracle as TO
+    import nerf.render_func.cuda_ray as CR
+    model, opt = build_model(["--hidden_dim_env", "64", "--num_levels", "8", "--log2_hashmap_size", "12", "--desired_resolution", "256",
+                              "--max_steps", "256"], cuda_ray=True)
+    g = torch.Generator().manual_seed(6)
+    enc = model.encoder
+    with torch.no_grad():
+        enc.embeddings.copy_(torch.rand(enc.embeddings.shape, generator=g) - 0.5)
+        model.sdf_density.beta.fill_(0.05)
+    offs = enc.offsets.numpy().astype(np.int32)
+
+    def enc_forward(inputs, bound=1):                                      # hashgrid.py:157-168
+        x01 = ((inputs + bound) / (2 * bound)).view(-1, 3)
+        return TO.hash_encode(x01, enc.embeddings, offs, float(enc.per_level_scale), int(enc.base_resolution), x01.requires_grad)
+    enc.forward = enc_forward
+
+    class RM:
+        @staticmethod
+        def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+            n, f = O.near_far_from_aabb(rays_o.detach().numpy(), rays_d.detach().numpy(), aabb.numpy(), min_near)
+            return torch.from_numpy(n), torch.from_numpy(f)
+
+        @staticmethod
+        def march_rays_train(rays_o, rays_d, bound, bitfield, C, H, nears, fars, step_counter=None, mean_count=-1, perturb=False, align=-1,
+                             force_all_rays=False, dt_gamma=0, max_steps=1024, early_stop_steps=-1):
+            assert not perturb and (force_all_rays or mean_count <= 0)
+            N = rays_o.shape[0]
+            x, d, dl, rays, cnt = O.march_rays_train(rays_o.detach().numpy(), rays_d.detach().numpy(), bound, bitfield.numpy(), C, H, nears.numpy(),
+                                                     fars.numpy(), N * max_steps, dt_gamma=dt_gamma, max_steps=max_steps,
+                                                     early_stop_steps=early_stop_steps)
+            m = int(cnt[0])
+            if align > 0:
+                m += align - m % align                                     # raymarching.py:235-241
+            return torch.from_numpy(x[:m]), torch.from_numpy(d[:m]), torch.from_numpy(dl[:m]), torch.from_numpy(rays)
+
+        @staticmethod
+        def composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh=1e-4, ret_weights=False, input_alpha=False):
+            return TO.composite_rays_train(sigmas, rgbs, deltas.numpy(), rays.numpy(), T_thresh, ret_weights, input_alpha)
+
+        @staticmethod
+        def get_scatter_idx(rays, dummy):
+            return torch.from_numpy(O.get_scatter_idx(rays.numpy(), dummy.shape[0]))
+    CR.raymarching = RM
+    bf = scene.make_bitfield()
+    model.density_bitfield = torch.from_numpy(bf)
+    model.train()
+    opt.indir_ref = False
+    opt.eikonal_loss = True
+    opt.backsdf_loss = False; opt.relsdf_loss = False; opt.orientation_loss = False; opt.dist_bound = False
+    ro, rd = scene.camera_rays(12, 12)
+    N = ro.shape[0]
+    r_img = torch.rand(1, N, 4, generator=g)
+    r_img[0, ::2, 3] = 0.95 + 0.05 * r_img[0, ::2, 3]
+    out = dict(rays_o=ro.numpy(), rays_d=rd.numpy(), r_images=r_img[0].numpy(), offsets=offs, per_level_scale=np.float64(enc.per_level_scale),
+               base_resolution=np.int32(enc.base_resolution), embeddings=enc.embeddings.detach().numpy().copy())
+    out.update(model_weights(model))
+    out["opt_beta_min"] = np.float32(opt.beta_min); out["opt_beta_max"] = np.float32(opt.beta_max)
+    kw = {k: v for k, v in vars(opt).items()}
+    names = ["sdf_net.0.weight", "sdf_net.2.bias", "env_net.1.weight", "renv_net.0.weight", "encoder.embeddings", "sdf_density.beta"]
+    params = dict(model.named_parameters())
+    for tag, ri in (("single", None), ("renv", r_img)):
+        model.zero_grad()
+        res = model.render(ro[None], rd[None], staged=False, bg_color=1, perturb=False, force_all_rays=True, get_normal_image=False,
+                           r_images=ri, **kw)
+        sdfs, sg = res["sdfs"], res["sdf_gradients"]
+        loss = 0.3 * res["image"].sum() + (res["weights_sum"] ** 2).sum() + 5 * (sdfs ** 2).mean() + ((sg.norm(dim=-1) - 1) ** 2).mean()
+        loss.backward()
+        f = lambda t: t.detach().numpy().astype(np.float32)
+        out.update({f"{tag}_image": f(res["image"][0]), f"{tag}_weights_sum": f(res["weights_sum"][0]), f"{tag}_depth": f(res["depth"][0]),
+                    f"{tag}_sdfs": f(sdfs), f"{tag}_sdf_gradients": f(sg), f"{tag}_sigmas": f(res["sigmas"]), f"{tag}_loss": np.float64(loss.item())})
+        for n in names:
+            gr = params[n].grad
+            out[f"{tag}_grad_{n.replace('.', '_')}"] = np.zeros(0, np.float32) if gr is None else f(gr)
+    np.savez_compressed(os.path.join(HERE, "train_branch.npz"), **out)
+    print("train_branch.npz: samples", out["single_sdfs"].shape[0], "loss", float(out["single_loss"]), float(out["renv_loss"]),
+          "ws mean", float(out["single_weights_sum"].mean()))
+
+
 if __name__ == "__main__":
     install_shims()
+    if "train" in sys.argv[1:]:
+        torch.set_num_threads(8)
+        gen_train_branch()
+        sys.exit(0)
     if "neus" in sys.argv[1:]:
         gen_neus()
         sys.exit(0)

@@ -239,3 +239,44 @@ def test_neus_alpha_matches_reference(golden_dir, tag):
     assert abs(g_var - float(z[f"{tag}_g_var"])) <= 1e-3 * abs(float(z[f"{tag}_g_var"])) + 1e-6
     if grads is not None:
         np.testing.assert_allclose(g_grads, z[f"{tag}_g_grads"], rtol=5e-4, atol=5e-5 * float(np.abs(z[f"{tag}_g_grads"]).max()) + 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# training branch: the train oracle vs the reference's OWN run_cuda training branch + NeRFNetwork methods run on
+# the CPU with the oracle's operators injected (tests/golden/make_golden.py::gen_train_branch)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["single", "renv"])
+def test_train_oracle_matches_reference_run_cuda_training_branch(golden_dir, tag):
+    from envidr_b200 import scene
+    from oracle import train_oracle as TO
+    z = np.load(os.path.join(golden_dir, "train_branch.npz"))
+    P = _P_from_glue(z, 5)
+    P.update(embeddings=z["embeddings"], offsets=z["offsets"].astype(np.int32), per_level_scale=float(z["per_level_scale"]),
+             base_resolution=int(z["base_resolution"]), density_scale=1.0, enabled_levels=-1)
+    th = TO.params_from_dict(P, torch.float64, frozen=())
+    bf = scene.make_bitfield()
+    out = TO.render_train(th, P, z["rays_o"], z["rays_d"], bf, max_steps=256, bg_color=1.0,
+                          r_images=z["r_images"] if tag == "renv" else None)
+    f = lambda t: t.detach().to(torch.float32).numpy()
+    assert out["sdfs"].shape[0] == z[f"{tag}_sdfs"].shape[0]                      # same samples, same padding
+    np.testing.assert_allclose(f(out["sdfs"]), z[f"{tag}_sdfs"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(f(out["sigmas"]), z[f"{tag}_sigmas"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(f(out["sdf_gradients"]), z[f"{tag}_sdf_gradients"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(f(out["image"]), z[f"{tag}_image"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(f(out["weights_sum"]), z[f"{tag}_weights_sum"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(f(out["depth"]), z[f"{tag}_depth"], rtol=0, atol=2e-5)
+    sg = out["sdf_gradients"]
+    loss = 0.3 * out["image"].sum() + (out["weights_sum"] ** 2).sum() + 5 * (out["sdfs"] ** 2).mean() + ((sg.norm(dim=-1) - 1) ** 2).mean()
+    assert abs(float(loss) - float(z[f"{tag}_loss"])) <= 2e-5 * abs(float(z[f"{tag}_loss"]))
+    names = {"sdf.0.weight": "sdf_net_0_weight", "sdf.2.bias": "sdf_net_2_bias", "env.1.weight": "env_net_1_weight",
+             "renv.0.weight": "renv_net_0_weight", "embeddings": "encoder_embeddings", "beta": "sdf_density_beta"}
+    grads = torch.autograd.grad(loss, [th[k] for k in names], allow_unused=True)
+    for (k, gk), g in zip(names.items(), grads):
+        ref = z[f"{tag}_grad_{gk}"]
+        if ref.size == 0 or (tag == "single" and k.startswith("renv")):
+            assert g is None or float(g.abs().max()) == 0.0 or ref.size == 0, k
+            continue
+        got = g.detach().to(torch.float32).numpy().reshape(ref.shape)
+        scale = float(np.abs(ref).max())
+        assert float(np.abs(got - ref).max()) <= 2e-3 * scale + 1e-9, (k, float(np.abs(got - ref).max()), scale)
