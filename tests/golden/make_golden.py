@@ -600,8 +600,86 @@ def gen_train_branch():
           "ws mean", float(out["single_weights_sum"].mean()))
 
 
+def gen_infer_branch():
+    """The reference's OWN inference path on the CPU: NeRFRenderer.render (renderer.py:364-531: single pass and the three-pass
+    indirect-reflection frame) -> run_cuda inference while-loop (cuda_ray.py:238-359, get_normal_image, visual items) -> NeRFNetwork
+    methods, with raymarching.near_far_from_aabb / march_rays / composite_rays bound to the oracle's C restatements (bit-exact against
+    the reference kernels on the GPU, tests/test_gpu_ops.py) and HashEncoder.forward to the oracle's hash_encode.
+    -> tests/golden/infer_branch.npz (weights, rays, all returned images of both frames)"""
+    sys.path.insert(0, REPO)
+    from envidr_b200 import scene
+    from oracle import oracle as O
+    from oracle import train_oracle as TO
+    import nerf.render_func.cuda_ray as CR
+    model, opt = build_model(["--hidden_dim_env", "64", "--num_levels", "8", "--log2_hashmap_size", "12", "--desired_resolution", "256",
+                              "--max_steps", "256", "--indir_max_steps", "256"], cuda_ray=True)
+    g = torch.Generator().manual_seed(7)
+    enc = model.encoder
+    # an SDF-like field: the analytic toaster through the synthetic-field construction, restricted to this small grid
+    fp = scene.make_synthetic_field(0, hidden_dim_env=64, ide_degree=5, num_levels=8, log2_hashmap_size=12, desired_resolution=256, beta=0.02)
+    assert tuple(fp.embeddings.shape) == tuple(enc.embeddings.shape) and np.array_equal(fp.offsets.numpy(), enc.offsets.numpy())
+    with torch.no_grad():
+        enc.embeddings.copy_(fp.embeddings)
+        for name in ("sdf", "env", "diffuse", "color", "renv"):
+            for lin, (W, b) in zip(getattr(model, name + "_net"), getattr(fp, name)):
+                lin.weight.copy_(W); lin.bias.copy_(b)
+        model.sdf_density.beta.fill_(0.02)
+    offs = enc.offsets.numpy().astype(np.int32)
+
+    def enc_forward(inputs, bound=1):
+        x01 = ((inputs + bound) / (2 * bound)).view(-1, 3)
+        return TO.hash_encode(x01, enc.embeddings, offs, float(enc.per_level_scale), int(enc.base_resolution), x01.requires_grad)
+    enc.forward = enc_forward
+
+    class RM:
+        @staticmethod
+        def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+            n, f = O.near_far_from_aabb(rays_o.detach().numpy(), rays_d.detach().numpy(), aabb.numpy(), min_near)
+            return torch.from_numpy(n), torch.from_numpy(f)
+
+        @staticmethod
+        def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, C, H, near, far, align=-1, perturb=False,
+                       dt_gamma=0, max_steps=1024):
+            assert not perturb
+            x, d, dl, _ = O.march_rays(n_alive, n_step, rays_alive.numpy(), rays_t.numpy(), rays_o.detach().numpy(), rays_d.detach().numpy(), bound,
+                                       bitfield.numpy(), C, H, near.numpy(), far.numpy(), align=align, dt_gamma=dt_gamma, max_steps=max_steps)
+            return torch.from_numpy(x), torch.from_numpy(d), torch.from_numpy(dl)
+
+        @staticmethod
+        def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2,
+                           input_alpha=False, accum_deltas=True):
+            O.composite_rays(n_alive, n_step, rays_alive.numpy(), rays_t.numpy(), sigmas.detach().numpy(), rgbs.detach().numpy(),
+                             deltas.detach().numpy(), weights_sum.numpy(), depth.numpy(), image.numpy(), T_thresh=T_thresh,
+                             input_alpha=bool(input_alpha), accum_deltas=bool(accum_deltas))      # in place through the shared memory
+            return tuple()
+    CR.raymarching = RM
+    bf = scene.make_bitfield()
+    model.density_bitfield = torch.from_numpy(bf)
+    model.eval()
+    W = 20
+    ro, rd = scene.camera_rays(W, W)
+    out = dict(rays_o=ro.numpy(), rays_d=rd.numpy(), offsets=offs, per_level_scale=np.float64(enc.per_level_scale),
+               base_resolution=np.int32(enc.base_resolution), embeddings=enc.embeddings.detach().numpy().copy())
+    out.update(model_weights(model))
+    out["opt_beta_min"] = np.float32(opt.beta_min); out["opt_beta_max"] = np.float32(opt.beta_max)
+    for tag, indir in (("one", False), ("three", True)):
+        opt.indir_ref = indir
+        kw = {k: v for k, v in vars(opt).items()}
+        res = model.render(ro[None], rd[None], staged=True, bg_color=1, perturb=False, get_normal_image=True, env_rot_radian=None, **kw)
+        f = lambda t: t.detach().numpy().astype(np.float32)
+        for k in ("image", "depth", "weights_sum", "normal_image", "diffuse_image", "specular_image", "roughness_image"):
+            if k in res and res[k] is not None:
+                out[f"{tag}_{k}"] = f(res[k]).reshape(W * W, -1)
+    np.savez_compressed(os.path.join(HERE, "infer_branch.npz"), **out)
+    print("infer_branch.npz: hit pixels", int((out["one_weights_sum"] > 0.5).sum()), "of", W * W, "keys", sorted(k for k in out if k.startswith("three_")))
+
+
 if __name__ == "__main__":
     install_shims()
+    if "infer" in sys.argv[1:]:
+        torch.set_num_threads(8)
+        gen_infer_branch()
+        sys.exit(0)
     if "train" in sys.argv[1:]:
         torch.set_num_threads(8)
         gen_train_branch()

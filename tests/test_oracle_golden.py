@@ -280,3 +280,26 @@ def test_train_oracle_matches_reference_run_cuda_training_branch(golden_dir, tag
         got = g.detach().to(torch.float32).numpy().reshape(ref.shape)
         scale = float(np.abs(ref).max())
         assert float(np.abs(got - ref).max()) <= 2e-3 * scale + 1e-9, (k, float(np.abs(got - ref).max()), scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# inference path: the render oracle vs the reference's OWN NeRFRenderer.render + run_cuda inference loop run on
+# the CPU with the oracle's operators injected (tests/golden/make_golden.py::gen_infer_branch): single pass and three-pass frame
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag,indir", [("one", False), ("three", True)])
+def test_render_oracle_matches_reference_inference_path(golden_dir, tag, indir):
+    from envidr_b200 import scene
+    z = np.load(os.path.join(golden_dir, "infer_branch.npz"))
+    P = _P_from_glue(z, 5)
+    P.update(embeddings=z["embeddings"], offsets=z["offsets"].astype(np.int32), per_level_scale=float(z["per_level_scale"]),
+             base_resolution=int(z["base_resolution"]), density_scale=1.0, enabled_levels=-1)
+    bf = scene.make_bitfield()
+    res = O.render(P, z["rays_o"], z["rays_d"], bf, indir_ref=indir, indir_max_steps=256, max_steps=256, bg_color=1.0)
+    assert int((z[f"{tag}_weights_sum"] > 0.5).sum()) >= 40                       # the frame sees the object
+    e = np.abs(res["image"] - z[f"{tag}_image"]).max(-1)
+    assert int((e > 1e-4).sum()) <= 2 and float(np.median(e)) <= 1e-5, (int((e > 1e-4).sum()), float(e.max()))
+    np.testing.assert_allclose(res["weights_sum"], z[f"{tag}_weights_sum"][:, 0], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(res["depth"], z[f"{tag}_depth"][:, 0], rtol=0, atol=2e-5)
+    en = np.abs(res["normal_image"] - z[f"{tag}_normal_image"]).max(-1)
+    assert int((en > 1e-3).sum()) <= 2, (int((en > 1e-3).sum()), float(en.max()))
