@@ -1,8 +1,12 @@
 """CPU oracle for the ENVIDR volumetric-render hot path -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-may import this module.  The product (envidr_b200/) never does; it fails loudly when its
-CUDA library is missing instead of falling back to anything in here.
+may import this module (tests/golden/make_golden.py injects its operators into the REFERENCE's
+own Python to produce the golden vectors; oracle/ref_cuda.py -- the reference's kernels around
+the reference's host logic -- is additionally timed as a baseline by bench.py's gpu_reference /
+density_update keys and the profiles/*_bench.py scripts).  The product (envidr_b200/) never
+imports anything from here; it fails loudly when its CUDA library is missing instead of
+falling back (tests/test_cabi.py::test_product_does_not_import_oracle).
 
 Two layers:
   * ctypes bindings to oracle/envidr_oracle.c (march / composite / grid encoders / freq / SH),
