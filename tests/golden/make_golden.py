@@ -662,10 +662,10 @@ def gen_infer_branch():
                base_resolution=np.int32(enc.base_resolution), embeddings=enc.embeddings.detach().numpy().copy())
     out.update(model_weights(model))
     out["opt_beta_min"] = np.float32(opt.beta_min); out["opt_beta_max"] = np.float32(opt.beta_max)
-    for tag, indir in (("one", False), ("three", True)):
+    for tag, indir, rot in (("one", False, None), ("three", True, None), ("rot", True, 0.7)):      # rot: one step of the relight sweep
         opt.indir_ref = indir
         kw = {k: v for k, v in vars(opt).items()}
-        res = model.render(ro[None], rd[None], staged=True, bg_color=1, perturb=False, get_normal_image=True, env_rot_radian=None, **kw)
+        res = model.render(ro[None], rd[None], staged=True, bg_color=1, perturb=False, get_normal_image=True, env_rot_radian=rot, **kw)
         f = lambda t: t.detach().numpy().astype(np.float32)
         for k in ("image", "depth", "weights_sum", "normal_image", "diffuse_image", "specular_image", "roughness_image"):
             if k in res and res[k] is not None:

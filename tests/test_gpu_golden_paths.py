@@ -35,9 +35,9 @@ def _field_from_golden(z, beta):
                        geo_feat_dim=12, ide_degree=5, beta=beta, beta_min=float(z["opt_beta_min"]), beta_max=float(z["opt_beta_max"]))
 
 
-@pytest.mark.parametrize("tag,indir", [("one", False), ("three", True)])
+@pytest.mark.parametrize("tag,indir,rot", [("one", False, None), ("three", True, None), ("rot", True, 0.7)])
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
-def test_cuda_render_matches_reference_python_images(dev, golden_dir, tag, indir, precision):
+def test_cuda_render_matches_reference_python_images(dev, golden_dir, tag, indir, rot, precision):
     from envidr_b200 import render, scene
     z = np.load(os.path.join(golden_dir, "infer_branch.npz"))
     fp = _field_from_golden(z, float(z["beta"]))
@@ -46,7 +46,8 @@ def test_cuda_render_matches_reference_python_images(dev, golden_dir, tag, indir
     bf = torch.from_numpy(scene.make_bitfield()).to(dev)
     ro, rd = torch.from_numpy(z["rays_o"]).to(dev), torch.from_numpy(z["rays_d"]).to(dev)
     cfg = render.RenderConfig(indir_ref=indir, max_steps=256, indir_max_steps=256)
-    res = render.render(fp, bf, ro, rd, cfg, bg_color=1.0, get_normal_image=True, visual_items=("diffuse", "specular", "roughness"))
+    res = render.render(fp, bf, ro, rd, cfg, bg_color=1.0, get_normal_image=True, env_rot_radian=rot,
+                        visual_items=("diffuse", "specular", "roughness"))
     e = (res["image"].cpu().numpy() - z[f"{tag}_image"]).__abs__().max(-1)
     assert int((e > 1e-4).sum()) <= 2 and float(np.median(e)) <= 2e-5, (int((e > 1e-4).sum()), float(e.max()))
     np.testing.assert_allclose(res["weights_sum"].cpu().numpy(), z[f"{tag}_weights_sum"][:, 0], rtol=0, atol=5e-5)

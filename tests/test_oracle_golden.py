@@ -287,15 +287,17 @@ def test_train_oracle_matches_reference_run_cuda_training_branch(golden_dir, tag
 # the CPU with the oracle's operators injected (tests/golden/make_golden.py::gen_infer_branch): single pass and three-pass frame
 # ---------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("tag,indir", [("one", False), ("three", True)])
-def test_render_oracle_matches_reference_inference_path(golden_dir, tag, indir):
+@pytest.mark.parametrize("tag,indir,rot", [("one", False, None), ("three", True, None), ("rot", True, 0.7)])
+def test_render_oracle_matches_reference_inference_path(golden_dir, tag, indir, rot):
     from envidr_b200 import scene
     z = np.load(os.path.join(golden_dir, "infer_branch.npz"))
     P = _P_from_glue(z, 5)
     P.update(embeddings=z["embeddings"], offsets=z["offsets"].astype(np.int32), per_level_scale=float(z["per_level_scale"]),
              base_resolution=int(z["base_resolution"]), density_scale=1.0, enabled_levels=-1)
     bf = scene.make_bitfield()
-    res = O.render(P, z["rays_o"], z["rays_d"], bf, indir_ref=indir, indir_max_steps=256, max_steps=256, bg_color=1.0)
+    res = O.render(P, z["rays_o"], z["rays_d"], bf, indir_ref=indir, indir_max_steps=256, max_steps=256, bg_color=1.0, env_rot_radian=rot)
+    if rot is not None:
+        assert float(np.abs(z["rot_image"] - z["three_image"]).max()) > 1e-2      # the rotation does change the frame
     assert int((z[f"{tag}_weights_sum"] > 0.5).sum()) >= 40                       # the frame sees the object
     e = np.abs(res["image"] - z[f"{tag}_image"]).max(-1)
     assert int((e > 1e-4).sum()) <= 2 and float(np.median(e)) <= 1e-5, (int((e > 1e-4).sum()), float(e.max()))
