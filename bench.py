@@ -197,29 +197,115 @@ def train_step_bench(fp_cpu, bf, ro, rd, dev, n_rays, steps=10, warmup=3):
                     "epilogue), fp32; ms_per_step_with_*: + optimizer step over all trainable tensors"}
 
 
-def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2):
-    """The reference's own CUDA path on this GPU (oracle/ref_cuda.py: unmodified reference kernels rebuilt for sm_100a + the
-    reference's host loop + torch fp32 MLPs with autograd normals) on the same frame: the "reference rays/sec on the same
-    B200" of the north star.  Reported next to the contract's figures; the driver's reference arm stays `--impl reference`."""
+def _timed_frames(fn, frames):
     import torch
+    ms = []
+    out = None
+    for _ in range(frames):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return sorted(ms)[len(ms) // 2], out
+
+
+def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2, train_rays=4096):
+    """The reference's own CUDA path on this GPU: the "reference rays/sec on the same B200" of the north star.  Reported next to
+    the contract's figures; the driver's reference arm stays `--impl reference`.
+
+    Preferred: the REAL reference -- its NeRFNetwork under configs/scenes/toaster.ini (oracle/_ref/py, the unmodified Python tree
+    shipped by oracle/build_ref.py) with the synthetic field loaded into its parameters, `model.render(...)` called with
+    Trainer.eval_step's arguments (utils.py:857-859) on its own kernels (oracle/_ref/_*.so rebuilt for sm_100a).  On the same
+    model object, the documented drop-ins are then timed: install() and install(patch_render=True), and
+    one Trainer.train_step forward + backward on the reference's kernels (`train`: the comparator of the train_step key).
+    Fallback when the tree was not shipped: oracle/ref_cuda.py (a restatement of the same host loop around the same kernels)."""
+    import torch
+    from oracle import ref_model as RM
     from oracle import ref_cuda
+    N = ro_d.shape[0]
+    if RM.available():
+        from envidr_b200 import render
+        RM.install_shims()
+        model, opt = RM.build_model([], cuda_ray=True)
+        RM.load_field(model, fp_cpu, bf)
+        model.to(dev).eval()
+        RM.use_backends("reference")
+        opt.indir_ref = indir
+        kw = RM.eval_kwargs(opt)
+        fn = lambda: model.render(ro_d[None], rd_d[None], **kw)
+        fn()                                                                     # warm-up (cuBLAS handles, allocator)
+        torch.cuda.synchronize()
+        t, out = _timed_frames(fn, frames)
+        res = {"value": N / (t * 1e-3), "unit": "rays/s", "ms_per_frame": t, "image": out["image"].reshape(N, 3).detach(),
+               "what": "the reference's own NeRFNetwork / NeRFRenderer.render / run_cuda (unmodified Python, toaster.ini, eval_step arguments) on its own "
+                       "kernels rebuilt for sm_100a, synthetic field loaded into the model, same frame"}
+        import nerf.render_func as RF
+        import nerf.renderer as R
+        dropin = {}
+        try:
+            RM.use_backends("envidr")
+            for tag, kwargs in (("install()", {}), ("install(patch_render=True)", dict(patch_render=True, renderer_class=R.NeRFRenderer))):
+                render.install(RF, **kwargs)
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                td, od = _timed_frames(fn, 5)
+                e = (od["image"].reshape(N, 3) - res["image"]).abs().max(-1).values
+                dropin[tag] = {"rays_per_sec": N / (td * 1e-3), "ms_per_frame": td, "pixels_over_1e-4_vs_reference": int((e > 1e-4).sum()),
+                               "rgb_linf_max_vs_reference": float(e.max())}
+        except Exception as e:
+            dropin["error"] = repr(e)[:200]
+        finally:
+            render.uninstall(RF, R.NeRFRenderer)
+            RM.use_backends("reference")
+        res["dropin_on_the_reference_model"] = dropin
+        try:                                                                     # Trainer.train_step on the reference's kernels
+            g = torch.Generator().manual_seed(0)
+            sel = torch.randperm(N, generator=g)[:train_rays].to(dev)
+            o, d = ro_d[sel][None], rd_d[sel][None]
+            images = torch.rand(1, train_rays, 4, generator=g).to(dev)
+            images[..., 3] = (images[..., 3] > 0.5).float()
+            opt.indir_ref = False
+            opt.color_space, opt.alpha_bg_mode = "srgb", "white"
+            opt.eikonal_loss = opt.cauchy_loss = opt.mask_loss = True
+            opt.backsdf_loss = opt.relsdf_loss = opt.orientation_loss = opt.dist_bound = opt.diffuse_loss = False
+            opt.eikonal_loss_weight, opt.cauchy_loss_weight, opt.entropy_loss_weight = 0.01, 0.001, 0
+            model.train()
+            def tstep():
+                model.zero_grad(set_to_none=True)
+                pred, gt, loss, ld = RM.train_step(model, opt, o, d, images)
+                loss.backward()
+                return loss
+            model.mean_count, model.local_step = 0, 0
+            model.step_counter.zero_()
+            tstep()                                                              # sizes mean_count as the first steps of an epoch do
+            torch.cuda.synchronize()
+            model.mean_count = int(model.step_counter[0, 0].item())
+            for _ in range(2):
+                tstep()
+            tt, _ = _timed_frames(tstep, 7)
+            res["train"] = {"ms_per_step_fwd_bwd": tt, "rays": train_rays, "samples": int(model.step_counter[(model.local_step - 1) % 16, 0].item()),
+                            "what": "Trainer.train_step (utils.py:560-808) forward + backward on the real reference model and kernels, "
+                                    "single pass without r_images (the Trainer feeds r_images only from a dataset; our train_step key includes the renv "
+                                    "branch, i.e. does more work per step), colour L1 + mask BCE + Cauchy + eikonal, no optimizer step"}
+        except Exception as e:
+            res["train"] = {"error": repr(e)[:300]}
+        finally:
+            model.eval()
+        return res
     if not ref_cuda.available():
         return {"unavailable": "oracle/_ref/*.so not present"}
     F_ = ref_cuda.RefField(fp_cpu.to_oracle(), dev)
     bft = torch.from_numpy(bf).to(dev)
-    ref_cuda.render(F_, bft, ro_d, rd_d, indir_ref=indir, bg_color=1.0)          # warm-up (cuBLAS handles, allocator)
+    fn = lambda: ref_cuda.render(F_, bft, ro_d, rd_d, indir_ref=indir, bg_color=1.0)
+    fn()
     torch.cuda.synchronize()
-    ms = []
-    for _ in range(frames):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = ref_cuda.render(F_, bft, ro_d, rd_d, indir_ref=indir, bg_color=1.0)
-        b.record()
-        torch.cuda.synchronize()
-        ms.append(a.elapsed_time(b))
-    t = sorted(ms)[len(ms) // 2]
-    return {"value": ro_d.shape[0] / (t * 1e-3), "unit": "rays/s", "ms_per_frame": t, "image": out["image"],
-            "what": "reference CUDA kernels (oracle/_ref, unmodified sources, sm_100a) + reference host loop + torch fp32 MLPs, same frame"}
+    t, out = _timed_frames(fn, frames)
+    return {"value": N / (t * 1e-3), "unit": "rays/s", "ms_per_frame": t, "image": out["image"],
+            "what": "reference CUDA kernels (oracle/_ref, unmodified sources, sm_100a) + restated reference host loop + torch fp32 MLPs "
+                    "(oracle/ref_cuda.py; the reference Python tree was not shipped), same frame"}
 
 
 def run_reference(args):
@@ -231,7 +317,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, samples, n = cpu_baseline(fp, bf, ro, rd, args, indir, max(1024, args.cpu_sample // 4))
+        v, dt, samples, n = cpu_baseline(fp, bf, ro, rd, args, indir, args.cpu_sample)      # the sample of the repo arm's cpu_baseline leg
         if i >= args.warmup:
             vals.append((v, dt, samples, n))
     v = sum(x[0] for x in vals) / len(vals)
@@ -240,7 +326,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(args, W, H, indir),
+        "data": "synthetic", "config": dict(config_dict(args, W, H, indir), schedule="the reference's iterative schedule in all passes "
+                                                   "(n_step = N // n_alive <= 8, cuda_ray.py:287), CPU port (oracle.render)", parallelism="host threads"),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -80,7 +80,7 @@ class _Raymarching:
 
     @staticmethod
     def get_scatter_idx(rays, N, idx_map):
-        check(lib().envidr_get_scatter_idx(ptr(rays), N, ptr(idx_map), stream()), "get_scatter_idx")
+        check(lib().envidr_get_scatter_idx(ptr(rays), N, int(idx_map.numel()), ptr(idx_map), stream()), "get_scatter_idx")
 
     @staticmethod
     def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, early_stop_steps, N, C, H, M, nears, fars,
@@ -225,3 +225,9 @@ def install_into_sys_modules():
         setattr(ext, f"_{pkg}", backend)
         sys.modules[f"{pkg}._ext"] = ext
         sys.modules[f"{pkg}._ext._{pkg}"] = backend
+    # wrappers that were imported before install(): `_backend` is a module global looked up at call time
+    for pkg, modname in (("raymarching", "raymarching.raymarching"), ("hashencoder", "hashencoder.hashgrid"), ("gridencoder", "gridencoder.grid"),
+                         ("shencoder", "shencoder.sphere_harmonics"), ("freqencoder", "freqencoder.freq")):
+        mod = sys.modules.get(modname)
+        if mod is not None and hasattr(mod, "_backend"):
+            mod._backend = table[pkg]

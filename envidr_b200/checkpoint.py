@@ -100,8 +100,16 @@ def field_from_state(sd: Dict[str, torch.Tensor], *, base_resolution: int = 16, 
     kw = dict(scalars)
     if "sdf_density.beta" in sd:
         kw.setdefault("beta", float(sd["sdf_density.beta"].reshape(-1)[0]))
-    geo = int(stacks["sdf"][-1][0].shape[0]) - 3                       # sdf, geo_feat, roughness, blend (network.py:415-448)
+    # out_dim = 1 + geo_feat_dim + use_roughness(1) + learn_indir_blend (network.py:415-448)
+    geo = int(stacks["sdf"][-1][0].shape[0]) - 1 - 1 - int(bool(kw.get("learn_indir_blend", True)))
     kw.setdefault("geo_feat_dim", geo)
+    env_out = int(stacks["env"][-1][0].shape[0])
+    for n, extra in (("diffuse", 0), ("color", 3 + 1)):                # diffuse: [geo | f_n]; colour: [geo | n(3) | f_r | n.w_o]
+        want = kw["geo_feat_dim"] + env_out + extra
+        got = int(stacks[n][0][0].shape[1])
+        if got != want:
+            raise EnvidrError(f"{n}_net expects {got} inputs but geo_feat_dim {kw['geo_feat_dim']} + env features {env_out} (+{extra}) = {want}: "
+                              "pass learn_indir_blend / geo_feat_dim matching the checkpoint's options")
     return FieldParams(embeddings=sd["encoder.embeddings"].detach().float().contiguous(), offsets=offsets, per_level_scale=pls,
                        base_resolution=base_resolution, bound=bound, sdf=stacks["sdf"], env=stacks["env"], diffuse=stacks["diffuse"],
                        color=stacks["color"], renv=stacks["renv"], ide_degree=ide_degree_from_env(stacks["env"]), **kw)

@@ -101,10 +101,12 @@ __global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid
 
 // reference: kernel_get_scatter_idx (raymarching.cu:302-322).  One warp per ray: lanes stride the
 // ray's contiguous sample range, so stores are coalesced.
-__global__ void __launch_bounds__(256) k_scatter_idx(const int32_t* __restrict__ rays, uint32_t N, int32_t* __restrict__ idx_map) {
+// Rays dropped by march_rays_train (offset + count > M; the reference kernel has no such guard and writes out of bounds) are skipped.
+__global__ void __launch_bounds__(256) k_scatter_idx(const int32_t* __restrict__ rays, uint32_t N, uint32_t M, int32_t* __restrict__ idx_map) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= N) return;
     const uint32_t id = rays[3 * w], off = rays[3 * w + 1], cnt = rays[3 * w + 2];
+    if (cnt == 0 || (uint64_t)off + cnt > M) return;
     for (uint32_t s = lane; s < cnt; s += 32) idx_map[off + s] = (int32_t)id;
 }
 
@@ -199,21 +201,11 @@ __global__ void __launch_bounds__(1024) k_scan_add(int32_t* __restrict__ rays, u
     if (n < N) rays[3 * n + 1] += (int32_t)block_tot[blockIdx.x];
 }
 
-// scratch for the block totals: grown on demand, one per process (the operator surface has no workspace argument to carry it)
-static uint32_t* g_scan_scratch = nullptr;
-static uint32_t g_scan_cap = 0;
-
+// scratch for the block totals: the operator surface has no workspace argument to carry it -> stream_scratch (error.cu)
 static int scan_ray_counts(int32_t* rays, uint32_t N, int32_t* counter, cudaStream_t st) {
     const uint32_t nb = ceil_div(N, 1024);
-    if (nb > g_scan_cap) {
-        if (g_scan_scratch) cudaFree(g_scan_scratch);
-        g_scan_cap = nb < 1024 ? 1024 : nb * 2;
-        if (cudaMalloc(&g_scan_scratch, (size_t)g_scan_cap * sizeof(uint32_t)) != cudaSuccess) {
-            g_scan_scratch = nullptr; g_scan_cap = 0;
-            set_error("march: scan scratch allocation failed");
-            return (int)cudaErrorMemoryAllocation;
-        }
-    }
+    uint32_t* g_scan_scratch = static_cast<uint32_t*>(stream_scratch(kScratchScan, (size_t)nb * sizeof(uint32_t), kScratchScanBytes, st));
+    if (!g_scan_scratch) return (int)cudaErrorMemoryAllocation;
     k_scan_blocks<<<nb, 1024, 0, st>>>(rays, N, g_scan_scratch);
     k_scan_tops<<<1, 1024, 0, st>>>(g_scan_scratch, nb, N, counter);
     k_scan_add<<<nb, 1024, 0, st>>>(rays, N, g_scan_scratch);
@@ -371,9 +363,7 @@ __global__ void __launch_bounds__(32) k_occ_box_reset(int* __restrict__ box) {
     if (threadIdx.x < 6) box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
 }
 
-// scratch of the chained scan: one 8-byte status word per block + the ticket + the occupied-cell box, grown on demand
-static unsigned long long* g_chain = nullptr;
-static uint32_t g_chain_cap = 0;
+// scratch of the chained scan: one 8-byte status word per block + the ticket + the occupied-cell box -> stream_scratch (error.cu)
 
 // ------------------------------------------------------------------------------------------------
 // replay of a pass with known per-ray sample counts (see envidr_march_rays_replay in the header)
@@ -711,10 +701,10 @@ int envidr_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t
     return check_launch("packbits");
 }
 
-int envidr_get_scatter_idx(const int32_t* rays, uint32_t N, int32_t* idx_map, envidr_stream_t stream) {
+int envidr_get_scatter_idx(const int32_t* rays, uint32_t N, uint32_t M, int32_t* idx_map, envidr_stream_t stream) {
     ENVIDR_REQUIRE(rays && idx_map, ENVIDR_E_BADARG, "null pointer");
     if (N == 0) return 0;
-    k_scatter_idx<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(rays, N, idx_map);
+    k_scatter_idx<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(rays, N, M, idx_map);
     return check_launch("get_scatter_idx");
 }
 
@@ -728,15 +718,10 @@ int envidr_march_rays_train(const float* rays_o, const float* rays_d, const uint
     if (N == 0) return 0;
     cudaStream_t st = as_stream(stream);
     const uint32_t nb = ceil_div(N, kRayBlock);
-    if (nb + 8 > g_chain_cap) {                       // (allocated by the warm-up calls that precede a CUDA-graph capture)
-        if (g_chain) cudaFree(g_chain);
-        g_chain_cap = nb + 8 < 8192 ? 8192 : 2 * (nb + 8);
-        if (cudaMalloc(&g_chain, (size_t)g_chain_cap * sizeof(unsigned long long)) != cudaSuccess) {
-            g_chain = nullptr; g_chain_cap = 0;
-            set_error("march_rays_train: scan scratch allocation failed");
-            return (int)cudaErrorMemoryAllocation;
-        }
-    }
+    // (allocated once per device and stream by the warm-up calls that precede a CUDA-graph capture; never moved afterwards)
+    unsigned long long* g_chain = static_cast<unsigned long long*>(
+        stream_scratch(kScratchChain, (size_t)(nb + 8) * sizeof(unsigned long long), kScratchChainBytes, st));
+    if (!g_chain) return (int)cudaErrorMemoryAllocation;
     cudaMemsetAsync(g_chain, 0, (size_t)(nb + 1) * sizeof(unsigned long long), st);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(g_chain + nb);
     int* box = reinterpret_cast<int*>(g_chain + nb + 1);

@@ -55,7 +55,8 @@ class FieldParams:
     indir_roughness_thresh: float = 0.1
     learn_indir_blend: bool = True
     enabled_levels: int = -1
-    precision: str = "fp32"             # "fp32": exact FFMA path; "tc": tcgen05 tensor cores, fp16 hi/lo split operands (3 MMAs)
+    precision: str = "tc"               # "tc": tcgen05 tensor cores, fp16 hi/lo split operands (3 MMAs), the default of every drop-in
+                                        # entry (from_reference_model, checkpoint loader); "fp32": the exact FFMA path (13x slower)
     _packed: Optional[torch.Tensor] = None
     _scratch: Optional[torch.Tensor] = None
 
@@ -185,7 +186,7 @@ class FieldParams:
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def from_reference_model(model) -> "FieldParams":
+    def from_reference_model(model, precision: str = "tc") -> "FieldParams":
         """Read the state of a reference NeRFNetwork (nerf/network.py) built for the shipped scene configs
         (encoding_pos=hashgrid_diff, ensemble_mlp, use_env_net, diffuse_with_env, wo_viewdir, ...)."""
         opt = model.opt
@@ -211,4 +212,4 @@ class FieldParams:
             roughness_act_scale=float(opt.roughness_act_scale), roughness_scale=float(opt.roughness_scale),
             diffuse_kappa_inv=float(opt.diffuse_kappa_inv), light_intensity_scale=float(opt.light_intensity_scale),
             intensity_scale=float(opt.intensity_scale), indir_roughness_thresh=float(opt.indir_roughness_thresh),
-            learn_indir_blend=bool(opt.learn_indir_blend), enabled_levels=int(opt.enabled_levels))
+            learn_indir_blend=bool(opt.learn_indir_blend), enabled_levels=int(opt.enabled_levels), precision=precision)

@@ -455,6 +455,21 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
 # ---------------------------------------------------------------------------------------------
 
 _reference_run_cuda = None
+_dropin_precision = "tc"          # install(precision=...): "tc" (tcgen05, the measured path) or "fp32" (exact FFMA path, 13x slower)
+
+
+def _model_field(model) -> FieldParams:
+    """FieldParams of a reference model, re-read and re-packed on EVERY call: the reference Trainer changes the weights between
+    evaluations without telling anybody (optimizer steps, ema.store / copy_to through `.data`, load_state_dict, env swaps), tensor
+    version counters do not see `.data` writes, and a stale image would silently render old MLPs with the current hash grid.
+    Re-packing costs one `beta.item()` and one launch over < 1 MB of weights; only the device buffers are kept between calls."""
+    field = FieldParams.from_reference_model(model, precision=_dropin_precision)
+    prev = getattr(model, "_envidr_field", None)
+    if prev is not None and prev.device == field.device:
+        field._packed, field._scratch = prev._packed, prev._scratch          # buffers only; pack() rewrites the image
+    field.pack()
+    model._envidr_field = field
+    return field
 
 
 def run_cuda(model, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4,
@@ -475,10 +490,7 @@ def run_cuda(model, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, fo
                                    geometry_only=geometry_only, grad_ray=grad_ray, bg_sphere=bg_sphere, env_rot_radian=env_rot_radian,
                                    **kwargs)
     prefix = rays_o.shape[:-1]
-    field = getattr(model, "_envidr_field", None)
-    if field is None or getattr(model, "_envidr_field_dirty", True):
-        field = FieldParams.from_reference_model(model).pack()
-        model._envidr_field, model._envidr_field_dirty = field, False
+    field = _model_field(model)
     cfg = RenderConfig(bound=float(model.bound), cascade=int(model.cascade), grid_size=int(model.grid_size), min_near=float(model.min_near),
                        dt_gamma=float(dt_gamma), max_steps=int(max_steps), T_thresh=float(T_thresh),
                        aabb=[float(v) for v in model.aabb_infer.tolist()])
@@ -517,12 +529,7 @@ def render_model(model, rays_o, rays_d, staged=False, max_ray_batch=4096, get_no
         return _reference_render(model, rays_o, rays_d, staged=staged, max_ray_batch=max_ray_batch, get_normal_image=get_normal_image,
                                  use_specular_color=use_specular_color, env_net_index=env_net_index, material=material, r_images=r_images,
                                  env_rot_radian=env_rot_radian, **kwargs)
-    field = getattr(model, "_envidr_field", None)
-    if field is None or getattr(model, "_envidr_field_dirty", True):
-        field = FieldParams.from_reference_model(model)
-        field.precision = "tc"
-        field = field.pack()
-        model._envidr_field, model._envidr_field_dirty = field, False
+    field = _model_field(model)
     ob = getattr(model, "obj_aabb", None)
     cfg = RenderConfig(bound=float(model.bound), cascade=int(model.cascade), grid_size=int(model.grid_size), min_near=float(model.min_near),
                        dt_gamma=float(kwargs.get("dt_gamma", 0)), max_steps=int(kwargs.get("max_steps", 1024)),
@@ -541,11 +548,14 @@ def render_model(model, rays_o, rays_d, staged=False, max_ray_batch=4096, get_no
     return out
 
 
-def install(render_func_module=None, patch_render: bool = False, renderer_class=None):
+def install(render_func_module=None, patch_render: bool = False, renderer_class=None, precision: str = "tc"):
     """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop.
     patch_render: also replace NeRFRenderer.render by `render_model` (the batched three-pass frame); renderer_class defaults to
-    nerf.renderer.NeRFRenderer."""
-    global _reference_run_cuda, _reference_render
+    nerf.renderer.NeRFRenderer.  precision: arithmetic of the fused field, "tc" (tensor cores, default) or "fp32"."""
+    global _reference_run_cuda, _reference_render, _dropin_precision
+    if precision not in ("tc", "fp32"):
+        raise _lib.EnvidrError(f"unknown precision {precision!r} (tc | fp32)")
+    _dropin_precision = precision
     from .backend import install_into_sys_modules
     install_into_sys_modules()
     if render_func_module is None:
@@ -562,3 +572,15 @@ def install(render_func_module=None, patch_render: bool = False, renderer_class=
             _reference_render = renderer_class.render
         renderer_class.render = render_model
     return render_func_module
+
+
+def uninstall(render_func_module=None, renderer_class=None):
+    """Undo install(): the reference's own run_cuda / NeRFRenderer.render again (the operator-level backends stay ours)."""
+    global _reference_run_cuda, _reference_render
+    import importlib
+    if _reference_run_cuda is not None:
+        (render_func_module or importlib.import_module("nerf.render_func")).run_cuda = _reference_run_cuda
+        _reference_run_cuda = None
+    if _reference_render is not None:
+        (renderer_class or importlib.import_module("nerf.renderer").NeRFRenderer).render = _reference_render
+        _reference_render = None

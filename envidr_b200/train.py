@@ -81,7 +81,9 @@ class TrainableField(nn.Module):
             self.n_layers[name] = 0 if st is None else len(st)
             for i, (W, b) in enumerate(st or []):
                 self.register_parameter(f"{name}_w{i}", nn.Parameter(W.detach().clone().float(), requires_grad=name not in frozen))
-                self.register_parameter(f"{name}_b{i}", nn.Parameter(b.detach().clone().float(), requires_grad=name not in frozen))
+                # mlp_bias=False stacks carry no bias (FieldParams / the checkpoint loader allow None)
+                self.register_parameter(f"{name}_b{i}", None if b is None else
+                                        nn.Parameter(b.detach().clone().float(), requires_grad=name not in frozen))
 
     # ------------------------------------------------------------------------------------------------
     def stack(self, name: str) -> List:
@@ -125,7 +127,8 @@ class TrainableField(nn.Module):
         kw = dict(self.cfg)
         kw["beta"] = float(self.beta.detach())
         for name in STACKS:
-            kw[name] = [(W.detach().clone(), b.detach().clone()) for W, b in self.stack(name)] if self.n_layers[name] else None
+            kw[name] = [(W.detach().clone(), None if b is None else b.detach().clone()) for W, b in self.stack(name)] \
+                if self.n_layers[name] else None
         return FieldParams(embeddings=self.embeddings.detach().clone(), offsets=self.offsets.clone(), **kw)
 
     # ------------------------------------------------------------------------------------------------

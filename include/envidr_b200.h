@@ -57,8 +57,9 @@ int envidr_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, envidr_
 int envidr_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, envidr_stream_t stream);
 /* raymarching.h:11  packbits(grid f32[8N], N, density_thresh, bitfield u8[N]) */
 int envidr_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, envidr_stream_t stream);
-/* raymarching.h:12  get_scatter_idx(rays i32[N,3], N, idx_map i32[M]) */
-int envidr_get_scatter_idx(const int32_t* rays, uint32_t N, int32_t* idx_map, envidr_stream_t stream);
+/* raymarching.h:12  get_scatter_idx(rays i32[N,3], N, idx_map i32[M]).  M = idx_map's length (the pybind signature reads it off
+ * the tensor): rays that march_rays_train dropped (offset + count > M) are skipped -- the reference kernel writes out of bounds there. */
+int envidr_get_scatter_idx(const int32_t* rays, uint32_t N, uint32_t M, int32_t* idx_map, envidr_stream_t stream);
 
 /* raymarching.h:14  march_rays_train(...).  rays[N,3] = (ray id, offset, count); counter[2] is
  * advanced by (total samples, N).  Unlike the reference (two atomicAdds, scheduling-dependent

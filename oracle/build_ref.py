@@ -4,7 +4,9 @@
 TEST INFRASTRUCTURE ONLY.  The reference's five pybind11 extension modules
 (raymarching, hashencoder, gridencoder, freqencoder, shencoder) are compiled from
 the sources *where they lie* under /root/reference (never copied into this repo)
-and linked into oracle/_ref/_<name>.so (git-ignored, but shipped to the GPU box).
+and linked into oracle/_ref/_<name>.so (git-ignored, but shipped to the GPU box).  The reference's Python files
+(model, renderer, wrappers, configs) are mirrored next to them into oracle/_ref/py/ (git-ignored as well) so
+that the reference's own NeRFNetwork / NeRFRenderer can run on the GPU box (oracle/ref_model.py).
 `tests/` (-m gpu) import these modules as the ground-truth checker for our own
 kernels; nothing in the product path (envidr_b200/) may import them.
 
@@ -67,11 +69,40 @@ def build_one(pkg, inc, libdir, force=False):
     return pkg, "built"
 
 
+def copy_py_tree():
+    """The reference's Python files (its model / renderer / wrappers / configs) -> oracle/_ref/py/ (git-ignored, shipped to the
+    GPU box): /root/reference does not exist there, and tests/test_gpu_refmodel.py + bench.py's gpu_reference run the reference's
+    OWN NeRFNetwork / NeRFRenderer.render / run_cuda on the B200 (oracle/ref_model.py).  Nothing is edited; data, figures,
+    notebooks and checkpoints are not copied."""
+    import shutil
+    dst_root = os.path.join(OUT, "py")
+    n = 0
+    for sub in ("nerf", "raymarching", "hashencoder", "gridencoder", "freqencoder", "shencoder", "ide_encoder", "configs"):
+        for dirpath, dirnames, filenames in os.walk(os.path.join(REF, sub)):
+            dirnames[:] = [d for d in dirnames if d not in ("src", "__pycache__", "build")]
+            for fn in filenames:
+                if not fn.endswith((".py", ".ini", ".txt")):
+                    continue
+                src = os.path.join(dirpath, fn)
+                dst = os.path.join(dst_root, os.path.relpath(src, REF))
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                    shutil.copy2(src, dst)
+                    n += 1
+    for fn in ("encoding.py", "activation.py", "loss.py"):
+        src, dst = os.path.join(REF, fn), os.path.join(dst_root, fn)
+        if os.path.exists(src) and (not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src)):
+            shutil.copy2(src, dst)
+            n += 1
+    print(f"[oracle/_ref] py/: {n} file(s) refreshed")
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
     if not os.path.isdir(REF):
         print(f"[oracle/_ref] {REF} not present; using prebuilt files in {OUT} if any")
         return 0
+    copy_py_tree()
     inc, libdir = _flags()
     pkgs = [p for p in argv if p in PKGS] or PKGS
     with ThreadPoolExecutor(max_workers=5) as ex:

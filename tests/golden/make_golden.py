@@ -31,71 +31,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 
 
-class _Stub(types.ModuleType):
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        sub = _Stub(self.__name__ + "." + name)
-        setattr(self, name, sub)
-        return sub
-
-    def __call__(self, *a, **k):
-        return _Stub("call")
-
-
 def install_shims():
-    np.math = math
-    for name in ["trimesh", "imageio", "tensorboardX", "mcubes", "lpips", "open3d", "open3d.visualization",
-                 "open3d.visualization.rendering", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "dearpygui",
-                 "dearpygui.dearpygui", "torch_ema"]:
-        sys.modules.setdefault(name, _Stub(name))
-    sys.modules["torch_ema"].ExponentialMovingAverage = object
-
-    # configargparse: argparse + "--config file.ini" (key = value lines; [a, b] lists)
-    cap = types.ModuleType("configargparse")
-
-    class ArgumentParser(argparse.ArgumentParser):
-        def add_argument(self, *a, **k):
-            self._cfg = getattr(self, "_cfg", None)
-            if k.pop("is_config_file", False):
-                self._cfg_dest = a[0].lstrip("-")
-            return super().add_argument(*a, **k)
-
-        def parse_args(self, args=None, namespace=None):
-            args = list(sys.argv[1:] if args is None else args)
-            extra = []
-            if "--config" in args:
-                path = args[args.index("--config") + 1]
-                for line in open(path):
-                    line = line.split("#")[0].split(";")[0].strip()
-                    if not line or "=" not in line:
-                        continue
-                    key, val = [s.strip() for s in line.split("=", 1)]
-                    if val in ("True", "true"):
-                        extra.append("--" + key)
-                    elif val in ("False", "false"):
-                        continue
-                    elif val.startswith("["):
-                        extra += ["--" + key] + [v.strip() for v in val.strip("[]").split(",") if v.strip()]
-                    else:
-                        extra += ["--" + key, val]
-            return super().parse_args(extra + args, namespace)
-
-    cap.ArgumentParser = ArgumentParser
-    sys.modules["configargparse"] = cap
-
-    # the reference's CUDA extension modules -> prebuilt oracle/_ref/*.so (import only)
-    sys.path.insert(0, os.path.join(REPO, "oracle", "_ref"))
-    sys.path.insert(0, REF)
-    for pkg in ["raymarching", "hashencoder", "gridencoder", "freqencoder", "shencoder"]:
-        ext = types.ModuleType(f"{pkg}._ext")
-        try:
-            mod = __import__(f"_{pkg}")
-        except Exception:
-            mod = _Stub(f"_{pkg}")
-        setattr(ext, f"_{pkg}", mod)
-        sys.modules[f"{pkg}._ext"] = ext
-        sys.modules[f"{pkg}._ext._{pkg}"] = mod
+    """Third-party stubs, numpy.math, configargparse and the <pkg>._ext modules: shared with the GPU-side checker (oracle/ref_model.py)."""
+    if REPO not in sys.path:
+        sys.path.insert(0, REPO)
+    from oracle import ref_model
+    ref_model.install_shims()
 
 
 def sd_to_np(sd, prefix=""):

@@ -136,7 +136,7 @@ def test_field_matches_reference_glue_golden(dev, golden_dir):
     base = scene.make_synthetic_field(3, hidden_dim_env=160, ide_degree=4)
     fp_cpu = FieldParams(embeddings=base.embeddings, offsets=base.offsets, per_level_scale=base.per_level_scale, base_resolution=16, bound=1.0,
                          sdf=base.sdf, env=L("env_net"), diffuse=L("diffuse_net"), color=L("color_net"), renv=L("renv_net"),
-                         geo_feat_dim=12, ide_degree=4, beta=0.01)
+                         geo_feat_dim=12, ide_degree=4, beta=0.01, precision="fp32")
     x, d = _samples(900, 9)
     _pin_scales(fp_cpu, dev)
     out = fp_cpu.to(dev).pack().forward(torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev), want=("rgb", "c_diffuse", "c_specular"))
@@ -158,7 +158,8 @@ def test_field_from_checkpoint_round_trip_renders_identically(dev, tmp_path):
     path = str(tmp_path / "ngp.pth")
     C.save_checkpoint(path, fp, epoch=3, global_step=48)
     back, meta = C.load_checkpoint(path, device=dev)
-    assert meta["epoch"] == 3 and back.embeddings.is_cuda
+    assert meta["epoch"] == 3 and back.embeddings.is_cuda and back.precision == "tc"      # the loader's default
+    back.precision = fp.precision
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(5000, 3, generator=g) * 1.2 - 0.6).to(dev)
     d = torch.nn.functional.normalize(torch.randn(5000, 3, generator=g), dim=-1).to(dev)

@@ -1,0 +1,177 @@
+"""The REAL reference on the B200, on top of this library.
+
+The reference's own NeRFNetwork (nerf/network.py) under configs/scenes/toaster.ini is built on the GPU box from the shipped copy
+of the reference Python tree (oracle/_ref/py, see oracle/build_ref.py / oracle/ref_model.py), the synthetic toaster field is
+loaded into its parameters, and `model.render(...)` is called with the exact arguments of Trainer.eval_step (utils.py:857-859):
+
+  (a) reference kernels (oracle/_ref/_*.so) + the reference's run_cuda            -> ground truth
+  (b) the SAME model / code with the wrappers' `_backend` bound to libenvidr_b200   (operator-level drop-in)
+  (c) after envidr_b200.render.install()                                           (fused inference loop behind run_cuda)
+  (d) after envidr_b200.render.install(patch_render=True)                          (batched three-pass frame behind render)
+
+for the single pass, the three-pass indirect-reflection frame and an environment rotation, plus one Trainer.train_step
+(utils.py:560-808: colour L1 + mask BCE + back-sdf + Cauchy + eikonal) with loss and parameter gradients compared.
+Bounds: RGB L-inf <= 1e-4 (north star) except pixels proved to be ReLU-kink flips of the analytic normal (see
+tests/test_gpu_outliers.py; the count is bounded here), weights_sum / depth 2e-5, normals 2e-3.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+W = 160
+
+
+@pytest.fixture(scope="module")
+def ref(dev):
+    from oracle import ref_model as RM
+    if not RM.available():
+        pytest.skip("reference tree / rebuilt extensions not shipped (oracle/build_ref.py)")
+    from envidr_b200 import scene
+    RM.install_shims()
+    model, opt = RM.build_model([], cuda_ray=True)                      # toaster.ini: env 256 / IDE degree 5, hash L16 T19
+    fp = scene.make_synthetic_field(0)
+    RM.load_field(model, fp, scene.make_bitfield())
+    model.to(dev).eval()
+    ro, rd = scene.camera_rays(W, W)
+    yield RM, model, opt, fp, ro.to(dev), rd.to(dev)
+    from envidr_b200 import render
+    render.uninstall()
+    RM.use_backends("reference")
+
+
+def _frame(RM, model, opt, ro, rd, indir, rot):
+    opt.indir_ref = indir
+    kw = RM.eval_kwargs(opt)
+    res = model.render(ro[None], rd[None], env_rot_radian=rot, **kw)
+    return {k: v.detach().float().reshape(ro.shape[0], -1).clone() for k, v in res.items() if torch.is_tensor(v)}
+
+
+def _check(a, b, tag, max_bad=2):
+    for k in ("image", "diffuse_image", "specular_image"):
+        if k in a and k in b:
+            e = (a[k] - b[k]).abs().max(-1).values
+            assert int((e > 1e-4).sum()) <= max_bad, (tag, k, int((e > 1e-4).sum()), float(e.max()))
+            assert float(e.median()) <= 2e-5, (tag, k, float(e.median()))
+    assert float((a["weights_sum"] - b["weights_sum"]).abs().max()) <= 2e-5, tag
+    assert float((a["depth"] - b["depth"]).abs().max()) <= 2e-5, tag
+    e = (a["normal_image"] - b["normal_image"]).abs().max(-1).values
+    assert int((e > 2e-3).sum()) <= max_bad, (tag, "normal", int((e > 2e-3).sum()), float(e.max()))
+    if "roughness_image" in a and "roughness_image" in b:
+        assert float((a["roughness_image"] - b["roughness_image"]).abs().max()) <= 1e-4, tag
+
+
+@pytest.mark.parametrize("indir,rot", [(False, None), (True, None), (True, 0.7)])
+def test_real_reference_model_renders_the_same_frame_on_this_library(ref, indir, rot):
+    from envidr_b200 import render
+    RM, model, opt, fp, ro, rd = ref
+    render.uninstall()
+    RM.use_backends("reference")
+    truth = _frame(RM, model, opt, ro, rd, indir, rot)
+    assert float(truth["weights_sum"].max()) > 0.99 and 0.05 < float((truth["weights_sum"] > 0.5).float().mean()) < 0.9
+    # (b) operator-level drop-in: the reference's wrappers, host loop and torch MLPs on our kernels
+    RM.use_backends("envidr")
+    ops = _frame(RM, model, opt, ro, rd, indir, rot)
+    _check(ops, truth, "operators")
+    # (c) fused loop behind run_cuda; the default precision of the drop-in is the tensor-core field
+    import nerf.render_func as RF
+    render.install(RF)
+    assert RF.run_cuda is render.run_cuda
+    fused = _frame(RM, model, opt, ro, rd, indir, rot)
+    assert model._envidr_field.precision == "tc"
+    _check(fused, truth, "install()")
+    # (d) batched three-pass frame behind NeRFRenderer.render
+    import nerf.renderer as R
+    render.install(RF, patch_render=True, renderer_class=R.NeRFRenderer)
+    batched = _frame(RM, model, opt, ro, rd, indir, rot)
+    _check(batched, truth, "install(patch_render=True)")
+    # exact arithmetic on request
+    render.install(RF, precision="fp32")
+    exact = _frame(RM, model, opt, ro, rd, indir, rot)
+    assert model._envidr_field.precision == "fp32"
+    _check(exact, truth, "install(precision='fp32')")
+    render.uninstall(RF, R.NeRFRenderer)
+    RM.use_backends("reference")
+
+
+def test_weight_updates_between_evaluations_are_seen(ref):
+    """the packed field must never go stale -- the Trainer updates weights / swaps EMA through `.data`."""
+    from envidr_b200 import render
+    import nerf.render_func as RF
+    RM, model, opt, fp, ro, rd = ref
+    RM.use_backends("envidr")
+    render.install(RF)
+    try:
+        a = _frame(RM, model, opt, ro, rd, False, None)
+        lin = model.color_net[-1]
+        keep = lin.bias.data.clone()
+        lin.bias.data.copy_(keep + 0.5)                                 # what ema.copy_to does: no version bump on the Parameter
+        b = _frame(RM, model, opt, ro, rd, False, None)
+        lin.bias.data.copy_(keep)
+        c = _frame(RM, model, opt, ro, rd, False, None)
+        hit = a["weights_sum"][:, 0] > 0.9
+        assert float((b["image"][hit] - a["image"][hit]).abs().mean()) > 1e-2
+        assert torch.equal(a["image"], c["image"])
+    finally:
+        render.uninstall(RF)
+        RM.use_backends("reference")
+
+
+def test_trainer_train_step_on_this_library_matches_the_reference_kernels(ref):
+    """Trainer.train_step (utils.py:560-808) -> NeRFRenderer.render -> run_cuda training branch (cuda_ray.py:64-237) of the real model:
+    reference kernels vs libenvidr_b200 behind the same wrappers; loss terms and parameter gradients."""
+    from envidr_b200 import render, scene
+    import nerf.render_func as RF
+    RM, model, opt, fp, _, _ = ref
+    dev = next(model.parameters()).device
+    ro, rd = scene.camera_rays(800, 800)
+    g = torch.Generator().manual_seed(0)
+    sel = torch.randperm(ro.shape[0], generator=g)[:4096]
+    ro, rd = ro[sel].to(dev)[None], rd[sel].to(dev)[None]
+    images = torch.rand(1, 4096, 4, generator=g).to(dev)
+    images[..., 3] = (images[..., 3] > 0.4).float()
+    opt.indir_ref = False
+    opt.color_space, opt.alpha_bg_mode = "srgb", "white"
+    opt.eikonal_loss = opt.cauchy_loss = opt.backsdf_loss = opt.mask_loss = True
+    opt.relsdf_loss = opt.orientation_loss = opt.dist_bound = opt.diffuse_loss = False
+    opt.eikonal_loss_weight, opt.cauchy_loss_weight, opt.backsdf_loss_weight = 0.01, 0.001, 1e-5
+    opt.entropy_loss_weight = 0
+    params = dict(model.named_parameters())
+    names = list(params)
+    model.train()
+    out = {}
+    try:
+        for mode in ("reference", "envidr", "installed"):
+            RM.use_backends("reference" if mode == "reference" else "envidr")
+            if mode == "installed":
+                render.install(RF)
+            model.zero_grad(set_to_none=True)
+            model.mean_count, model.local_step = 0, 0                    # renderer.py:118-119: first step marches N * max_steps slots
+            model.step_counter.zero_()
+            torch.manual_seed(3)
+            pred, gt, loss, ld = RM.train_step(model, opt, ro, rd, images)
+            loss.backward()
+            out[mode] = dict(loss=float(loss), terms={k: float(v) for k, v in ld.items()}, pred=pred.detach().clone(),
+                             grads={n: params[n].grad.detach().clone() for n in names if params[n].grad is not None})
+    finally:
+        render.uninstall(RF)
+        RM.use_backends("reference")
+        model.eval()
+        model.zero_grad(set_to_none=True)
+    r = out["reference"]
+    assert {"color", "mask", "cauchy", "eikonal"} <= set(r["terms"]), r["terms"]
+    assert "encoder.embeddings" in r["grads"] and "env_net.0.weight" in r["grads"]
+    for mode in ("envidr", "installed"):
+        o = out[mode]
+        assert abs(o["loss"] - r["loss"]) <= 2e-5 * max(1.0, abs(r["loss"])), (mode, o["loss"], r["loss"])
+        for k, v in r["terms"].items():
+            assert abs(o["terms"][k] - v) <= 1e-4 * max(abs(v), 1e-2), (mode, k, o["terms"][k], v)
+        assert float((o["pred"] - r["pred"]).abs().max()) <= 1e-4, mode
+        for n, gr in r["grads"].items():
+            scale = float(gr.abs().max())
+            err = float((o["grads"][n] - gr).abs().max())
+            assert err <= 2e-3 * scale + 1e-12, (mode, n, err, scale)

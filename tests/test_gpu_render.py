@@ -241,7 +241,7 @@ def test_single_pass_deferred_shading_equals_loop(dev, W, env_width, deg):
         assert float((a["depth"] - b["depth"]).abs().max()) <= 1e-5
 
 
-def test_render_model_routes_the_three_pass_frame(dev):
+def test_render_model_routes_the_three_pass_frame(dev, monkeypatch):
     """render.render_model (the NeRFRenderer.render replacement) on an object with the reference model's attributes: the evaluation
     three-pass frame equals render.render bit for bit with the reference's output shapes ([1, N, ...]); ineligible calls are forwarded."""
     import types
@@ -258,8 +258,11 @@ def test_render_model_routes_the_three_pass_frame(dev):
                                 use_diffuse=True)
     model = types.SimpleNamespace(opt=opt, cuda_ray=True, training=False, bg_radius=-1, bound=1.0, cascade=1, grid_size=128, min_near=0.2,
                                   aabb_infer=torch.tensor([-1.0, -1, -1, 1, 1, 1]), obj_aabb=None, density_bitfield=bf,
-                                  _envidr_field=fp, _envidr_field_dirty=False)
+                                  )
     kw = dict(bg_color=None, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=1e-4, early_stop_steps=-1)
+    # the stub has no weights to read: hand the packed field over (the real NeRFNetwork goes through render._model_field ->
+    # FieldParams.from_reference_model on every call, tests/test_gpu_refmodel.py)
+    monkeypatch.setattr(render, "_model_field", lambda m: fp)
     out = render.render_model(model, ro[None], rd[None], staged=True, get_normal_image=True, env_rot_radian=0.4, **kw)
     ref = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True), bg_color=0.0, get_normal_image=True, env_rot_radian=0.4,
                         visual_items=("specular", "roughness", "diffuse"))
