@@ -16,11 +16,11 @@ void timing_commit();
 
 
 void set_error(const char* fmt, ...);
-// error.cu: fixed-size scratch per (device, stream, kind), never freed or grown; nullptr (+ last error) when bytes > fixed_bytes or
-// the one-time allocation fails
+// error.cu: fixed-size scratch slot per (device, stream, kind) out of one never-freed allocation per device and kind; nullptr
+// (+ last error) when bytes > fixed_bytes, the one-time allocation fails, or more than 8 streams ask
 void* stream_scratch(int kind, size_t bytes, size_t fixed_bytes, cudaStream_t st);
 constexpr int kScratchScan = 0, kScratchChain = 1;
-constexpr size_t kScratchScanBytes = 1u << 20, kScratchChainBytes = 8u << 20;
+constexpr size_t kScratchScanBytes = 256u << 10, kScratchChainBytes = 2u << 20;   // N <= 64 M / 32 M rays
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

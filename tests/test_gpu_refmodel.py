@@ -27,6 +27,13 @@ W = 160
 
 
 @pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
 def ref(dev):
     from oracle import ref_model as RM
     if not RM.available():
