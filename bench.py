@@ -519,7 +519,9 @@ def main():
         gref = None
         if world == 1 and not args.no_gpu_reference:
             try:
-                gref = gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir)
+                import contextlib
+                with contextlib.redirect_stdout(sys.stderr):          # the reference prints while it parses options / builds the model
+                    gref = gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir)
                 if "image" in gref:
                     gimg = gref.pop("image")
                     e = (gimg - out["image"]).abs().max(-1).values

@@ -4,25 +4,38 @@
 // This is >90 % of the FLOPs of the render path (610,304 of 651,008 FLOP/sample at toaster dims).
 // The reference runs it as 8 cuBLAS fp32 GEMMs + 8 elementwise launches per render iteration (network.py:527-607).
 //
-// Design (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      producer: streams the pre-packed weight images of every layer from L2 into a 3-stage shared-memory
-//               ring with 1-D bulk async copies (TMA engine, cp.async.bulk -> UBLKCP), one 16-wide K step per stage
-//   warp 1      issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128 rows, N = layer width,
-//               K = 16) with the fp32 accumulator tile [128 x N] in tensor memory (TMEM, 256 columns)
+// Design (one persistent CTA per SM, 896 threads, warp-specialised):
+//   warp 0      producer: streams the pre-packed weight images of every layer from L2 into a 3-stage x 16 KB shared-memory
+//               ring with 1-D bulk async copies (TMA engine, cp.async.bulk -> UBLKCP), as many K steps per stage as fit
+//   warp 1      issuer (warp-uniform code, elect.sync inside the asm): tcgen05.mma.cta_group::1 (M = 128 rows, N = layer
+//               width) with two fp32 accumulator tiles [128 x 256] ping-ponging in tensor memory (TMEM, 512 columns)
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue (2 threads per accumulator row): after each layer read their 32-column slices of the
-//               accumulator with tcgen05.ld, apply bias + ReLU, re-split into fp16 hi/lo and write the next layer's
-//               A operand to shared memory (in place); the last layer's epilogue unit-normalises the env feature
-//   warps 12-19 IDE (2 threads per row, even / odd orders m): directional encoding of the NEXT tile straight into a
-//               separate layer-0 A-operand buffer while the current tile occupies the tensor pipe
+//               accumulator with tcgen05.ld, apply bias + ReLU, re-split and write the next layer's A operand to shared
+//               memory, published per 32-column chunk (8 mbarriers) so that the next layer's MMAs start under the epilogue;
+//               the last layer's epilogue unit-normalises the env feature
+//   warps 12-27 IDE (16 warps): directional encoding of the NEXT tile straight into a separate layer-0 A-operand buffer
+//               while the current tile occupies the tensor pipe
 //   Synchronisation is mbarrier-only between roles (full/empty ring, accumulator-ready / IDE-buffer-free via
 //   tcgen05.commit, operand-ready via arrive after fence.proxy.async).
 //
 // Precision: the reference computes these layers in fp32 and the parity bar is 1e-4 on RGB, which a single fp16/bf16/
-// tf32 pass does not meet (measured ~1e-3 on the env feature).  Every operand is therefore split x = hi + lo into two
-// fp16 values (22 significant bits) and each K step issues three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32;
-// the dropped lo*lo term is below 2^-22 relative.  Effective tensor throughput is a third of the fp16 rate.
+// tf32 pass does not meet (measured ~1e-3 on the env feature).  Every operand is split x = hi + lo (hi = fp16(x)).
+//   mode 0 (ENVIDR_ENV_TC_MODE=0): three kind::f16 MMAs per K step, hi*hi + lo*hi + hi*lo, fp32 accumulate; the dropped lo*lo
+//       term is below 2^-22 relative.  Tensor work = 3x the algorithmic FLOPs.
+//   mode 1 (default; hidden layers whose K is a multiple of 32): the two CORRECTION products only need ~4 significant bits
+//       (they are 2^-11 of the main product), so they run as kind::f8f6f4 MMAs on e4m3 operands (K = 32 per instruction, twice
+//       the fp16 rate), and the main product hi*hi stays kind::f16:
+//           phase A  D  = e4m3(lo_a 2^14) * e4m3(w 2^4)^T + e4m3(a 2^3) * e4m3(lo_w 2^15)^T        (corrections x 2^18)
+//           phase B  D  = hi_a * (hi_w 2^3)^T + D * 2^-15     (first main MMA: tcgen05.mma scale-input-d = 15), then accumulate
+//           epilogue v  = D * 2^-3 + bias
+//       Tensor work = 1 + 1/2 + 1/2 = 2x the algorithmic FLOPs instead of 3x, shared-memory operand bytes unchanged (hi16 +
+//       hi8 + lo8 = 4 B per element, as hi16 + lo16).  Error of a correction term: 2^-11 (its size) x 2^-4 (e4m3 rounding of each
+//       factor) = 2^-15 of one product term, summed incoherently over K: measured on CPU with torch.float8_e4m3fn against
+//       float64 (profiles/fp8_correction_sim.py) RGB L-inf 3e-6 (xavier 256-wide) / 1.2e-5 (shipped trained 160-wide env_net)
+//       against 3e-7 for mode 0 and 1e-4 for a single fp16 product.  Layer 0 (K = 72 -> 80, the IDE features) stays mode 0.
 #include <math.h>
+#include <cuda_fp8.h>
 #include "common.cuh"
 #include "ide_tables.cuh"
 #include "tc_common.cuh"
@@ -59,6 +72,25 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// mode-1 scales (powers of two, exact): activations hi8 x 2^3, lo8 x 2^14; weights hi8 x 2^4, lo8 x 2^15, main hi16 x 2^3
+constexpr float kF8ActHi = 8.0f, kF8ActLo = 16384.0f, kF8WHi = 16.0f, kF8WLo = 32768.0f, kF8WMain = 8.0f, kF8DScale = 0.125f;
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+// kind::f8f6f4 (e4m3 x e4m3 -> fp32, K = 32) and the kind::f16 MMA that first scales the accumulator by 2^-15
+__device__ __forceinline__ void mma_f8_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+                 " @e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_scale15_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, 1, 0;\n"
+                 " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+
 // CTAS = 1: one CTA per tile, tcgen05 cta_group::1.
 // CTAS = 2: thread-block cluster of two CTAs (one TPC) working as a CTA pair: every MMA is M = 256 (128 rows = one tile per
 //   CTA), each CTA streams only ITS half of every weight stage (N/2 rows of B) and the tensor cores read the other half from the
@@ -67,13 +99,16 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 //   writes ~ 2.6 MB per tile at 128 B/clk = 20 k cycles vs 14.6 k of tensor-pipe time).  The leader (rank 0) issues; the peer's
 //   operand-ready signals go to the leader's mbarriers through shared::cluster arrives, completions come back by multicast
 //   commit.
-template <int CTAS>
+// F8 = true (CTAS = 1 only): layers with E.L[l].f8 run in mode 1 (see the file header); F8 = false: mode 0 everywhere.
+template <int CTAS, bool F8>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
          unsigned long long* __restrict__ prof, uint32_t prof_cap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA_hi = smem;                                   // hidden-layer A operand (written by the epilogues)
     uint8_t* sA_lo = smem + kTcARegion;
+    uint8_t* sA_h8 = sA_lo;                                  // mode 1: e4m3(a 2^3)    [128 x 256] (16-element K chunks), 32 KB
+    uint8_t* sA_l8 = sA_lo + kTcARegion / 2;                 // mode 1: e4m3(lo_a 2^14), 32 KB
     uint8_t* sI_hi = smem + 2 * kTcARegion;                  // layer-0 A operand (written by the IDE warps)
     uint8_t* sI_lo = sI_hi + kTcIdeRegion;
     uint8_t* ring = sI_lo + kTcIdeRegion;
@@ -143,18 +178,28 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 // a ring stage carries as many K steps as fit in kTcStageBytes (1 for a 256-wide layer, all 16 for the 16-wide
                 // last layer: otherwise that layer is bound by 16 ring round trips of 1 KB each).  CTAS = 2: this CTA's half
                 // of B (rows rank * N/2 ...) is a contiguous image of its own, so a stage holds twice the K steps.
-                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64 / CTAS;
-                const uint32_t kper = max(1u, kTcStageBytes / kbytes);
-                const uint8_t* src = E.blob + (CTAS == 2 ? E.L[l].img2_off + rank * ksteps * kbytes : E.L[l].img_off);
-                for (uint32_t s = 0; s < ksteps; s += kper) {
-                    const uint32_t bytes = min(kper, ksteps - s) * kbytes;
-                    tc::mbar_wait(&empty[stage], phase ^ 1);
-                    if (lane == 0) {
-                        tc::mbar_arrive_expect_tx(&full[stage], bytes);
-                        tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * kbytes, bytes, &full[stage]);
+                auto stream = [&](const uint8_t* src, uint32_t units, uint32_t ubytes) {
+                    const uint32_t uper = max(1u, kTcStageBytes / ubytes);
+                    for (uint32_t s = 0; s < units; s += uper) {
+                        const uint32_t bytes = min(uper, units - s) * ubytes;
+                        tc::mbar_wait(&empty[stage], phase ^ 1);
+                        if (lane == 0) {
+                            tc::mbar_arrive_expect_tx(&full[stage], bytes);
+                            tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * ubytes, bytes, &full[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                };
+                if (F8 && E.L[l].f8) {
+                    // mode 1: phase A = Kp/32 chunks of (hi8 | lo8) x Np x 32 B, then phase B = Kp/16 steps of hi16 x Np x 32 B
+                    const uint32_t chunks = E.L[l].Kp / 32, cbytes = E.L[l].Np * 64;
+                    const uint8_t* src = E.blob + E.L[l].img8_off;
+                    stream(src, chunks, cbytes);
+                    stream(src + (size_t)chunks * cbytes, E.L[l].Kp / 16, E.L[l].Np * 32);
+                } else {
+                    const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64 / CTAS;
+                    stream(E.blob + (CTAS == 2 ? E.L[l].img2_off + rank * ksteps * kbytes : E.L[l].img_off), ksteps, kbytes);
                 }
             }
         }
@@ -191,6 +236,56 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 const uint32_t buf = gl & 1u;
                 const uint32_t d_tmem = tmem + buf * 256u;
                 gl++;
+                if (F8 && E.L[l].f8) {
+                    // ---- mode 1: corrections on e4m3 (phase A, chunk by chunk as the epilogue publishes them), then hi16 * hi16
+                    uint64_t da_h8 = tc::make_smem_desc(tc::smem_u32(sA_h8), 2048, 128);
+                    uint64_t da_l8 = tc::make_smem_desc(tc::smem_u32(sA_l8), 2048, 128);
+                    uint64_t da_m = tc::make_smem_desc(tc::smem_u32(sA_hi), 2048, 128);
+                    const uint64_t db0 = tc::make_smem_desc(ring0, Np * 16, 128);
+                    const uint32_t chunks = ksteps / 2, cbytes = Np * 64, cper = max(1u, kTcStageBytes / cbytes);
+                    for (uint32_t c0 = 0; c0 < chunks; c0 += cper) {
+                        const unsigned long long t1 = prof ? clock64() : 0;
+                        tc::mbar_wait(&full[stage], phase);
+                        if (prof) w_f += clock64() - t1;
+                        const uint32_t cend = min(chunks, c0 + cper);
+                        uint64_t db = tc::desc_advance(db0, stage * kTcStageBytes);
+                        for (uint32_t c = c0; c < cend; c++) {
+                            const unsigned long long t0 = prof ? clock64() : 0;
+                            tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u);
+                            chunk_par ^= 1u << c;
+                            if (prof) w_a += clock64() - t0;
+                            tc::tc_fence_after();
+                            __syncwarp();
+                            mma_f8_ss_w(d_tmem, da_l8, db, idesc, c > 0);                              // lo_a * hi_w
+                            mma_f8_ss_w(d_tmem, da_h8, tc::desc_advance(db, Np * 32), idesc, 1);       // hi_a * lo_w
+                            da_l8 = tc::desc_advance(da_l8, 4096); da_h8 = tc::desc_advance(da_h8, 4096);
+                            db = tc::desc_advance(db, cbytes);
+                        }
+                        tc::mma_commit_w(&empty[stage]);
+                        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    }
+                    const uint32_t sbytes = Np * 32, sper = max(1u, kTcStageBytes / sbytes);
+                    for (uint32_t s0 = 0; s0 < ksteps; s0 += sper) {
+                        const unsigned long long t1 = prof ? clock64() : 0;
+                        tc::mbar_wait(&full[stage], phase);
+                        if (prof) w_f += clock64() - t1;
+                        const uint32_t kend = min(ksteps, s0 + sper);
+                        uint64_t db = tc::desc_advance(db0, stage * kTcStageBytes);
+                        for (uint32_t s = s0; s < kend; s++) {
+                            tc::tc_fence_after();
+                            __syncwarp();
+                            if (s == 0) mma_f16_ss_scale15_w(d_tmem, da_m, db, idesc);                 // D = hi_a * hi_w + D * 2^-15
+                            else tc::mma_f16_ss_w(d_tmem, da_m, db, idesc, 1);
+                            da_m = tc::desc_advance(da_m, 4096);
+                            db = tc::desc_advance(db, sbytes);
+                        }
+                        tc::mma_commit_w(&empty[stage]);
+                        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    }
+                    tc::mma_commit_w(&acc_ready[buf]);
+                    if (prof && lane == 0 && l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; }
+                    continue;
+                }
                 uint64_t da_hi, da_lo;
                 if (l == 0) {
                     if (prof && lane == 0) stamp(ti, 0, clock64());
@@ -275,7 +370,51 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 tc::tc_fence_after();
                 const uint32_t acc = tmem + lane_addr + buf * 256u;
                 const float* bias = s_bias + l * 256;
-                if (l < nl - 1) {
+                const float dsc = E.L[l].dscale;
+                if (l < nl - 1 && F8 && E.L[l + 1].f8) {
+                    // next layer runs in mode 1: its A operand = hi16 (main) + e4m3(a 2^3) + e4m3((a - hi16) 2^14)
+                    const uint32_t nchunks = E.L[l].N / 32;
+                    for (uint32_t cb = g; cb < nchunks; cb += 2) {
+                        uint32_t r[32];
+                        tc::tmem_ld32(acc + cb * 32, r);
+                        tc::tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
+                        #pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {                  // 16 columns = one e4m3 K chunk = two fp16 K chunks
+                            uint32_t h8[4], l8[4];
+                            #pragma unroll
+                            for (int j2 = 0; j2 < 2; j2++) {
+                                const int j = 2 * jj + j2;
+                                const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+                                float v[8];
+                                v[0] = fmaxf(fmaf(__uint_as_float(r[8 * j + 0]), dsc, ba.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[8 * j + 1]), dsc, ba.y), 0.f);
+                                v[2] = fmaxf(fmaf(__uint_as_float(r[8 * j + 2]), dsc, ba.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[8 * j + 3]), dsc, ba.w), 0.f);
+                                v[4] = fmaxf(fmaf(__uint_as_float(r[8 * j + 4]), dsc, bb.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[8 * j + 5]), dsc, bb.y), 0.f);
+                                v[6] = fmaxf(fmaf(__uint_as_float(r[8 * j + 6]), dsc, bb.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[8 * j + 7]), dsc, bb.w), 0.f);
+                                uint32_t ph[4];
+                                float lo[8];
+                                #pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                                    const float2 hf = __half22float2(h);
+                                    ph[e] = *reinterpret_cast<const uint32_t*>(&h);
+                                    lo[2 * e] = (v[2 * e] - hf.x) * kF8ActLo; lo[2 * e + 1] = (v[2 * e + 1] - hf.y) * kF8ActLo;
+                                }
+                                *reinterpret_cast<uint4*>(sA_hi + tc::op_off(128, row, cb * 32 + j * 8)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                h8[2 * j2] = pack_e4m3x4(v[0] * kF8ActHi, v[1] * kF8ActHi, v[2] * kF8ActHi, v[3] * kF8ActHi);
+                                h8[2 * j2 + 1] = pack_e4m3x4(v[4] * kF8ActHi, v[5] * kF8ActHi, v[6] * kF8ActHi, v[7] * kF8ActHi);
+                                l8[2 * j2] = pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
+                                l8[2 * j2 + 1] = pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]);
+                            }
+                            const uint32_t off8 = (cb * 2 + jj) * 2048 + row * 16;      // 16-element K chunk (cb * 32 + jj * 16) / 16
+                            *reinterpret_cast<uint4*>(sA_h8 + off8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                            *reinterpret_cast<uint4*>(sA_l8 + off8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+                        }
+                        tc::tc_fence_before();
+                        tc::fence_proxy_async_smem();
+                        arrive_issuer(a_rdy_addr + cb * 8);
+                    }
+                } else if (l < nl - 1) {
                     const uint32_t nchunks = E.L[l].N / 32;
                     for (uint32_t cb = g; cb < nchunks; cb += 2) {
                         uint32_t r[32];
@@ -306,7 +445,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     float f[16], ss = 0.f;
                     #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        f[i] = (i < Ef) ? __uint_as_float(r[i]) + bias[i] : 0.0f;
+                        f[i] = (i < Ef) ? fmaf(__uint_as_float(r[i]), dsc, bias[i]) : 0.0f;
                         ss += f[i] * f[i];
                     }
                     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(eps = 1e-12)
@@ -443,6 +582,33 @@ __global__ void k_pack_tc2(const float* __restrict__ W, uint8_t* __restrict__ im
     }
 }
 
+// mode-1 image of one layer (see the file header): phase A chunk c (K in [32c, 32c + 32)) = [hi8: 2 K chunks of 16 x Np x 16 B][lo8: same],
+// then phase B step s (K in [16s, 16s + 16)) = [hi16 x 2^3: 2 K chunks of 8 x Np x 16 B]
+__global__ void k_pack_tc8(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K, uint32_t N, uint32_t Kp, uint32_t Np) {
+    const uint32_t total = Kp * Np;
+    const size_t phase_b = (size_t)(Kp / 32) * Np * 64;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t n = i / Kp, k = i - n * Kp;
+        const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+        const __half h = __float2half_rn(v);
+        const float lo = v - __half2float(h);
+        const uint32_t c = k >> 5, kk = k & 31;
+        const size_t a = (size_t)c * Np * 64 + (kk >> 4) * (Np * 16) + n * 16 + (kk & 15);
+        img[a] = (uint8_t)__nv_cvt_float_to_fp8(v * kF8WHi, __NV_SATFINITE, __NV_E4M3);
+        img[a + (size_t)Np * 32] = (uint8_t)__nv_cvt_float_to_fp8(lo * kF8WLo, __NV_SATFINITE, __NV_E4M3);
+        const uint32_t s = k >> 4, k16 = k & 15;
+        const size_t b = phase_b + (size_t)s * Np * 32 + (k16 >> 3) * (Np * 16) + n * 16 + (k16 & 7) * 2;
+        *reinterpret_cast<__half*>(img + b) = __float2half_rn(__half2float(h) * kF8WMain);
+    }
+}
+
+// ENVIDR_ENV_TC_MODE=0 selects three fp16 products per K step everywhere (mode 0); default is mode 1 (e4m3 corrections).
+int env_tc_mode() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ENVIDR_ENV_TC_MODE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
 static uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 // Lays the tensor-core images out after `base_bytes` of the packed blob.  Returns false if the env_net shape is outside
@@ -469,6 +635,11 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
         off += (uint64_t)(L.Kp / 16) * L.Np * 64;
         L.bias_off = boff;
         boff += L.Np;
+        // mode 1 for every layer after the first whose K is a whole number of e4m3 MMAs (K = 32); the image exists either way
+        L.f8 = (i > 0 && L.Kp % 32 == 0) ? 1u : 0u;
+        L.dscale = 1.0f;
+        L.img8_off = (uint32_t)off;
+        if (L.f8) off += (uint64_t)(L.Kp / 16) * L.Np * 64;
     }
     if (f->env[0].in_dim != 2 * P) return false;
     off = rup((uint32_t)off, 256);
@@ -496,6 +667,7 @@ int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st
         const uint32_t il = (i == 0) ? t.P : 0u;
         k_pack_tc<<<128, 256, 0, st>>>(f->env[i].weight, f->env[i].bias, blob + L.img_off, bias + L.bias_off, L.K, L.N, L.Kp, L.Np, il);
         k_pack_tc2<<<128, 256, 0, st>>>(f->env[i].weight, blob + L.img2_off, L.K, L.N, L.Kp, L.Np, il);
+        if (L.f8) k_pack_tc8<<<128, 256, 0, st>>>(f->env[i].weight, blob + L.img8_off, L.K, L.N, L.Kp, L.Np);
     }
     return check_launch("field_pack_tc");
 }
@@ -521,8 +693,9 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
     }
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_env_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_error("env_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
@@ -537,14 +710,20 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
         if (e != cudaSuccess) { set_error("env_tc (CTA pair) launch: %s", cudaGetErrorString(e)); return (int)e; }
         return check_launch("env_tc2");
     }
     uint32_t grid = kSMs;
     if (!M_dev) grid = min((uint32_t)kSMs, n_tiles_host);
     if (grid == 0) return 0;
-    k_env_tc<1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+    if (env_tc_mode() == 1) {
+        TcEnv t8 = t;
+        for (uint32_t i = 0; i < t8.n_layers; i++) if (t8.L[i].f8) t8.L[i].dscale = kF8DScale;
+        k_env_tc<1, true><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+    } else {
+        k_env_tc<1, false><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+    }
     return check_launch("env_tc");
 }
 

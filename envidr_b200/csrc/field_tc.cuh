@@ -12,6 +12,9 @@ struct TcLayer {
     uint32_t img_off;             // byte offset of the layer image in the blob; stage s at img_off + s * Np * 64
     uint32_t img2_off;            // CTA-pair image: rank r at img2_off + r * (Kp/16) * (Np/2) * 64, K step s at + s * (Np/2) * 64
     uint32_t bias_off;            // float offset in the bias region
+    uint32_t img8_off;            // fp8-correction image (f8 != 0): [phase A: Kp/32 chunks x (hi8 | lo8) x Np x 32 B][phase B: Kp/16 steps x hi16 x Np x 32 B]
+    uint32_t f8;                  // this layer runs as hi16*hi16 (kind::f16) + e4m3 corrections (kind::f8f6f4), see field_tc.cu
+    float dscale;                 // accumulator -> value scale of the layer (2^-3 for f8 layers, whose main weights are stored x 2^3)
 };
 struct TcEnv {
     const uint8_t* blob;          // weight images
@@ -62,5 +65,6 @@ int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const
 bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes);
 int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st);
 int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st);
+int env_tc_mode();               // 0: three fp16 products per K step; 1 (default): fp16 main product + two e4m3 correction products
 
 }  // namespace envidr
