@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--no-extra-warmup", action="store_true", help="profiling runs (ncu --launch-skip counts on exactly W warm-up frames)")
     ap.add_argument("--no-density", action="store_true", help="skip the auxiliary occupancy-grid update measurement (SURVEY 8 f-1)")
     ap.add_argument("--train-rays", type=int, default=4096)
+    ap.add_argument("--sweep-width", type=int, default=1600, help="frame width of the relight sweep (BASELINE config 5)")
+    ap.add_argument("--sweep-rotations", type=int, default=4, help="light rotations per timed sweep (5-degree steps of the 72-step sweep)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 measurements at N = 1")
+    ap.add_argument("--config", default="toaster", choices=["toaster", "neus"], help="neus: BASELINE config 4 (NeuS geometry, no hash grid)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="env_net arithmetic: tc = tcgen05 tensor cores with fp16 hi/lo split operands (default), fp32 = FFMA path")
     return ap.parse_args()
@@ -308,6 +312,201 @@ def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2, train_rays
                     "(oracle/ref_cuda.py; the reference Python tree was not shipped), same frame"}
 
 
+def _timed_region(fn, steps, world, dev, flush=None):
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events per step, MAX over ranks of the summed time (ms)."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for i, (a, b) in enumerate(ev):
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        fn(i)
+        b.record()
+    barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def config5(args, fp, bft, dev, world, rank, steps, flush, e2e=True):
+    """BASELINE config 5: toaster 1600x1600 relight sweep (env_rot 0..360 in 72 steps, utils.py:1297-1303), rays sharded over the ranks
+    in interleaved 8x8-pixel tiles, one all-gather of the packed outputs per frame (envidr_b200.dist.render_sharded).
+      frame : every rotation renders the FULL three-pass frame (what the reference does per rotation): the strong-scaling workload
+      sweep : the rotation-independent passes (geometry, reflected-ray geometry) are computed once per camera and each rotation only
+              shades (render.prepare_sweep / render_sweep_frame); timed over prepare + R rotations"""
+    import numpy as np
+    import torch
+    from envidr_b200 import render, scene
+    from envidr_b200 import dist as edist
+    Wd = args.sweep_width
+    ro, rd = scene.camera_rays(Wd, Wd)
+    idx = edist.tile_shard_indices(Wd, Wd, rank, world)
+    o_h, d_h = ro[idx].contiguous().pin_memory(), rd[idx].contiguous().pin_memory()
+    o_s, d_s = o_h.to(dev), d_h.to(dev)
+    N5 = Wd * Wd
+    cfg = render.RenderConfig(indir_ref=True)
+    rots = [2 * np.pi * k / 72 for k in range(72)]
+    img_h = torch.empty(N5, 3).pin_memory()
+
+    def frame(i, o=o_s, d=d_s):
+        return edist.render_sharded(lambda a, b: render.render(fp, bft, a, b, cfg, bg_color=1.0, env_rot_radian=rots[i % 72], get_normal_image=True),
+                                    o, d, Wd, Wd, presharded=True)
+
+    def frame_e2e(i):
+        out = frame(i, o_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True))
+        img_h.copy_(out["image"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    R = args.sweep_rotations
+
+    def sweep(i):
+        geom = render.prepare_sweep(fp, bft, o_s, d_s, cfg)
+        for k in range(R):
+            edist.render_sharded(lambda a, b: render.render_sweep_frame(fp, geom, cfg, rots[(i * R + k) % 72], bg_color=1.0), o_s, d_s, Wd, Wd,
+                                 presharded=True)
+    for i in range(3):
+        frame(i)
+    st = []
+    render.render(fp, bft, o_s, d_s, cfg, bg_color=1.0, env_rot_radian=rots[0], stats=st)
+    torch.cuda.synchronize()
+    res = {"width": Wd, "rays_per_frame": N5, "rays_per_frame_per_rank": int(idx.numel()), "stats": st}
+    res["frame_ms_total"] = _timed_region(frame, steps, world, dev, flush)
+    if e2e:
+        frame_e2e(0)
+        res["frame_e2e_ms_total"] = _timed_region(frame_e2e, steps, world, dev, flush)
+    sweep(0)
+    n_sw = max(1, steps // 4)
+    res["sweep_ms_total"] = _timed_region(sweep, n_sw, world, dev, flush)
+    res["sweep_steps"], res["sweep_rotations"] = n_sw, R
+    return res
+
+
+def run_multi(args, fp_cpu, bf, dev, world, rank, local):
+    """N > 1: the timed step is one full 1600x1600 three-pass frame of the relight sweep (BASELINE config 5), its rays sharded over the N
+    ranks; `value` = rays of the frame / time (max over ranks) -- strong scaling: the frame is the same whatever N is.  Extra keys:
+    `config5_sweep` (the sweep with the rotation-independent passes shared between rotations) and `replica_frames` (round 1's weak
+    form: one 800x800 frame per rank + all-gather of the N frames)."""
+    import ctypes
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from envidr_b200 import _lib, render
+    from envidr_b200 import dist as edist
+    fp_cpu.precision = args.precision
+    fp = fp_cpu.to(dev).pack()
+    bft = torch.from_numpy(bf).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.lib()
+    steps = args.steps
+    # warm-up (>= 3 frames inside config5) + steady state, then the instrumented measurement
+    warm = config5(args, fp, bft, dev, world, rank, max(3, args.warmup), flush, e2e=False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
+    lib.envidr_render_timing(1)
+    l0 = lib.envidr_launch_count()
+    t0 = time.time()
+    c5 = config5(args, fp, bft, dev, world, rank, steps, flush)
+    t1 = time.time()
+    launches_all = int(lib.envidr_launch_count() - l0)
+    lib.envidr_render_timing(0)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    # dominant kernel on this rank, timed alone over `steps` frames with the event hook on
+    lib.envidr_render_timing(1)
+    from envidr_b200 import scene
+    Wd = args.sweep_width
+    ro, rd = scene.camera_rays(Wd, Wd)
+    idx = edist.tile_shard_indices(Wd, Wd, rank, world)
+    o_s, d_s = ro[idx].to(dev), rd[idx].to(dev)
+    cfg = render.RenderConfig(indir_ref=True)
+    l1 = lib.envidr_launch_count()
+    for i in range(steps):
+        render.render(fp, bft, o_s, d_s, cfg, bg_color=1.0, env_rot_radian=0.1 * i)
+    torch.cuda.synchronize()
+    launches = int(lib.envidr_launch_count() - l1)
+    fms, fl = ctypes.c_float(), ctypes.c_uint32()
+    lib.envidr_render_field_time(ctypes.byref(fms), ctypes.byref(fl))
+    lib.envidr_render_timing(0)
+    # weak form of round 1 (one 800x800 frame of the sweep per rank)
+    W8 = args.width
+    ro8, rd8 = scene.camera_rays(W8, W8)
+    ro8, rd8 = ro8.to(dev), rd8.to(dev)
+    rot = 2 * np.pi * rank / world
+
+    def replica(i):
+        out = render.render(fp, bft, ro8, rd8, cfg, bg_color=1.0, env_rot_radian=rot, get_normal_image=True)
+        edist.gather_frames(out["image"])
+    for i in range(3):
+        replica(i)
+    rep_ms = _timed_region(replica, steps, world, dev, flush) / steps
+    if rank == 0:
+        N5 = c5["rays_per_frame"]
+        ms = c5["frame_ms_total"] / steps
+        value = N5 / (ms * 1e-3)
+        e2e_ms = c5["frame_e2e_ms_total"] / steps
+        st = c5["stats"]
+        shaded = st[1].get("shaded", st[1]["samples"]) + st[2]["samples"]
+        flop_step = shaded * FLOP_ENV
+        kernel_ms = fms.value / steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = flop_step / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+        sw_ms = c5["sweep_ms_total"] / c5["sweep_steps"]
+        R = c5["sweep_rotations"]
+        c5 = None
+        if not args.no_sweep and indir and tcp:
+            try:
+                n5 = max(2, args.steps // 2)
+                r5 = config5(args, fp, bft, dev, 1, 0, n5, flush, e2e=False)
+                N5 = r5["rays_per_frame"]
+                c5 = {"frame": {"rays_per_sec": N5 / (r5["frame_ms_total"] / n5 * 1e-3), "ms_per_frame": r5["frame_ms_total"] / n5},
+                      "sweep": {"rays_per_sec": r5["sweep_rotations"] * N5 / (r5["sweep_ms_total"] / r5["sweep_steps"] * 1e-3),
+                                "ms_per_rotation": r5["sweep_ms_total"] / r5["sweep_steps"] / r5["sweep_rotations"], "rotations": r5["sweep_rotations"]},
+                      "width": r5["width"], "samples": [s["samples"] for s in r5["stats"]],
+                      "what": "BASELINE config 5 on ONE GPU (the workload bench.py --gpus N > 1 shards): frame = full three-pass 1600x1600 frame per "
+                              "light rotation; sweep = rotation-independent passes shared between the rotations (render.prepare_sweep)"}
+            except Exception as e:
+                c5 = {"error": repr(e)[:300]}
+        line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (env_net: fp16 hi+lo split operands on tensor cores, fp32 accumulate)", "data": "synthetic",
+                "config": dict(config_dict(args, Wd, Wd, True),
+                               workload=f"BASELINE config 5: synthetic toaster-dims scene {Wd}x{Wd} relight sweep (env_rot 5-degree steps), use_renv + indir_ref (3 passes); "
+                                        f"one step = one full frame, rays sharded over {world} ranks in interleaved 8x8-pixel tiles, one all-gather per frame",
+                               rays_per_step_per_gpu=c5["rays_per_frame_per_rank"],
+                               parallelism=f"ray sharding x{world} (interleaved 8x8 tiles) + one all_gather_into_tensor of 32 B/ray per frame",
+                               n1_comparison="bench.py --gpus 1 renders the 800x800 frame of the metric; its `config5` key holds this workload on ONE GPU "
+                                             "(the exact strong-scaling denominator)"),
+                "samples_per_step_per_gpu": sum(s["samples"] for s in st),
+                "e2e": {"value": N5 / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 2 * c5["rays_per_frame_per_rank"] * 12,
+                        "d2h_bytes_per_step": N5 * 12, "ms_per_step": e2e_ms},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "k_env_tc (rank 0's share of the frame)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": ach / peak_tf, "traffic": None, "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": fl.value / steps,
+                             "algorithmic_flop_per_step": flop_step, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
+                "cpu_baseline": None, "clocks": clocks,
+                "config5_sweep": {"rays_per_sec": R * N5 / (sw_ms * 1e-3), "ms_per_sweep": sw_ms, "rotations": R, "ms_per_rotation": sw_ms / R,
+                                  "what": "geometry pass + reflected-ray geometry once per camera, every rotation only shades (render.prepare_sweep / "
+                                          "render_sweep_frame); sharded like the frames, one all-gather per rotation"},
+                "replica_frames": {"rays_per_sec": world * W8 * W8 / (rep_ms * 1e-3), "ms_per_step": rep_ms,
+                                   "what": f"weak form (round 1): one {W8}x{W8} frame of the sweep per rank + all-gather of the {world} frames"}}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,6 +564,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     fp_cpu, bf, ro, rd, W, H = workload(args)
+    if world > 1:
+        return run_multi(args, fp_cpu, bf, dev, world, rank, local)
     N = W * H
     indir = not args.no_indir
     fp_cpu.precision = args.precision
@@ -561,7 +762,7 @@ def main():
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens, "sharded_frame": sharded}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens, "config5": c5}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

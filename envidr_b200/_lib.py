@@ -36,7 +36,7 @@ class Field(ctypes.Structure):
         ("indir_roughness_thresh", ctypes.c_float), ("learn_indir_blend", ctypes.c_int32),
         ("has_env_rot", ctypes.c_int32), ("env_rot", ctypes.c_float * 9),
         ("packed", ctypes.c_void_p), ("packed_bytes", ctypes.c_uint64),
-        ("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("precision", ctypes.c_int32), ("rec_unrotated", ctypes.c_int32),
         ("scratch", ctypes.c_void_p), ("scratch_samples", ctypes.c_uint64),
     ]
 

@@ -786,6 +786,10 @@ int envidr_field_forward_records(const envidr_field* field, const float* rec, co
     float* feat = reinterpret_cast<float*>(field->scratch);
     cudaEvent_t* ev = timing_acquire();
     if (ev) cudaEventRecord(ev[0], st);
+    if (field->rec_unrotated && field->has_env_rot) {
+        tcenv.has_rot = 1;
+        for (int i = 0; i < 9; i++) tcenv.rot[i] = field->env_rot[i];
+    }
     rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, nullptr, M, st);
     if (ev) { cudaEventRecord(ev[1], st); timing_commit(); }
     if (rc) return rc;

@@ -145,9 +145,12 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&acc_ready[0], 1);
         tc::mbar_init(&acc_ready[1], 1);
-        for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 * CTAS);
+        // CTAS = 2: every CTA's threads arrive on their OWN barriers; the peer's relay warp forwards each completed phase to the
+        // leader with ONE cluster-scope arrive (+1 below) instead of 128 / 512 remote arrives serialising on the leader's barrier
+        const uint32_t fwd = (CTAS == 2 && rank == 0) ? 1u : 0u;
+        for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 + fwd);
         for (int i = 0; i < kTcStages; i++) tc::mbar_init(&pfull[i], 1);
-        tc::mbar_init(ide_full, kTcIdeThreads * CTAS);
+        tc::mbar_init(ide_full, kTcIdeThreads + fwd);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
     }
@@ -163,11 +166,10 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     if (CTAS == 2) tc::cluster_sync_all(); else __syncthreads();       // barriers of BOTH CTAs initialised before any remote arrive
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // where operand-ready signals go: the issuing CTA's copy of the barrier (rank 0 of the pair)
-    auto to_issuer = [&](uint64_t* bar) { return CTAS == 2 ? tc::map_to_rank(tc::smem_u32(bar), 0) : tc::smem_u32(bar); };
+    // operand-ready signals: arrive on this CTA's own barrier (the peer's are forwarded by its relay warp, below)
+    auto to_issuer = [&](uint64_t* bar) { return tc::smem_u32(bar); };
     auto arrive_issuer = [&](uint32_t addr) {
-        if (CTAS == 2) tc::mbar_arrive_cluster(addr);
-        else asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
+        asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
     };
 
     if (warp == 0) {
@@ -215,6 +217,26 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     if (lane == 0) tc::mbar_arrive_cluster(tc::map_to_rank(tc::smem_u32(&pfull[stage]), 0));
                     __syncwarp();
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && CTAS == 2 && rank == 1) {
+        // ===================== peer relay: "IDE operand / A-operand chunk c of my tile is ready" -> leader's issuer ==========
+        // in the order the issuer consumes them; one release.cluster arrive per phase
+        uint32_t ide_par = 0, chunk_par = 0;
+        const uint32_t l_ide = tc::map_to_rank(tc::smem_u32(ide_full), 0), l_rdy = tc::map_to_rank(tc::smem_u32(&a_rdy[0]), 0);
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
+            tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;
+            tc::fence_proxy_async_smem();
+            if (lane == 0) tc::mbar_arrive_cluster(l_ide);
+            __syncwarp();
+            for (int l = 0; l + 1 < nl; l++) {
+                const uint32_t nchunks = E.L[l].N / 32;
+                for (uint32_t c = 0; c < nchunks; c++) {
+                    tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
+                    tc::fence_proxy_async_smem();
+                    if (lane == 0) tc::mbar_arrive_cluster(l_rdy + c * 8);
+                    __syncwarp();
                 }
             }
         }
@@ -480,6 +502,11 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 const float* q = rec + (size_t)m * kTcRecFloats;
                 dx = q[22 + 3 * branch]; dy = q[23 + 3 * branch]; dz = q[24 + 3 * branch];
                 kap = branch ? q[20] : E.kappa_diffuse;
+                if (E.has_rot) {                                  // v @ rot_theta[:3,:3] (renderer.py:160-161, 171-172)
+                    const float a0 = dx * E.rot[0] + dy * E.rot[3] + dz * E.rot[6], a1 = dx * E.rot[1] + dy * E.rot[4] + dz * E.rot[7],
+                                a2 = dx * E.rot[2] + dy * E.rot[5] + dz * E.rot[8];
+                    dx = a0; dy = a1; dz = a2;
+                }
             }
             if (pw) stamp(ti, 8, clock64());
             tc::mbar_wait(ide_empty, empty_par); empty_par ^= 1;

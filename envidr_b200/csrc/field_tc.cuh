@@ -22,6 +22,7 @@ struct TcEnv {
     uint32_t n_layers, P, E;
     uint32_t ide_nb0;             // bands evaluated for the normal-direction (constant kappa) encoding, see tc_layout
     float kappa_diffuse, light_scale;
+    int has_rot; float rot[9];    // records hold unrotated directions: d <- d @ rot before the encoding (envidr_field.rec_unrotated)
     TcLayer L[kTcMaxLayers];
 };
 

@@ -57,15 +57,38 @@ def shard_sizes(H: int, W: int, world_size: int, tile: int = TILE):
     return [int(tile_shard_indices(H, W, r, world_size, tile).numel()) for r in range(world_size)]
 
 
+_inv_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _gather_index(H: int, W: int, world_size: int, device) -> torch.Tensor:
+    """inv [H*W] int64: pixel p lives at row inv[p] of the all-gathered [world_size * n_max, C] buffer (rank r's rows start at
+    r * n_max, in the order of tile_shard_indices).  The frame is assembled with ONE index_select."""
+    key = (H, W, world_size, str(device))
+    if key not in _inv_cache:
+        if len(_inv_cache) > 16:
+            _inv_cache.clear()
+        sizes = shard_sizes(H, W, world_size)
+        n_max = max(sizes)
+        inv = torch.empty(H * W, dtype=torch.int64)
+        for r in range(world_size):
+            idx = tile_shard_indices(H, W, r, world_size)
+            inv[idx] = r * n_max + torch.arange(idx.numel())
+        _inv_cache[key] = inv.to(device)
+    return _inv_cache[key]
+
+
 def render_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, torch.Tensor]], rays_o: torch.Tensor, rays_d: torch.Tensor,
-                   H: int, W: int, keys=("image", "depth", "weights_sum", "normal_image"), group=None) -> Dict[str, torch.Tensor]:
+                   H: int, W: int, keys=("image", "depth", "weights_sum", "normal_image"), group=None, presharded: bool = False) -> Dict[str, torch.Tensor]:
     """Strong-scaling render of ONE frame: every rank renders its interleaved tiles with `render_fn(rays_o, rays_d)` and
     one all-gather of the packed per-ray outputs ([n_r, C] fp32, C = 8 for rgb+depth+ws+normal = 32 B/ray) assembles the full
-    frame on every rank.  rays_o / rays_d are the full [H*W, 3] tensors (replicated inputs)."""
+    frame on every rank.  rays_o / rays_d are the full [H*W, 3] tensors (replicated inputs), or with presharded=True this rank's rows."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    idx = _dev_idx(H, W, rank, ws, rays_o.device)
-    res = render_fn(rays_o[idx].contiguous(), rays_d[idx].contiguous())
+    if presharded:                                                   # rays_o / rays_d are already this rank's tile_shard_indices rows
+        res = render_fn(rays_o, rays_d)
+    else:
+        idx = _dev_idx(H, W, rank, ws, rays_o.device)
+        res = render_fn(rays_o[idx].contiguous(), rays_d[idx].contiguous())
     cols = []
     for k in keys:
         v = res[k]
@@ -73,18 +96,16 @@ def render_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, t
     packed = torch.cat(cols, -1).contiguous()
     C = packed.shape[1]
     if ws == 1:
-        gathered = [packed]
+        out = packed
     else:
-        sizes = shard_sizes(H, W, ws)
-        n_max = max(sizes)
-        buf = packed.new_zeros(n_max, C)
-        buf[: packed.shape[0]] = packed
+        n_max = max(shard_sizes(H, W, ws))
+        if packed.shape[0] != n_max:                                 # ragged frame sizes only: equal contributions are sent as they are
+            buf = packed.new_zeros(n_max, C)
+            buf[: packed.shape[0]] = packed
+            packed = buf
         out = packed.new_empty(ws * n_max, C)
-        dist.all_gather_into_tensor(out, buf, group=group)           # the one collective of the path
-        gathered = [out[r * n_max: r * n_max + sizes[r]] for r in range(ws)]
-    full = packed.new_empty(H * W, C)
-    for r in range(ws):
-        full[_dev_idx(H, W, r, ws, full.device)] = gathered[r]
+        dist.all_gather_into_tensor(out, packed, group=group)        # the one collective of the path
+    full = out.index_select(0, _gather_index(H, W, ws, out.device))  # de-interleave the tiles: one gather kernel
     outd, c0 = {}, 0
     for k in keys:
         w = res[k].reshape(res[k].shape[0], -1).shape[1]

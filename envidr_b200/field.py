@@ -103,8 +103,9 @@ class FieldParams:
         return P
 
     # ------------------------------------------------------------------------------------------
-    def cstruct(self, env_rot_radian: Optional[float] = None) -> _lib.Field:
+    def cstruct(self, env_rot_radian: Optional[float] = None, rec_unrotated: bool = False) -> _lib.Field:
         f = _lib.Field()
+        f.rec_unrotated = int(rec_unrotated)
         f.embeddings = self.embeddings.data_ptr()
         f.offsets = self.offsets.data_ptr()
         f.num_levels = self.num_levels

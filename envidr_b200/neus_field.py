@@ -1,0 +1,327 @@
+"""BASELINE config 4: the NeuS-style field (use_neus_sdf + encoding_pos=frequency + geometric_init) on libenvidr_b200.
+
+Reference path (per render iteration, nerf/render_func/cuda_ray.py:296-318 with use_neus): FreqEncoder -> 8 weight-normed 256-wide
+layers with Softplus(beta=100) and a skip connection (nerf/network.py:154-222, 415-421) -> normal by autograd.grad
+(nerf/renderer.py:182-198) -> NeuSDensity alpha (network.py:69-102) -> IDE / env_net / diffuse / colour heads
+(network.py:524-698) -> composite_rays(input_alpha=True).
+
+Here:
+  * dense layers of the geometry network, forward AND the reverse pass of the analytic normal g <- (g . softplus'(z)) W, run on
+    tensor cores (csrc/linear_tc.cu: tcgen05, fp16 hi/lo split, fp32 accumulate), weight norm folded into the weights at pack time;
+  * everything between them is one kernel each (csrc/neus_field.cu), the frequency encoding and its transpose-Jacobian product are
+    the library's freq_encode kernels, the opacity is envidr_neus_alpha_forward;
+  * shading reuses the tensor-core env_net / heads kernels on 32-float geometry records (envidr_field_forward_records);
+  * `render_rays_neus` is the inference loop with the reference's schedule (n_step = clamp(N // n_alive, 1, 8)) on the library's march
+    and composite kernels, geometry-only with deferred shading: the loop evaluates geometry + alpha per iteration (ray termination
+    needs nothing else), logs the composited samples ray by ray, and env_net + heads run ONCE over them.
+No CPU fallback: CUDA tensors only.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+from .field import FieldParams, rot_theta3
+from .linear_tc import _image, _run
+
+SQRT3 = 3 ** 0.5
+
+
+def fold_weight_norm(lin) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Effective (W, b) of an nn.Linear, with torch.nn.utils.weight_norm folded: W = g * v / ||v||_row (network.py:218-219)."""
+    if hasattr(lin, "weight_g") and hasattr(lin, "weight_v"):
+        v, g = lin.weight_v.detach().float(), lin.weight_g.detach().float()
+        W = v * (g / v.norm(dim=1, keepdim=True))
+    elif hasattr(lin, "parametrizations") and hasattr(lin.parametrizations, "weight"):
+        W = lin.weight.detach().float()
+    else:
+        W = lin.weight.detach().float()
+    b = None if lin.bias is None else lin.bias.detach().float().contiguous()
+    return W.contiguous(), b
+
+
+@dataclasses.dataclass
+class NeusField:
+    sdf: List[Tuple[torch.Tensor, Optional[torch.Tensor]]]      # effective weights [out, in] of the geometry network
+    skip_layers: Sequence[int]
+    multires: int                                                # FreqEncoder degree (39 = 3 + 2 * 3 * 6 inputs for 6)
+    variance: torch.Tensor                                       # NeuSDensity.variance (device scalar)
+    shading: FieldParams                                         # env / diffuse / colour / renv stacks + scalars (tensor-core kernels)
+    geo_feat_dim: int = 12
+    cos_anneal_ratio: float = 1.0
+    base_steps: int = 1024
+    beta_act: float = 100.0
+    _img: Optional[list] = None
+    _imgT: Optional[list] = None
+
+    @property
+    def device(self):
+        return self.sdf[0][0].device
+
+    @property
+    def in_dim(self) -> int:
+        return 3 + 2 * 3 * self.multires
+
+    def pack(self) -> "NeusField":
+        self._img = [_image(W) for W, _ in self.sdf]
+        self._imgT = [_image(W.t().contiguous()) for W, _ in self.sdf]
+        self.shading.pack()
+        return self
+
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def shading_params(env, diffuse, color, renv, device, **scalars) -> FieldParams:
+        """FieldParams that carries only the rendering MLPs: the hash grid / sdf slots get inert placeholders (never evaluated:
+        only envidr_field_forward_records is called on it)."""
+        G = int(scalars.get("geo_feat_dim", 12))
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        sdf = [(z(64, 2), z(64)), (z(1 + G + 2, 64), z(1 + G + 2))]
+        mv = lambda st: None if st is None else [(W.detach().float().contiguous().to(device), None if b is None else b.detach().float().contiguous().to(device))
+                                                 for W, b in st]
+        return FieldParams(embeddings=z(8, 2), offsets=torch.tensor([0, 8], dtype=torch.int32, device=device), per_level_scale=2.0,
+                           base_resolution=2, bound=float(scalars.pop("bound", 1.0)), sdf=sdf, env=mv(env), diffuse=mv(diffuse), color=mv(color),
+                           renv=mv(renv), precision="tc", **scalars)
+
+    @staticmethod
+    def from_reference_model(model) -> "NeusField":
+        """Read a reference NeRFNetwork built with use_neus_sdf / encoding_pos=frequency (the config-4 family)."""
+        opt = model.opt
+        ok = (opt.use_sdf and opt.use_neus_sdf and opt.encoding_pos == "frequency" and opt.ensemble_mlp and opt.use_env_net and opt.use_diffuse
+              and opt.diffuse_with_env and opt.wo_viewdir and opt.normal_with_mlp and opt.use_n_dot_viewdir and opt.use_roughness
+              and opt.geo_feat_act == "unitNorm" and opt.env_feat_act == "unitNorm" and opt.encoding_ref == "integrated_dir"
+              and opt.color_act == "sigmoid" and opt.diffuse_env_fusion == "concat" and not opt.split_diffuse_env
+              and float(getattr(opt, "normal_anneal_ratio", 1)) >= 1 and not getattr(model, "w_material", False))
+        if not ok:
+            raise _lib.EnvidrError("NeuS field: model configuration is outside the supported config-4 family")
+        dev = next(model.parameters()).device
+        lin = lambda net: [(l.weight.detach().float().contiguous(), None if l.bias is None else l.bias.detach().float().contiguous()) for l in net]
+        shading = NeusField.shading_params(
+            lin(model.env_net), lin(model.diffuse_net), lin(model.color_net),
+            lin(model.renv_net) if getattr(model, "renv_net", None) is not None else None, dev,
+            geo_feat_dim=int(model.geo_feat_dim), ide_degree=int(opt.sh_degree), bound=float(model.bound),
+            roughness_bias=float(model.roughness_bias), roughness_act_scale=float(opt.roughness_act_scale),
+            roughness_scale=float(opt.roughness_scale), diffuse_kappa_inv=float(opt.diffuse_kappa_inv),
+            light_intensity_scale=float(opt.light_intensity_scale), intensity_scale=float(opt.intensity_scale),
+            indir_roughness_thresh=float(opt.indir_roughness_thresh), learn_indir_blend=bool(opt.learn_indir_blend))
+        act = model.sdf_act
+        beta_act = float(getattr(act, "beta", 100.0)) if isinstance(act, torch.nn.Softplus) else None
+        if beta_act is None:
+            raise _lib.EnvidrError("NeuS field: geometric_init (Softplus activations) expected")
+        return NeusField(sdf=[fold_weight_norm(l) for l in model.sdf_net], skip_layers=tuple(int(s) for s in opt.skip_layers),
+                         multires=int(opt.multires), variance=model.sdf_density.variance.detach().float().reshape(1).contiguous(),
+                         shading=shading, geo_feat_dim=int(model.geo_feat_dim), cos_anneal_ratio=float(opt.cos_anneal_ratio),
+                         base_steps=int(model.sdf_density.base_steps), beta_act=beta_act).pack()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def geometry(self, xyzs: torch.Tensor, dirs: torch.Tensor, dists: Optional[torch.Tensor] = None, env_rot_radian: Optional[float] = None,
+                 want_rec: bool = True) -> Dict[str, torch.Tensor]:
+        """forward_sigma of the config-4 model for M samples: sdf, unit normal, roughness, alpha (NeuSDensity) and the geometry record
+        for the shading kernels.  dists: deltas[:, 0] ([M]) or None = the module's base distance."""
+        if self._img is None:
+            self.pack()
+        xyzs = xyzs.float().contiguous().view(-1, 3)
+        dirs = dirs.float().contiguous().view(-1, 3)
+        M, dev = xyzs.shape[0], xyzs.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        L = lib()
+        C = self.in_dim
+        enc = torch.empty(M, C, **f32)
+        check(L.envidr_freq_encode_forward(ptr(xyzs), M, 3, self.multires, C, ptr(enc), stream()), "freq_encode_forward")
+        nl = len(self.sdf)
+        h, derivs, skip_in = enc, [], {}
+        for l, (W, b) in enumerate(self.sdf):
+            if l in self.skip_layers:                                    # h = cat([h, x]) / sqrt(2)   (network.py:417-418)
+                Nh = h.shape[1]
+                cat = torch.empty(M, Nh + C, **f32)
+                check(L.envidr_skip_concat_forward(ptr(h), ptr(enc), M, Nh, C, 1.0 / math.sqrt(2.0), ptr(cat), stream()), "skip_concat_forward")
+                skip_in[l] = Nh
+                h = cat
+            z = _run(h, self._img[l], b, W.shape[0], False)
+            if l != nl - 1:
+                s = torch.empty_like(z)
+                check(L.envidr_softplus_forward(ptr(z), z.numel(), self.beta_act, ptr(z), ptr(s), stream()), "softplus_forward")
+                derivs.append(s)
+            h = z
+        head = h                                                          # [M, 1 + G + 2]
+        # reverse pass: g = d sdf / d (input of layer l), from the sdf row of the last layer down to the encoding
+        g = None
+        g_enc_skip = None
+        for l in range(nl - 1, -1, -1):
+            W = self.sdf[l][0]
+            if l == nl - 1:
+                gz = torch.empty(M, W.shape[1], **f32)                    # W_last[0, :] . softplus'(z_{last-1})
+                check(L.envidr_mul_rows(None, ptr(W[0].contiguous()), ptr(derivs[l - 1]), M, W.shape[1], ptr(gz), stream()), "mul_rows")
+                g = gz
+                continue
+            gin = _run(g, self._imgT[l], None, W.shape[1], False)         # g @ W_l  (the image of W_l^T)
+            if l in skip_in:
+                Nh = skip_in[l]
+                gh = torch.empty(M, Nh, **f32)
+                g_enc_skip = torch.empty(M, C, **f32)
+                check(L.envidr_skip_concat_backward(ptr(gin), M, Nh, C, 1.0 / math.sqrt(2.0), ptr(gh), ptr(g_enc_skip), 0, stream()),
+                      "skip_concat_backward")
+                gin = gh
+            if l == 0:
+                g = gin
+                break
+            gz = torch.empty_like(gin)
+            check(L.envidr_mul_rows(ptr(gin), None, ptr(derivs[l - 1]), M, gin.shape[1], ptr(gz), stream()), "mul_rows")
+            g = gz
+        if g_enc_skip is not None:
+            g = g + g_enc_skip
+        grad_x = torch.empty(M, 3, **f32)
+        check(L.envidr_freq_encode_backward(ptr(g.contiguous()), ptr(enc), M, 3, self.multires, C, ptr(grad_x), stream()), "freq_encode_backward")
+        sh = self.shading
+        out = dict(sdf=torch.empty(M, **f32), normal=torch.empty(M, 3, **f32), roughness=torch.empty(M, **f32), grad_x=grad_x)
+        rec = torch.empty(M, 32, **f32) if want_rec else None
+        rot = None
+        if env_rot_radian is not None:
+            rot = (ctypes.c_float * 9)(*[float(v) for v in rot_theta3(float(env_rot_radian)).reshape(-1)])
+        check(L.envidr_neus_records(ptr(head), head.shape[1], ptr(grad_x), ptr(dirs), M, self.geo_feat_dim, sh.roughness_bias, sh.roughness_act_scale,
+                                    sh.roughness_scale, int(head.shape[1] > 2 + self.geo_feat_dim), rot, ptr(out["sdf"]), ptr(out["normal"]),
+                                    ptr(out["roughness"]), ptr(rec), stream()), "neus_records")
+        alpha = torch.empty(M, **f32)
+        d_t = None if dists is None else dists.float().contiguous().view(-1)
+        check(L.envidr_neus_alpha_forward(ptr(out["sdf"]), ptr(dirs), ptr(out["normal"]), ptr(d_t), 2 * SQRT3 / self.base_steps, ptr(self.variance),
+                                          float(self.cos_anneal_ratio), M, ptr(alpha), stream()), "neus_alpha_forward")
+        out["sigma"] = alpha
+        if rec is not None:
+            out["rec"] = rec
+        return out
+
+    def shade(self, rec: torch.Tensor, r_images: Optional[torch.Tensor] = None, want=("rgb",)) -> Dict[str, torch.Tensor]:
+        """env_net + diffuse / colour (/ renv) heads on geometry records: forward_color (network.py:524-698)."""
+        M, dev = rec.shape[0], rec.device
+        sh = self.shading
+        shapes = dict(rgb=(M, 3), c_diffuse=(M, 3), c_specular=(M, 3))
+        outs = {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in want}
+        if M == 0:
+            return outs
+        if sh._scratch is None or sh._scratch.numel() < 32 * (M + 2):
+            sh._scratch = torch.empty(32 * (M + 2), dtype=torch.float32, device=dev)
+        fo = _lib.FieldOut()
+        for k, t in outs.items():
+            setattr(fo, k, t.data_ptr())
+        f = sh.cstruct()
+        ri = None if r_images is None else r_images.float().contiguous().view(-1, 4)
+        check(lib().envidr_field_forward_records(ctypes.byref(f), ptr(rec), ptr(ri), M, ctypes.byref(fo), stream()), "field_forward_records")
+        return outs
+
+    def forward(self, xyzs, dirs, dists=None, r_images=None, env_rot_radian=None, want=("sigma", "rgb", "normal")) -> Dict[str, torch.Tensor]:
+        g = self.geometry(xyzs, dirs, dists, env_rot_radian)
+        sw = tuple(k for k in want if k in ("rgb", "c_diffuse", "c_specular"))
+        out = dict(g)
+        if sw:
+            out.update(self.shade(g["rec"], r_images, sw))
+        return {k: out[k] for k in want}
+
+
+def render_rays_neus(field: NeusField, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, *, bound: float = 1.0,
+                     cascade: int = 1, grid_size: int = 128, min_near: float = 0.2, dt_gamma: float = 0.0, max_steps: int = 1024,
+                     T_thresh: float = 1e-4, bg_color=1.0, aabb: Optional[Sequence[float]] = None, env_rot_radian: Optional[float] = None,
+                     r_images: Optional[torch.Tensor] = None, geometry_only: bool = False, visual_items: Sequence[str] = (),
+                     stats: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """run_cuda's inference branch (cuda_ray.py:238-359) for the NeuS-style field, input_alpha compositing.
+
+    The loop keeps the reference's schedule and samples; per iteration it evaluates geometry + alpha only and composites the normal
+    image (which also yields weights_sum, depth and -- through the alive list -- ray termination, none of which depend on colour).
+    Every sample a ray composited is logged ray by ray; env_net + the shading heads then run once over the logged records and
+    envidr_composite_rays_replay reproduces the colour compositing sample by sample."""
+    from . import raymarching as rm
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N, dev = rays_o.shape[0], rays_o.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    aabb_t = torch.tensor(list(aabb) if aabb is not None else [-bound] * 3 + [bound] * 3, **f32)
+    nears, fars = rm.near_far_from_aabb(rays_o, rays_d, aabb_t, min_near)
+    ws, depth, n_img = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, 3, **f32)
+    alive = torch.arange(N, dtype=torch.int32, device=dev)
+    rays_t = nears.clone()
+    counts = torch.zeros(N, dtype=torch.int64, device=dev)
+    log_rec, log_alpha, log_delta, log_ray = [], [], [], []
+    step = iters = samples = 0
+    while step < max_steps:
+        n_alive = alive.shape[0]
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        xyzs, dirs, deltas = rm.march_rays(n_alive, n_step, alive, rays_t, rays_o, rays_d, bound, bitfield, cascade, grid_size, nears, fars, -1,
+                                           False, dt_gamma, max_steps)
+        g = field.geometry(xyzs, dirs, deltas[:, 0], env_rot_radian, want_rec=not geometry_only)
+        alpha = g["sigma"]
+        # which samples will the compositor use?  a ray stops at the first zero-delta slot or once its transmittance BEFORE the sample
+        # is below T_thresh (raymarching.cu:996-1039); reproduce that here to log exactly the composited samples
+        if not geometry_only:
+            alive_idx = alive.long()                                     # copy: composite_rays marks dead rays with -1 in place
+            ws_before = ws[alive_idx]
+        rm.composite_rays(n_alive, n_step, alive, rays_t, alpha, g["normal"], deltas, ws, depth, n_img, T_thresh, True)
+        if not geometry_only:
+            a = alpha.view(n_alive, n_step)
+            valid = deltas[:, 0].view(n_alive, n_step) > 0
+            T = 1 - ws_before
+            used = torch.zeros(n_alive, n_step, dtype=torch.bool, device=dev)
+            go = torch.ones(n_alive, dtype=torch.bool, device=dev)
+            for s in range(n_step):
+                go = go & valid[:, s]
+                used[:, s] = go
+                w = a[:, s] * T
+                go = go & ~(T < T_thresh)
+                T = torch.where(used[:, s], T - w, T)
+            sel = used.view(-1)
+            ray_of = alive_idx[:, None].expand(-1, n_step).reshape(-1)
+            log_rec.append(g["rec"][sel]); log_alpha.append(alpha[sel]); log_delta.append(deltas[sel]); log_ray.append(ray_of[sel])
+            counts.index_add_(0, ray_of[sel], torch.ones_like(ray_of[sel]))
+        samples += int((deltas[:, 0] > 0).sum()) if stats is not None else 0
+        alive = alive[alive >= 0]
+        step += n_step
+        iters += 1
+    if stats is not None:
+        stats.update(samples=samples, iterations=iters)
+    res = {"depth": depth, "weights_sum": ws, "normal_image": torch.nn.functional.normalize(n_img, dim=-1, eps=1e-10)}
+    if geometry_only:
+        res["image"] = None
+        return res
+    # deferred shading: samples ordered ray by ray (stable: iteration order within a ray is preserved)
+    ray_all = torch.cat(log_ray) if log_ray else torch.zeros(0, dtype=torch.int64, device=dev)
+    order = torch.argsort(ray_all, stable=True)
+    rec = torch.cat(log_rec)[order] if log_rec else torch.zeros(0, 32, **f32)
+    alpha = torch.cat(log_alpha)[order] if log_alpha else torch.zeros(0, **f32)
+    delta = torch.cat(log_delta)[order] if log_delta else torch.zeros(0, 2, **f32)
+    Mtot = int(rec.shape[0])
+    off = (torch.cumsum(counts, 0) - counts).to(torch.int32)
+    rays = torch.stack([torch.arange(N, dtype=torch.int32, device=dev), off, counts.to(torch.int32)], -1).contiguous()
+    r_s = None
+    if r_images is not None:
+        r_s = torch.empty(Mtot, 4, **f32)
+        check(lib().envidr_scatter_ray_rows4(ptr(rays), N, Mtot, ptr(r_images.float().contiguous().view(-1, 4)), ptr(r_s), stream()), "scatter_ray_rows4")
+    want = ["rgb"] + (["c_diffuse"] if "diffuse" in visual_items else []) + (["c_specular"] if "specular" in visual_items else [])
+    sh = field.shade(rec, r_s, tuple(want))
+    rough = rec[:, 20].contiguous() if ("roughness" in visual_items or "specular" in visual_items) else None
+    img = {"image": torch.empty(N, 3, **f32), "weights_sum": torch.empty(N, **f32), "depth": torch.empty(N, **f32)}
+    if "c_diffuse" in sh:
+        img["diffuse_image"] = torch.empty(N, 3, **f32)
+    if "c_specular" in sh:
+        img["specular_image"] = torch.empty(N, 3, **f32)
+    if rough is not None:
+        img["roughness_image"] = torch.empty(N, **f32)
+    check(lib().envidr_composite_rays_replay(ptr(alpha), ptr(sh["rgb"]), None, ptr(sh.get("c_diffuse")), ptr(sh.get("c_specular")), ptr(rough), ptr(delta),
+                                             ptr(rays), ptr(nears), Mtot, N, T_thresh, 1, ptr(img["weights_sum"]), ptr(img["depth"]), ptr(img["image"]), None,
+                                             ptr(img.get("diffuse_image")), ptr(img.get("specular_image")), ptr(img.get("roughness_image")), stream()),
+          "composite_rays_replay")
+    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32)
+    res["image"] = img["image"] + (1 - ws).unsqueeze(-1) * bg
+    for k in ("diffuse_image", "specular_image"):
+        if k in img:
+            res[k] = img[k]
+    if "roughness_image" in img:
+        res["roughness_image"] = img["roughness_image"][..., None]
+    if stats is not None:
+        stats["shaded"] = Mtot
+    return res

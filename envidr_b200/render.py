@@ -182,14 +182,10 @@ def _sample_log(device, need: int, slot: str = "primary") -> SampleLogBuffers:
     return lg
 
 
-def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor],
-                         cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
-                         visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
-    """A pass shaded from a geometry-only pass's sample log: the samples of the rays `ray_idx` (int64 indices into the logged
-    pass's rays, ascending; None = all of them) are gathered ray by ray (envidr_permute_sample_log), shaded from their geometry
-    records (envidr_field_forward_records: env_net + shading heads only) and composited (envidr_composite_rays_replay).
-    counts [N_all] = samples composited per ray of the logged pass; r_images [n_selected, 4] in the order of ray_idx.
-    Returns per-selected-ray images.  One host synchronisation (the batch size M sizes the buffers)."""
+def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor]) -> Dict:
+    """Ray-contiguous copy of the logged samples of the rays `ray_idx` (int64 indices into the logged pass's rays, ascending; None =
+    all of them): envidr_permute_sample_log.  Nothing here depends on colour, r_images or the light rotation, so one prepared batch
+    serves every frame of a relight sweep.  One host synchronisation (the batch size M sizes the buffers)."""
     dev = counts.device
     f32 = dict(dtype=torch.float32, device=dev)
     n_all = counts.shape[0]
@@ -210,6 +206,17 @@ def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, 
           "permute_sample_log")
     # rays of the pass in selected order: (ray id = position among the selected rays, offset, count)
     rays = torch.stack([torch.arange(n_r, dtype=torch.int32, device=dev), off, cs.to(torch.int32)], -1).contiguous()
+    return dict(rec=rec, sigma=sigma, delta=delta, rays=rays, n_r=n_r, M=M)
+
+
+def shade_prepared(field: FieldParams, prep: Dict, cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
+                   visual_items: Sequence[str] = (), env_rot_radian: Optional[float] = None, rec_unrotated: bool = False) -> Dict[str, torch.Tensor]:
+    """env_net + shading heads over a prepared batch (envidr_field_forward_records) and the inference compositor over it
+    (envidr_composite_rays_replay).  r_images [n_r, 4] in the order of the prepared rays.  rec_unrotated: the records were captured
+    without a light rotation and `env_rot_radian` is applied inside the env_net kernel."""
+    rec, sigma, delta, rays, n_r, M = (prep[k] for k in ("rec", "sigma", "delta", "rays", "n_r", "M"))
+    dev = rec.device
+    f32 = dict(dtype=torch.float32, device=dev)
     r_s = None
     if r_images is not None:
         r_s = torch.empty(M, 4, **f32)
@@ -226,7 +233,7 @@ def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, 
     fo = _lib.FieldOut()
     for k, t in want.items():
         setattr(fo, k, t.data_ptr())
-    f = field.cstruct()
+    f = field.cstruct(env_rot_radian if rec_unrotated else None, rec_unrotated=rec_unrotated)
     check(lib().envidr_field_forward_records(ctypes.byref(f), ptr(rec), ptr(r_s), M, ctypes.byref(fo), stream()), "field_forward_records")
     res = {"image": torch.empty(n_r, 3, **f32), "depth": torch.empty(n_r, **f32), "weights_sum": torch.empty(n_r, **f32)}
     if "c_diffuse" in want:
@@ -246,6 +253,16 @@ def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, 
         res["roughness_image"] = res["roughness_image"][..., None]
     res["_samples"] = M
     return res
+
+
+def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor],
+                         cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
+                         visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+    """A pass shaded from a geometry-only pass's sample log: gather ray by ray (prepare_from_log), shade from the geometry records and
+    composite (shade_prepared).  counts [N_all] = samples composited per ray of the logged pass; r_images [n_selected, 4] in the order
+    of ray_idx.  Returns per-selected-ray images."""
+    return shade_prepared(field, prepare_from_log(log, total, counts, ray_idx), cfg, bg_color=bg_color, r_images=r_images,
+                          visual_items=visual_items)
 
 
 _aabb_cache: Dict[tuple, torch.Tensor] = {}
@@ -447,6 +464,102 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
     if "weights_sum" in results and get_normal_image and "normal_image" in results:
         w = results["weights_sum"][..., None]
         results["normal_image"] = results["normal_image"] * w + (1 - w)
+    return results
+
+
+# ---------------------------------------------------------------------------------------------
+# relight sweep (BASELINE config 5; Trainer.test with env_rot_degree_range, nerf/utils.py:1297-1303, 1325-1328)
+# ---------------------------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class SweepGeometry:
+    """Everything of a three-pass frame that does not depend on the light rotation: the geometry pass (depth, normals, masks, the
+    per-sample geometry records of the main-pass rays) and the geometry of the reflected secondary pass.  The reference re-renders all
+    three passes for each of the 72 rotations of a sweep; here they are computed once per camera and every rotation only runs
+    env_net + the shading heads + the compositor over the prepared records (the rotation is applied inside the env_net kernel)."""
+    N: int
+    normals: torch.Tensor
+    depth: torch.Tensor
+    ray_idx: torch.Tensor
+    ref_idx: torch.Tensor
+    pos_in_ray: torch.Tensor
+    main: Dict
+    secondary: Optional[Dict]
+    samples: Dict[str, int]
+
+
+def prepare_sweep(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, cfg: RenderConfig) -> SweepGeometry:
+    """Rotation-independent part of `render(..., cfg.indir_ref=True)` for the tensor-core field (renderer.py:439-486)."""
+    assert field.precision == "tc", "the relight sweep reuses the tensor-core path's geometry records"
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N = rays_o.shape[0]
+    dt = 2 * SQRT3 / cfg.indir_max_steps
+    log = _sample_log(rays_o.device, _log_need.get(N, 8 * 1 << 20), "sweep-primary")
+    while True:
+        geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, sample_count=True, log=log)
+        st = last_stats()
+        if st["samples"] <= log.capacity:
+            break
+        log = _sample_log(rays_o.device, int(st["samples"] * 1.25) + 4096, "sweep-primary")
+    _log_need[N] = int(st["samples"] * 1.25) + 4096
+    normals, depth, ws = geo["normal_image"], geo["depth"] - dt, geo["weights_sum"]
+    ref_mask = (depth != 0) & (ws > 0.9)
+    ray_mask = (depth != 0) & (ws > 0.3)
+    ref_o = rays_o + depth[:, None] * rays_d
+    ref_d = reflect_dir(-rays_d, normals)
+    if cfg.obj_aabb is not None:
+        ob = torch.tensor(cfg.obj_aabb, dtype=torch.float32, device=rays_o.device)
+        ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
+    ref_idx = ref_mask.nonzero().squeeze(-1)
+    ray_idx = ray_mask.nonzero().squeeze(-1)
+    pos_in_ray = torch.cumsum(ray_mask, 0) - 1
+    main = prepare_from_log(log, st["samples"], geo["sample_count"], ray_idx)
+    samples = dict(geometry=int(st["samples"]), main=int(main["M"]))
+    sec = None
+    if ref_idx.numel() > 0:
+        sec_o, sec_d = ref_o[ref_idx], ref_d[ref_idx]
+        log2 = _sample_log(rays_o.device, _log_need.get(("sec", N), 4 * 1 << 20), "sweep-secondary")
+        while True:
+            geo2 = render_rays(field, bitfield, sec_o, sec_d, cfg, geometry_only=True, max_steps=cfg.indir_max_steps, min_near=dt * 2,
+                               n_step_floor=cfg.secondary_n_step_floor, sample_count=True, log=log2)
+            st2 = last_stats()
+            if st2["samples"] <= log2.capacity:
+                break
+            log2 = _sample_log(rays_o.device, int(st2["samples"] * 1.25) + 4096, "sweep-secondary")
+        _log_need[("sec", N)] = int(st2["samples"] * 1.25) + 4096
+        sec = prepare_from_log(log2, st2["samples"], geo2["sample_count"], None)
+        samples.update(secondary_marched=int(st2["samples"]), secondary=int(sec["M"]))
+    return SweepGeometry(N=N, normals=normals, depth=depth, ray_idx=ray_idx, ref_idx=ref_idx, pos_in_ray=pos_in_ray, main=main, secondary=sec,
+                         samples=samples)
+
+
+def render_sweep_frame(field: FieldParams, geom: SweepGeometry, cfg: RenderConfig, env_rot_radian: Optional[float], *, bg_color=1.0,
+                       get_normal_image: bool = True, visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+    """One frame of the sweep: the three-pass frame `render()` returns for this light rotation, from the shared geometry."""
+    dev = geom.normals.device
+    n_main = int(geom.ray_idx.shape[0])
+    r_img = geom.normals.new_zeros(n_main, 4)
+    if geom.secondary is not None:
+        ref = shade_prepared(field, geom.secondary, cfg, bg_color=0.0, env_rot_radian=env_rot_radian, rec_unrotated=True)
+        r_img[geom.pos_in_ray[geom.ref_idx]] = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)
+    main = shade_prepared(field, geom.main, cfg, bg_color=0.0, r_images=r_img, visual_items=visual_items, env_rot_radian=env_rot_radian,
+                          rec_unrotated=True)
+    N = geom.N
+    results = {"normal_image": geom.normals, "depth": geom.depth}
+    for k in ("image", "specular_image", "diffuse_image", "roughness_image"):
+        if k in main:
+            v = geom.normals.new_zeros(N, main[k].shape[-1])
+            v[geom.ray_idx] = main[k]
+            results[k] = v
+    ws_full = geom.normals.new_zeros(N)
+    ws_full[geom.ray_idx] = main["weights_sum"]
+    bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(bg_color, dtype=torch.float32, device=dev)
+    results["image"] = (torch.zeros_like(geom.normals) + bg) * (1 - ws_full[:, None]) + results["image"]
+    results["weights_sum"] = ws_full
+    if get_normal_image:
+        w = ws_full[..., None]
+        results["normal_image"] = geom.normals * w + (1 - w)
     return results
 
 

@@ -190,3 +190,86 @@ def make_bitfield(scene_scale: float = 0.65, bound: float = 1.0, grid_size: int 
     flat = np.zeros(H ** 3, np.uint8)
     flat[m.reshape(-1)] = occ.reshape(-1)
     return np.packbits(flat.reshape(-1, 8), axis=-1, bitorder="little").reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: NeuS-style geometry without a hash grid (materials.ini + use_neus_sdf, encoding_pos=frequency,
+# multires 6, geometric_init, 8 x 256 layers, skip_layers [4])
+# ---------------------------------------------------------------------------------------------
+
+def make_neus_weights(seed: int = 0, *, hidden_dim: int = 256, num_layers: int = 8, skip_layers=(4,), multires: int = 6,
+                      geo_feat_dim: int = 12, radius: float = 0.5):
+    """Effective (weight norm folded) weights of the geometry network in the state geometric_init leaves it in
+    (nerf/network.py:195-216: the SDF of a sphere of radius `geo_init_bias`), with the feature rows of the head seeded random so that
+    geo_feat / roughness / blend vary over space.  Returns [(W [out, in], b [out])] as float32 numpy arrays."""
+    rng = np.random.default_rng(seed)
+    in_dim = 3 + 2 * 3 * multires
+    layers = []
+    for l in range(num_layers):
+        k = in_dim if l == 0 else hidden_dim
+        if l == num_layers - 1:
+            n = 1 + geo_feat_dim + 2
+        elif l + 1 in skip_layers:
+            n = hidden_dim - in_dim
+        else:
+            n = hidden_dim
+        if l == num_layers - 1:
+            W = rng.normal(np.sqrt(np.pi) / np.sqrt(k), 1e-4, size=(n, k))
+            b = np.full(n, -radius)
+            W[1:] = rng.normal(0.0, 1.0 / np.sqrt(k), size=(n - 1, k))
+            b[1:] = rng.normal(0.0, 0.3, size=n - 1)
+        elif l == 0:
+            W = np.zeros((n, k))
+            W[:, :3] = rng.normal(0.0, np.sqrt(2) / np.sqrt(n), size=(n, 3))
+            b = np.zeros(n)
+        elif l in skip_layers:
+            W = rng.normal(0.0, np.sqrt(2) / np.sqrt(n), size=(n, k))
+            W[:, -(in_dim - 3):] = 0.0
+            b = np.zeros(n)
+        else:
+            W = rng.normal(0.0, np.sqrt(2) / np.sqrt(n), size=(n, k))
+            b = np.zeros(n)
+        layers.append((W.astype(np.float32), b.astype(np.float32)))
+    return layers
+
+
+def make_sphere_bitfield(radius: float = 0.5, bound: float = 1.0, grid_size: int = 128, margin_cells: float = 2.5) -> np.ndarray:
+    """Occupancy bit field of the geometric-init sphere (interior and a thin shell), reference layout (see make_bitfield)."""
+    H = grid_size
+    c = ((np.arange(H) + 0.5) / H * 2 - 1) * bound
+    gx, gy, gz = np.meshgrid(c, c, c, indexing="ij")
+    occ = (np.sqrt(gx * gx + gy * gy + gz * gz) - radius) < margin_cells * (2 * bound / H)
+
+    def spread(v):
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+
+    i = np.arange(H, dtype=np.uint64)
+    m = (spread(i)[:, None, None] | (spread(i)[None, :, None] << 1) | (spread(i)[None, None, :] << 2)).astype(np.int64)
+    flat = np.zeros(H ** 3, np.uint8)
+    flat[m.reshape(-1)] = occ.reshape(-1)
+    return np.packbits(flat.reshape(-1, 8), axis=-1, bitorder="little").reshape(-1)
+
+
+def make_neus_field(seed: int = 0, *, hidden_dim_env: int = 256, ide_degree: int = 5, variance: float = 0.6, radius: float = 0.5,
+                    device="cpu", **kw):
+    """Config-4 field: geometry network of make_neus_weights + the rendering MLPs of make_synthetic_field(seed)."""
+    from .neus_field import NeusField
+    base = make_synthetic_field(seed, hidden_dim_env=hidden_dim_env, ide_degree=ide_degree, num_levels=2, log2_hashmap_size=10, desired_resolution=32)
+    layers = make_neus_weights(seed, radius=radius, **kw)
+    dev = torch.device(device)
+    sdf = [(torch.from_numpy(W).to(dev), torch.from_numpy(b).to(dev)) for W, b in layers]
+    shading = NeusField.shading_params(base.env, base.diffuse, base.color, base.renv, dev, geo_feat_dim=12, ide_degree=ide_degree)
+    return NeusField(sdf=sdf, skip_layers=tuple(kw.get("skip_layers", (4,))), multires=int(kw.get("multires", 6)),
+                     variance=torch.tensor([variance], dtype=torch.float32, device=dev), shading=shading, geo_feat_dim=12)
+
+
+def neus_to_oracle(nf) -> dict:
+    """Plain numpy / scalar dict of a NeusField for oracle.neus_oracle (tests / CPU baseline only)."""
+    P = nf.shading.to_oracle()
+    P.update(sdf=[(W.detach().cpu().numpy(), b.detach().cpu().numpy()) for W, b in nf.sdf], skip_layers=tuple(nf.skip_layers), multires=nf.multires,
+             variance=float(nf.variance.reshape(-1)[0]), cos_anneal_ratio=nf.cos_anneal_ratio, geo_feat_dim=nf.geo_feat_dim)
+    return P

@@ -208,7 +208,10 @@ typedef struct envidr_field {
     const void* packed; uint64_t packed_bytes;
     /* arithmetic of the env_net passes: 0 = fp32 FFMA (bit-faithful path); 1 = tcgen05 tensor cores with every operand
      * split into two fp16 values and three MMAs per K step (fp32 accumulate; ~1e-6 relative to the fp32 path). */
-    int32_t precision; int32_t reserved;
+    int32_t precision;
+    int32_t rec_unrotated;  /* envidr_field_forward_records only: the records hold UNROTATED n_env / w_r (a geometry pass captured without
+                             * env_rot) and env_rot is applied inside the env_net kernel -- one geometry pass serves every light
+                             * rotation of a relight sweep (BASELINE config 5, utils.py:1297-1303) */
     /* precision = 1 only: device scratch of 256 bytes per sample for at least scratch_samples >= M samples */
     void* scratch; uint64_t scratch_samples;
 } envidr_field;
@@ -368,6 +371,30 @@ uint64_t envidr_neus_workspace_bytes(void);
 int envidr_neus_alpha_backward(const float* grad_alpha, const float* sdf, const float* dirs, const float* gradients, const float* dists,
                                float dist_scalar, const float* variance, float cos_anneal_ratio, uint32_t M, float* grad_sdf,
                                float* grad_gradients, float* grad_variance, void* workspace, uint64_t workspace_bytes, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NeuS-style geometry network (BASELINE config 4; nerf/network.py:154-222 construction, :415-421 forward with skip_layers,
+ * nerf/renderer.py:182-198 normals): the kernels between the dense layers, which run on envidr_linear_tc.  The reference has no
+ * operator boundary here (nn.Linear + Softplus(beta=100) + torch.cat + autograd.grad driven from Python);
+ * envidr_b200/neus_field.py drives the chain.
+ * ---------------------------------------------------------------------------------------------- */
+/* h = Softplus(beta, threshold 20)(z) and, when dh != NULL, dh = sigmoid(beta z) (its derivative); n elements; h may alias z. */
+int envidr_softplus_forward(const float* z, uint64_t n, float beta, float* h, float* dh, envidr_stream_t stream);
+/* out [M,N] = a [M,N] * b [M,N], or a_row [N] (broadcast over rows, a == NULL) * b.  The reverse pass g <- g . softplus'. */
+int envidr_mul_rows(const float* a, const float* a_row, const float* b, uint64_t M, uint32_t N, float* out, envidr_stream_t stream);
+/* out [M, Nh+Nx] = cat(h [M,Nh], x [M,Nx]) * scale (network.py:417-418, scale = 1/sqrt(2)), and its reverse: gh = g[:, :Nh] * scale,
+ * gx (+)= g[:, Nh:] * scale. */
+int envidr_skip_concat_forward(const float* h, const float* x, uint64_t M, uint32_t Nh, uint32_t Nx, float scale, float* out,
+                               envidr_stream_t stream);
+int envidr_skip_concat_backward(const float* g, uint64_t M, uint32_t Nh, uint32_t Nx, float scale, float* gh, float* gx, int accumulate,
+                                envidr_stream_t stream);
+/* Head of the geometry network -> inputs of the shading kernels: h [M, ld] = (sdf, geo_feat[G], roughness, [blend]) rows of the last
+ * layer (network.py:424-448), grad_x [M,3] = d sdf / d x.  Outputs (any may be NULL): sdf [M], normal [M,3] (F.normalize, eps 1e-10),
+ * roughness [M], rec [M,32] = the geometry record consumed by envidr_field_forward_records (reflected / normal directions of
+ * renderer.py:147-180, rotated by rot9 = HOST float[9] rot_theta[:3,:3] when given). */
+int envidr_neus_records(const float* h, uint32_t ld, const float* grad_x, const float* dirs, uint32_t M, uint32_t geo_feat_dim,
+                        float roughness_bias, float roughness_act_scale, float roughness_scale, int has_blend, const float* rot9,
+                        float* sdf, float* normal, float* roughness, float* rec, envidr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Occupancy-grid maintenance: the caller either side of the march.

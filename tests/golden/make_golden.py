@@ -615,8 +615,92 @@ def gen_infer_branch():
     print("infer_branch.npz: hit pixels", int((out["one_weights_sum"] > 0.5).sum()), "of", W * W, "keys", sorted(k for k in out if k.startswith("three_")))
 
 
+def gen_neus_field():
+    """BASELINE config 4 -- the reference's OWN NeRFNetwork built with use_neus_sdf / encoding_pos=frequency / geometric_init /
+    8 x 256 layers / skip_layers [4] (weight-normed layers, Softplus(beta=100); network.py:154-222, 415-448), run on the CPU:
+    forward_sigma (normals by autograd, NeuSDensity alpha) + get_color_mlp_extra_params + forward_color on seeded samples, and
+    NeRFRenderer.render -> run_cuda inference loop (input_alpha compositing) on a 16 x 16 frame with raymarching bound to the oracle's
+    C restatements.  The CUDA-only FreqEncoder is replaced by the torch formula of its kernel (oracle.neus_oracle.freq_encode, checked
+    against the C restatement of freqencoder.cu in tests/test_oracle_golden.py).  -> tests/golden/neus_field.npz"""
+    sys.path.insert(0, REPO)
+    from envidr_b200 import scene
+    from oracle import oracle as O
+    from oracle import neus_oracle as NO
+    import nerf.render_func.cuda_ray as CR
+    flags = ["--use_neus_sdf", "--encoding_pos", "frequency", "--multires", "6", "--geometric_init", "--num_layers", "8", "--hidden_dim", "256",
+             "--skip_layers", "4", "--init_variance", "0.6", "--geo_init_bias", "0.5", "--hidden_dim_env", "64", "--sh_degree", "4",
+             "--max_steps", "256"]
+    model, opt = build_model(flags, cuda_ray=True)
+    nf = scene.make_neus_field(0, hidden_dim_env=64, ide_degree=4)
+    with torch.no_grad():
+        for lin, (W, b) in zip(model.sdf_net, nf.sdf):
+            assert tuple(lin.weight_v.shape) == tuple(W.shape), (lin.weight_v.shape, W.shape)
+            lin.weight_v.copy_(W); lin.weight_g.copy_(W.norm(dim=1, keepdim=True)); lin.bias.copy_(b)
+        sh = nf.shading
+        for name in ("env", "diffuse", "color", "renv"):
+            for lin, (W, b) in zip(getattr(model, name + "_net"), getattr(sh, name)):
+                lin.weight.copy_(W); lin.bias.copy_(b)
+
+    class Enc(torch.nn.Module):
+        def forward(self, x, bound=1, **kw):
+            return NO.freq_encode(x, 6)
+    model.encoder = Enc()
+    model.eval()
+    g = torch.Generator().manual_seed(11)
+    M = 256
+    u = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    x = (u * (0.25 + 0.4 * torch.rand(M, 1, generator=g))).requires_grad_(True)          # around the surface (r = 0.37 .. 0.48)
+    d = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    dists = torch.full((M,), 2 * 3 ** 0.5 / 256)
+    sdfs, alpha, geo, normals, _ = model.forward_sigma(x, use_sdf_sigma_grad=True, dirs=d, dists=dists)
+    rough = model.roughness
+    n_enc, w_r_enc, n_dot, n_env_enc = model.get_color_mlp_extra_params(normals, d, rough, None)
+    rgb = model.forward_color(geo, d, n_enc, w_r_enc, n_dot, True, n_env_enc=n_env_enc, r_images=None, roughness=rough)
+    f = lambda t: t.detach().numpy().astype(np.float32)
+    out = dict(x=f(x), d=f(d), dists=f(dists), sdf=f(sdfs), alpha=f(alpha).reshape(-1), geo=f(geo), normal=f(normals), roughness=f(rough), rgb=f(rgb),
+               c_diffuse=f(model.c_diffuse), c_specular=f(model.c_specular), blend=f(model.blend_weight))
+    # ---- the inference loop through NeRFRenderer.render
+    class RM:
+        @staticmethod
+        def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+            n, fr = O.near_far_from_aabb(rays_o.detach().numpy(), rays_d.detach().numpy(), aabb.numpy(), min_near)
+            return torch.from_numpy(n), torch.from_numpy(fr)
+
+        @staticmethod
+        def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, C, H, near, far, align=-1, perturb=False,
+                       dt_gamma=0, max_steps=1024):
+            xx, dd, dl, _ = O.march_rays(n_alive, n_step, rays_alive.numpy(), rays_t.numpy(), rays_o.detach().numpy(), rays_d.detach().numpy(), bound,
+                                         bitfield.numpy(), C, H, near.numpy(), far.numpy(), align=align, dt_gamma=dt_gamma, max_steps=max_steps)
+            return torch.from_numpy(xx), torch.from_numpy(dd), torch.from_numpy(dl)
+
+        @staticmethod
+        def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2,
+                           input_alpha=False, accum_deltas=True):
+            O.composite_rays(n_alive, n_step, rays_alive.numpy(), rays_t.numpy(), sigmas.detach().numpy(), rgbs.detach().numpy(),
+                             deltas.detach().numpy(), weights_sum.numpy(), depth.numpy(), image.numpy(), T_thresh=T_thresh,
+                             input_alpha=bool(input_alpha), accum_deltas=bool(accum_deltas))
+            return tuple()
+    CR.raymarching = RM
+    bf = scene.make_sphere_bitfield()
+    model.density_bitfield = torch.from_numpy(bf)
+    Wd = 16
+    ro, rd = scene.camera_rays(Wd, Wd)
+    opt.indir_ref = False
+    kw = {k: v for k, v in vars(opt).items()}
+    res = model.render(ro[None], rd[None], staged=True, bg_color=1, perturb=False, get_normal_image=True, **kw)
+    out.update(rays_o=ro.numpy(), rays_d=rd.numpy())
+    for k in ("image", "depth", "weights_sum", "normal_image"):
+        out[f"frame_{k}"] = f(res[k]).reshape(Wd * Wd, -1)
+    np.savez_compressed(os.path.join(HERE, "neus_field.npz"), **out)
+    print("neus_field.npz: alpha range", float(out["alpha"].min()), float(out["alpha"].max()), "hit pixels", int((out["frame_weights_sum"] > 0.5).sum()), "of", Wd * Wd)
+
+
 if __name__ == "__main__":
     install_shims()
+    if "neus_field" in sys.argv[1:]:
+        torch.set_num_threads(8)
+        gen_neus_field()
+        sys.exit(0)
     if "infer" in sys.argv[1:]:
         torch.set_num_threads(8)
         gen_infer_branch()

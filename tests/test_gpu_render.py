@@ -284,3 +284,30 @@ def test_render_model_routes_the_three_pass_frame(dev, monkeypatch):
     with pytest.raises(Exception):
         model.training = True
         render.render_model(model, ro[None], rd[None], **kw)          # no reference method installed: fails loudly
+
+
+def test_relight_sweep_shares_the_rotation_independent_passes(dev):
+    """BASELINE config 5 (Trainer.test with env_rot_degree_range, utils.py:1297-1303): render.prepare_sweep computes the geometry pass and
+    the reflected-ray geometry once (records captured WITHOUT a light rotation), render.render_sweep_frame shades them for each rotation
+    with the rotation applied inside the env_net kernel (envidr_field.rec_unrotated).  Every frame must equal the full three-pass
+    `render(..., env_rot_radian=theta)` of that rotation: same geometry outputs bit for bit, colours to rounding (the rotation is the
+    same three FMAs, applied to the same unit vectors, in another kernel)."""
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=64, ide_degree=5, precision="tc").to(dev).pack()
+    bf = torch.from_numpy(scene.make_bitfield()).to(dev)
+    ro, rd = scene.camera_rays(96, 96)
+    ro, rd = ro.to(dev), rd.to(dev)
+    cfg = render.RenderConfig(indir_ref=True)
+    geom = render.prepare_sweep(fp, bf, ro, rd, cfg)
+    assert geom.samples["main"] > 10000 and geom.samples["secondary"] > 1000
+    frames = []
+    for th in (0.0, 0.7, 2.1, 5.5):
+        full = render.render(fp, bf, ro, rd, cfg, bg_color=1.0, env_rot_radian=th, visual_items=("diffuse", "specular", "roughness"))
+        fast = render.render_sweep_frame(fp, geom, cfg, th, bg_color=1.0, visual_items=("diffuse", "specular", "roughness"))
+        for k in ("depth", "weights_sum", "normal_image", "roughness_image"):
+            assert torch.equal(fast[k], full[k]), k
+        for k in ("image", "diffuse_image", "specular_image"):
+            assert float((fast[k] - full[k]).abs().max()) <= 2e-6, (th, k, float((fast[k] - full[k]).abs().max()))
+        frames.append(fast["image"])
+    hit = geom.ray_idx
+    assert float((frames[1][hit] - frames[0][hit]).abs().mean()) > 1e-3          # the light really moved

@@ -305,3 +305,43 @@ def test_render_oracle_matches_reference_inference_path(golden_dir, tag, indir, 
     np.testing.assert_allclose(res["depth"], z[f"{tag}_depth"][:, 0], rtol=0, atol=2e-5)
     en = np.abs(res["normal_image"] - z[f"{tag}_normal_image"]).max(-1)
     assert int((en > 1e-3).sum()) <= 2, (int((en > 1e-3).sum()), float(en.max()))
+
+
+def test_neus_oracle_matches_reference_config4_model(golden_dir):
+    """BASELINE config 4: oracle/neus_oracle.py against the reference's OWN NeRFNetwork (use_neus_sdf, frequency encoding, geometric_init,
+    8 x 256 weight-normed Softplus layers with skip_layers [4]) run on the CPU by tests/golden/make_golden.py::gen_neus_field:
+    per-sample sdf / normal / NeuS alpha / geo_feat / roughness / rgb, and the 16 x 16 frame of NeRFRenderer.render -> run_cuda with
+    input_alpha compositing.  Also: the torch formula of the frequency encoding equals the C restatement of freqencoder.cu."""
+    import os
+    from envidr_b200 import scene
+    from oracle import neus_oracle as NO
+    from oracle import oracle as O
+    z = np.load(os.path.join(golden_dir, "neus_field.npz"))
+    x = z["x"]
+    a = NO.freq_encode(torch.from_numpy(x).double(), 6).numpy()
+    b = O.freq_encode_forward(x, 6)
+    np.testing.assert_allclose(a, b, atol=3e-6)               # sinf of the fp32 argument 2^f x (+ pi/2) vs float64: argument rounding up to 32 * 6e-8
+    nf = scene.make_neus_field(0, hidden_dim_env=64, ide_degree=4)
+    P = scene.neus_to_oracle(nf)
+    out = NO.field_forward(P, x, z["d"], z["dists"])
+    np.testing.assert_allclose(out["sdf"], z["sdf"], atol=2e-6)
+    np.testing.assert_allclose(out["normal"], z["normal"], atol=2e-5)
+    np.testing.assert_allclose(out["sigma"], z["alpha"], atol=2e-4)     # inv_s = e^6 = 403 amplifies the fp32 sdf rounding of the reference
+    np.testing.assert_allclose(out["geo_feat"], z["geo"], atol=2e-6)
+    np.testing.assert_allclose(out["roughness"], z["roughness"], atol=1e-6)
+    np.testing.assert_allclose(out["blend"], z["blend"], atol=1e-6)
+    np.testing.assert_allclose(out["c_diffuse"], z["c_diffuse"], atol=2e-5)
+    np.testing.assert_allclose(out["c_specular"], z["c_specular"], atol=2e-5)
+    np.testing.assert_allclose(out["rgb"], z["rgb"], atol=3e-5)
+    assert 0.05 < float((z["alpha"] > 0.5).mean()) < 0.95 and float(z["alpha"].max()) == 1.0
+    P256 = dict(P)
+    fr = NO.render_rays(P, z["rays_o"], z["rays_d"], scene.make_sphere_bitfield(), max_steps=256, bg_color=1.0, dtype=torch.float32)
+    assert int((z["frame_weights_sum"] > 0.5).sum()) >= 30
+    np.testing.assert_allclose(fr["weights_sum"], z["frame_weights_sum"][:, 0], atol=2e-4)
+    np.testing.assert_allclose(fr["depth"], z["frame_depth"][:, 0], atol=1e-3)
+    e = np.abs(fr["image"] - z["frame_image"]).max(-1)
+    assert float(e.max()) <= 3e-4 and float(np.median(e)) <= 2e-5, (float(e.max()), float(np.median(e)))
+    ws = z["frame_weights_sum"]
+    n_ref = (z["frame_normal_image"] - (1 - ws)) / np.maximum(ws, 1e-6)                       # undo renderer.py:529-530
+    hit = ws[:, 0] > 0.5
+    assert float(np.abs(fr["normal_image"][hit] - n_ref[hit]).max()) <= 2e-3
