@@ -466,20 +466,6 @@ def run_multi(args, fp_cpu, bf, dev, world, rank, local):
         ach = flop_step / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
         sw_ms = c5["sweep_ms_total"] / c5["sweep_steps"]
         R = c5["sweep_rotations"]
-        c5 = None
-        if not args.no_sweep and indir and tcp:
-            try:
-                n5 = max(2, args.steps // 2)
-                r5 = config5(args, fp, bft, dev, 1, 0, n5, flush, e2e=False)
-                N5 = r5["rays_per_frame"]
-                c5 = {"frame": {"rays_per_sec": N5 / (r5["frame_ms_total"] / n5 * 1e-3), "ms_per_frame": r5["frame_ms_total"] / n5},
-                      "sweep": {"rays_per_sec": r5["sweep_rotations"] * N5 / (r5["sweep_ms_total"] / r5["sweep_steps"] * 1e-3),
-                                "ms_per_rotation": r5["sweep_ms_total"] / r5["sweep_steps"] / r5["sweep_rotations"], "rotations": r5["sweep_rotations"]},
-                      "width": r5["width"], "samples": [s["samples"] for s in r5["stats"]],
-                      "what": "BASELINE config 5 on ONE GPU (the workload bench.py --gpus N > 1 shards): frame = full three-pass 1600x1600 frame per "
-                              "light rotation; sweep = rotation-independent passes shared between the rotations (render.prepare_sweep)"}
-            except Exception as e:
-                c5 = {"error": repr(e)[:300]}
         line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (env_net: fp16 hi+lo split operands on tensor cores, fp32 accumulate)", "data": "synthetic",
@@ -505,6 +491,131 @@ def run_multi(args, fp_cpu, bf, dev, world, rank, local):
                                    "what": f"weak form (round 1): one {W8}x{W8} frame of the sweep per rank + all-gather of the {world} frames"}}
         print(json.dumps(line))
     dist.destroy_process_group()
+
+
+def run_neus(args):
+    """BASELINE config 4 (--config neus): 800x800 inference of the NeuS-style field (frequency encoding, 8 x 256 weight-normed Softplus
+    layers with a skip connection, NeuS opacity, input_alpha compositing; no hash grid) through envidr_b200.neus_field.render_rays_neus.
+    Same JSON contract; the dominant kernel is k_linear_tc (the dense layers of the geometry network, forward + reverse pass)."""
+    import contextlib
+    import numpy as np
+    import torch
+    from envidr_b200 import _lib, scene
+    from envidr_b200 import neus_field as NF
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    W = H = args.width
+    N = W * H
+    nf_cpu = scene.make_neus_field(0)
+    nf = nf_cpu.to(dev).pack()
+    bf = scene.make_sphere_bitfield()
+    bft = torch.from_numpy(bf).to(dev)
+    ro, rd = scene.camera_rays(W, H)
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+    ro_h, rd_h = ro.pin_memory(), rd.pin_memory()
+    img_h = torch.empty(N, 3).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.lib()
+    st = {}
+
+    def step(i, stats=None):
+        return NF.render_rays_neus(nf, bft, ro_d, rd_d, bg_color=1.0, stats=stats)
+
+    def step_e2e(i):
+        out = NF.render_rays_neus(nf, bft, ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True), bg_color=1.0)
+        img_h.copy_(out["image"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for i in range(max(3, args.warmup)):
+        out = step(i, st)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    time.sleep(0.5)
+    NF.LINEAR_TIMING = []
+    l0 = lib.envidr_launch_count()
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    launches = int(lib.envidr_launch_count() - l0)
+    kt = sum(a.elapsed_time(b) for a, b, _ in NF.LINEAR_TIMING) / args.steps
+    kflop = sum(f for _, _, f in NF.LINEAR_TIMING) / args.steps
+    klaunch = len(NF.LINEAR_TIMING) / args.steps
+    NF.LINEAR_TIMING = None
+    t0 = time.time()
+    ms = _timed_region(step, args.steps, 1, dev, flush) / args.steps
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    e2e_ms = _timed_region(step_e2e, args.steps, 1, dev, flush) / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = kflop / (kt * 1e-3) / 1e12 if kt > 0 else 0.0
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import neus_oracle as NO
+        torch.set_num_threads(os.cpu_count() or 1)
+        n = max(256, args.cpu_sample // 8)
+        sel = np.arange(0, N, max(1, N // n))[:n]
+        ost = {}
+        t = time.perf_counter()
+        NO.render_rays(scene.neus_to_oracle(nf_cpu), ro.numpy()[sel], rd.numpy()[sel], bf, bg_color=1.0, dtype=torch.float32, stats=ost)
+        dt = time.perf_counter() - t
+        cpu = {"value": len(sel) / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{len(sel)} rays (stride sample of the {W}x{H} frame, {ost['samples']} samples) in {dt:.1f} s; oracle/neus_oracle.py "
+                         "(C march / composite + torch-CPU fp32 MLPs with autograd normals, all host threads)"}
+    gref = None
+    if not args.no_gpu_reference:
+        try:
+            from oracle import ref_model as RM
+            if RM.available():
+                with contextlib.redirect_stdout(sys.stderr):
+                    RM.install_shims()
+                    model, opt = RM.build_model(["--use_neus_sdf", "--encoding_pos", "frequency", "--multires", "6", "--geometric_init", "--num_layers", "8",
+                                                 "--hidden_dim", "256", "--skip_layers", "4", "--init_variance", "0.6", "--geo_init_bias", "0.5"], cuda_ray=True)
+                    with torch.no_grad():
+                        for lin, (Wt, b) in zip(model.sdf_net, nf_cpu.sdf):
+                            lin.weight_v.copy_(Wt); lin.weight_g.copy_(Wt.norm(dim=1, keepdim=True)); lin.bias.copy_(b)
+                        for name in ("env", "diffuse", "color", "renv"):
+                            for lin, (Wt, b) in zip(getattr(model, name + "_net"), getattr(nf_cpu.shading, name)):
+                                lin.weight.copy_(Wt); lin.bias.copy_(b)
+                        model.density_bitfield.copy_(torch.from_numpy(bf))
+                    model.to(dev).eval()
+                    RM.use_backends("reference")
+                    opt.indir_ref = False
+                    kw = RM.eval_kwargs(opt)
+                    fn = lambda: model.render(ro_d[None], rd_d[None], **kw)
+                    fn()
+                    torch.cuda.synchronize()
+                    t, o = _timed_frames(fn, 2)
+                e = (o["image"].reshape(N, 3) - out["image"]).abs().max(-1).values
+                gref = {"value": N / (t * 1e-3), "unit": "rays/s", "ms_per_frame": t, "speedup_ours_over_gpu_reference": (N / (ms * 1e-3)) / (N / (t * 1e-3)),
+                        "rgb_linf_max_vs_ours": float(e.max()), "pixels_over_1e-4": int((e > 1e-4).sum()),
+                        "what": "the reference's own NeRFNetwork (use_neus_sdf, frequency, geometric_init, 8 x 256, skip [4]) / NeRFRenderer.render / run_cuda on "
+                                "its own kernels, same weights, same frame"}
+        except Exception as e:
+            gref = {"error": repr(e)[:300]}
+    line = {"metric": "rays_per_sec", "value": N / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (dense layers: fp16 hi+lo split operands on tensor cores, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: NeuS-style geometry without hash grid, {W}x{H} inference, single pass (materials.ini + use_neus_sdf, "
+                                   "encoding_pos=frequency multires 6, geometric_init, 8 x 256 layers, skip_layers [4]; definition: SURVEY.md 8d)",
+                       "scene": "geometric-init sphere SDF (radius 0.37-0.48), variance 0.6 (inv_s = 403), seeded rendering MLPs (env 256 / IDE degree 5)",
+                       "rays_per_step_per_gpu": N, "schedule": "the reference's iterative schedule (n_step = N // n_alive <= 8), geometry + opacity per iteration, "
+                                                                "deferred shading over the composited samples",
+                       "cache": "L2 flushed between timed steps by writing a 256 MB buffer"},
+            "samples_per_step_per_gpu": st.get("samples"), "march_iterations_per_step": st.get("iterations"), "shaded_samples_per_step": st.get("shaded"),
+            "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "k_linear_tc (dense layers of the geometry network, forward + reverse pass; fp16 hi/lo split, 3 MMAs per K step)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "kernel_ms_per_step": kt, "kernel_launches_per_step": klaunch, "kernel_share_of_step": kt / ms, "algorithmic_flop_per_step": kflop,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
+                         "note": "each launch timed with its own CUDA event pair in a separate untimed pass (events perturb the step)"},
+            "cpu_baseline": cpu, "clocks": clocks, "gpu_reference": gref}
+    print(json.dumps(line))
 
 
 def run_reference(args):
@@ -548,6 +659,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "neus":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_neus(args)
+        return
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -753,6 +868,39 @@ def main():
                                 "reference = its own kernels + torch ops + mean().item() (oracle/ref_cuda.update_extra_state)")
             except Exception as e:                      # auxiliary: never take the headline line down with it
                 dens = {"error": repr(e)[:200]}
+        poses = None
+        try:
+            if args.no_sweep:
+                raise RuntimeError("skipped (--no-sweep)"): 8 camera poses theta = 0, 45, ..., 315 (the headline is theta = 40)
+            from envidr_b200 import scene as _scene
+            per = {}
+            for th in range(0, 360, 45):
+                o8, d8 = _scene.camera_rays(W, H, theta_deg=float(th))
+                o8, d8 = o8.to(dev), d8.to(dev)
+                fn8 = lambda i: render.render(fp, bft, o8, d8, cfg, bg_color=1.0, get_normal_image=True)
+                fn8(0)
+                st8 = []
+                render.render(fp, bft, o8, d8, cfg, bg_color=1.0, stats=st8)
+                per[str(th)] = {"ms_per_frame": _timed_region(fn8, 3, 1, dev, flush) / 3, "samples": sum(s["samples"] for s in st8)}
+            v = [N / (p["ms_per_frame"] * 1e-3) for p in per.values()]
+            poses = {"rays_per_sec_mean": sum(v) / len(v), "rays_per_sec_min": min(v), "rays_per_sec_max": max(v), "per_theta_deg": per,
+                     "what": "the same frame from the 8 camera poses of SURVEY 8d (theta = 0..315 step 45, phi = -30, radius 4), 3 timed frames each"}
+        except Exception as e:
+            poses = {"error": repr(e)[:200]}
+        c5 = None
+        if not args.no_sweep and indir and tcp:
+            try:
+                n5 = max(2, args.steps // 2)
+                r5 = config5(args, fp, bft, dev, 1, 0, n5, flush, e2e=False)
+                N5 = r5["rays_per_frame"]
+                c5 = {"frame": {"rays_per_sec": N5 / (r5["frame_ms_total"] / n5 * 1e-3), "ms_per_frame": r5["frame_ms_total"] / n5},
+                      "sweep": {"rays_per_sec": r5["sweep_rotations"] * N5 / (r5["sweep_ms_total"] / r5["sweep_steps"] * 1e-3),
+                                "ms_per_rotation": r5["sweep_ms_total"] / r5["sweep_steps"] / r5["sweep_rotations"], "rotations": r5["sweep_rotations"]},
+                      "width": r5["width"], "samples": [s["samples"] for s in r5["stats"]],
+                      "what": "BASELINE config 5 on ONE GPU (the workload bench.py --gpus N > 1 shards): frame = full three-pass 1600x1600 frame per "
+                              "light rotation; sweep = rotation-independent passes shared between the rotations (render.prepare_sweep)"}
+            except Exception as e:
+                c5 = {"error": repr(e)[:300]}
         line = {"metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "warmup_extra_steps": warm_extra, "ms_each_step": [round(x, 3) for x in step_ms],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -762,7 +910,7 @@ def main():
                 "march_iterations_per_step": iters_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens, "config5": c5}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "train_step": trn, "gpu_reference": gref, "density_update": dens, "config5": c5, "poses": poses}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -29,9 +29,22 @@ import torch
 from . import _lib
 from ._lib import check, lib, ptr, stream
 from .field import FieldParams, rot_theta3
-from .linear_tc import _image, _run
+from .linear_tc import _image
+from .linear_tc import _run as _linear_run
 
 SQRT3 = 3 ** 0.5
+LINEAR_TIMING: Optional[list] = None      # bench.py: when a list, every dense-layer launch appends (start event, end event, flop)
+
+
+def _run(x, img, bias, N, relu):
+    if LINEAR_TIMING is None:
+        return _linear_run(x, img, bias, N, relu)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    y = _linear_run(x, img, bias, N, relu)
+    b.record()
+    LINEAR_TIMING.append((a, b, 2.0 * x.shape[0] * x.shape[1] * N))
+    return y
 
 
 def fold_weight_norm(lin) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -68,6 +81,12 @@ class NeusField:
     @property
     def in_dim(self) -> int:
         return 3 + 2 * 3 * self.multires
+
+    def to(self, device) -> "NeusField":
+        mv = lambda t: None if t is None else t.detach().to(device=device, dtype=torch.float32).contiguous()
+        sh = self.shading.to(device)
+        sh.precision = "tc"
+        return dataclasses.replace(self, sdf=[(mv(W), mv(b)) for W, b in self.sdf], variance=mv(self.variance), shading=sh, _img=None, _imgT=None)
 
     def pack(self) -> "NeusField":
         self._img = [_image(W) for W, _ in self.sdf]

@@ -591,8 +591,29 @@ def run_cuda(model, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, fo
     """Replacement for nerf.render_func.run_cuda.  The inference branch (cuda_ray.py:238-359) runs in the fused
     loop; training / debug / ray_depth / background-sphere calls are forwarded to the reference implementation
     (which then reaches our kernels through the operator-level `_backend` modules)."""
-    fused_ok = (not model.training and not model.opt.debug and ray_depth is None and not (model.bg_radius > 0 and bg_sphere)
-                and not model.opt.use_neus_sdf)
+    fused_ok = not model.training and not model.opt.debug and ray_depth is None and not (model.bg_radius > 0 and bg_sphere)
+    if fused_ok and model.opt.use_neus_sdf:
+        # BASELINE config 4 family (NeuS geometry, frequency encoding): envidr_b200.neus_field; other NeuS variants -> reference code
+        from .neus_field import NeusField, render_rays_neus
+        try:
+            nf = NeusField.from_reference_model(model)
+        except _lib.EnvidrError:
+            nf = None
+        if nf is not None and not perturb:
+            prefix = rays_o.shape[:-1]
+            res = render_rays_neus(nf, model.density_bitfield, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), bound=float(model.bound),
+                                   cascade=int(model.cascade), grid_size=int(model.grid_size), min_near=float(model.min_near), dt_gamma=float(dt_gamma),
+                                   max_steps=int(max_steps), T_thresh=float(T_thresh), bg_color=1.0 if bg_color is None else bg_color,
+                                   aabb=[float(v) for v in model.aabb_infer.tolist()], env_rot_radian=env_rot_radian,
+                                   r_images=None if r_images is None else r_images.reshape(-1, 4), geometry_only=geometry_only,
+                                   visual_items=tuple(model.opt.visual_items) if model.opt.use_diffuse else ())
+            results = {"depth": res["depth"].view(*prefix), "weights_sum": res["weights_sum"].view(*prefix),
+                       "image": None if geometry_only else res["image"].view(*prefix, 3), "normal_image": res["normal_image"].view(*prefix, 3)}
+            for k in ("diffuse_image", "specular_image", "roughness_image"):
+                if k in res:
+                    results[k] = res[k]
+            return results
+        fused_ok = False
     if not fused_ok:
         if _reference_run_cuda is None:
             raise _lib.EnvidrError("run_cuda: this call needs the reference training branch; call install() first")

@@ -25,14 +25,14 @@ fi
 if [[ "$WHAT" == *" launches "* ]]; then
   # launch list of the whole run (8 frames of ~210 launches); the summary keeps the whole frames between the first two L2 flushes
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
-      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-extra-warmup > $OUT/${TAG}_launches.log 2>&1
+      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-sweep --no-extra-warmup > $OUT/${TAG}_launches.log 2>&1
   python profiles/summarize_launches.py $OUT/${TAG}_launches.csv --frames > $OUT/${TAG}_launches.md 2>&1
   cat $OUT/${TAG}_launches.md
 fi
 if [[ "$WHAT" == *" full "* ]]; then
   for K in k_env_tc k_geom_tc k_shade_tc k_march_compact; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 140 --launch-count 1 -f \
-        -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-extra-warmup > $OUT/${TAG}_full_$K.log 2>&1
+        -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-sweep --no-extra-warmup > $OUT/${TAG}_full_$K.log 2>&1
     echo "ncu full $K exit $?"
   done
 fi
