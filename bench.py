@@ -869,9 +869,9 @@ def main():
             except Exception as e:                      # auxiliary: never take the headline line down with it
                 dens = {"error": repr(e)[:200]}
         poses = None
-        try:
+        try:                                              # 8 camera poses theta = 0, 45, ..., 315 (the headline is theta = 40)
             if args.no_sweep:
-                raise RuntimeError("skipped (--no-sweep)"): 8 camera poses theta = 0, 45, ..., 315 (the headline is theta = 40)
+                raise RuntimeError("skipped (--no-sweep)")
             from envidr_b200 import scene as _scene
             per = {}
             for th in range(0, 360, 45):
