@@ -169,11 +169,14 @@ class TrainableField(nn.Module):
         lis = c["light_intensity_scale"]
         w_r_enc = ops.ide_encode(w_r, roughness, deg) * lis
         n_enc = ops.ide_encode(normals, c["diffuse_kappa_inv"], deg) * lis
-        f_n = F.normalize(self.mlp("env", n_enc), dim=-1)
+        # env_net sees both direction sets in ONE batch (rows [0, M) = normal, [M, 2M) = reflected): half the layer launches of the
+        # reference's two calls (network.py:527-541, 589-607), twice the rows per weight-gradient GEMM; same per-row arithmetic
+        M = n_enc.shape[0]
+        f_both = F.normalize(self.mlp("env", torch.cat([n_enc, w_r_enc], 0)), dim=-1)
+        f_n, f_r = f_both[:M], f_both[M:]
         c_d = torch.sigmoid(self.mlp("diffuse", torch.cat([geo, f_n], -1)))
-        f_r = F.normalize(self.mlp("env", w_r_enc), dim=-1)
         hh = torch.cat([geo, normals], -1)
-        c_s = torch.sigmoid(self.mlp("color", torch.cat([hh, f_r, n_dot], -1)))
+        x_s = torch.cat([hh, f_r, n_dot], -1)
         if r_images is not None and self.n_layers["renv"]:                                    # network.py:612-659, 682-690
             mask = roughness.squeeze(-1) < c["indir_roughness_thresh"]
             ri = r_images
@@ -184,8 +187,12 @@ class TrainableField(nn.Module):
             rr = torch.sqrt(roughness / c["roughness_scale"] / 0.75)
             bw = 0.98 * blend if c["learn_indir_blend"] else 0.95 * torch.sigmoid(80 * (rr - 0.18))
             f_e = F.normalize(self.mlp("renv", torch.cat([ri, rr], -1)), dim=-1)
-            c_e = torch.sigmoid(self.mlp("color", torch.cat([hh, f_e, n_dot], -1)))
+            # the two colour evaluations (reflected-light feature, inter-reflection feature) as one batch of 2M rows
+            c_both = torch.sigmoid(self.mlp("color", torch.cat([x_s, torch.cat([hh, f_e, n_dot], -1)], 0)))
+            c_s, c_e = c_both[:M], c_both[M:]
             c_s = torch.where(mask[:, None], c_s * bw + c_e * (1 - bw), c_s)
+        else:
+            c_s = torch.sigmoid(self.mlp("color", x_s))
         return (c_d + c_s) * c["intensity_scale"]
 
 

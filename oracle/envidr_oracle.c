@@ -10,7 +10,7 @@
  * reference checkout).  Parity status: the reference ships no tests or golden
  * vectors for these kernels, so the oracle is pinned against the
  * reference kernels themselves, rebuilt unmodified for sm_100a into oracle/_ref/
- * (oracle/build_ref.py) and compared on the GPU box by tests/test_oracle_vs_ref.py.
+ * (oracle/build_ref.py) and compared on the GPU box by tests/test_oracle_c.py / tests/test_gpu_ops.py.
  *
  * Floating-point contract.  nvcc contracts a*b+c into one FMA (--fmad=true); gcc is
  * run with -ffp-contract=off and the contractions nvcc performs on the march path
