@@ -389,6 +389,52 @@ def config5(args, fp, bft, dev, world, rank, steps, flush, e2e=True):
     return res
 
 
+def dp_train_bench(fp_cpu, bf, dev, world, rank, n_rays, steps):
+    """Data-parallel training (optional): the 4,096-ray batch of BASELINE config 3 split over the ranks, every rank replays its
+    captured forward + loss + backward on its share, ONE all-reduce over the flat gradient buffer of the replicated state (48.8 MB hash
+    table + MLPs; envidr_b200.dist.allreduce_gradients), then the fused Adam step on every rank.  Time = max over ranks."""
+    import torch
+    from envidr_b200 import render, scene, train
+    from envidr_b200 import dist as edist
+    from envidr_b200.optim import FusedAdam
+    n_local = n_rays // world
+    ro, rd = scene.camera_rays(800, 800)
+    g = torch.Generator().manual_seed(0)
+    sel = torch.randperm(ro.shape[0], generator=g)[:n_rays][rank * n_local:(rank + 1) * n_local]
+    o, d = ro[sel].to(dev), rd[sel].to(dev)
+    gt_rgb = torch.rand(n_rays, 3, generator=g)[rank * n_local:(rank + 1) * n_local].to(dev)
+    gt_mask = (torch.rand(n_rays, generator=g) > 0.5).float()[rank * n_local:(rank + 1) * n_local].to(dev)
+    r_img = torch.rand(n_rays, 4, generator=g)[rank * n_local:(rank + 1) * n_local].to(dev)
+    field = train.TrainableField(fp_cpu.to(dev))
+    bft = torch.from_numpy(bf).to(dev)
+    cfg = render.RenderConfig()
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    out = train.render_train(field, bft, o, d, cfg, r_images=r_img, perturb=True, force_all_rays=True, mean_count=-1, step_counter=counter)
+    torch.cuda.synchronize()
+    mean_count = int(out["xyzs"].shape[0]) - 128 + 2048              # head-room: the per-rank sample count varies with the noise
+    del out
+    graphed = train.GraphedTrainStep(field, bft, cfg, n_local, mean_count)
+    params = [p for p in field.parameters() if p.requires_grad]
+    opt = FusedAdam(params, lr=1e-4, betas=(0.9, 0.99), eps=1e-15)
+
+    def local_only(i):
+        graphed(o, d, gt_rgb, gt_mask, r_img)
+
+    def full(i):
+        graphed(o, d, gt_rgb, gt_mask, r_img)
+        edist.allreduce_gradients(params)
+        opt.step()
+    for i in range(3):
+        full(i)
+    ms_local = _timed_region(local_only, steps, world, dev) / steps
+    ms_full = _timed_region(full, steps, world, dev) / steps
+    nbytes = sum(p.numel() for p in params) * 4
+    return {"rays_global": n_local * world, "rays_per_rank": n_local, "ms_per_step_fwd_bwd": ms_local, "ms_per_step_with_allreduce_and_adam": ms_full,
+            "rays_per_sec": n_local * world / (ms_full * 1e-3), "allreduce_bytes": nbytes,
+            "what": "config-3 train step, batch split over the ranks; graph replay of forward + loss + backward, one NCCL all-reduce of the flat "
+                    "gradient buffer, fused Adam; max over ranks"}
+
+
 def run_multi(args, fp_cpu, bf, dev, world, rank, local):
     """N > 1: the timed step is one full 1600x1600 three-pass frame of the relight sweep (BASELINE config 5), its rays sharded over the N
     ranks; `value` = rays of the frame / time (max over ranks) -- strong scaling: the frame is the same whatever N is.  Extra keys:
@@ -448,6 +494,12 @@ def run_multi(args, fp_cpu, bf, dev, world, rank, local):
     for i in range(3):
         replica(i)
     rep_ms = _timed_region(replica, steps, world, dev, flush) / steps
+    dp = None
+    if not args.no_train:
+        try:
+            dp = dp_train_bench(fp_cpu, bf, dev, world, rank, args.train_rays, steps)
+        except Exception as e:
+            dp = {"error": repr(e)[:300]}
     if rank == 0:
         N5 = c5["rays_per_frame"]
         ms = c5["frame_ms_total"] / steps
@@ -487,6 +539,7 @@ def run_multi(args, fp_cpu, bf, dev, world, rank, local):
                 "config5_sweep": {"rays_per_sec": R * N5 / (sw_ms * 1e-3), "ms_per_sweep": sw_ms, "rotations": R, "ms_per_rotation": sw_ms / R,
                                   "what": "geometry pass + reflected-ray geometry once per camera, every rotation only shades (render.prepare_sweep / "
                                           "render_sweep_frame); sharded like the frames, one all-gather per rotation"},
+                "dp_train_step": dp,
                 "replica_frames": {"rays_per_sec": world * W8 * W8 / (rep_ms * 1e-3), "ms_per_step": rep_ms,
                                    "what": f"weak form (round 1): one {W8}x{W8} frame of the sweep per rank + all-gather of the {world} frames"}}
         print(json.dumps(line))
