@@ -662,7 +662,9 @@ def run_neus(args):
             "samples_per_step_per_gpu": st.get("samples"), "march_iterations_per_step": st.get("iterations"), "shaded_samples_per_step": st.get("shaded"),
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12, "ms_per_step": e2e_ms},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "k_linear_tc (dense layers of the geometry network, forward + reverse pass; fp16 hi/lo split, 3 MMAs per K step)",
+            "roofline": {"bound": "tensor", "kernel": ("k_neus_geom_tc (the whole geometry network per 128-sample tile: 8 forward + 7 reverse GEMMs, Softplus, skip, "
+                                                     "frequency encoding and its transpose-Jacobian; fp16 hi/lo split, 3 MMAs per K step)") if nf.fused and nf.fused_supported()
+                         else "k_linear_tc (dense layers of the geometry network, one launch per layer and direction)",
                          "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                          "kernel_ms_per_step": kt, "kernel_launches_per_step": klaunch, "kernel_share_of_step": kt / ms, "algorithmic_flop_per_step": kflop,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",

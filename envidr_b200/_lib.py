@@ -41,6 +41,15 @@ class Field(ctypes.Structure):
     ]
 
 
+class NeusLayer(ctypes.Structure):
+    _fields_ = [("img", ctypes.c_void_p), ("imgT", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("in_dim", ctypes.c_uint32), ("out_dim", ctypes.c_uint32)]
+
+
+class NeusNet(ctypes.Structure):
+    _fields_ = [("layers", NeusLayer * 8), ("head_row", ctypes.c_void_p), ("n_layers", ctypes.c_uint32), ("skip_layer", ctypes.c_int32),
+                ("multires", ctypes.c_uint32), ("beta", ctypes.c_float)]
+
+
 class FieldOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("sigma", "rgb", "normal", "sdf", "c_diffuse", "c_specular", "roughness", "grad_x")]
 

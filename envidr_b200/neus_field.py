@@ -73,6 +73,9 @@ class NeusField:
     beta_act: float = 100.0
     _img: Optional[list] = None
     _imgT: Optional[list] = None
+    _scratch: Optional[torch.Tensor] = None
+    _head_row: Optional[torch.Tensor] = None
+    fused: bool = True           # one kernel for the whole geometry network (csrc/neus_geom_tc.cu); False: the composed chain of dense-layer launches
 
     @property
     def device(self):
@@ -91,8 +94,54 @@ class NeusField:
     def pack(self) -> "NeusField":
         self._img = [_image(W) for W, _ in self.sdf]
         self._imgT = [_image(W.t().contiguous()) for W, _ in self.sdf]
+        self._head_row = self.sdf[-1][0][0].contiguous()
         self.shading.pack()
         return self
+
+    def fused_supported(self) -> bool:
+        """Shapes the fused kernel takes (include/envidr_b200.h, envidr_neus_geometry); anything else runs the composed chain."""
+        r16 = lambda v: (v + 15) // 16 * 16
+        nl = len(self.sdf)
+        if not (2 <= nl <= 8 and 1 <= self.multires <= 7 and len(self.skip_layers) <= 1 and all(b is not None for _, b in self.sdf)):
+            return False
+        if self.skip_layers and not (1 <= self.skip_layers[0] < nl - 1):
+            return False
+        if self.sdf[-1][0].shape[0] > 16:
+            return False
+        for l, (W, _) in enumerate(self.sdf):
+            n, k = W.shape
+            if n > 256 or k > 256 or (l + 1 < nl and r16(n) % 32) or (l > 0 and r16(k) % 32):
+                return False
+        return True
+
+    def _geometry_fused(self, xyzs: torch.Tensor):
+        """-> head [M,16], grad_x [M,3] through envidr_neus_geometry."""
+        M, dev = xyzs.shape[0], xyzs.device
+        L = lib()
+        nl = len(self.sdf)
+        need = int(L.envidr_neus_geometry_scratch_bytes(nl))
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+        net = _lib.NeusNet()
+        for l, (W, b) in enumerate(self.sdf):
+            net.layers[l].img, net.layers[l].imgT, net.layers[l].bias = self._img[l].data_ptr(), self._imgT[l].data_ptr(), b.data_ptr()
+            net.layers[l].in_dim, net.layers[l].out_dim = int(W.shape[1]), int(W.shape[0])
+        net.head_row, net.n_layers = self._head_row.data_ptr(), nl
+        net.skip_layer = int(self.skip_layers[0]) if self.skip_layers else -1
+        net.multires, net.beta = int(self.multires), float(self.beta_act)
+        head = torch.empty(M, 16, dtype=torch.float32, device=dev)
+        grad_x = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        ev = None
+        if LINEAR_TIMING is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        check(L.envidr_neus_geometry(ctypes.byref(net), ptr(xyzs), M, ptr(head), ptr(grad_x), ptr(self._scratch), self._scratch.numel(), stream()),
+              "neus_geometry")
+        if ev is not None:
+            ev[1].record()
+            flop = sum(2.0 * W.shape[0] * W.shape[1] for W, _ in self.sdf) + sum(2.0 * W.shape[0] * W.shape[1] for W, _ in self.sdf[:-1])
+            LINEAR_TIMING.append((ev[0], ev[1], flop * M))
+        return head, grad_x
 
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -150,6 +199,9 @@ class NeusField:
         M, dev = xyzs.shape[0], xyzs.device
         f32 = dict(dtype=torch.float32, device=dev)
         L = lib()
+        if self.fused and M > 0 and self.fused_supported():
+            head, grad_x = self._geometry_fused(xyzs)
+            return self._finish_geometry(head, grad_x, dirs, dists, env_rot_radian, want_rec)
         C = self.in_dim
         enc = torch.empty(M, C, **f32)
         check(L.envidr_freq_encode_forward(ptr(xyzs), M, 3, self.multires, C, ptr(enc), stream()), "freq_encode_forward")
@@ -197,6 +249,13 @@ class NeusField:
             g = g + g_enc_skip
         grad_x = torch.empty(M, 3, **f32)
         check(L.envidr_freq_encode_backward(ptr(g.contiguous()), ptr(enc), M, 3, self.multires, C, ptr(grad_x), stream()), "freq_encode_backward")
+        return self._finish_geometry(head, grad_x, dirs, dists, env_rot_radian, want_rec)
+
+    def _finish_geometry(self, head, grad_x, dirs, dists, env_rot_radian, want_rec) -> Dict[str, torch.Tensor]:
+        """Head + gradient -> unit normal, roughness, geometry record, NeuS opacity."""
+        M, dev = head.shape[0], head.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        L = lib()
         sh = self.shading
         out = dict(sdf=torch.empty(M, **f32), normal=torch.empty(M, 3, **f32), roughness=torch.empty(M, **f32), grad_x=grad_x)
         rec = torch.empty(M, 32, **f32) if want_rec else None

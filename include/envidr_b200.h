@@ -378,6 +378,29 @@ int envidr_neus_alpha_backward(const float* grad_alpha, const float* sdf, const 
  * operator boundary here (nn.Linear + Softplus(beta=100) + torch.cat + autograd.grad driven from Python);
  * envidr_b200/neus_field.py drives the chain.
  * ---------------------------------------------------------------------------------------------- */
+/* The whole geometry network in ONE kernel per batch (csrc/neus_geom_tc.cu): frequency encoding -> the dense layers with Softplus(beta)
+ * and an optional skip concat -> head [M,16] (row of the last layer: sdf, geo_feat, roughness, blend, zero padded) and the reverse pass
+ * through the same layers -> grad_x [M,3] = d sdf / d xyz.  img / imgT: envidr_linear_tc_pack images of W [out,in] and of W^T [in,out]
+ * (weight norm folded by the caller); hidden widths must pad (to 16) to multiples of 32, <= 256; multires <= 7; one skip layer at most.
+ * scratch: envidr_neus_geometry_scratch_bytes(n_layers) (the softplus derivatives of one tile per SM, reused by every call). */
+#define ENVIDR_NEUS_MAX_LAYERS 8
+typedef struct envidr_neus_layer {
+    const void* img;        /* image of W  [out_dim, in_dim]                         */
+    const void* imgT;       /* image of W^T [in_dim, out_dim] (reverse pass)          */
+    const float* bias;      /* [out_dim]                                              */
+    uint32_t in_dim, out_dim;
+} envidr_neus_layer;
+typedef struct envidr_neus_net {
+    envidr_neus_layer layers[ENVIDR_NEUS_MAX_LAYERS];
+    const float* head_row;  /* W_last[0, :] (device, in_dim of the last layer floats) */
+    uint32_t n_layers;
+    int32_t skip_layer;     /* opt.skip_layers[0], or -1                              */
+    uint32_t multires;      /* FreqEncoder degree                                     */
+    float beta;             /* Softplus beta (100)                                    */
+} envidr_neus_net;
+uint64_t envidr_neus_geometry_scratch_bytes(uint32_t n_layers);
+int envidr_neus_geometry(const envidr_neus_net* net, const float* xyzs, uint32_t M, float* head, float* grad_x, void* scratch,
+                         uint64_t scratch_bytes, envidr_stream_t stream);
 /* h = Softplus(beta, threshold 20)(z) and, when dh != NULL, dh = sigmoid(beta z) (its derivative); n elements; h may alias z. */
 int envidr_softplus_forward(const float* z, uint64_t n, float beta, float* h, float* dh, envidr_stream_t stream);
 /* out [M,N] = a [M,N] * b [M,N], or a_row [N] (broadcast over rows, a == NULL) * b.  The reverse pass g <- g . softplus'. */

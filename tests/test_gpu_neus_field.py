@@ -143,3 +143,26 @@ def test_real_reference_neus_model_on_its_own_kernels_vs_this_library(dev):
     n_t = truth["normal_image"].reshape(-1, 3)
     n_o = res["normal_image"] * res["weights_sum"][:, None] + (1 - res["weights_sum"][:, None])       # renderer.py:529-530
     assert float((n_o - n_t).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("M", [77, 128 * 148 * 2 + 5])
+def test_fused_geometry_kernel_equals_the_composed_chain(dev, M):
+    """csrc/neus_geom_tc.cu (the whole geometry network, forward + reverse pass, in one kernel) against the chain of dense-layer launches
+    + glue kernels (same tensor-core arithmetic per layer): head and d sdf / d x to rounding; ragged and multi-tile-per-SM batches."""
+    from envidr_b200 import scene
+    nf = _to(scene.make_neus_field(0, hidden_dim_env=64, ide_degree=4), dev)
+    assert nf.fused_supported()
+    rng = np.random.default_rng(M)
+    u = rng.standard_normal((M, 3)); u /= np.linalg.norm(u, axis=-1, keepdims=True)
+    x = torch.from_numpy((u * rng.uniform(0.05, 0.9, (M, 1))).astype(np.float32)).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
+    nf.fused = True
+    a = nf.geometry(x, d)
+    nf.fused = False
+    b = nf.geometry(x, d)
+    assert float((a["sdf"] - b["sdf"]).abs().max()) <= 2e-6
+    assert float((a["grad_x"] - b["grad_x"]).abs().max()) <= 2e-5
+    assert float((a["normal"] - b["normal"]).abs().max()) <= 2e-5
+    assert float((a["roughness"] - b["roughness"]).abs().max()) <= 2e-6
+    assert float((a["rec"] - b["rec"]).abs().max()) <= 2e-5
+    assert float((a["sigma"] - b["sigma"]).abs().max()) <= 2e-3              # inv_s = 403 on a 2e-6 sdf difference
