@@ -656,8 +656,8 @@ def run_neus(args):
             "config": {"workload": f"BASELINE config 4: NeuS-style geometry without hash grid, {W}x{H} inference, single pass (materials.ini + use_neus_sdf, "
                                    "encoding_pos=frequency multires 6, geometric_init, 8 x 256 layers, skip_layers [4]; definition: SURVEY.md 8d)",
                        "scene": "geometric-init sphere SDF (radius 0.37-0.48), variance 0.6 (inv_s = 403), seeded rendering MLPs (env 256 / IDE degree 5)",
-                       "rays_per_step_per_gpu": N, "schedule": "the reference's iterative schedule (n_step = N // n_alive <= 8), geometry + opacity per iteration, "
-                                                                "deferred shading over the composited samples",
+                       "rays_per_step_per_gpu": N, "schedule": "the reference's iterative schedule (n_step = N // n_alive <= 8): per iteration one fused geometry launch, "
+                                                                "opacity, shading and one composite per image",
                        "cache": "L2 flushed between timed steps by writing a 256 MB buffer"},
             "samples_per_step_per_gpu": st.get("samples"), "march_iterations_per_step": st.get("iterations"), "shaded_samples_per_step": st.get("shaded"),
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 2 * N * 12, "d2h_bytes_per_step": N * 12, "ms_per_step": e2e_ms},

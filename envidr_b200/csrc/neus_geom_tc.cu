@@ -13,10 +13,10 @@
 //               4 x 16 KB ring with 1-D bulk copies (k_linear_pack layout: per 16-wide K step [hi | lo], fp16)
 //   warp 1      issuer: tcgen05.mma kind::f16, M = 128, three MMAs per K step (hi*hi + lo*hi + hi*lo, fp32 accumulate), two 256-column
 //               accumulators ping-pong in TMEM so that the epilogue of GEMM i overlaps the MMAs of GEMM i + 1 chunk by chunk
-//   warps 4-11  epilogue: tcgen05.ld -> bias + Softplus and its derivative (forward) or x saved derivative (reverse) -> fp16 hi/lo
+//   warps 4-19  epilogue: tcgen05.ld -> bias + Softplus and its derivative (forward) or x saved derivative (reverse) -> fp16 hi/lo
 //               re-split -> next A operand in shared memory, 32 columns at a time; skip concat / split, head, final transpose-Jacobian
 //               product of the frequency encoding (d sdf / d x)
-//   warps 12-15 frequency encoding of the next tile's layer-0 operand
+//   warps 20-23 frequency encoding of the next tile's layer-0 operand
 // The softplus derivatives s_l = sigmoid(beta z_l) are needed again in the reverse pass: 7 x 128 x 256 fp32 = 896 KB per tile do not
 // fit next to the operands, so each CTA spills them to its own slice of a scratch buffer (L2-resident; every thread reads back
 // exactly what it wrote).  Everything else (activations, operands, gradients) stays in shared / tensor memory.
@@ -26,7 +26,8 @@
 
 namespace envidr {
 
-constexpr int kNgThreads = 16 * 32;
+constexpr int kNgEpiWarps = 16, kNgEpiGroups = kNgEpiWarps / 4;
+constexpr int kNgThreads = (4 + kNgEpiWarps + 4) * 32;       // 4 control warps, 16 epilogue warps, 4 encode warps
 constexpr int kNgStages = 4;
 constexpr uint32_t kNgStageBytes = 16384;
 constexpr uint32_t kNgARegion = 65536;             // 128 rows x 256 K x 2 B
@@ -78,7 +79,7 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
     uint64_t* empty = bars + kNgStages;             // [4]
     uint64_t* acc_ready = bars + 2 * kNgStages;     // [2]
     uint64_t* enc_full = acc_ready + 2;             // encode warps -> issuer (128 arrivals)
-    uint64_t* tile_done = acc_ready + 3;            // epilogue warps -> encode warps (256 arrivals)
+    uint64_t* tile_done = acc_ready + 3;            // epilogue warps -> encode warps (all epilogue threads)
     uint64_t* a_rdy = acc_ready + 4;                // [8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 8);
 
@@ -91,7 +92,7 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
     if (tid == 0) {
         for (int i = 0; i < kNgStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&acc_ready[0], 1); tc::mbar_init(&acc_ready[1], 1);
-        tc::mbar_init(enc_full, 128); tc::mbar_init(tile_done, 256);
+        tc::mbar_init(enc_full, 128); tc::mbar_init(tile_done, kNgEpiWarps * 32);
         for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128);
         tc::mbar_fence_init();
     }
@@ -174,22 +175,28 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
                 tc::mma_commit_w(&acc_ready[buf]);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 4 + kNgEpiWarps) {
         // ===================== epilogue warps =====================
+        // 16 warps = 4 groups x 4 TMEM lane quarters; group g owns the 32-column chunks cb = g (mod 4) and works through each in two
+        // 16-column halves (register budget of a 768-thread CTA).  Measured with 8 warps and 32-column steps (ncu, run 18): the kernel
+        // was bound by these warps' instruction issue (0.94 IPC per SM, the issuer waiting 77 % of its time for A-operand chunks).
         const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_addr = (quarter * 32u) << 16;
         float* S_cta = S + (size_t)blockIdx.x * P.n_slots * 128 * 256;
         const uint32_t in_dim = P.in_dim;
         uint32_t acc_par = 0, gl = 0;
-        auto publish = [&](uint32_t cb, const float (&v)[32]) {
+        const float inv_beta = 1.0f / P.beta;
+        auto store16 = [&](uint32_t c0, const float (&v)[16]) {           // 16 columns of the next A operand, starting at column c0
             #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 2; q++) {
                 float w[8];
                 #pragma unroll
                 for (int j = 0; j < 8; j++) w[j] = v[8 * q + j];
-                tc::store_chunk8(sA_hi, sA_lo, row, cb * 32 + q * 8, w);
+                tc::store_chunk8(sA_hi, sA_lo, row, c0 + q * 8, w);
             }
+        };
+        auto publish = [&](uint32_t cb) {
             tc::tc_fence_before();
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&a_rdy[cb]);
@@ -212,37 +219,51 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
                     const float* bias = s_bias + i * 256;
                     float* Srow = S_cta + ((size_t)L.s_slot * 128 + row) * 256;
                     const uint32_t nmax = max(nin, L.out_chunks);
-                    for (uint32_t cb = g; cb < nmax; cb += 2) {
-                        float v[32];
-                        if (cb < nin) {
-                            uint32_t r[32];
-                            tc::tmem_ld32(acc + cb * 32, r);
-                            tc::tmem_ld_wait();
-                            float sv[32];
-                            #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const float z = __uint_as_float(r[j]) + bias[cb * 32 + j];
-                                const float bz = P.beta * z;
-                                const float e = expf(-fabsf(bz));
-                                const float sp = (bz > 20.0f) ? z : (fmaxf(bz, 0.0f) + log1pf(e)) / P.beta;
-                                sv[j] = (bz >= 0.0f) ? 1.0f / (1.0f + e) : e / (1.0f + e);
-                                v[j] = (cb * 32 + j < L.N) ? sp * L.scale : 0.0f;
+                    const float scale = L.scale;
+                    for (uint32_t cb = g; cb < nmax; cb += kNgEpiGroups) {
+                        #pragma unroll 1
+                        for (uint32_t hf = 0; hf < 2; hf++) {
+                            const uint32_t c0 = cb * 32 + hf * 16;
+                            float v[16];
+                            if (cb < nin) {
+                                uint32_t r[16];
+                                tc::tmem_ld16(acc + c0, r);
+                                tc::tmem_ld_wait();
+                                float sv[16];
+                                // Softplus(beta, threshold 20) and its derivative from ONE exponential: e = exp(-|beta z|) in (0, 1], so
+                                // log(1 + e) needs no log1p (absolute error 6e-8, i.e. 6e-10 after / beta) and the fast intrinsics (MUFU
+                                // ex2 / lg2 / rcp, relative 2^-21) keep h and s within 1e-6 of the libm formulation
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    const float z = __uint_as_float(r[j]) + bias[c0 + j];
+                                    const float bz = P.beta * z;
+                                    const float e = __expf(-fabsf(bz));
+                                    const float rc = __frcp_rn(1.0f + e);
+                                    const float sp = (bz > 20.0f) ? z : (fmaxf(bz, 0.0f) + __logf(1.0f + e)) * inv_beta;
+                                    sv[j] = (bz >= 0.0f) ? rc : e * rc;
+                                    v[j] = sp * scale;
+                                }
+                                if (c0 + 16 > L.N) {                     // padded columns of the operand are zero (or the encoding, below)
+                                    #pragma unroll
+                                    for (int j = 0; j < 16; j++) if (c0 + j >= L.N) v[j] = 0.0f;
+                                }
+                                float4* s4 = reinterpret_cast<float4*>(Srow + c0);
+                                #pragma unroll
+                                for (int q = 0; q < 4; q++) s4[q] = make_float4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+                            } else {
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) v[j] = 0.0f;
                             }
-                            float4* s4 = reinterpret_cast<float4*>(Srow + cb * 32);
-                            #pragma unroll
-                            for (int q = 0; q < 8; q++) s4[q] = make_float4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
-                        } else {
-                            #pragma unroll
-                            for (int j = 0; j < 32; j++) v[j] = 0.0f;
-                        }
-                        if (L.append_enc) {                              // h = cat([h, x_enc]) / sqrt(2)   (network.py:417-418)
-                            #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const uint32_t col = cb * 32 + j;
-                                if (col >= L.N && col < L.N + in_dim) v[j] = ng_enc(px, py, pz, col - L.N) * L.scale;
+                            if (L.append_enc && c0 + 16 > L.N) {         // h = cat([h, x_enc]) / sqrt(2)   (network.py:417-418)
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    const uint32_t col = c0 + j;
+                                    if (col >= L.N && col < L.N + in_dim) v[j] = ng_enc(px, py, pz, col - L.N) * scale;
+                                }
                             }
+                            if (cb < L.out_chunks) store16(c0, v);
                         }
-                        if (cb < L.out_chunks) publish(cb, v);
+                        if (cb < L.out_chunks) publish(cb);
                     }
                 } else if (L.kind == 1) {
                     // ---- forward head: (sdf, features) out; first reverse operand g = W_last[0, :] . s of the last hidden layer
@@ -260,65 +281,77 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
                         }
                     }
                     const float* Srow = S_cta + ((size_t)L.s_slot * 128 + row) * 256;
-                    for (uint32_t cb = g; cb < L.out_chunks; cb += 2) {
-                        float v[32];
-                        const float4* s4 = reinterpret_cast<const float4*>(Srow + cb * 32);
-                        #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float4 s = s4[q];
-                            const uint32_t c = cb * 32 + 4 * q;
-                            v[4 * q] = (c < L.s_cols) ? s.x * s_wrow[c] : 0.f;         v[4 * q + 1] = (c + 1 < L.s_cols) ? s.y * s_wrow[c + 1] : 0.f;
-                            v[4 * q + 2] = (c + 2 < L.s_cols) ? s.z * s_wrow[c + 2] : 0.f; v[4 * q + 3] = (c + 3 < L.s_cols) ? s.w * s_wrow[c + 3] : 0.f;
+                    for (uint32_t cb = g; cb < L.out_chunks; cb += kNgEpiGroups) {
+                        #pragma unroll 1
+                        for (uint32_t hf = 0; hf < 2; hf++) {
+                            const uint32_t c0 = cb * 32 + hf * 16;
+                            float v[16];
+                            const float4* s4 = reinterpret_cast<const float4*>(Srow + c0);
+                            #pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float4 sq = s4[q];
+                                const uint32_t c = c0 + 4 * q;
+                                v[4 * q] = sq.x * s_wrow[c]; v[4 * q + 1] = sq.y * s_wrow[c + 1];
+                                v[4 * q + 2] = sq.z * s_wrow[c + 2]; v[4 * q + 3] = sq.w * s_wrow[c + 3];
+                            }
+                            if (c0 + 16 > L.s_cols) {
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) if (c0 + j >= L.s_cols) v[j] = 0.0f;
+                            }
+                            store16(c0, v);
                         }
-                        publish(cb, v);
+                        publish(cb);
                     }
                 } else if (L.kind == 2) {
                     // ---- reverse hidden: D = g_in = g_z W_l; next g_z = g_in . s_{l-1}; at the skip layer the trailing columns are d / d enc
                     const float* Srow = S_cta + ((size_t)L.s_slot * 128 + row) * 256;
                     const uint32_t nmax = max(nin, L.out_chunks);
-                    for (uint32_t cb = g; cb < nmax; cb += 2) {
-                        float v[32];
-                        uint32_t r[32];
-                        if (cb < nin) { tc::tmem_ld32(acc + cb * 32, r); tc::tmem_ld_wait(); }
-                        else {
-                            #pragma unroll
-                            for (int j = 0; j < 32; j++) r[j] = 0u;
-                        }
-                        float sv[32];
-                        if (cb * 32 < L.s_cols) {
-                            const float4* s4 = reinterpret_cast<const float4*>(Srow + cb * 32);
-                            #pragma unroll
-                            for (int q = 0; q < 8; q++) { const float4 s = s4[q]; sv[4 * q] = s.x; sv[4 * q + 1] = s.y; sv[4 * q + 2] = s.z; sv[4 * q + 3] = s.w; }
-                        } else {
-                            #pragma unroll
-                            for (int j = 0; j < 32; j++) sv[j] = 0.0f;
-                        }
-                        #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const uint32_t col = cb * 32 + j;
-                            const float d = __uint_as_float(r[j]) * L.scale;
-                            if (L.split_skip && col >= L.Nh) {
-                                if (col < L.Nh + in_dim) sGskip[(col - L.Nh) * 128 + row] = d;
-                                v[j] = 0.0f;
+                    const float scale = L.scale;
+                    const uint32_t lim = L.split_skip ? L.Nh : L.s_cols;   // columns < lim continue down the stack
+                    for (uint32_t cb = g; cb < nmax; cb += kNgEpiGroups) {
+                        #pragma unroll 1
+                        for (uint32_t hf = 0; hf < 2; hf++) {
+                            const uint32_t c0 = cb * 32 + hf * 16;
+                            float v[16], sv[16];
+                            uint32_t r[16];
+                            if (c0 < lim) {                              // the saved derivatives first: their L2 latency overlaps the tcgen05.ld
+                                const float4* s4 = reinterpret_cast<const float4*>(Srow + c0);
+                                #pragma unroll
+                                for (int q = 0; q < 4; q++) { const float4 sq = s4[q]; sv[4 * q] = sq.x; sv[4 * q + 1] = sq.y; sv[4 * q + 2] = sq.z; sv[4 * q + 3] = sq.w; }
                             } else {
-                                v[j] = (col < L.s_cols) ? d * sv[j] : 0.0f;
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) sv[j] = 0.0f;
                             }
+                            if (cb < nin) { tc::tmem_ld16(acc + c0, r); tc::tmem_ld_wait(); }
+                            else {
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) r[j] = 0u;
+                            }
+                            #pragma unroll
+                            for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) * scale * sv[j];
+                            if (c0 + 16 > lim) {
+                                #pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    const uint32_t col = c0 + j;
+                                    if (col >= lim) {
+                                        if (L.split_skip && col < L.Nh + in_dim) sGskip[(col - L.Nh) * 128 + row] = __uint_as_float(r[j]) * scale;
+                                        v[j] = 0.0f;
+                                    }
+                                }
+                            }
+                            if (cb < L.out_chunks) store16(c0, v);
                         }
-                        if (cb < L.out_chunks) publish(cb, v);
+                        if (cb < L.out_chunks) publish(cb);
                     }
                 } else if (g == 0) {
                     // ---- reverse into the encoding: g_enc = D (+ skip part); d sdf / d x = J_freq^T g_enc   (freqencoder.cu:82-90)
                     float ge[kNgMaxIn];
-                    {
-                        uint32_t r[32];
-                        tc::tmem_ld32(acc, r);
-                        tc::tmem_ld_wait();
+                    #pragma unroll
+                    for (int t3 = 0; t3 < 3; t3++) {
+                        uint32_t r[16];
+                        if ((uint32_t)t3 * 16 < L.Np) { tc::tmem_ld16(acc + t3 * 16, r); tc::tmem_ld_wait(); }
                         #pragma unroll
-                        for (int j = 0; j < 32; j++) ge[j] = __uint_as_float(r[j]);
-                        uint32_t r2[16];
-                        if (L.Np > 32) { tc::tmem_ld16(acc + 32, r2); tc::tmem_ld_wait(); }
-                        #pragma unroll
-                        for (int j = 0; j < 16; j++) ge[32 + j] = (L.Np > 32) ? __uint_as_float(r2[j]) : 0.0f;
+                        for (int j = 0; j < 16; j++) ge[t3 * 16 + j] = ((uint32_t)t3 * 16 < L.Np) ? __uint_as_float(r[j]) : 0.0f;
                     }
                     if (P.has_skip) {
                         #pragma unroll
@@ -344,9 +377,9 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
             }
             tc::mbar_arrive(tile_done);
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 4 + kNgEpiWarps) {
         // ===================== frequency encoding of the next tile's layer-0 operand =====================
-        const uint32_t row = tid - 12 * 32;
+        const uint32_t row = tid - (4 + kNgEpiWarps) * 32;
         const uint32_t Kp0 = P.L[0].Kp;
         uint32_t done_par = 0, it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {

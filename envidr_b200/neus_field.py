@@ -6,14 +6,15 @@ layers with Softplus(beta=100) and a skip connection (nerf/network.py:154-222, 4
 (network.py:524-698) -> composite_rays(input_alpha=True).
 
 Here:
-  * dense layers of the geometry network, forward AND the reverse pass of the analytic normal g <- (g . softplus'(z)) W, run on
-    tensor cores (csrc/linear_tc.cu: tcgen05, fp16 hi/lo split, fp32 accumulate), weight norm folded into the weights at pack time;
-  * everything between them is one kernel each (csrc/neus_field.cu), the frequency encoding and its transpose-Jacobian product are
-    the library's freq_encode kernels, the opacity is envidr_neus_alpha_forward;
+  * the whole geometry network -- frequency encoding, the dense layers forward AND the reverse pass of the analytic normal
+    g <- (g . softplus'(z)) W, Softplus, skip concat / split, head -- is ONE tensor-core kernel per batch (csrc/neus_geom_tc.cu: tcgen05,
+    fp16 hi/lo split, fp32 accumulate, activations stay on the SM), weight norm folded into the weights at pack time;
+    `NeusField.fused = False` (or a shape outside the kernel's range) runs the same math as a chain of envidr_linear_tc launches with
+    one glue kernel between them (csrc/neus_field.cu) -- the first version, kept as the cross-check;
+  * the head -> normal / roughness / shading record and the NeuS opacity are one kernel each (envidr_neus_records, envidr_neus_alpha_forward);
   * shading reuses the tensor-core env_net / heads kernels on 32-float geometry records (envidr_field_forward_records);
   * `render_rays_neus` is the inference loop with the reference's schedule (n_step = clamp(N // n_alive, 1, 8)) on the library's march
-    and composite kernels, geometry-only with deferred shading: the loop evaluates geometry + alpha per iteration (ray termination
-    needs nothing else), logs the composited samples ray by ray, and env_net + heads run ONCE over them.
+    and composite kernels.
 No CPU fallback: CUDA tensors only.
 """
 from __future__ import annotations
@@ -306,12 +307,11 @@ def render_rays_neus(field: NeusField, bitfield: torch.Tensor, rays_o: torch.Ten
                      T_thresh: float = 1e-4, bg_color=1.0, aabb: Optional[Sequence[float]] = None, env_rot_radian: Optional[float] = None,
                      r_images: Optional[torch.Tensor] = None, geometry_only: bool = False, visual_items: Sequence[str] = (),
                      stats: Optional[dict] = None) -> Dict[str, torch.Tensor]:
-    """run_cuda's inference branch (cuda_ray.py:238-359) for the NeuS-style field, input_alpha compositing.
-
-    The loop keeps the reference's schedule and samples; per iteration it evaluates geometry + alpha only and composites the normal
-    image (which also yields weights_sum, depth and -- through the alive list -- ray termination, none of which depend on colour).
-    Every sample a ray composited is logged ray by ray; env_net + the shading heads then run once over the logged records and
-    envidr_composite_rays_replay reproduces the colour compositing sample by sample."""
+    """run_cuda's inference branch (cuda_ray.py:238-359) for the NeuS-style field, input_alpha compositing: the reference's schedule
+    (n_step = clamp(N // n_alive, 1, 8)) and samples on the library's march / composite kernels; per iteration ONE fused geometry launch
+    (csrc/neus_geom_tc.cu), the record / opacity kernels, the tensor-core shading kernels and one composite_rays per image, each on its
+    own copy of the alive list exactly as the reference keeps them (cuda_ray.py:318-342).  One host synchronisation per iteration
+    (the alive count sizes the next batch, as in the reference)."""
     from . import raymarching as rm
     rays_o = rays_o.float().contiguous().view(-1, 3)
     rays_d = rays_d.float().contiguous().view(-1, 3)
@@ -319,11 +319,18 @@ def render_rays_neus(field: NeusField, bitfield: torch.Tensor, rays_o: torch.Ten
     f32 = dict(dtype=torch.float32, device=dev)
     aabb_t = torch.tensor(list(aabb) if aabb is not None else [-bound] * 3 + [bound] * 3, **f32)
     nears, fars = rm.near_far_from_aabb(rays_o, rays_d, aabb_t, min_near)
-    ws, depth, n_img = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, 3, **f32)
+    z1, z3 = (lambda: torch.zeros(N, **f32)), (lambda: torch.zeros(N, 3, **f32))
+    ws, depth, image = z1(), z1(), z3()
+    n_ws, n_depth, n_img = z1(), z1(), z3()
+    want = [] if geometry_only else ["rgb"]
+    extra = {}
+    if not geometry_only and "diffuse" in visual_items:
+        want.append("c_diffuse"); extra["diffuse"] = (z1(), z1(), z3())
+    if not geometry_only and "specular" in visual_items:
+        want.append("c_specular"); extra["specular"] = (z1(), z1(), z3())
     alive = torch.arange(N, dtype=torch.int32, device=dev)
     rays_t = nears.clone()
-    counts = torch.zeros(N, dtype=torch.int64, device=dev)
-    log_rec, log_alpha, log_delta, log_ray = [], [], [], []
+    ri = None if r_images is None else r_images.float().contiguous().view(-1, 4)
     step = iters = samples = 0
     while step < max_steps:
         n_alive = alive.shape[0]
@@ -334,29 +341,25 @@ def render_rays_neus(field: NeusField, bitfield: torch.Tensor, rays_o: torch.Ten
                                            False, dt_gamma, max_steps)
         g = field.geometry(xyzs, dirs, deltas[:, 0], env_rot_radian, want_rec=not geometry_only)
         alpha = g["sigma"]
-        # which samples will the compositor use?  a ray stops at the first zero-delta slot or once its transmittance BEFORE the sample
-        # is below T_thresh (raymarching.cu:996-1039); reproduce that here to log exactly the composited samples
-        if not geometry_only:
-            alive_idx = alive.long()                                     # copy: composite_rays marks dead rays with -1 in place
-            ws_before = ws[alive_idx]
-        rm.composite_rays(n_alive, n_step, alive, rays_t, alpha, g["normal"], deltas, ws, depth, n_img, T_thresh, True)
-        if not geometry_only:
-            a = alpha.view(n_alive, n_step)
-            valid = deltas[:, 0].view(n_alive, n_step) > 0
-            T = 1 - ws_before
-            used = torch.zeros(n_alive, n_step, dtype=torch.bool, device=dev)
-            go = torch.ones(n_alive, dtype=torch.bool, device=dev)
-            for s in range(n_step):
-                go = go & valid[:, s]
-                used[:, s] = go
-                w = a[:, s] * T
-                go = go & ~(T < T_thresh)
-                T = torch.where(used[:, s], T - w, T)
-            sel = used.view(-1)
-            ray_of = alive_idx[:, None].expand(-1, n_step).reshape(-1)
-            log_rec.append(g["rec"][sel]); log_alpha.append(alpha[sel]); log_delta.append(deltas[sel]); log_ray.append(ray_of[sel])
-            counts.index_add_(0, ray_of[sel], torch.ones_like(ray_of[sel]))
-        samples += int((deltas[:, 0] > 0).sum()) if stats is not None else 0
+        if stats is not None:
+            samples += int((deltas[:, 0] > 0).sum())
+        if geometry_only:
+            rm.composite_rays(n_alive, n_step, alive, rays_t, alpha, g["normal"], deltas, ws, depth, n_img, T_thresh, True)
+        else:
+            r_s = None if ri is None else ri[alive.long()][:, None, :].expand(-1, n_step, -1).reshape(-1, 4).contiguous()
+            sh = field.shade(g["rec"], r_s, tuple(want))
+            # the normal / diffuse / specular images are composited on copies of the alive list: same opacities, same schedule, so
+            # they evolve exactly like the reference's separately kept lists
+            rm.composite_rays(n_alive, n_step, alive.clone(), rays_t.clone(), alpha, g["normal"], deltas, n_ws, n_depth, n_img, T_thresh, True)
+            if "diffuse" in extra:
+                w_, d_, im_ = extra["diffuse"]
+                rm.composite_rays(n_alive, n_step, alive.clone(), rays_t.clone(), alpha, sh["c_diffuse"], deltas, w_, d_, im_, T_thresh, True)
+            if "specular" in extra:                                      # roughness composited into `depth` (cuda_ray.py:326-335)
+                w_, d_, im_ = extra["specular"]
+                dl = deltas.clone()
+                dl[:, 1] = g["roughness"]
+                rm.composite_rays(n_alive, n_step, alive.clone(), rays_t.clone(), alpha, sh["c_specular"], dl, w_, d_, im_, T_thresh, True, False)
+            rm.composite_rays(n_alive, n_step, alive, rays_t, alpha, sh["rgb"], deltas, ws, depth, image, T_thresh, True)
         alive = alive[alive >= 0]
         step += n_step
         iters += 1
@@ -366,40 +369,11 @@ def render_rays_neus(field: NeusField, bitfield: torch.Tensor, rays_o: torch.Ten
     if geometry_only:
         res["image"] = None
         return res
-    # deferred shading: samples ordered ray by ray (stable: iteration order within a ray is preserved)
-    ray_all = torch.cat(log_ray) if log_ray else torch.zeros(0, dtype=torch.int64, device=dev)
-    order = torch.argsort(ray_all, stable=True)
-    rec = torch.cat(log_rec)[order] if log_rec else torch.zeros(0, 32, **f32)
-    alpha = torch.cat(log_alpha)[order] if log_alpha else torch.zeros(0, **f32)
-    delta = torch.cat(log_delta)[order] if log_delta else torch.zeros(0, 2, **f32)
-    Mtot = int(rec.shape[0])
-    off = (torch.cumsum(counts, 0) - counts).to(torch.int32)
-    rays = torch.stack([torch.arange(N, dtype=torch.int32, device=dev), off, counts.to(torch.int32)], -1).contiguous()
-    r_s = None
-    if r_images is not None:
-        r_s = torch.empty(Mtot, 4, **f32)
-        check(lib().envidr_scatter_ray_rows4(ptr(rays), N, Mtot, ptr(r_images.float().contiguous().view(-1, 4)), ptr(r_s), stream()), "scatter_ray_rows4")
-    want = ["rgb"] + (["c_diffuse"] if "diffuse" in visual_items else []) + (["c_specular"] if "specular" in visual_items else [])
-    sh = field.shade(rec, r_s, tuple(want))
-    rough = rec[:, 20].contiguous() if ("roughness" in visual_items or "specular" in visual_items) else None
-    img = {"image": torch.empty(N, 3, **f32), "weights_sum": torch.empty(N, **f32), "depth": torch.empty(N, **f32)}
-    if "c_diffuse" in sh:
-        img["diffuse_image"] = torch.empty(N, 3, **f32)
-    if "c_specular" in sh:
-        img["specular_image"] = torch.empty(N, 3, **f32)
-    if rough is not None:
-        img["roughness_image"] = torch.empty(N, **f32)
-    check(lib().envidr_composite_rays_replay(ptr(alpha), ptr(sh["rgb"]), None, ptr(sh.get("c_diffuse")), ptr(sh.get("c_specular")), ptr(rough), ptr(delta),
-                                             ptr(rays), ptr(nears), Mtot, N, T_thresh, 1, ptr(img["weights_sum"]), ptr(img["depth"]), ptr(img["image"]), None,
-                                             ptr(img.get("diffuse_image")), ptr(img.get("specular_image")), ptr(img.get("roughness_image")), stream()),
-          "composite_rays_replay")
     bg = bg_color if torch.is_tensor(bg_color) else torch.tensor(float(bg_color), **f32)
-    res["image"] = img["image"] + (1 - ws).unsqueeze(-1) * bg
-    for k in ("diffuse_image", "specular_image"):
-        if k in img:
-            res[k] = img[k]
-    if "roughness_image" in img:
-        res["roughness_image"] = img["roughness_image"][..., None]
-    if stats is not None:
-        stats["shaded"] = Mtot
+    res["image"] = image + (1 - ws).unsqueeze(-1) * bg
+    if "diffuse" in extra:
+        res["diffuse_image"] = extra["diffuse"][2]
+    if "specular" in extra:
+        res["specular_image"] = extra["specular"][2]
+        res["roughness_image"] = extra["specular"][1][..., None]
     return res
