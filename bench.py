@@ -730,7 +730,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its banner goes to stdout, ahead of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):  # the version banner goes to stdout, ahead of the one JSON line
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     fp_cpu, bf, ro, rd, W, H = workload(args)

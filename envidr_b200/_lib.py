@@ -58,7 +58,8 @@ class RenderOpts(ctypes.Structure):
     _fields_ = [("bound", ctypes.c_float), ("dt_gamma", ctypes.c_float), ("T_thresh", ctypes.c_float), ("min_near", ctypes.c_float),
                 ("max_steps", ctypes.c_uint32), ("cascade", ctypes.c_uint32), ("grid_size", ctypes.c_uint32),
                 ("aabb", ctypes.c_float * 6), ("bg_color", ctypes.c_float * 3),
-                ("geometry_only", ctypes.c_int32), ("input_alpha", ctypes.c_int32), ("n_step_floor", ctypes.c_uint32)]
+                ("geometry_only", ctypes.c_int32), ("input_alpha", ctypes.c_int32), ("n_step_floor", ctypes.c_uint32),
+                ("n_step_cap", ctypes.c_uint32)]
 
 
 class SampleLog(ctypes.Structure):

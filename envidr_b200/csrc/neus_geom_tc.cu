@@ -55,6 +55,9 @@ struct NgParams {
     float beta;
 };
 
+__device__ __forceinline__ float exp2f_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float log2f_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ float ng_enc(float x, float y, float z, uint32_t e) {
     if (e < 3) return e == 0 ? x : (e == 1 ? y : z);
     const uint32_t col = e / 3 - 1, d = e % 3, f = col >> 1;
@@ -220,6 +223,7 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
                     float* Srow = S_cta + ((size_t)L.s_slot * 128 + row) * 256;
                     const uint32_t nmax = max(nin, L.out_chunks);
                     const float scale = L.scale;
+                    const float k_t = P.beta * 1.4426950408889634f, k_out = 0.6931471805599453f * inv_beta * scale;
                     for (uint32_t cb = g; cb < nmax; cb += kNgEpiGroups) {
                         #pragma unroll 1
                         for (uint32_t hf = 0; hf < 2; hf++) {
@@ -233,15 +237,17 @@ k_neus_geom_tc(const NgParams P, const float* __restrict__ xyzs, uint32_t M, flo
                                 // Softplus(beta, threshold 20) and its derivative from ONE exponential: e = exp(-|beta z|) in (0, 1], so
                                 // log(1 + e) needs no log1p (absolute error 6e-8, i.e. 6e-10 after / beta) and the fast intrinsics (MUFU
                                 // ex2 / lg2 / rcp, relative 2^-21) keep h and s within 1e-6 of the libm formulation
+                                // In base 2: t = beta z log2(e) (one FMA on the accumulator, bias pre-scaled), e = 2^-|t|,
+                                // softplus = (max(t, 0) + log2(1 + e)) ln2 / beta.  No threshold branch: for beta z > 20, 1 + e rounds to 1 and
+                                // the expression returns beta z / beta, torch's threshold value to 1 ulp.
                                 #pragma unroll
                                 for (int j = 0; j < 16; j++) {
-                                    const float z = __uint_as_float(r[j]) + bias[c0 + j];
-                                    const float bz = P.beta * z;
-                                    const float e = __expf(-fabsf(bz));
-                                    const float rc = __frcp_rn(1.0f + e);
-                                    const float sp = (bz > 20.0f) ? z : (fmaxf(bz, 0.0f) + __logf(1.0f + e)) * inv_beta;
-                                    sv[j] = (bz >= 0.0f) ? rc : e * rc;
-                                    v[j] = sp * scale;
+                                    const float t = fmaf(__uint_as_float(r[j]), k_t, bias[c0 + j] * k_t);
+                                    const float e = exp2f_fast(-fabsf(t));
+                                    const float ope = 1.0f + e;
+                                    const float rc = __frcp_rn(ope);
+                                    sv[j] = (t >= 0.0f) ? rc : e * rc;
+                                    v[j] = (fmaxf(t, 0.0f) + log2f_fast(ope)) * k_out;
                                 }
                                 if (c0 + 16 > L.N) {                     // padded columns of the operand are zero (or the encoding, below)
                                     #pragma unroll

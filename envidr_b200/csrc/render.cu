@@ -22,7 +22,8 @@ int field_forward_launch(const envidr_field* field, const float* xyzs, const flo
                          cudaEvent_t* ev, int* ev_recorded, const RecCapture* cap);
 
 constexpr int kMarchBlock = 128;
-constexpr int kMaxNStep = 8;
+constexpr int kMaxNStep = 16;          // hard upper bound (staging array of k_march_compact); the reference schedule caps at 8
+constexpr int kRefNStepCap = 8;
 
 struct Counters {
     uint32_t n_alive;        // alive rays entering the current iteration
@@ -207,7 +208,8 @@ __global__ void __launch_bounds__(kMarchBlock) k_march_compact(
 // composite this iteration's samples into the per-ray accumulators, decide which rays stay alive, compact
 // the alive list, and (last block) advance the iteration counters.
 __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, float T_thresh, uint32_t max_steps, int geometry_only,
-                                                                  int input_alpha, uint32_t n_step_floor, RenderBuffers B, RenderOutDev O) {
+                                                                  int input_alpha, uint32_t n_step_floor, uint32_t n_step_cap, RenderBuffers B,
+                                                                  RenderOutDev O) {
     Counters* ctr = B.ctr;
     const uint32_t n_alive = ctr->n_alive, n_step = ctr->n_step;
     const bool active = !(n_alive == 0 || ctr->step_total >= max_steps);
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
             ctr->n_alive_next = 0;
             ctr->M = 0;
             uint32_t ns = next ? N / next : 1;
-            ns = ns > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : ns;
+            ns = ns > n_step_cap ? n_step_cap : ns;
             ctr->n_step = ns < n_step_floor ? n_step_floor : ns;
         }
         ctr->done_blocks = 0;
@@ -357,7 +359,8 @@ static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 struct WsLayout {
     uint64_t nears, fars, rays_t, alive0, alive1, slot, s_xyz, s_dir, s_delta, s_rimg, s_sigma, s_rgb, s_normal, s_cd, s_cs, s_rough, ctr, occ_box, scratch, total;
 };
-static uint32_t clamp_floor(uint32_t f) { return f < 1 ? 1u : (f > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : f); }
+static uint32_t clamp_floor(uint32_t f) { return f < 1 ? 1u : (f > (uint32_t)kRefNStepCap ? (uint32_t)kRefNStepCap : f); }
+static uint32_t clamp_cap(uint32_t c) { return c == 0 ? (uint32_t)kRefNStepCap : (c > (uint32_t)kMaxNStep ? (uint32_t)kMaxNStep : c); }
 static WsLayout ws_layout(uint32_t N, uint32_t n_step_floor = 1) {
     WsLayout L{};
     uint64_t off = 0;
@@ -414,6 +417,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
                    "cascades must be 1..8, grid size <= 1024");
     if (N == 0) return 0;
     const uint32_t nsf = clamp_floor(opts->n_step_floor);
+    const uint32_t nsc = clamp_cap(opts->n_step_cap) < nsf ? nsf : clamp_cap(opts->n_step_cap);
     const WsLayout L = ws_layout(N, nsf);
     ENVIDR_REQUIRE(workspace_bytes >= L.total, ENVIDR_E_WORKSPACE, "workspace too small (envidr_render_workspace_bytes)");
     ENVIDR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ENVIDR_E_BADARG, "workspace must be 256-byte aligned");
@@ -491,7 +495,7 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
             if (timed && recorded) g_tev_used++;
             g_launches += (fld.precision == 1 && !opts->geometry_only) ? 5 : 3;      // march, [geom, env, shade | field], composite
             k_composite_compact<<<march_grid, kMarchBlock, 0, st>>>(N, opts->T_thresh, opts->max_steps, opts->geometry_only,
-                                                                   opts->input_alpha, nsf, B, O);
+                                                                   opts->input_alpha, nsf, nsc, B, O);
         }
         rc = check_launch("render_loop");
         if (rc) return rc;

@@ -259,6 +259,9 @@ typedef struct envidr_render_opts {
                              * Only the batching changes: every ray still composites the same samples (positions to the ulp-level
                              * re-synchronisation of rays_t), but a pass over few rays no longer starts with N / n_alive = 1, i.e. with
                              * launches of at most N samples.  The workspace must be sized with envidr_render_workspace_bytes_ex. */
+    uint32_t n_step_cap;    /* 0 / 8: the reference's cap of n_step (cuda_ray.py:287); up to 16: a pass whose alive list has shrunk below N / 8
+                             * marches up to that many samples per ray and iteration -- fewer, larger iterations in the long tail of a pass
+                             * (again only the batching changes; at most cap - 1 samples per ray are marched past its termination) */
 } envidr_render_opts;
 
 /* Optional capture of a geometry-only pass (tensor-core field): one entry per MARCHED sample, in iteration-major order.
