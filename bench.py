@@ -250,7 +250,7 @@ def gpu_reference_bench(fp_cpu, bf, ro_d, rd_d, dev, indir, frames=2, train_rays
         dropin = {}
         try:
             RM.use_backends("envidr")
-            for tag, kwargs in (("install()", {}), ("install(patch_render=True)", dict(patch_render=True, renderer_class=R.NeRFRenderer))):
+            for tag, kwargs in (("install(patch_render=False)", dict(patch_render=False)), ("install()", dict(patch_render=True, renderer_class=R.NeRFRenderer))):
                 render.install(RF, **kwargs)
                 for _ in range(3):
                     fn()

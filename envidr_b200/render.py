@@ -690,10 +690,12 @@ def render_model(model, rays_o, rays_d, staged=False, max_ray_batch=4096, get_no
     return out
 
 
-def install(render_func_module=None, patch_render: bool = False, renderer_class=None, precision: str = "tc"):
-    """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop.
-    patch_render: also replace NeRFRenderer.render by `render_model` (the batched three-pass frame); renderer_class defaults to
-    nerf.renderer.NeRFRenderer.  precision: arithmetic of the fused field, "tc" (tensor cores, default) or "fp32"."""
+def install(render_func_module=None, patch_render: bool = True, renderer_class=None, precision: str = "tc"):
+    """Route the reference's renderer through this library: operator-level `_backend`s + fused inference loop behind
+    `nerf.render_func.run_cuda` + (patch_render, default) `NeRFRenderer.render` replaced by `render_model`, which runs the
+    evaluation-time three-pass frame as one batched schedule (16.8 ms instead of 25.0 ms per 800x800 frame) and forwards every other
+    call to the reference method; renderer_class defaults to nerf.renderer.NeRFRenderer.  patch_render=False patches run_cuda only.
+    precision: arithmetic of the fused field, "tc" (tensor cores, default) or "fp32"."""
     global _reference_run_cuda, _reference_render, _dropin_precision
     if precision not in ("tc", "fp32"):
         raise _lib.EnvidrError(f"unknown precision {precision!r} (tc | fp32)")

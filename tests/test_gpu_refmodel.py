@@ -6,8 +6,8 @@ loaded into its parameters, and `model.render(...)` is called with the exact arg
 
   (a) reference kernels (oracle/_ref/_*.so) + the reference's run_cuda            -> ground truth
   (b) the SAME model / code with the wrappers' `_backend` bound to libenvidr_b200   (operator-level drop-in)
-  (c) after envidr_b200.render.install()                                           (fused inference loop behind run_cuda)
-  (d) after envidr_b200.render.install(patch_render=True)                          (batched three-pass frame behind render)
+  (c) after envidr_b200.render.install(patch_render=False)                         (fused inference loop behind run_cuda only)
+  (d) after envidr_b200.render.install()  [patch_render=True is the default]       (batched three-pass frame behind render)
 
 for the single pass, the three-pass indirect-reflection frame and an environment rotation, plus one Trainer.train_step
 (utils.py:560-808: colour L1 + mask BCE + back-sdf + Cauchy + eikonal) with loss and parameter gradients compared.
@@ -86,11 +86,11 @@ def test_real_reference_model_renders_the_same_frame_on_this_library(ref, indir,
     _check(ops, truth, "operators")
     # (c) fused loop behind run_cuda; the default precision of the drop-in is the tensor-core field
     import nerf.render_func as RF
-    render.install(RF)
+    render.install(RF, patch_render=False)
     assert RF.run_cuda is render.run_cuda
     fused = _frame(RM, model, opt, ro, rd, indir, rot)
     assert model._envidr_field.precision == "tc"
-    _check(fused, truth, "install()")
+    _check(fused, truth, "install(patch_render=False)")
     # (d) batched three-pass frame behind NeRFRenderer.render
     import nerf.renderer as R
     render.install(RF, patch_render=True, renderer_class=R.NeRFRenderer)
@@ -111,7 +111,7 @@ def test_weight_updates_between_evaluations_are_seen(ref):
     import nerf.render_func as RF
     RM, model, opt, fp, ro, rd = ref
     RM.use_backends("envidr")
-    render.install(RF)
+    render.install(RF, patch_render=False)
     try:
         a = _frame(RM, model, opt, ro, rd, False, None)
         lin = model.color_net[-1]
@@ -155,7 +155,7 @@ def test_trainer_train_step_on_this_library_matches_the_reference_kernels(ref):
         for mode in ("reference", "envidr", "installed"):
             RM.use_backends("reference" if mode == "reference" else "envidr")
             if mode == "installed":
-                render.install(RF)
+                render.install(RF, patch_render=False)
             model.zero_grad(set_to_none=True)
             model.mean_count, model.local_step = 0, 0                    # renderer.py:118-119: first step marches N * max_steps slots
             model.step_counter.zero_()
