@@ -18,6 +18,21 @@
 //               while the current tile occupies the tensor pipe
 //   Synchronisation is mbarrier-only between roles (full/empty ring, accumulator-ready / IDE-buffer-free via
 //   tcgen05.commit, operand-ready via arrive after fence.proxy.async).
+//   Issue order: the NEXT tile's layer 0 is issued ahead of this tile's 16-wide last layer (it depends on nothing of this tile and
+//   fills the tensor pipe while the epilogue drains the last hidden layer): 8.04 -> 7.61 ms of k_env_tc per frame (run r3_03).
+//
+// What bounds a tile (clock64 timelines + timing experiments of round 2, ENVIDR_ENV_TC_DEBUG, runs r3_10 / r3_11): a tile takes ~21.5 k
+// cycles for 14.2 k cycles of MMA work.  Removing the weight copies altogether saves 2 %, removing the IDE arithmetic 4 %, and issuing ONE
+// product instead of three (1/3 of the tensor work) only 10 %: the tile is a latency chain, layer after layer -- commit -> epilogue wakes ->
+// tcgen05.ld (TMEM read-out of a 128 x 256 fp32 accumulator: 128 KB, ~64 B/clk) -> convert -> st.shared -> fence -> arrive -> issuer
+// wakes -> MMAs -- with a chunk pair published every ~900 cycles whatever the number of epilogue warps (8 or 16, run r3_12), a ring
+// handshake of ~300 cycles per K step even without data movement, and a ~7 k-cycle tail (epilogue of the last hidden layer, the 16-wide
+// layer, its epilogue, first chunk of the next tile) in which only the next tile's layer 0 has independent MMA work.  Shared memory (A
+// operand 128 KB in place) and tensor memory (two 256-column accumulators) are full, so a second tile cannot be interleaved.
+// Variants kept behind environment switches, all parity-green, none faster: e4m3 corrections (ENVIDR_ENV_TC_MODE=1), CTA pair
+// with cta_group::2 MMAs (ENVIDR_ENV_TC_CTAS=2; round 2: the peer's weight halves arrive by tensor-map TMA that signals the leader's
+// barrier, operand-ready by named barrier + one remote arrive, no relay warps: 9.39 -> 8.68 ms, still behind), weight multicast
+// across a cluster of 2 / 4 CTAs (ENVIDR_ENV_TC_MULTICAST).
 //
 // Precision: the reference computes these layers in fp32 and the parity bar is 1e-4 on RGB, which a single fp16/bf16/
 // tf32 pass does not meet (measured ~1e-3 on the env feature).  Every operand is split x = hi + lo (hi = fp16(x)).
@@ -35,6 +50,8 @@
 //       float64 (profiles/fp8_correction_sim.py) RGB L-inf 3e-6 (xavier 256-wide) / 1.2e-5 (shipped trained 160-wide env_net)
 //       against 3e-7 for mode 0 and 1e-4 for a single fp16 product.  Layer 0 (K = 72 -> 80, the IDE features) stays mode 0.
 #include <math.h>
+#include <stdio.h>
+#include <cuda.h>
 #include <cuda_fp8.h>
 #include "common.cuh"
 #include "ide_tables.cuh"
@@ -48,9 +65,13 @@ namespace envidr {
 // with the shipped kappa = 0.64 their bands l >= 8 are attenuated by exp(-36 * 0.64) = 1e-10 and below, so only l <= 4 is
 // evaluated there (see ide_nb0 in env_tc_launch) and the rest of those rows stays zero.
 constexpr int kTcIdeThreads = 512;
-constexpr int kTcThreads = (4 + 8) * 32 + kTcIdeThreads;   // 4 control warps + 8 epilogue warps + 16 IDE warps
-constexpr int kTcStages = 3;
-constexpr uint32_t kTcStageBytes = 16384;          // one K step (16) of a 256-wide layer: 2 (hi,lo) x 2 chunks x 256 x 16 B
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = (4 + kTcEpiWarps) * 32 + kTcIdeThreads;   // 4 control warps + 8 epilogue warps + 16 IDE warps = 896
+constexpr int kTcStagesMax = 6;
+constexpr uint32_t kTcRingBytes = 49152;           // weight ring: 3 x 16 KB, a stage = one K step (16) of a 256-wide layer, 2 (hi,lo) x 2 chunks x 256 x 16 B.
+                                                   // (6 x 8 KB stages holding the hi / lo halves separately measured SLOWER, run r3_04: 8.02 vs 7.61 ms per
+                                                   // frame -- the weight stream is bound by L2 bandwidth, not by bytes in flight: 148 SMs x 16 KB per 460
+                                                   // cycles is 82 % of the L2 read bandwidth.  Hence the multicast ring below.)
 constexpr uint32_t kTcARegion = 65536;             // 128 rows x 256 K x 2 B
 constexpr uint32_t kTcIdeRegion = 20480;           // 128 rows x 80 K x 2 B (IDE features, deg_view <= 5, K padded to 16)
 __constant__ IdeTables c_ide_tc;
@@ -59,7 +80,9 @@ static int g_ide_tc_deg = 0;
 //   issuer : 0 wait(ide_full) start, 1 end, 2 layer-0 issued, 3 last layer issued, 4 cycles spent in wait(a_rdy), 5 in wait(full)
 //   IDE w12: 8 wait(ide_empty) start, 9 end, 10 operand written
 //   epilogue w4: 12 + 2*l wait(acc_ready) end, 13 + 2*l layer epilogue done (l < 4)
-constexpr uint32_t kProfPerTile = 24;
+//   layer 2 in detail: 24 + c issuer's wait(a_rdy[c]) end (c < 8), 32 issuer committed acc_ready, 33 + i / 37 + i: warp 4 / warp 8 published its
+//   i-th chunk of layer 1's epilogue (the A operand of layer 2), 41 warp 8 wait(acc_ready) end of layer 1, 42 issuer: first MMA of layer 2 issued
+constexpr uint32_t kProfPerTile = 48;
 static unsigned long long* g_prof = nullptr;
 static uint32_t g_prof_cap = 0;
 
@@ -91,6 +114,28 @@ __device__ __forceinline__ void mma_f16_ss_scale15_w(uint32_t d_tmem, uint64_t a
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
 }
 
+// Barrier waits of k_env_tc.  Built with -DENVIDR_TC_WATCHDOG (ENVIDR_TC_WATCHDOG=1 python -m envidr_b200.build --force) a wait that lasts
+// longer than ~2 s prints who is stuck where (tag: 1 producer/empty, 2-4 issuer/full|a_rdy (mode 1), 5 issuer/ide_full, 6 issuer/full,
+// 7 issuer/a_rdy, 8 epilogue/acc_ready, 9 IDE/ide_empty) and traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef ENVIDR_TC_WATCHDOG
+    const unsigned long long t0 = clock64();
+    while (!tc::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ull) {
+            if ((threadIdx.x & 31) == 0) printf("k_env_tc stuck: block %d warp %d tag %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, parity);
+            __trap();
+        }
+    }
+#else
+    (void)tag;
+    tc::mbar_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ void wait_tag_cluster(uint64_t* bar, uint32_t parity, int tag) {
+    (void)tag;
+    tc::mbar_wait_cluster(bar, parity);
+}
+
 // CTAS = 1: one CTA per tile, tcgen05 cta_group::1.
 // CTAS = 2: thread-block cluster of two CTAs (one TPC) working as a CTA pair: every MMA is M = 256 (128 rows = one tile per
 //   CTA), each CTA streams only ITS half of every weight stage (N/2 rows of B) and the tensor cores read the other half from the
@@ -100,10 +145,21 @@ __device__ __forceinline__ void mma_f16_ss_scale15_w(uint32_t d_tmem, uint64_t a
 //   operand-ready signals go to the leader's mbarriers through shared::cluster arrives, completions come back by multicast
 //   commit.
 // F8 = true (CTAS = 1 only): layers with E.L[l].f8 run in mode 1 (see the file header); F8 = false: mode 0 everywhere.
-template <int CTAS, bool F8>
+// MC > 1 (CTAS = 1 only): thread-block cluster of MC CTAs that work on their own tiles with their own cta_group::1 MMAs and share
+//   nothing but the WEIGHT STREAM: every ring stage is fetched from L2 once per cluster -- CTA r loads the r-th 1/MC of the stage and
+//   multicasts it into the same ring slot of every CTA of the cluster (cp.async.bulk ... .multicast::cluster, complete_tx on every
+//   CTA's full barrier), and a slot is refilled when the MMAs of ALL MC CTAs that read it have retired (tcgen05.commit ...
+//   .multicast::cluster onto every CTA's empty barrier, count MC).  Why: all 148 SMs stream the same 608 KB of weight images per
+//   tile from L2; at a 256 x 256 layer that is 148 x 16 KB per ~460 cycles = 82 % of the L2 read bandwidth, and the layer ran at the
+//   supply rate (7.4 k cycles) instead of the MMA rate (6.1 k).  The CTAs stay coupled only through the 3-stage ring.
+template <int CTAS, bool F8, int MC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
-         unsigned long long* __restrict__ prof, uint32_t prof_cap) {
+         unsigned long long* __restrict__ prof, uint32_t prof_cap, const __grid_constant__ CUtensorMap tmap,
+         const __grid_constant__ CUtensorMap tmap1) {
+    constexpr int kTcStages = 3;
+    constexpr uint32_t kTcStageBytes = kTcRingBytes / kTcStages;
+    constexpr int GROUP = CTAS == 2 ? 2 : MC;             // CTAs per cluster
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA_hi = smem;                                   // hidden-layer A operand (written by the epilogues)
     uint8_t* sA_lo = smem + kTcARegion;
@@ -112,28 +168,40 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint8_t* sI_hi = smem + 2 * kTcARegion;                  // layer-0 A operand (written by the IDE warps)
     uint8_t* sI_lo = sI_hi + kTcIdeRegion;
     uint8_t* ring = sI_lo + kTcIdeRegion;
-    float* s_bias = reinterpret_cast<float*>(ring + kTcStages * kTcStageBytes);         // [8 * 256]
+    float* s_bias = reinterpret_cast<float*>(ring + kTcRingBytes);         // [8 * 256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kTcMaxLayers * 256);
-    uint64_t* full = bars;                           // [3]  producer -> issuer (TMA bytes landed)
-    uint64_t* empty = bars + kTcStages;              // [3]  issuer -> producer (MMAs reading the stage retired)
-    uint64_t* acc_ready = bars + 2 * kTcStages;      // [2] issuer -> epilogue warps (accumulator buffer b of a layer complete)
+    uint64_t* full = bars;                           // [stages]  producer -> issuer (TMA bytes landed)
+    uint64_t* empty = bars + kTcStagesMax;           // [stages]  issuer -> producer (MMAs reading the stage retired)
+    uint64_t* acc_ready = bars + 2 * kTcStagesMax;   // [2] issuer -> epilogue warps (accumulator buffer b of a layer complete)
     uint64_t* ide_full = acc_ready + 2;              // IDE warps -> issuer (kTcIdeThreads arrivals per CTA)
     uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
     uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
                                                      //     shared memory (128 arrivals per CTA: the 4 warps that own chunk parity c & 1)
-    uint64_t* pfull = a_rdy + 8;                     // [3] CTAS = 2: peer's relay warp -> leader's issuer (peer's half of the stage landed)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + kTcStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 8);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
     const uint32_t M = M_dev ? *M_dev : M_host;
     const uint32_t n_tiles = (2 * M + 127) / 128;     // 64 samples x 2 directions per tile
     const int nl = (int)E.n_layers;
+    // Issue order (producer, issuer): L0(first tile), then per tile L1 .. L(nl-2), L0(NEXT tile), L(nl-1).  The next tile's layer 0
+    // depends on nothing of this tile, so its MMAs fill the tensor pipe while the epilogue drains layer nl-2 (the 16-wide last layer
+    // needs that whole epilogue and left the pipe idle for ~3 k cycles per tile, timeline r3_02).  Accumulators: layer l <= nl-2 of
+    // tile ti -> buffer base(ti) ^ (l & 1); the last layer -> columns [0, 16) of layer nl-2's buffer (its first MMA waits for chunk 0 of
+    // that epilogue, which has read columns [0, 32) by then); the next tile's layer 0 -> the other buffer, hence base alternates
+    // from tile to tile when nl is even.  Epilogue order is unchanged (L0 .. L(nl-1) per tile).
+    const uint32_t base_flip = (uint32_t)((nl & 1) ^ 1);
+    const bool early_l0 = E.reorder != 0;                // 0 (ENVIDR_ENV_TC_REORDER=0): plain order L0 .. L(nl-1) per tile, accumulators alternate per layer
+    auto acc_buf = [&](uint32_t ti, int l) -> uint32_t {
+        if (!early_l0) return (ti * (uint32_t)nl + (uint32_t)l) & 1u;
+        const uint32_t base = (ti * base_flip) & 1u;
+        return base ^ (uint32_t)((l == nl - 1 ? nl - 2 : l) & 1);
+    };
     // work units: tiles (CTAS = 1) or tile pairs (CTAS = 2: CTA `rank` of cluster u takes tile 2 * unit + rank; a tile past
     // n_tiles is all-invalid rows, computed as zeros and never stored)
-    const uint32_t rank = CTAS == 2 ? tc::cluster_ctarank() : 0u;
-    const uint32_t unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
-    const uint32_t n_units = (n_tiles + CTAS - 1) / CTAS;
+    const uint32_t rank = GROUP > 1 ? tc::cluster_ctarank() : 0u;
+    const uint32_t unit0 = blockIdx.x / GROUP, unit_step = gridDim.x / GROUP;
+    const uint32_t n_units = (n_tiles + GROUP - 1) / GROUP;
     if (unit0 >= n_units) return;                     // nothing to do for this CTA / cluster (tail iterations of the render loop)
     if (blockIdx.x != 0) prof = nullptr;
     auto stamp = [&](uint32_t tile_i, uint32_t slot, unsigned long long v) {
@@ -142,14 +210,13 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     };
 
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kTcStages; i++) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], MC); }
         tc::mbar_init(&acc_ready[0], 1);
         tc::mbar_init(&acc_ready[1], 1);
-        // CTAS = 2: every CTA's threads arrive on their OWN barriers; the peer's relay warp forwards each completed phase to the
-        // leader with ONE cluster-scope arrive (+1 below) instead of 128 / 512 remote arrives serialising on the leader's barrier
+        // CTAS = 2: the leader's threads arrive on its barriers; the peer's role groups meet on a named barrier and ONE thread sends a
+        // cluster-scope arrive to the leader (+1 below) instead of 128 / 512 remote arrives serialising on the leader's barrier
         const uint32_t fwd = (CTAS == 2 && rank == 0) ? 1u : 0u;
         for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 + fwd);
-        for (int i = 0; i < kTcStages; i++) tc::mbar_init(&pfull[i], 1);
         tc::mbar_init(ide_full, kTcIdeThreads + fwd);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
@@ -163,20 +230,27 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         s_bias[i] = (c < E.L[l].Np) ? __ldg(E.bias + E.L[l].bias_off + c) : 0.0f;
     }
     tc::tc_fence_before();
-    if (CTAS == 2) tc::cluster_sync_all(); else __syncthreads();       // barriers of BOTH CTAs initialised before any remote arrive
+    if (GROUP > 1) tc::cluster_sync_all(); else __syncthreads();       // barriers of ALL CTAs of the cluster initialised before any remote arrive
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // operand-ready signals: arrive on this CTA's own barrier (the peer's are forwarded by its relay warp, below)
-    auto to_issuer = [&](uint64_t* bar) { return tc::smem_u32(bar); };
-    auto arrive_issuer = [&](uint32_t addr) {
-        asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
+    // operand-ready signals.  Leader (and CTAS = 1): every thread of the role group arrives on the CTA's own barrier.  Peer of a CTA
+    // pair: the group (`count` threads) meets on named barrier `bar_id` after its proxy fences, then one thread arrives on the LEADER's
+    // barrier with release.cluster -- one hop, no relay warp polling in between.
+    auto to_issuer = [&](uint64_t* bar) { return (CTAS == 2 && rank == 1) ? tc::map_to_rank(tc::smem_u32(bar), 0) : tc::smem_u32(bar); };
+    auto arrive_issuer = [&](uint32_t addr, uint32_t bar_id, uint32_t count, bool first) {
+        if (CTAS == 2 && rank == 1) {
+            tc::bar_sync_named(bar_id, count);
+            if (first) tc::mbar_arrive_cluster(addr);
+        } else {
+            asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
+        }
     };
 
     if (warp == 0) {
         // ===================== producer =====================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
-            for (int l = 0; l < nl; l++) {
+        auto stream_layer = [&](int l) {
+            {
                 // a ring stage carries as many K steps as fit in kTcStageBytes (1 for a 256-wide layer, all 16 for the 16-wide
                 // last layer: otherwise that layer is bound by 16 ring round trips of 1 KB each).  CTAS = 2: this CTA's half
                 // of B (rows rank * N/2 ...) is a contiguous image of its own, so a stage holds twice the K steps.
@@ -184,10 +258,32 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     const uint32_t uper = max(1u, kTcStageBytes / ubytes);
                     for (uint32_t s = 0; s < units; s += uper) {
                         const uint32_t bytes = min(uper, units - s) * ubytes;
-                        tc::mbar_wait(&empty[stage], phase ^ 1);
+                        wait_tag(&empty[stage], phase ^ 1, 1);
                         if (lane == 0) {
-                            tc::mbar_arrive_expect_tx(&full[stage], bytes);
-                            tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * ubytes, bytes, &full[stage]);
+                            if (CTAS == 2) {
+                                // each CTA pulls ITS half of the stage as 8 KB boxes of the blob's tensor map; both halves complete_tx
+                                // on the leader's full barrier, which the leader arms with the bytes of both
+                                const uint32_t lfull = tc::map_to_rank(tc::smem_u32(&full[stage]), 0);
+                                if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+                                const uint32_t row0 = (uint32_t)((src + (size_t)s * ubytes - E.blob) >> 10);
+                                // 8 KB boxes, then 1 KB boxes for the remainder (layer widths that are not multiples of 256)
+                                uint32_t b = 0;
+                                for (; b + 8192 <= bytes; b += 8192)
+                                    tc::tma2_load_2d(tc::smem_u32(ring + stage * kTcStageBytes + b), &tmap, 0, (int32_t)(row0 + (b >> 10)), lfull);
+                                for (; b < bytes; b += 1024)
+                                    tc::tma2_load_2d(tc::smem_u32(ring + stage * kTcStageBytes + b), &tmap1, 0, (int32_t)(row0 + (b >> 10)), lfull);
+                            } else if (MC > 1) {
+                                // this CTA arms its own barrier with the whole stage and multicasts ITS 1/MC of it to every CTA
+                                const uint32_t part = bytes / MC;
+                                tc::mbar_arrive_expect_tx(&full[stage], bytes);
+                                tc::bulk_g2s_multicast(ring + stage * kTcStageBytes + rank * part, src + (size_t)s * ubytes + rank * part, part,
+                                                       &full[stage], (uint16_t)((1u << MC) - 1));
+                            } else if (E.debug & 1u) {
+                                tc::mbar_arrive(&full[stage]);              // timing experiment: no weight traffic (results are garbage)
+                            } else {
+                                tc::mbar_arrive_expect_tx(&full[stage], bytes);
+                                tc::bulk_g2s(ring + stage * kTcStageBytes, src + (size_t)s * ubytes, bytes, &full[stage]);
+                            }
                         }
                         __syncwarp();
                         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
@@ -204,43 +300,14 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     stream(E.blob + (CTAS == 2 ? E.L[l].img2_off + rank * ksteps * kbytes : E.L[l].img_off), ksteps, kbytes);
                 }
             }
-        }
-    } else if (warp == 3 && CTAS == 2 && rank == 1) {
-        // ===================== peer relay: "my half of the stage landed" -> leader's issuer =====================
-        uint32_t stage = 0, phase = 0;
+        };
         for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
-            for (int l = 0; l < nl; l++) {
-                const uint32_t ksteps = E.L[l].Kp / 16, kbytes = E.L[l].Np * 64 / CTAS;
-                const uint32_t kper = max(1u, kTcStageBytes / kbytes);
-                for (uint32_t s = 0; s < ksteps; s += kper) {
-                    tc::mbar_wait(&full[stage], phase);
-                    if (lane == 0) tc::mbar_arrive_cluster(tc::map_to_rank(tc::smem_u32(&pfull[stage]), 0));
-                    __syncwarp();
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-                }
-            }
+            if (unit == unit0 || !early_l0) stream_layer(0);
+            for (int l = 1; l < nl - 1; l++) stream_layer(l);
+            if (early_l0 && unit + unit_step < n_units) stream_layer(0);
+            stream_layer(nl - 1);
         }
-    } else if (warp == 1 && CTAS == 2 && rank == 1) {
-        // ===================== peer relay: "IDE operand / A-operand chunk c of my tile is ready" -> leader's issuer ==========
-        // in the order the issuer consumes them; one release.cluster arrive per phase
-        uint32_t ide_par = 0, chunk_par = 0;
-        const uint32_t l_ide = tc::map_to_rank(tc::smem_u32(ide_full), 0), l_rdy = tc::map_to_rank(tc::smem_u32(&a_rdy[0]), 0);
-        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
-            tc::mbar_wait(ide_full, ide_par); ide_par ^= 1;
-            tc::fence_proxy_async_smem();
-            if (lane == 0) tc::mbar_arrive_cluster(l_ide);
-            __syncwarp();
-            for (int l = 0; l + 1 < nl; l++) {
-                const uint32_t nchunks = E.L[l].N / 32;
-                for (uint32_t c = 0; c < nchunks; c++) {
-                    tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u); chunk_par ^= 1u << c;
-                    tc::fence_proxy_async_smem();
-                    if (lane == 0) tc::mbar_arrive_cluster(l_rdy + c * 8);
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (warp == 1 && rank == 0) {
+    } else if (warp == 1 && (CTAS == 1 || rank == 0)) {
         // ===================== MMA issuer (leader CTA) =====================
         // All 32 lanes run this code with warp-uniform values; one elected lane issues (tc::*_w helpers).
         // Accumulators ping-pong between TMEM columns [0,256) and [256,512) from layer to layer, so the epilogue of layer g
@@ -248,16 +315,15 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         // chunk 0 is in shared memory.  Hazards: MMA(g+2) reuses the accumulator of layer g; it is issued after the last
         // K step of MMA(g+1), which waited for every chunk of epilogue(g) (or, across tiles, behind chunk 0 of
         // epilogue(g+1), which the same warps run after epilogue(g)).
-        uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0, gl = 0, ti = 0;
+        uint32_t stage = 0, phase = 0, ide_par = 0, chunk_par = 0;
         const uint32_t ring0 = tc::smem_u32(ring);
-        for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
-            unsigned long long w_a = 0, w_f = 0;
-            for (int l = 0; l < nl; l++) {
+        unsigned long long w_a = 0, w_f = 0;
+        auto issue_layer = [&](int l, uint32_t ti) {
+            {
                 const uint32_t ksteps = E.L[l].Kp / 16, Np = E.L[l].Np, Nb = Np / CTAS;     // Nb: rows of B held by one CTA
                 const uint32_t idesc = tc::make_idesc_f16(128 * CTAS, Np);
-                const uint32_t buf = gl & 1u;
+                const uint32_t buf = acc_buf(ti, l);
                 const uint32_t d_tmem = tmem + buf * 256u;
-                gl++;
                 if (F8 && E.L[l].f8) {
                     // ---- mode 1: corrections on e4m3 (phase A, chunk by chunk as the epilogue publishes them), then hi16 * hi16
                     uint64_t da_h8 = tc::make_smem_desc(tc::smem_u32(sA_h8), 2048, 128);
@@ -267,13 +333,13 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     const uint32_t chunks = ksteps / 2, cbytes = Np * 64, cper = max(1u, kTcStageBytes / cbytes);
                     for (uint32_t c0 = 0; c0 < chunks; c0 += cper) {
                         const unsigned long long t1 = prof ? clock64() : 0;
-                        tc::mbar_wait(&full[stage], phase);
+                        wait_tag(&full[stage], phase, 2);
                         if (prof) w_f += clock64() - t1;
                         const uint32_t cend = min(chunks, c0 + cper);
                         uint64_t db = tc::desc_advance(db0, stage * kTcStageBytes);
                         for (uint32_t c = c0; c < cend; c++) {
                             const unsigned long long t0 = prof ? clock64() : 0;
-                            tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u);
+                            wait_tag(&a_rdy[c], (chunk_par >> c) & 1u, 3);
                             chunk_par ^= 1u << c;
                             if (prof) w_a += clock64() - t0;
                             tc::tc_fence_after();
@@ -289,7 +355,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                     const uint32_t sbytes = Np * 32, sper = max(1u, kTcStageBytes / sbytes);
                     for (uint32_t s0 = 0; s0 < ksteps; s0 += sper) {
                         const unsigned long long t1 = prof ? clock64() : 0;
-                        tc::mbar_wait(&full[stage], phase);
+                        wait_tag(&full[stage], phase, 4);
                         if (prof) w_f += clock64() - t1;
                         const uint32_t kend = min(ksteps, s0 + sper);
                         uint64_t db = tc::desc_advance(db0, stage * kTcStageBytes);
@@ -305,13 +371,13 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                     }
                     tc::mma_commit_w(&acc_ready[buf]);
-                    if (prof && lane == 0 && l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; }
-                    continue;
+                    if (prof && lane == 0 && l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; w_a = w_f = 0; }
+                    return;
                 }
                 uint64_t da_hi, da_lo;
                 if (l == 0) {
                     if (prof && lane == 0) stamp(ti, 0, clock64());
-                    if (CTAS == 2) tc::mbar_wait_cluster(ide_full, ide_par); else tc::mbar_wait(ide_full, ide_par);
+                    if (CTAS == 2) wait_tag_cluster(ide_full, ide_par, 5); else wait_tag(ide_full, ide_par, 5);
                     ide_par ^= 1;                                            // IDE operand of this tile (pair) is in smem
                     if (prof && lane == 0) stamp(ti, 1, clock64());
                     da_hi = tc::make_smem_desc(tc::smem_u32(sI_hi), 2048, 128);
@@ -325,8 +391,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 const uint32_t kper = max(1u, kTcStageBytes / kbytes);
                 for (uint32_t s0 = 0; s0 < ksteps; s0 += kper) {
                     const unsigned long long t1 = prof ? clock64() : 0;
-                    tc::mbar_wait(&full[stage], phase);
-                    if (CTAS == 2) tc::mbar_wait_cluster(&pfull[stage], phase);
+                    wait_tag(&full[stage], phase, 6);            // CTAS = 2: both CTAs' halves (complete_tx of both TMA streams)
                     if (prof) w_f += clock64() - t1;
                     const uint32_t kend = min(ksteps, s0 + kper);
                     uint64_t db_hi = tc::desc_advance(db0, stage * kTcStageBytes);
@@ -334,10 +399,11 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         if (l > 0 && (s & 1u) == 0) {                        // K steps 2c, 2c+1 read chunk c of the A operand
                             const uint32_t c = s >> 1;
                             const unsigned long long t0 = prof ? clock64() : 0;
-                            if (CTAS == 2) tc::mbar_wait_cluster(&a_rdy[c], (chunk_par >> c) & 1u);
-                            else tc::mbar_wait(&a_rdy[c], (chunk_par >> c) & 1u);
+                            if (CTAS == 2) wait_tag_cluster(&a_rdy[c], (chunk_par >> c) & 1u, 7);
+                            else wait_tag(&a_rdy[c], (chunk_par >> c) & 1u, 7);
                             chunk_par ^= 1u << c;
                             if (prof) w_a += clock64() - t0;
+                            if (prof && lane == 0 && l == 2 && c < 8) stamp(ti, 24 + c, clock64());
                         }
                         tc::tc_fence_after();
                         __syncwarp();
@@ -348,14 +414,18 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                             tc::mma2_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
                         } else {
                             tc::mma_f16_ss_w(d_tmem, da_hi, db_hi, idesc, s > 0);
-                            tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
-                            tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                            if (!(E.debug & 4u)) {                            // timing experiment: hi*hi only
+                                tc::mma_f16_ss_w(d_tmem, da_lo, db_hi, idesc, 1);
+                                tc::mma_f16_ss_w(d_tmem, da_hi, db_lo, idesc, 1);
+                            }
                         }
                         da_hi = tc::desc_advance(da_hi, 4096); da_lo = tc::desc_advance(da_lo, 4096);
                         db_hi = tc::desc_advance(db_hi, kbytes);
                     }
                     // frees the ring slot (in both CTAs) when these MMAs retire
-                    if (CTAS == 2) tc::mma2_commit_w(&empty[stage]); else tc::mma_commit_w(&empty[stage]);
+                    if (CTAS == 2) tc::mma2_commit_w(&empty[stage]);
+                    else if (MC > 1) tc::mma_commit_mc_w(&empty[stage], (uint16_t)((1u << MC) - 1));
+                    else tc::mma_commit_w(&empty[stage]);
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
                 if (CTAS == 2) {
@@ -364,31 +434,43 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 } else {
                     if (l == 0) tc::mma_commit_w(ide_empty);      // IDE buffer may be refilled for the next tile
                     tc::mma_commit_w(&acc_ready[buf]);
+                    if (prof && lane == 0 && l == 2) stamp(ti, 32, clock64());
                 }
                 if (prof && lane == 0) {
                     if (l == 0) stamp(ti, 2, clock64());
                     if (l == nl - 1) { stamp(ti, 3, clock64()); stamp(ti, 4, w_a); stamp(ti, 5, w_f); prof[0] = ti + 1; }
                 }
+                if (l == nl - 1) w_a = w_f = 0;
             }
+        };
+        uint32_t ti = 0;
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
+            if (unit == unit0 || !early_l0) issue_layer(0, ti);
+            for (int l = 1; l < nl - 1; l++) issue_layer(l, ti);
+            if (early_l0 && unit + unit_step < n_units) issue_layer(0, ti + 1);
+            issue_layer(nl - 1, ti);
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 4 + kTcEpiWarps) {
         // ===================== epilogue warps =====================
-        const uint32_t quarter = warp & 3, g = (warp - 4) >> 2;
+        // 8 warps: quarter = TMEM lane quarter (rows), g = chunk parity of the 32-column chunks this warp converts.  (16 warps on
+        // 16-column halves -- the layout that paid off in k_neus_geom_tc -- measured no faster here, run r3_12: the chunk cadence stayed at
+        // ~900 cycles per chunk pair, i.e. the accumulator read-out is not bound by the per-warp dependent chain.)
+        const uint32_t quarter = warp & 3, g = (warp - 4) >> 2, g4 = g;
         const uint32_t row = quarter * 32 + lane;
         const uint32_t branch = row >> 6;
         const uint32_t lane_addr = (quarter * 32u) << 16;
-        uint32_t acc_par = 0, gl = 0, ti = 0;
+        uint32_t acc_par = 0, ti = 0;
         const bool pw = prof && tid == 4 * 32;
         const uint32_t a_rdy_addr = to_issuer(&a_rdy[0]);
         for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
-            const uint32_t tile = unit * CTAS + rank;
+            const uint32_t tile = unit * GROUP + rank;
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             for (int l = 0; l < nl; l++) {
-                const uint32_t buf = gl & 1u;
-                gl++;
-                tc::mbar_wait(&acc_ready[buf], (acc_par >> buf) & 1u); acc_par ^= 1u << buf;
+                const uint32_t buf = acc_buf(ti, l);
+                wait_tag(&acc_ready[buf], (acc_par >> buf) & 1u, 8); acc_par ^= 1u << buf;
                 if (pw && l < 4) stamp(ti, 12 + 2 * l, clock64());
+                if (prof && l == 1 && tid == 8 * 32) stamp(ti, 41, clock64());
                 tc::tc_fence_after();
                 const uint32_t acc = tmem + lane_addr + buf * 256u;
                 const float* bias = s_bias + l * 256;
@@ -434,7 +516,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         }
                         tc::tc_fence_before();
                         tc::fence_proxy_async_smem();
-                        arrive_issuer(a_rdy_addr + cb * 8);
+                        arrive_issuer(a_rdy_addr + cb * 8, 1 + g, 128, quarter == 0 && lane == 0);
                     }
                 } else if (l < nl - 1) {
                     const uint32_t nchunks = E.L[l].N / 32;
@@ -457,9 +539,10 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         }
                         tc::tc_fence_before();
                         tc::fence_proxy_async_smem();
-                        arrive_issuer(a_rdy_addr + cb * 8);         // chunk cb of the next layer's A operand is ready
+                        arrive_issuer(a_rdy_addr + cb * 8, 1 + g, 128, quarter == 0 && lane == 0);         // chunk cb of the next layer's A operand is ready
+                        if (prof && l == 1 && lane == 0 && quarter == 0 && (cb >> 1) < 4) stamp(ti, (g ? 37 : 33) + (cb >> 1), clock64());
                     }
-                } else if (g == 0) {
+                } else if (g4 == 0) {
                     uint32_t r[16];
                     tc::tmem_ld16(acc, r);
                     tc::tmem_ld_wait();
@@ -483,18 +566,18 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 if (pw && l < 4) stamp(ti, 13 + 2 * l, clock64());
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 4 + kTcEpiWarps) {
         // ===================== IDE warps: directional encoding of the NEXT tile while the current one is in the MMA pipe ====
-        const uint32_t t2 = tid - 12 * 32;               // 0 .. 511
+        const uint32_t t2 = tid - (4 + kTcEpiWarps) * 32;               // 0 .. 511
         const uint32_t branch = t2 < 384 ? 1u : 0u;      // warp-uniform
         const uint32_t part = branch ? t2 >> 6 : (t2 - 384) >> 6;                // 0..5 (reflected) / 0..1 (normal), warp-uniform
         const uint32_t row = branch ? 64 + (t2 & 63) : (t2 - 384) & 63;
         const uint32_t Kp0 = E.L[0].Kp, P = E.P;
         uint32_t empty_par = 1, ti = 0;                  // first wait passes
-        const bool pw = prof && tid == 12 * 32;
+        const bool pw = prof && tid == (4 + kTcEpiWarps) * 32;
         const uint32_t ide_full_addr = to_issuer(ide_full);
         for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
-            const uint32_t tile = unit * CTAS + rank;
+            const uint32_t tile = unit * GROUP + rank;
             const uint32_t m = tile * 64 + (row & 63);
             const bool valid = m < M;
             float dx = 0.f, dy = 0.f, dz = 1.f, kap = 0.f;
@@ -509,9 +592,9 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 }
             }
             if (pw) stamp(ti, 8, clock64());
-            tc::mbar_wait(ide_empty, empty_par); empty_par ^= 1;
+            wait_tag(ide_empty, empty_par, 9); empty_par ^= 1;
             if (pw) stamp(ti, 9, clock64());
-            if (valid) {
+            if (valid && !(E.debug & 2u)) {                   // debug bit 1: timing experiment without the IDE arithmetic
                 // layer-0 K order is interleaved (column 2i = Re_i, 2i+1 = Im_i; the weight image is packed with the same
                 // permutation, k_pack_tc `interleave`): one packed fp16x2 store per (hi, lo) instead of four 2-byte stores,
                 // and the packed conversion instead of scalar ones
@@ -563,12 +646,12 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 }
             }
             tc::fence_proxy_async_smem();
-            arrive_issuer(ide_full_addr);
+            arrive_issuer(ide_full_addr, 3, kTcIdeThreads, t2 == 0);
             if (pw) stamp(ti, 10, clock64());
         }
     }
     tc::tc_fence_before();
-    if (CTAS == 2) tc::cluster_sync_all(); else __syncthreads();       // peer may still read this CTA's B half / signal its barriers
+    if (GROUP > 1) tc::cluster_sync_all(); else __syncthreads();       // peers may still read this CTA's B half / write its ring / signal its barriers
     if (warp == 2) { if (CTAS == 2) tc::tmem_dealloc2(tmem, 512); else tc::tmem_dealloc(tmem, 512); }
 }
 
@@ -673,6 +756,7 @@ bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t*
     const uint64_t bias_bytes_off = off;
     off += (uint64_t)boff * 4;
     t.n_layers = f->n_env; t.P = P; t.E = f->env[f->n_env - 1].out_dim;
+    t.reorder = 1;
     t.kappa_diffuse = f->diffuse_kappa_inv; t.light_scale = f->light_intensity_scale;
     // bands of the normal-direction encoding whose attenuation exp(-sigma_l * kappa) is below e^-21 = 7.6e-10 are not evaluated
     // (their features stay exactly zero; the reference computes values of that magnitude, 5 orders below the parity bar):
@@ -699,18 +783,59 @@ int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st
     return check_launch("field_pack_tc");
 }
 
-constexpr size_t kTcSmem = 2 * kTcARegion + 2 * kTcIdeRegion + kTcStages * kTcStageBytes + kTcMaxLayers * 256 * sizeof(float) + 256;
+constexpr size_t kTcSmem = 2 * kTcARegion + 2 * kTcIdeRegion + kTcRingBytes + kTcMaxLayers * 256 * sizeof(float) + 256;
 
 // ENVIDR_ENV_TC_CTAS=2 selects the CTA-pair kernel.  Default is the single-CTA kernel: measured on B200 (profiles/r01_run12.md) the
 // pair kernel is correct but not faster yet -- the per-tile critical path is the epilogue / operand hand-off chain, not the
 // shared-memory bandwidth the pair relieves, and the remote (cluster-scope) arrives lengthen that chain.
+static CUtensorMap g_no_tmap{};
+
+// Tensor map of the weight blob for the CTA-pair kernel: the blob as a 2-D array of 1 KB rows (256 x uint32), box = 8 rows = 8 KB (one K
+// step of one CTA's half of a 256-wide layer; every image offset and every stage size is a multiple of it).  cuTensorMapEncodeTiled is
+// resolved through the runtime (no link-time dependency on a driver symbol version); one map per (blob address, size), cached.
+static const CUtensorMap* blob_tensor_map(const TcEnv& t) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static const uint8_t* cached_blob = nullptr;
+    static uint64_t cached_rows = 0;
+    static CUtensorMap cached[2]{};           // [0]: 8 KB boxes, [1]: 1 KB boxes
+    const uint64_t rows = ((uint64_t)(reinterpret_cast<const uint8_t*>(t.bias) - t.blob) + 1023) >> 10;
+    if (cached_blob == t.blob && cached_rows == rows) return cached;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available"); return nullptr; }
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t gdim[2] = {256, rows};
+    const cuuint64_t gstride[1] = {1024};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 2; i++) {
+        const cuuint32_t box[2] = {256, i == 0 ? 8u : 1u};
+        CUresult r = encode(&cached[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(t.blob), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); cached_blob = nullptr; return nullptr; }
+    }
+    cached_blob = t.blob; cached_rows = rows;
+    return cached;
+}
+
 static int env_tc_ctas() {
     static int v = 0;
     if (!v) { const char* e = getenv("ENVIDR_ENV_TC_CTAS"); v = (e && e[0] == '2') ? 2 : 1; }
     return v;
 }
 
-int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
+// ENVIDR_ENV_TC_MULTICAST = 1 | 2 | 4: CTAs per weight-multicast cluster of the default kernel (1 = every CTA streams for itself)
+static int env_tc_multicast() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("ENVIDR_ENV_TC_MULTICAST"); v = e ? atoi(e) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
+    return v;
+}
+
+int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
     if ((int)ide_degree != g_ide_tc_deg) {
         IdeTables tab;
         if (!ide_build_tables((int)ide_degree, &tab)) return ENVIDR_E_UNSUPPORTED;
@@ -720,14 +845,25 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
     }
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_env_tc<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_tc<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_error("env_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     const uint32_t n_tiles_host = (2 * M_host + 127) / 128;
+    static int reorder = -1;
+    if (reorder < 0) { const char* e = getenv("ENVIDR_ENV_TC_REORDER"); reorder = (e && e[0] == '0') ? 0 : 1; }
+    TcEnv t = t_in;
+    t.reorder = (uint32_t)reorder;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ENVIDR_ENV_TC_DEBUG"); dbg = e ? atoi(e) : 0; }      // timing experiments only, see TcEnv::debug
+    t.debug = (uint32_t)dbg;
     if (env_tc_ctas() == 2) {
+        const CUtensorMap* tmap = blob_tensor_map(t);
+        if (!tmap) return ENVIDR_E_UNSUPPORTED;
         uint32_t grid = kSMs & ~1u;                    // whole CTA pairs
         if (!M_dev) grid = min(grid, 2 * ((n_tiles_host + 1) / 2));
         if (grid == 0) return 0;
@@ -737,7 +873,7 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false, 1>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, tmap[0], tmap[1]);
         if (e != cudaSuccess) { set_error("env_tc (CTA pair) launch: %s", cudaGetErrorString(e)); return (int)e; }
         return check_launch("env_tc2");
     }
@@ -747,9 +883,23 @@ int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* 
     if (env_tc_mode() == 1) {
         TcEnv t8 = t;
         for (uint32_t i = 0; i < t8.n_layers; i++) if (t8.L[i].f8) t8.L[i].dscale = kF8DScale;
-        k_env_tc<1, true><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+        k_env_tc<1, true, 1><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
+    } else if (env_tc_multicast() > 1) {
+        // weight-multicast clusters (opt-in; measured no faster, run r3_09): whole clusters only; a cluster whose tiles are all past the end returns at once
+        const uint32_t mc = (uint32_t)env_tc_multicast();
+        grid = kSMs / mc * mc;
+        if (!M_dev) grid = min(grid, (n_tiles_host + mc - 1) / mc * mc);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = mc == 4 ? cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 4>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap)
+                                : cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
+        if (e != cudaSuccess) { set_error("env_tc (multicast cluster) launch: %s", cudaGetErrorString(e)); return (int)e; }
     } else {
-        k_env_tc<1, false><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap);
+        k_env_tc<1, false, 1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
     }
     return check_launch("env_tc");
 }

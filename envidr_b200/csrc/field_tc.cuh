@@ -21,6 +21,8 @@ struct TcEnv {
     const float* bias;            // [sum Np] floats
     uint32_t n_layers, P, E;
     uint32_t ide_nb0;             // bands evaluated for the normal-direction (constant kappa) encoding, see tc_layout
+    uint32_t debug;               // timing experiments (ENVIDR_ENV_TC_DEBUG bit mask; results are wrong): 1 no weight copies, 2 no IDE arithmetic, 4 hi*hi product only
+    uint32_t reorder;             // issue the NEXT tile's layer 0 ahead of this tile's last layer (field_tc.cu, default 1)
     float kappa_diffuse, light_scale;
     int has_rot; float rot[9];    // records hold unrotated directions: d <- d @ rot before the encoding (envidr_field.rec_unrotated)
     TcLayer L[kTcMaxLayers];

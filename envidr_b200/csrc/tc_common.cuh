@@ -41,6 +41,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same copy delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster, complete_tx on the barrier at the
+// same offset in each of them
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 // make generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -113,6 +119,12 @@ __device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
     asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
                  " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
 }
+// commit that arrives on the barrier at the same offset in every CTA of `cta_mask` (cta_group::1 MMAs of this CTA)
+__device__ __forceinline__ void mma_commit_mc_w(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+                 " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 // descriptor of the same operand `bytes` further in shared memory (address field is in 16-byte units)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
@@ -155,6 +167,19 @@ __device__ __forceinline__ void mma2_commit_w(uint64_t* bar) {
                  " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
                  ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- CTA-pair weight loads: 2-D tiled TMA whose completion is signalled on the LEADER's mbarrier -------------------
+// cp.async.bulk.tensor with .cta_group::2 may complete_tx on a barrier of either CTA of the pair (a plain cp.async.bulk can only signal
+// a barrier of the CTA that owns the destination), so the peer's half of a weight stage needs no relay warp.
+__device__ __forceinline__ void tma2_load_2d(uint32_t smem_dst_u32, const void* tmap, int32_t c0, int32_t c1, uint32_t mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst_u32), "l"(tmap), "r"(c0), "r"(c1), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar_u32, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar_u32), "r"(bytes) : "memory");
+}
+// named barrier over `count` threads (multiple of 32) of this CTA
+__device__ __forceinline__ void bar_sync_named(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // fp32 -> (hi, lo) fp16 pair with hi + lo ~= x to ~2^-22 relative (lo may be subnormal: absolute error <= 3e-8)
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
