@@ -23,7 +23,7 @@ def _sources():
     return [s for s in SOURCES + EXTRA_SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-EXTRA_SOURCES = ["field_tc.cu", "tc_probe.cu", "geom_tc.cu", "shade_tc.cu", "linear_tc.cu", "density.cu", "optim.cu", "epilogue.cu", "neus.cu", "neus_field.cu", "neus_geom_tc.cu"]
+EXTRA_SOURCES = ["field_tc.cu", "tc_probe.cu", "geom_tc.cu", "shade_tc.cu", "linear_tc.cu", "density.cu", "optim.cu", "epilogue.cu", "neus.cu", "neus_field.cu", "neus_geom_tc.cu", "env_train_tc.cu"]
 
 
 def _stale():

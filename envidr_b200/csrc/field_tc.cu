@@ -152,11 +152,14 @@ __device__ __forceinline__ void wait_tag_cluster(uint64_t* bar, uint32_t parity,
 //   .multicast::cluster onto every CTA's empty barrier, count MC).  Why: all 148 SMs stream the same 608 KB of weight images per
 //   tile from L2; at a 256 x 256 layer that is 148 x 16 KB per ~460 cycles = 82 % of the L2 read bandwidth, and the layer ran at the
 //   supply rate (7.4 k cycles) instead of the MMA rate (6.1 k).  The CTAs stay coupled only through the 3-stage ring.
-template <int CTAS, bool F8, int MC>
+// SAVE (training forward, csrc/env_train_tc.cu): every hidden layer's post-ReLU activations [2M, N] (fp32, row = branch * M + sample:
+//   the operand of the weight-gradient GEMMs) and their ReLU bit masks [2M, N / 32] go to HBM, and the inverse norm of the un-normalised
+//   env feature is left in slot 12 of the feature row (the backward of F.normalize needs it).
+template <int CTAS, bool F8, int MC, bool SAVE = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
          unsigned long long* __restrict__ prof, uint32_t prof_cap, const __grid_constant__ CUtensorMap tmap,
-         const __grid_constant__ CUtensorMap tmap1) {
+         const __grid_constant__ CUtensorMap tmap1, const TcSave SV) {
     constexpr int kTcStages = 3;
     constexpr uint32_t kTcStageBytes = kTcRingBytes / kTcStages;
     constexpr int GROUP = CTAS == 2 ? 2 : MC;             // CTAs per cluster
@@ -525,18 +528,31 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         tc::tmem_ld32(acc + cb * 32, r);
                         tc::tmem_ld_wait();
                         const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
+                        uint32_t mk = 0;
                         #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
                             uint32_t ph[4], pl[4];
-                            split2(fmaxf(__uint_as_float(r[8 * j + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(r[8 * j + 1]) + ba.y, 0.f), ph[0], pl[0]);
-                            split2(fmaxf(__uint_as_float(r[8 * j + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r[8 * j + 3]) + ba.w, 0.f), ph[1], pl[1]);
-                            split2(fmaxf(__uint_as_float(r[8 * j + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[8 * j + 5]) + bb.y, 0.f), ph[2], pl[2]);
-                            split2(fmaxf(__uint_as_float(r[8 * j + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(r[8 * j + 7]) + bb.w, 0.f), ph[3], pl[3]);
+                            const float v0 = fmaxf(__uint_as_float(r[8 * j + 0]) + ba.x, 0.f), v1 = fmaxf(__uint_as_float(r[8 * j + 1]) + ba.y, 0.f);
+                            const float v2 = fmaxf(__uint_as_float(r[8 * j + 2]) + ba.z, 0.f), v3 = fmaxf(__uint_as_float(r[8 * j + 3]) + ba.w, 0.f);
+                            const float v4 = fmaxf(__uint_as_float(r[8 * j + 4]) + bb.x, 0.f), v5 = fmaxf(__uint_as_float(r[8 * j + 5]) + bb.y, 0.f);
+                            const float v6 = fmaxf(__uint_as_float(r[8 * j + 6]) + bb.z, 0.f), v7 = fmaxf(__uint_as_float(r[8 * j + 7]) + bb.w, 0.f);
+                            if (SAVE && valid) {
+                                float4* dst = reinterpret_cast<float4*>(SV.act[l] + ((size_t)branch * SV.M + m) * E.L[l].N + cb * 32 + j * 8);
+                                dst[0] = make_float4(v0, v1, v2, v3);
+                                dst[1] = make_float4(v4, v5, v6, v7);
+                                mk |= ((v0 > 0.f ? 1u : 0u) | (v1 > 0.f ? 2u : 0u) | (v2 > 0.f ? 4u : 0u) | (v3 > 0.f ? 8u : 0u) | (v4 > 0.f ? 16u : 0u) |
+                                       (v5 > 0.f ? 32u : 0u) | (v6 > 0.f ? 64u : 0u) | (v7 > 0.f ? 128u : 0u)) << (8 * j);
+                            }
+                            split2(v0, v1, ph[0], pl[0]);
+                            split2(v2, v3, ph[1], pl[1]);
+                            split2(v4, v5, ph[2], pl[2]);
+                            split2(v6, v7, ph[3], pl[3]);
                             const uint32_t off = tc::op_off(128, row, cb * 32 + j * 8);
                             *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                             *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                         }
+                        if (SAVE && valid) SV.mask[l][((size_t)branch * SV.M + m) * (E.L[l].N / 32) + cb] = mk;
                         tc::tc_fence_before();
                         tc::fence_proxy_async_smem();
                         arrive_issuer(a_rdy_addr + cb * 8, 1 + g, 128, quarter == 0 && lane == 0);         // chunk cb of the next layer's A operand is ready
@@ -559,7 +575,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         dst[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
                         dst[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
                         dst[2] = make_float4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
-                        dst[3] = make_float4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
+                        dst[3] = make_float4(SAVE ? inv : f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);      // SAVE: E <= 12 (checked at launch)
                     }
                     tc::tc_fence_before();
                 }
@@ -835,7 +851,8 @@ static int env_tc_multicast() {
     return v;
 }
 
-int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st) {
+int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st,
+                  const TcSave* save) {
     if ((int)ide_degree != g_ide_tc_deg) {
         IdeTables tab;
         if (!ide_build_tables((int)ide_degree, &tab)) return ENVIDR_E_UNSUPPORTED;
@@ -854,6 +871,20 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         attr = true;
     }
     const uint32_t n_tiles_host = (2 * M_host + 127) / 128;
+    if (save) {
+        // training forward: the default single-CTA kernel with the SAVE epilogue
+        ENVIDR_REQUIRE(!M_dev && t_in.E <= 12 && t_in.n_layers >= 2 && t_in.n_layers <= 4, ENVIDR_E_UNSUPPORTED, "env_net training forward: 2..4 layers, env_feat <= 12");
+        static bool attr_s = false;
+        if (!attr_s) {
+            cudaError_t e = cudaFuncSetAttribute(k_env_tc<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+            if (e != cudaSuccess) { set_error("env_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_s = true;
+        }
+        const uint32_t grid_s = min((uint32_t)kSMs, n_tiles_host);
+        if (grid_s == 0) return 0;
+        k_env_tc<1, false, 1, true><<<grid_s, kTcThreads, kTcSmem, st>>>(t_in, rec, feat, nullptr, M_host, nullptr, 0, g_no_tmap, g_no_tmap, *save);
+        return check_launch("env_tc(train forward)");
+    }
     static int reorder = -1;
     if (reorder < 0) { const char* e = getenv("ENVIDR_ENV_TC_REORDER"); reorder = (e && e[0] == '0') ? 0 : 1; }
     TcEnv t = t_in;
@@ -873,7 +904,7 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false, 1>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, tmap[0], tmap[1]);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false, 1>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, tmap[0], tmap[1], TcSave{});
         if (e != cudaSuccess) { set_error("env_tc (CTA pair) launch: %s", cudaGetErrorString(e)); return (int)e; }
         return check_launch("env_tc2");
     }
@@ -883,7 +914,7 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
     if (env_tc_mode() == 1) {
         TcEnv t8 = t;
         for (uint32_t i = 0; i < t8.n_layers; i++) if (t8.L[i].f8) t8.L[i].dscale = kF8DScale;
-        k_env_tc<1, true, 1><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
+        k_env_tc<1, true, 1><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
     } else if (env_tc_multicast() > 1) {
         // weight-multicast clusters (opt-in; measured no faster, run r3_09): whole clusters only; a cluster whose tiles are all past the end returns at once
         const uint32_t mc = (uint32_t)env_tc_multicast();
@@ -895,11 +926,11 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = mc == 4 ? cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 4>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap)
-                                : cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
+        cudaError_t e = mc == 4 ? cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 4>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{})
+                                : cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
         if (e != cudaSuccess) { set_error("env_tc (multicast cluster) launch: %s", cudaGetErrorString(e)); return (int)e; }
     } else {
-        k_env_tc<1, false, 1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap);
+        k_env_tc<1, false, 1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
     }
     return check_launch("env_tc");
 }

@@ -67,7 +67,14 @@ int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const
 // layout / packing / launch (field_tc.cu)
 bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes);
 int tc_pack(const envidr_field* f, const TcEnv& t, void* packed, cudaStream_t st);
-int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st);
+// training forward (csrc/env_train_tc.cu): what the SAVE instantiation of k_env_tc leaves in HBM next to the features
+struct TcSave {
+    float* act[3];                // post-ReLU activations of the hidden layers, [2M, N_l] fp32, row = branch * M + sample (branch 0: normal direction)
+    uint32_t* mask[3];            // their ReLU bit masks, [2M, N_l / 32]
+    uint32_t M;
+};
+int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st,
+                  const TcSave* save = nullptr);
 int env_tc_mode();               // 0: three fp16 products per K step; 1 (default): fp16 main product + two e4m3 correction products
 
 }  // namespace envidr

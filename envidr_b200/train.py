@@ -90,6 +90,7 @@ class TrainableField(nn.Module):
         return [(getattr(self, f"{name}_w{i}"), getattr(self, f"{name}_b{i}")) for i in range(self.n_layers[name])]
 
     tc_linear: bool = True      # env / colour / diffuse / renv layers through csrc/linear_tc.cu on CUDA tensors
+    fused_env: bool = True      # env_net (both evaluations, IDE included) as one forward + one backward kernel (env_train.py)
     tc_sdf: bool = True         # sdf_net through the any-order-differentiable nt / nn / tn family of linear_tc.py (False: torch layers)
 
     def mlp(self, name: str, x: torch.Tensor) -> torch.Tensor:
@@ -167,13 +168,21 @@ class TrainableField(nn.Module):
         w_r = 2 * n_dot * normals - w_o                                                       # renderer.py:20-39
         deg = int(c["ide_degree"])
         lis = c["light_intensity_scale"]
-        w_r_enc = ops.ide_encode(w_r, roughness, deg) * lis
-        n_enc = ops.ide_encode(normals, c["diffuse_kappa_inv"], deg) * lis
-        # env_net sees both direction sets in ONE batch (rows [0, M) = normal, [M, 2M) = reflected): half the layer launches of the
-        # reference's two calls (network.py:527-541, 589-607), twice the rows per weight-gradient GEMM; same per-row arithmetic
-        M = n_enc.shape[0]
-        f_both = F.normalize(self.mlp("env", torch.cat([n_enc, w_r_enc], 0)), dim=-1)
-        f_n, f_r = f_both[:M], f_both[M:]
+        M = normals.shape[0]
+        f_n = None
+        if self.fused_env and self.tc_linear and ops is default_ops() and normals.is_cuda and normals.dtype == torch.float32 and M > 0:
+            # IDE x 2 -> env_net x 2 -> unit norm as ONE forward kernel, and one fused backward kernel (envidr_b200/env_train.py)
+            from . import env_train
+            layers = self.stack("env")
+            if env_train.supported([W for W, _ in layers], deg):
+                f_n, f_r = env_train.env_features(normals, w_r, roughness, layers, deg, c["diffuse_kappa_inv"], lis)
+        if f_n is None:
+            w_r_enc = ops.ide_encode(w_r, roughness, deg) * lis
+            n_enc = ops.ide_encode(normals, c["diffuse_kappa_inv"], deg) * lis
+            # env_net sees both direction sets in ONE batch (rows [0, M) = normal, [M, 2M) = reflected): half the layer launches of the
+            # reference's two calls (network.py:527-541, 589-607), twice the rows per weight-gradient GEMM; same per-row arithmetic
+            f_both = F.normalize(self.mlp("env", torch.cat([n_enc, w_r_enc], 0)), dim=-1)
+            f_n, f_r = f_both[:M], f_both[M:]
         c_d = torch.sigmoid(self.mlp("diffuse", torch.cat([geo, f_n], -1)))
         hh = torch.cat([geo, normals], -1)
         x_s = torch.cat([hh, f_r, n_dot], -1)

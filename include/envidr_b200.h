@@ -363,6 +363,38 @@ int envidr_wgrad_tc(const float* dY, const float* X, uint32_t M, uint32_t N, uin
                     int variant, envidr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * env_net of the TRAINING branch as one forward and one backward kernel (csrc/env_train_tc.cu).
+ * Reference: the two env_net evaluations of get_color_mlp_extra_params / forward_color (nerf/network.py:527-541, 589-607:
+ * IDE(n, diffuse_kappa_inv) and IDE(w_r, roughness) -> nn.Linear + ReLU stack -> F.normalize) and their autograd backward; the
+ * reference has no operator boundary here (nn.Linear driven from Python), envidr_b200/env_train.py wraps these entries in a
+ * torch.autograd.Function with the reference's argument meaning.
+ *   forward : rec [M,32] sample records (floats 20 roughness, 22..24 normal, 25..27 reflected direction; the record of the inference path)
+ *             -> feat [M,32]: unit-norm env feature of the normal direction at 0.., of the reflected direction at 16.. (slots 12 / 28 hold
+ *             1 / |raw feature|), plus, per hidden layer l, act_l [2M, N_l] (post-ReLU, fp32) and mask_l [2M, N_l / 32] (ReLU bit masks);
+ *             rows of the [2M] batch: [0, M) normal direction, [M, 2M) reflected direction.
+ *   backward: gfeat [M,32] (gradient w.r.t. feat; slots >= env_feat ignored) -> gy [2M,16] (w.r.t. the raw feature), gact_l [2M, N_l]
+ *             (w.r.t. the PRE-activation of hidden layer l: dW_l = gact_l^T act_{l-1}, db_l = column sums), gx0 [2M, input_cols]
+ *             (w.r.t. the IDE features in the kernel's interleaved column order: column 2i = Re_i, 2i + 1 = Im_i, zero padded).
+ * The weight images (forward + transposed) live in `blob` and are rebuilt by envidr_env_mlp_pack whenever the weights change.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct envidr_env_mlp {
+    uint32_t n_layers;                           /* 2..4 */
+    uint32_t dims[ENVIDR_MAX_LAYERS + 1];        /* dims[0] = 2 P (IDE features), dims[i + 1] = outputs of layer i; hidden widths multiples of 32 in 64..256, last <= 12 */
+    const float* weight[ENVIDR_MAX_LAYERS];      /* [dims[i + 1], dims[i]] row-major (torch layout), device */
+    const float* bias[ENVIDR_MAX_LAYERS];        /* [dims[i + 1]] or NULL */
+    uint32_t ide_degree;
+    float diffuse_kappa_inv, light_intensity_scale;
+} envidr_env_mlp;
+uint64_t envidr_env_mlp_blob_bytes(const envidr_env_mlp* d);      /* 0: shape outside the fused kernels */
+uint64_t envidr_env_mlp_input_cols(const envidr_env_mlp* d);      /* columns of gx0 (2 P rounded up to 16) */
+int envidr_env_mlp_pack(const envidr_env_mlp* d, void* blob, uint64_t blob_bytes, envidr_stream_t stream);
+int envidr_env_mlp_forward(const envidr_env_mlp* d, const void* blob, const float* rec, uint32_t M, float* feat, float* act0, float* act1,
+                           float* act2, uint32_t* mask0, uint32_t* mask1, uint32_t* mask2, envidr_stream_t stream);
+int envidr_env_mlp_backward(const envidr_env_mlp* d, const void* blob, const float* gfeat, const float* feat, const uint32_t* mask0,
+                            const uint32_t* mask1, const uint32_t* mask2, uint32_t M, float* gact0, float* gact1, float* gact2, float* gy,
+                            float* gx0, envidr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * NeuS-style opacity: NeuSDensity.forward (nerf/network.py:46-102), the density of the use_neus_sdf configs,
  * consumed by the compositors with input_alpha = 1.  variance: device scalar (the module's parameter); dists: [M] or NULL
  * (then dist_scalar, the module's base_dist); gradients [M,3] or NULL (the reference's gradient-free branch).

@@ -17,7 +17,7 @@ Two layers:
     loop (nerf/render_func/cuda_ray.py:238-359).
 
 Parity status: the reference ships no tests for this path.  The C layer is pinned on the GPU
-box against the reference's own kernels rebuilt for sm_100a (oracle/_ref, tests/test_oracle_vs_ref.py);
+box against the reference's own kernels rebuilt for sm_100a (oracle/_ref, tests/test_gpu_ops.py);
 the torch layer is pinned against tests/golden/*.npz, produced by importing the reference's
 Python modules in the build container (tests/golden/make_golden.py).
 """
