@@ -40,6 +40,7 @@ struct TcGeom {
     uint32_t L, H; float S, bound; int enabled_levels; uint32_t geo_dim;
     float beta, density_scale, rough_bias, rough_act_scale, rough_scale;
     int has_rot; float rot[9];
+    uint32_t stage_bytes;                      // shared-memory staging area for the coarsest level table (0 = off), set at launch
 };
 bool geom_tc_layout(const envidr_field* f, uint64_t base_bytes, TcGeom* out, uint64_t* total_bytes);
 int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStream_t st);

@@ -22,6 +22,13 @@ constexpr int kGThreads = 576;                     // warps 0-7 chain (2 groups 
 constexpr uint32_t kGEnc = 16384, kGEncHalf = 8192;    // encoding operand: 128 rows x 32 K x 2 B, hi | lo
 constexpr uint32_t kGHid = 32768, kGHidHalf = 16384;   // hidden operand:   128 rows x 64 K x 2 B, hi | lo
 constexpr uint32_t kGJacBase = 128, kGJacCols = 96;    // TMEM columns: 2 accumulators x 64, then 4 jacobian slots x 96
+// Shared-memory copy of the coarsest level table (north star: "shared-memory staging of level tables").  Level 0 of the shipped grid is
+// 16^3 x 2 floats = 32 KB and fits next to the 150 KB of weight images and operands; level 1 (23^3 x 8 B = 97 KB) does not.  Every
+// persistent CTA pulls it in once with a bulk copy; its 8 corner loads per sample then never leave the SM.  Measured (run r3_17, ncu over
+// 12 mid-loop launches, staged vs not): 49.3 vs 48.1 us per launch, L1 hit rate 70.0 vs 71.3 %, lts throughput 7.2 vs 7.3 %, issue slots
+// 22.3 vs 22.8 %, frame 15.90 vs 15.78 ms -- no gain: the 32 KB table already lives in L1 (the kernel leaves ~100 KB of it), and the
+// staging area takes that capacity away from the finer levels.  Kept behind ENVIDR_GEOM_STAGE=1, default off.
+constexpr uint32_t kGStageBytes = 32768;
 
 struct GeomOutDev { float *sigma, *normal, *sdf, *roughness, *grad_x; };
 struct GLevel { uint32_t off2, size, res, hashed, magic, on; float scale; uint32_t res2; };
@@ -69,6 +76,7 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
     uint8_t* s_hid = s_enc + 2 * kGEnc;                            // one hidden operand per chain group (rewritten in place)
     GLevel* s_lvl = reinterpret_cast<GLevel*>(s_hid + 2 * kGHid);  // [16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_lvl + 16);
+    const float2* s_tab = reinterpret_cast<const float2*>(reinterpret_cast<uint8_t*>(s_lvl + 16) + 16 * 8);     // staged level-0 table (G.stage_bytes > 0)
     uint64_t* w_full = bars;              // resident weights landed
     uint64_t* enc_full = bars + 1;        // [2] gather -> issuer (256 arrivals)
     uint64_t* enc_free = bars + 3;        // [2] issuer (commit of the stage-0 MMA) -> gather
@@ -118,8 +126,15 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // level 0 is staged when it is a dense level that fits the staging area (decided identically by every thread from the offsets)
+    const uint32_t lvl0_bytes = (uint32_t)(G.offsets[1] - G.offsets[0]) * 8u;
+    const bool stage0 = G.stage_bytes > 0 && lvl0_bytes <= G.stage_bytes && (lvl0_bytes & 15u) == 0 && G.offsets[0] == 0;
     if (warp == 17 && lane == 0) {                 // one-time: pull the resident region in with a few bulk copies
-        tc::mbar_arrive_expect_tx(w_full, G.res_bytes);
+        tc::mbar_arrive_expect_tx(w_full, G.res_bytes + (stage0 ? lvl0_bytes : 0u));
+        if (stage0)
+            for (uint32_t o = 0; o < lvl0_bytes; o += 16384)
+                tc::bulk_g2s(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(s_tab)) + o, reinterpret_cast<const uint8_t*>(G.table) + o,
+                             min(16384u, lvl0_bytes - o), w_full);
         for (uint32_t o = 0; o < G.res_bytes; o += 16384) {
             const uint32_t b = min(16384u, G.res_bytes - o);
             tc::bulk_g2s(s_w + o, G.blob + o, b, w_full);
@@ -171,6 +186,7 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
         const uint32_t s = quarter * 32 + lane;
         const uint32_t lane_addr = (quarter * 32u) << 16;
         float xn[3] = {0.f, 0.f, 0.f};
+        if (stage0) tc::mbar_wait(w_full, 0);     // the staged table arrives with the weight images
         {
             const uint32_t m = blockIdx.x * 128 + s;
             if (m < M) {
@@ -238,10 +254,18 @@ k_geom_tc(const TcGeom G, const float* __restrict__ xyzs, const float* __restric
                                 #pragma unroll
                                 for (uint32_t c = 0; c < 8; c++) raw[c] = pg[0] + (c & 1u) + yz[c >> 1];
                             }
-                            #pragma unroll
-                            for (uint32_t c = 0; c < 8; c++) {
-                                const float2 t = __ldg(grid + g_mod(raw[c], lv.size, lv.magic));
-                                rows[u][c][0] = t.x; rows[u][c][1] = t.y;
+                            if (stage0 && l == 0) {            // warp-uniform: the level is a function of the warp's parity and loop counter
+                                #pragma unroll
+                                for (uint32_t c = 0; c < 8; c++) {
+                                    const float2 t = s_tab[g_mod(raw[c], lv.size, lv.magic)];
+                                    rows[u][c][0] = t.x; rows[u][c][1] = t.y;
+                                }
+                            } else {
+                                #pragma unroll
+                                for (uint32_t c = 0; c < 8; c++) {
+                                    const float2 t = __ldg(grid + g_mod(raw[c], lv.size, lv.magic));
+                                    rows[u][c][0] = t.x; rows[u][c][1] = t.y;
+                                }
                             }
                         }
                     }
@@ -515,7 +539,11 @@ int geom_tc_pack(const envidr_field* f, const TcGeom& g, void* packed, cudaStrea
 
 int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const uint32_t* M_dev, uint32_t M_host, int mode, float* rec,
                    const envidr_field_out* out, cudaStream_t st, const uint32_t* rec_base_dev, uint32_t rec_cap) {
-    const size_t smem = (size_t)g.res_bytes_al + 2 * kGEnc + 2 * kGHid + 16 * sizeof(GLevel) + 16 * 8;
+    static int stage = -1;
+    if (stage < 0) { const char* e = getenv("ENVIDR_GEOM_STAGE"); stage = (e && e[0] == '1') ? 1 : 0; }
+    TcGeom gs = g;
+    gs.stage_bytes = (stage && (reinterpret_cast<uintptr_t>(g.table) & 15u) == 0) ? kGStageBytes : 0u;
+    const size_t smem = (size_t)g.res_bytes_al + 2 * kGEnc + 2 * kGHid + 16 * sizeof(GLevel) + 16 * 8 + gs.stage_bytes;
     static size_t attr_set = 0;
     if (attr_set < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_geom_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -526,7 +554,7 @@ int geom_tc_launch(const TcGeom& g, const float* xyzs, const float* dirs, const 
     if (!M_dev) grid = min((uint32_t)kSMs, (M_host + 127) / 128);
     if (grid == 0) return 0;
     GeomOutDev O{out->sigma, out->normal, out->sdf, out->roughness, out->grad_x};
-    k_geom_tc<<<grid, kGThreads, smem, st>>>(g, xyzs, dirs, M_dev, M_host, mode, rec, O, rec_base_dev, rec_cap);
+    k_geom_tc<<<grid, kGThreads, smem, st>>>(gs, xyzs, dirs, M_dev, M_host, mode, rec, O, rec_base_dev, rec_cap);
     return check_launch("geom_tc");
 }
 
