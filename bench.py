@@ -194,8 +194,19 @@ def train_step_bench(fp_cpu, bf, ro, rd, dev, n_rays, steps=10, warmup=3):
             res[f"ms_per_step_with_{name}"] = timed(full)
         except Exception as e:
             res[f"{name}_error"] = repr(e)[:160]
+    # the same step with env_net as one launch per layer and direction (round-1 form: k_linear_tc x 8, IDE kernels, normalize, ...) instead of the
+    # fused forward / backward kernels (envidr_b200/env_train.py), for the comparison in the same run
+    try:
+        field.fused_env = False
+        graphed_pl = train.GraphedTrainStep(field, bft, cfg, n_rays, mean_count)
+        res["ms_per_step_fwd_bwd_env_per_layer"] = timed(lambda: graphed_pl(o, d, gt_rgb, gt_mask, r_img))
+    except Exception as e:
+        res["env_per_layer_error"] = repr(e)[:160]
+    finally:
+        field.fused_env = True
     return {"rays": n_rays, "samples": n_samples, "ms_per_step_fwd_bwd": ms, "rays_per_sec": n_rays / (ms * 1e-3),
             "ms_per_step_fwd_bwd_eager": ms_eager, **res,
+            "env_net": "one fused forward kernel (IDE -> layers -> unit norm, k_env_tc<SAVE>) + one fused backward kernel (k_env_bwd_tc) + one weight-gradient GEMM per layer",
             "mode": "CUDA graph replay of the captured step (train.GraphedTrainStep); host copies the step's inputs in",
             "what": "run_cuda train branch fwd+bwd (use_renv, r_images; colour L1 + mask BCE + Cauchy + eikonal through the fused loss "
                     "epilogue), fp32; ms_per_step_with_*: + optimizer step over all trainable tensors"}
