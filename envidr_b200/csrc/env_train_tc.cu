@@ -24,7 +24,7 @@ constexpr int kBwThreads = 12 * 32;               // warp 0 producer, 1 issuer, 
 constexpr int kBwStages = 3;
 constexpr uint32_t kBwStageBytes = 16384;
 constexpr uint32_t kBwARegion = 65536;            // 128 rows x 256 K x 2 B
-constexpr uint32_t kBwGRegion = 4096;             // 128 rows x 16 K x 2 B (d y operand of the first GEMM)
+constexpr uint32_t kBwGRegion = 16384;            // 128 rows x 64 K x 2 B: operand of the first GEMM (d y: K = 16; generic forward input: K <= 64)
 
 struct BwLayer { uint32_t Kp, Np, img_off; };      // B operand image: [Np rows = inputs of the forward layer][Kp = its outputs]
 struct EnvBwd {
@@ -39,10 +39,21 @@ struct EnvBwd {
     float* gy;                                     // out: gradient w.r.t. the raw feature, [2M, 16] (zero padded)
     float* gx0;                                    // out: gradient w.r.t. the layer-0 input in ITS column order, [2M, L[n-1].Np]
     uint32_t M;
+    // ---- generic chain (MODE 1: backward of a small ReLU MLP, MODE 2: its forward; envidr_mlp_* entries) ----
+    const float* in;                               // MODE 1: d Y [rows, in_ld] (in_cols <= 16 used); MODE 2: X [rows, in_ld] (in_cols <= 64 used)
+    uint32_t in_ld, in_cols, rows;
+    const float* bias[4];                          // MODE 2: bias of forward layer l or NULL
+    uint32_t nout[4];                              // MODE 2: true output width of forward layer l
+    uint32_t* mask_out[3];                         // MODE 2: ReLU masks of hidden layer l, [rows, N_l / 32]
+    float* act_out[3];                             // MODE 2: post-ReLU activations [rows, N_l] or NULL (only needed when the layer above trains)
+    float* y;                                      // MODE 2: output [rows, 16], zero padded
 };
 
+// MODE 0: backward of env_net (input = gradient of the unit-norm features, rows = the [2M] batch of the forward kernel)
+// MODE 1: backward of a generic small MLP (input = d Y rows);  MODE 2: forward of a generic small MLP (bias + ReLU epilogues, masks saved)
+template <int MODE>
 __global__ void __launch_bounds__(kBwThreads, 1)
-k_env_bwd_tc(const EnvBwd B) {
+k_chain_tc(const EnvBwd B) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA_hi = smem;
     uint8_t* sA_lo = smem + kBwARegion;
@@ -60,7 +71,7 @@ k_env_bwd_tc(const EnvBwd B) {
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const uint32_t rows_total = 2 * B.M;
+    const uint32_t rows_total = MODE == 0 ? 2 * B.M : B.rows;
     const uint32_t n_tiles = (rows_total + 127) / 128;
     const int nl = (int)B.n_layers;
     if (blockIdx.x >= n_tiles) return;
@@ -158,13 +169,44 @@ k_env_bwd_tc(const EnvBwd B) {
             const uint32_t R = tile * 128 + row;                  // row of the [2M] batch: branch * M + sample
             const bool valid = R < rows_total;
             const uint32_t branch = (valid && R >= B.M) ? 1u : 0u, m = valid ? R - branch * B.M : 0u;
-            if (g == 0) {
+            if (g == 0 && MODE == 2) {
+                // ---- generic forward: the row of X as the first operand (K = L[0].Kp <= 64, zero padded), no scaling
+                const uint32_t K0 = B.L[0].Kp;
+                const float* xr = B.in + (size_t)R * B.in_ld;
+                for (uint32_t k0 = 0; k0 < K0; k0 += 8) {
+                    float c[8];
+                    #pragma unroll
+                    for (int i = 0; i < 8; i++) c[i] = (valid && k0 + i < B.in_cols) ? __ldg(xr + k0 + i) : 0.f;
+                    tc::store_chunk8(sG_hi, sG_lo, row, k0, c);
+                }
+                s_inv[row] = 1.0f;
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(g_full);
+            } else if (g == 0) {
                 // ---- backward of F.normalize(y): d y = (g - f (f . g)) / |y|, per-row power-of-two scale, fp16 hi/lo operand (K = 16)
                 float gyv[16];
                 #pragma unroll
                 for (int i = 0; i < 16; i++) gyv[i] = 0.f;
                 float inv_scale = 1.0f;
-                if (valid) {
+                if (valid && MODE == 1) {
+                    // generic backward: the row of d Y as it is
+                    const float* gr = B.in + (size_t)R * B.in_ld;
+                    float mx = 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        gyv[i] = (uint32_t)i < B.in_cols ? __ldg(gr + i) : 0.f;
+                        mx = fmaxf(mx, fabsf(gyv[i]));
+                    }
+                    if (mx > 0.f && mx < 3.0e38f) {
+                        int ex;
+                        frexpf(mx, &ex);
+                        ex = max(-120, min(120, ex - 1));
+                        const float sc = ldexpf(1.0f, -ex);
+                        inv_scale = ldexpf(1.0f, ex);
+                        #pragma unroll
+                        for (int i = 0; i < 16; i++) gyv[i] *= sc;
+                    }
+                } else if (valid) {
                     const float4* gp = reinterpret_cast<const float4*>(B.gfeat + (size_t)m * kTcRecFloats + 16 * branch);
                     const float4* fp = reinterpret_cast<const float4*>(B.feat + (size_t)m * kTcRecFloats + 16 * branch);
                     float gv[16], fv[16];
@@ -212,10 +254,11 @@ k_env_bwd_tc(const EnvBwd B) {
             for (int j = 0; j < nl; j++) {
                 const uint32_t buf = gl & 1u;
                 gl++;
-                const int fl = nl - 2 - j;                        // forward hidden layer whose pre-activation gradient this chain layer produces
+                // backward: forward hidden layer whose pre-activation gradient this chain layer produces; forward: the hidden layer itself
+                const int fl = MODE == 2 ? (j < nl - 1 ? j : -1) : nl - 2 - j;
                 const uint32_t Np = B.L[j].Np;
                 uint32_t mk[4] = {0u, 0u, 0u, 0u};
-                if (fl >= 0 && valid) {                           // masks of this thread's chunks, fetched before the accumulator is ready
+                if (MODE != 2 && fl >= 0 && valid) {              // masks of this thread's chunks, fetched before the accumulator is ready
                     const uint32_t nch = Np / 32;
                     #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -235,14 +278,40 @@ k_env_bwd_tc(const EnvBwd B) {
                         uint32_t r[32];
                         tc::tmem_ld32(acc + cb * 32, r);
                         tc::tmem_ld_wait();
+                        if (MODE == 2) {
+                            // forward hidden layer: h = relu(D + b); mask (and, if a layer above trains, h itself) to HBM; next operand
+                            const float* bl = B.bias[fl];
+                            uint32_t bits2 = 0;
+                            #pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                float v[8];
+                                #pragma unroll
+                                for (int e = 0; e < 8; e++) {
+                                    const uint32_t c = cb * 32 + 8 * jj + e;
+                                    v[e] = fmaxf(__uint_as_float(r[8 * jj + e]) + ((bl && c < B.nout[fl]) ? __ldg(bl + c) : 0.f), 0.f);
+                                    bits2 |= (v[e] > 0.f ? 1u : 0u) << (8 * jj + e);
+                                }
+                                if (valid && B.act_out[fl]) {
+                                    float* adst = B.act_out[fl] + (size_t)R * Np + cb * 32 + 8 * jj;
+                                    reinterpret_cast<float4*>(adst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                    reinterpret_cast<float4*>(adst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                                }
+                                tc::store_chunk8(sA_hi, sA_lo, row, cb * 32 + jj * 8, v);
+                            }
+                            if (valid) B.mask_out[fl][(size_t)R * nch + cb] = bits2;
+                            tc::tc_fence_before();
+                            tc::fence_proxy_async_smem();
+                            tc::mbar_arrive(&a_rdy[cb]);
+                            continue;
+                        }
                         const uint32_t bits = mk[q];
-                        float* gdst = B.gact[fl] + (size_t)R * Np + cb * 32;
+                        float* gdst = B.gact[fl] ? B.gact[fl] + (size_t)R * Np + cb * 32 : nullptr;
                         #pragma unroll
                         for (int jj = 0; jj < 4; jj++) {
                             float v[8];
                             #pragma unroll
                             for (int e = 0; e < 8; e++) v[e] = ((bits >> (8 * jj + e)) & 1u) ? __uint_as_float(r[8 * jj + e]) : 0.f;
-                            if (valid) {
+                            if (valid && gdst) {
                                 reinterpret_cast<float4*>(gdst + 8 * jj)[0] = make_float4(v[0] * inv_scale, v[1] * inv_scale, v[2] * inv_scale, v[3] * inv_scale);
                                 reinterpret_cast<float4*>(gdst + 8 * jj)[1] = make_float4(v[4] * inv_scale, v[5] * inv_scale, v[6] * inv_scale, v[7] * inv_scale);
                             }
@@ -252,6 +321,23 @@ k_env_bwd_tc(const EnvBwd B) {
                         tc::fence_proxy_async_smem();
                         tc::mbar_arrive(&a_rdy[cb]);
                     }
+                } else if (MODE == 2) {
+                    // last forward layer: y = D + b, 16 columns (zero padded)
+                    if (g == 0) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(acc, r);
+                        tc::tmem_ld_wait();
+                        if (valid) {
+                            const float* bl = B.bias[nl - 1];
+                            float o[16];
+                            #pragma unroll
+                            for (int i = 0; i < 16; i++) o[i] = (uint32_t)i < B.nout[nl - 1] ? __uint_as_float(r[i]) + (bl ? __ldg(bl + i) : 0.f) : 0.f;
+                            float4* dst = reinterpret_cast<float4*>(B.y + (size_t)R * 16);
+                            #pragma unroll
+                            for (int i = 0; i < 4; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        }
+                    }
+                    tc::tc_fence_before();
                 } else {
                     // last chain layer: gradient w.r.t. the layer-0 input, Np columns in 16-column units (no mask)
                     const uint32_t nu = Np / 16;
@@ -283,13 +369,15 @@ k_env_bwd_tc(const EnvBwd B) {
 // transposed operand image of one forward layer W [N_out, K_in] (torch layout): B operand rows n = forward INPUT index (Np = K_in rounded
 // up to 16), K = forward OUTPUT index (Kp = N_out rounded up to 16).  `interleave` = P > 0 (forward layer 0): row n < 2P is input column
 // (n & 1) * P + (n >> 1), the K order the forward kernel's IDE warps emit ([Re_0, Im_0, Re_1, ...]), so that d x0 comes out in that order too.
+// transpose = 0: the plain forward image, rows n = forward OUTPUT index (Np), K = forward INPUT index (Kp).
 __global__ void k_pack_tcT(const float* __restrict__ W, uint8_t* __restrict__ img, uint32_t K_in, uint32_t N_out, uint32_t Np, uint32_t Kp,
-                           uint32_t interleave) {
+                           uint32_t interleave, int transpose = 1) {
     const uint32_t total = Np * Kp;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t n = i / Kp, k = i - n * Kp;
         const uint32_t ns = (interleave && n < 2 * interleave) ? (n & 1u) * interleave + (n >> 1) : n;
-        const float v = (ns < K_in && k < N_out) ? W[(size_t)k * K_in + ns] : 0.0f;
+        const float v = transpose ? ((ns < K_in && k < N_out) ? W[(size_t)k * K_in + ns] : 0.0f)
+                                  : ((n < N_out && k < K_in) ? W[(size_t)n * K_in + k] : 0.0f);
         __half h, lo;
         tc::split_f16(v, h, lo);
         const uint32_t s = k >> 4, kk = k & 15;
@@ -340,6 +428,33 @@ static bool env_train_layout(const envidr_env_mlp* d, const void* blob, EnvTrain
         if (b.Np > 256 || b.Kp > 256 || b.Np % 16 != 0) return false;
     }
     L.total_bytes = off;
+    return true;
+}
+
+// generic small MLP (colour / diffuse / renv heads of the training branch): forward images + transposed images in one blob
+struct MlpLayout { BwLayer fw[4], bw[4]; uint64_t total_bytes; uint32_t n; };
+static bool mlp_layout(const envidr_env_mlp* d, MlpLayout* out) {
+    MlpLayout& L = *out;
+    L = MlpLayout{};
+    const uint32_t n = d->n_layers;
+    if (n < 2 || n > 4 || d->dims[0] < 1 || d->dims[0] > 64 || d->dims[n] < 1 || d->dims[n] > 16) return false;
+    for (uint32_t i = 1; i < n; i++) if (d->dims[i] % 32 != 0 || d->dims[i] < 32 || d->dims[i] > 256) return false;
+    uint64_t off = 0;
+    for (uint32_t l = 0; l < n; l++) {                       // forward layer l: rows = outputs, K = inputs
+        L.fw[l].Kp = rup_t(d->dims[l], 16);
+        L.fw[l].Np = (l == n - 1) ? 16 : d->dims[l + 1];
+        L.fw[l].img_off = (uint32_t)off;
+        off += (uint64_t)(L.fw[l].Kp / 16) * L.fw[l].Np * 64;
+    }
+    for (uint32_t j = 0; j < n; j++) {                       // chain layer j of the backward = transpose of forward layer n-1-j
+        const uint32_t fl = n - 1 - j;
+        L.bw[j].Kp = rup_t(d->dims[fl + 1], 16);
+        L.bw[j].Np = (fl == 0) ? rup_t(d->dims[0], 16) : d->dims[fl];
+        L.bw[j].img_off = (uint32_t)off;
+        off += (uint64_t)(L.bw[j].Kp / 16) * L.bw[j].Np * 64;
+    }
+    L.total_bytes = off;
+    L.n = n;
     return true;
 }
 
@@ -414,13 +529,95 @@ int envidr_env_mlp_backward(const envidr_env_mlp* d, const void* blob, const flo
     B.gy = gy; B.gx0 = gx0; B.M = M;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_chain_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem);
         if (e != cudaSuccess) { set_error("env_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     const uint32_t n_tiles = (2 * M + 127) / 128;
-    k_env_bwd_tc<<<min((uint32_t)kSMs, n_tiles), kBwThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(B);
+    k_chain_tc<0><<<min((uint32_t)kSMs, n_tiles), kBwThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(B);
     return check_launch("env_mlp_backward");
+}
+
+uint64_t envidr_mlp_blob_bytes(const envidr_env_mlp* d) {
+    MlpLayout L;
+    return (d && mlp_layout(d, &L)) ? L.total_bytes : 0;
+}
+
+int envidr_mlp_pack(const envidr_env_mlp* d, void* blob, uint64_t blob_bytes, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(d && blob, ENVIDR_E_BADARG, "null argument");
+    MlpLayout L;
+    ENVIDR_REQUIRE(mlp_layout(d, &L), ENVIDR_E_UNSUPPORTED, "MLP outside the fused chain kernels (2..4 layers, inputs <= 64, hidden widths multiples of 32 <= 256, outputs <= 16)");
+    ENVIDR_REQUIRE(blob_bytes >= L.total_bytes, ENVIDR_E_WORKSPACE, "blob too small (envidr_mlp_blob_bytes)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* b = reinterpret_cast<uint8_t*>(blob);
+    for (uint32_t l = 0; l < L.n; l++)
+        k_pack_tcT<<<16, 256, 0, st>>>(d->weight[l], b + L.fw[l].img_off, d->dims[l], d->dims[l + 1], L.fw[l].Np, L.fw[l].Kp, 0u, 0);
+    for (uint32_t j = 0; j < L.n; j++) {
+        const uint32_t fl = L.n - 1 - j;
+        k_pack_tcT<<<16, 256, 0, st>>>(d->weight[fl], b + L.bw[j].img_off, d->dims[fl], d->dims[fl + 1], L.bw[j].Np, L.bw[j].Kp, 0u, 1);
+    }
+    return check_launch("mlp_pack");
+}
+
+static int chain_attr() {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem);
+        if (e != cudaSuccess) { set_error("mlp chain smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    return 0;
+}
+
+int envidr_mlp_forward(const envidr_env_mlp* d, const void* blob, const float* X, uint32_t x_ld, uint32_t rows, float* Y, uint32_t* mask0,
+                       uint32_t* mask1, uint32_t* mask2, float* act0, float* act1, float* act2, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(d && blob && X && Y, ENVIDR_E_BADARG, "null argument");
+    MlpLayout L;
+    ENVIDR_REQUIRE(mlp_layout(d, &L), ENVIDR_E_UNSUPPORTED, "MLP outside the fused chain kernels");
+    ENVIDR_REQUIRE(x_ld >= d->dims[0], ENVIDR_E_BADARG, "row stride of X smaller than the input width");
+    if (rows == 0) return 0;
+    EnvBwd B{};
+    B.blob = reinterpret_cast<const uint8_t*>(blob);
+    B.n_layers = L.n;
+    for (uint32_t l = 0; l < L.n; l++) { B.L[l] = L.fw[l]; B.bias[l] = d->bias[l]; B.nout[l] = d->dims[l + 1]; }
+    uint32_t* masks[3] = {mask0, mask1, mask2};
+    float* acts[3] = {act0, act1, act2};
+    for (uint32_t l = 0; l + 1 < L.n; l++) {
+        ENVIDR_REQUIRE(masks[l], ENVIDR_E_BADARG, "mask buffer missing");
+        B.mask_out[l] = masks[l]; B.act_out[l] = acts[l];
+    }
+    B.in = X; B.in_ld = x_ld; B.in_cols = d->dims[0]; B.rows = rows; B.y = Y;
+    int rc = chain_attr();
+    if (rc) return rc;
+    const uint32_t n_tiles = (rows + 127) / 128;
+    k_chain_tc<2><<<min((uint32_t)kSMs, n_tiles), kBwThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(B);
+    return check_launch("mlp_forward");
+}
+
+int envidr_mlp_backward(const envidr_env_mlp* d, const void* blob, const float* gY, uint32_t gy_ld, const uint32_t* mask0, const uint32_t* mask1,
+                        const uint32_t* mask2, uint32_t rows, float* gz0, float* gz1, float* gz2, float* gX, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(d && blob && gY && gX, ENVIDR_E_BADARG, "null argument");
+    MlpLayout L;
+    ENVIDR_REQUIRE(mlp_layout(d, &L), ENVIDR_E_UNSUPPORTED, "MLP outside the fused chain kernels");
+    ENVIDR_REQUIRE(gy_ld >= d->dims[L.n], ENVIDR_E_BADARG, "row stride of dY smaller than the output width");
+    if (rows == 0) return 0;
+    EnvBwd B{};
+    B.blob = reinterpret_cast<const uint8_t*>(blob);
+    B.n_layers = L.n;
+    for (uint32_t j = 0; j < L.n; j++) B.L[j] = L.bw[j];
+    const uint32_t* masks[3] = {mask0, mask1, mask2};
+    float* gzs[3] = {gz0, gz1, gz2};
+    for (uint32_t l = 0; l + 1 < L.n; l++) {
+        ENVIDR_REQUIRE(masks[l], ENVIDR_E_BADARG, "mask buffer missing");
+        B.mask[l] = masks[l]; B.gact[l] = gzs[l];
+    }
+    B.in = gY; B.in_ld = gy_ld; B.in_cols = d->dims[L.n]; B.rows = rows; B.gx0 = gX;
+    int rc = chain_attr();
+    if (rc) return rc;
+    const uint32_t n_tiles = (rows + 127) / 128;
+    k_chain_tc<1><<<min((uint32_t)kSMs, n_tiles), kBwThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(B);
+    return check_launch("mlp_backward");
 }
 
 uint64_t envidr_env_mlp_input_cols(const envidr_env_mlp* d) {

@@ -148,3 +148,91 @@ def env_features(normals: torch.Tensor, w_r: torch.Tensor, roughness: torch.Tens
     for W, b in layers:
         wb += [W, b]
     return _EnvNetFused.apply(normals, w_r, roughness, int(deg), float(diffuse_kappa_inv), float(light_intensity_scale), len(layers), *wb)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The small ReLU heads (diffuse_net, color_net, renv_net) through the same pair of chain kernels
+# ---------------------------------------------------------------------------------------------------------------------
+
+def mlp_supported(Ws: Sequence[torch.Tensor]) -> bool:
+    """2..4 layers, inputs <= 64, hidden widths multiples of 32 (<= 256), outputs <= 16."""
+    if not (2 <= len(Ws) <= 4) or not Ws[0].is_cuda:
+        return False
+    return lib().envidr_mlp_blob_bytes(ctypes.byref(_desc(Ws, [None] * len(Ws), 1, 0.0, 1.0))) > 0
+
+
+class _MlpFused(Function):
+    @staticmethod
+    def forward(ctx, x, n_layers, *wb):
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        Ws = [wb[2 * i].detach().float().contiguous() for i in range(n_layers)]
+        bs = [None if wb[2 * i + 1] is None else wb[2 * i + 1].detach().float().contiguous() for i in range(n_layers)]
+        x2 = x.detach().float().contiguous()
+        rows, K0 = x2.shape
+        d = _desc(Ws, bs, 1, 0.0, 1.0)
+        nbytes = lib().envidr_mlp_blob_bytes(ctypes.byref(d))
+        if nbytes == 0:
+            raise EnvidrError("MLP outside the fused chain kernels (envidr_mlp_blob_bytes)")
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib().envidr_mlp_pack(ctypes.byref(d), ptr(blob), nbytes, stream()), "mlp_pack")
+        hidden = [int(W.shape[0]) for W in Ws[:-1]]
+        trains = any(ctx.needs_input_grad[2:])                 # some weight / bias wants a gradient: keep the activations
+        masks = [torch.empty(rows, h // 32, dtype=torch.int32, device=dev) for h in hidden]
+        acts = [torch.empty(rows, h, **f32) for h in hidden] if trains else []
+        y = torch.empty(rows, 16, **f32)
+        pm = [ptr(m) for m in masks] + [None] * (3 - len(masks))
+        pa = [ptr(a) for a in acts] + [None] * (3 - len(acts))
+        check(lib().envidr_mlp_forward(ctypes.byref(d), ptr(blob), ptr(x2), K0, rows, ptr(y), pm[0], pm[1], pm[2], pa[0], pa[1], pa[2], stream()),
+              "mlp_forward")
+        ctx.save_for_backward(x2, blob, *Ws, *masks, *acts)
+        ctx.meta = (n_layers, [b is not None for b in bs], trains)
+        return y[:, :Ws[-1].shape[0]].contiguous()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        nl, has_b, trains = ctx.meta
+        sv = ctx.saved_tensors
+        x2, blob = sv[:2]
+        Ws = list(sv[2:2 + nl])
+        masks = list(sv[2 + nl:2 + nl + nl - 1])
+        acts = list(sv[2 + nl + nl - 1:])
+        dev = x2.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        rows, K0 = x2.shape
+        N = Ws[-1].shape[0]
+        d = _desc(Ws, [None] * nl, 1, 0.0, 1.0)
+        gy16 = torch.zeros(rows, 16, **f32)
+        gy16[:, :N] = gy
+        gzs = [torch.empty(rows, int(W.shape[0]), **f32) for W in Ws[:-1]] if trains else []
+        cols = (K0 + 15) // 16 * 16
+        gx = torch.empty(rows, cols, **f32)
+        pm = [ptr(m) for m in masks] + [None] * (3 - len(masks))
+        pg = [ptr(g) for g in gzs] + [None] * (3 - len(gzs))
+        check(lib().envidr_mlp_backward(ctypes.byref(d), ptr(blob), ptr(gy16), 16, pm[0], pm[1], pm[2], rows, pg[0], pg[1], pg[2], ptr(gx), stream()),
+              "mlp_backward")
+        grads: List[Optional[torch.Tensor]] = []
+        if trains:
+            a_in = [x2] + acts
+            gz = gzs + [gy16]
+            for l in range(nl):
+                want_w, want_b = ctx.needs_input_grad[2 + 2 * l], has_b[l] and ctx.needs_input_grad[3 + 2 * l]
+                dW = db = None
+                if want_w or want_b:
+                    dW, db = wgrad_tc(gz[l], a_in[l], with_bias=True)
+                    if l == nl - 1:
+                        dW, db = dW[:N], db[:N]
+                grads += [dW if want_w else None, db if want_b else None]
+        else:
+            grads = [None] * (2 * nl)
+        return (gx[:, :K0] if ctx.needs_input_grad[0] else None, None, *grads)
+
+
+def mlp_fused(x: torch.Tensor, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]]) -> torch.Tensor:
+    """relu-MLP(x) for x [rows, K] (CUDA fp32): one forward kernel, one backward kernel for the data-gradient chain, one tensor-core
+    weight-gradient GEMM per layer that trains."""
+    wb = []
+    for W, b in layers:
+        wb += [W, b]
+    return _MlpFused.apply(x, len(layers), *wb)

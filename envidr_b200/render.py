@@ -662,7 +662,7 @@ def render_model(model, rays_o, rays_d, staged=False, max_ray_batch=4096, get_no
     opt = model.opt
     fast = (getattr(model, "cuda_ray", False) and not model.training and opt.indir_ref and not opt.debug and not opt.use_neus_sdf
             and not opt.error_bound_sample and not opt.env_sph_mode and not opt.render_env_on_sphere and not (model.bg_radius > 0)
-            and material is None and env_net_index is None and use_specular_color and r_images is None
+            and material is None and use_specular_color and r_images is None      # env_net_index only selects among env_nets in env_sph_mode (network.py:530, 590), excluded above
             and not kwargs.get("perturb", False) and kwargs.get("ray_depth") is None and int(getattr(opt, "max_ray_batch_cuda", 0)) <= 0
             and rays_o.shape[0] == 1)
     if not fast:

@@ -90,11 +90,17 @@ class TrainableField(nn.Module):
         return [(getattr(self, f"{name}_w{i}"), getattr(self, f"{name}_b{i}")) for i in range(self.n_layers[name])]
 
     tc_linear: bool = True      # env / colour / diffuse / renv layers through csrc/linear_tc.cu on CUDA tensors
+    fused_heads: bool = True    # diffuse / colour / renv heads: one forward + one backward kernel each (env_train.mlp_fused)
     fused_env: bool = True      # env_net (both evaluations, IDE included) as one forward + one backward kernel (env_train.py)
     tc_sdf: bool = True         # sdf_net through the any-order-differentiable nt / nn / tn family of linear_tc.py (False: torch layers)
 
     def mlp(self, name: str, x: torch.Tensor) -> torch.Tensor:
         layers = self.stack(name)
+        if self.fused_heads and self.tc_linear and name != "sdf" and x.is_cuda and x.dtype == torch.float32 and x.shape[0] > 0:
+            # the whole head as one forward kernel and one backward kernel (envidr_b200/env_train.py::mlp_fused)
+            from . import env_train
+            if env_train.mlp_supported([W for W, _ in layers]):
+                return env_train.mlp_fused(x, layers)
         if self.tc_linear and name != "sdf" and x.is_cuda and x.dtype == torch.float32:
             from .linear_tc import linear_tc
             for i, (W, b) in enumerate(layers):

@@ -394,6 +394,20 @@ int envidr_env_mlp_backward(const envidr_env_mlp* d, const void* blob, const flo
                             const uint32_t* mask1, const uint32_t* mask2, uint32_t M, float* gact0, float* gact1, float* gact2, float* gy,
                             float* gx0, envidr_stream_t stream);
 
+/* The same pair of kernels for the small ReLU heads of the training branch (diffuse_net, color_net / specular_net, renv_net:
+ * nerf/network.py:335-366, 555-607, 612-659; nn.Linear stacks under autograd in the reference): Y = W_n(... relu(W_1 X + b_1) ...) + b_n as
+ * ONE forward kernel (masks, and optionally the hidden activations for the weight gradients, saved once) and ONE backward kernel for the
+ * whole data-gradient chain.  The descriptor is envidr_env_mlp with the IDE fields ignored: 2..4 layers, dims[0] <= 64, hidden widths
+ * multiples of 32 (<= 256), dims[n] <= 16.  X [rows, x_ld], Y [rows, 16] (zero padded), mask_l [rows, N_l / 32], act_l [rows, N_l] or NULL;
+ * backward: gY [rows, gy_ld] -> gz_l [rows, N_l] (gradient w.r.t. the pre-activation of hidden layer l, NULL = not needed) and
+ * gX [rows, dims[0] rounded up to 16]. */
+uint64_t envidr_mlp_blob_bytes(const envidr_env_mlp* d);
+int envidr_mlp_pack(const envidr_env_mlp* d, void* blob, uint64_t blob_bytes, envidr_stream_t stream);
+int envidr_mlp_forward(const envidr_env_mlp* d, const void* blob, const float* X, uint32_t x_ld, uint32_t rows, float* Y, uint32_t* mask0,
+                       uint32_t* mask1, uint32_t* mask2, float* act0, float* act1, float* act2, envidr_stream_t stream);
+int envidr_mlp_backward(const envidr_env_mlp* d, const void* blob, const float* gY, uint32_t gy_ld, const uint32_t* mask0, const uint32_t* mask1,
+                        const uint32_t* mask2, uint32_t rows, float* gz0, float* gz1, float* gz2, float* gX, envidr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * NeuS-style opacity: NeuSDensity.forward (nerf/network.py:46-102), the density of the use_neus_sdf configs,
  * consumed by the compositors with input_alpha = 1.  variance: device scalar (the module's parameter); dists: [M] or NULL

@@ -85,8 +85,53 @@ def test_fused_env_forward_backward_match_float64(dev, width, deg, M):
         close_rows(b32.grad, b64.grad, f"db{i}")
 
 
+@pytest.mark.parametrize("dims,rows,train", [((28, 64, 64, 3), 9000, False), ((24, 32, 3), 300, False), ((4, 64, 64, 64, 12), 64 * 148 + 5, True),
+                                             ((64, 256, 160, 16), 700, True)])
+def test_fused_small_mlp_forward_backward_match_float64(dev, dims, rows, train):
+    """env_train.mlp_fused (k_chain_tc forward / backward modes) for the head shapes of the training branch (colour, diffuse, renv) and a
+    wide one: outputs 2e-6 of the output scale, input gradients per row and parameter gradients within 2e-3 of their tensor's scale (<= 3
+    rows moved by a ReLU-kink flip between fp32 and float64)."""
+    from envidr_b200 import env_train
+    g = torch.Generator().manual_seed(sum(dims) + rows)
+    layers64 = []
+    for i in range(len(dims) - 1):
+        a = (6.0 / (dims[i] + dims[i + 1])) ** 0.5
+        W = ((torch.rand(dims[i + 1], dims[i], generator=g, dtype=torch.float64) * 2 - 1) * a).requires_grad_(train)
+        b = (torch.randn(dims[i + 1], generator=g, dtype=torch.float64) * 0.05).requires_grad_(train)
+        layers64.append((W, b))
+    x64 = torch.randn(rows, dims[0], generator=g, dtype=torch.float64).requires_grad_(True)
+    h = x64
+    for i, (W, b) in enumerate(layers64):
+        h = F.linear(h, W, b)
+        if i != len(layers64) - 1:
+            h = F.relu(h)
+    c = torch.randn(rows, dims[-1], generator=g, dtype=torch.float64) * 1e-6
+    (h * c).sum().backward()
+    leaf = lambda t, rg=True: t.detach().float().to(dev).requires_grad_(rg)
+    x32 = leaf(x64)
+    layers32 = [(leaf(W, train), leaf(b, train)) for W, b in layers64]
+    assert env_train.mlp_supported([W for W, _ in layers32])
+    y = env_train.mlp_fused(x32, layers32)
+    assert y.shape == (rows, dims[-1])
+    assert float((y.detach().double().cpu() - h.detach()).abs().max()) <= 2e-6 * max(1.0, float(h.detach().abs().max()))
+    (y * c.float().to(dev)).sum().backward()
+
+    def close_rows(a, b64, what):
+        scale = float(b64.abs().max())
+        err = (a.double().cpu() - b64).abs().reshape(b64.shape[0], -1).amax(-1)
+        assert int((err > 2e-3 * scale).sum()) <= 3 and float(err.max()) <= 5e-2 * scale, (what, float(err.max()), scale)
+
+    close_rows(x32.grad, x64.grad, "dx")
+    if train:
+        for i, ((W32, b32), (W64, b64)) in enumerate(zip(layers32, layers64)):
+            close_rows(W32.grad, W64.grad, f"dW{i}")
+            close_rows(b32.grad, b64.grad, f"db{i}")
+    else:
+        assert all(W.grad is None for W, _ in layers32)
+
+
 def test_fused_env_equals_the_per_layer_path_in_the_train_step(dev):
-    """render_train with fused_env on / off: same loss, same gradients (both are fp32-level evaluations of the same graph)."""
+    """render_train with the fused env_net / head kernels on and off: same loss, same gradients (both are fp32-level evaluations of the same graph)."""
     from envidr_b200 import scene, train
     from envidr_b200.render import RenderConfig
     fp = scene.make_synthetic_field(0, hidden_dim_env=256, ide_degree=5).to(dev)
@@ -100,7 +145,7 @@ def test_fused_env_equals_the_per_layer_path_in_the_train_step(dev):
     res = {}
     for fused in (True, False):
         field = train.TrainableField(fp, frozen=("diffuse", "color")).to(dev)
-        field.fused_env = fused
+        field.fused_env = field.fused_heads = fused
         out = train.render_train(field, bf, ro, rd, cfg, r_images=ri)
         loss = train.loss_epilogue(field, out, gt, gm)
         loss.backward()
