@@ -713,8 +713,10 @@ def config_dict(args, W, H, indir):
             "rays_per_step_per_gpu": W * H, "hash": "L16 C2 base16 res2048 T2^19 (48.8 MB fp32)",
             "mlps": "sdf 32-64-64-15, env IDE72-256-256-256-12 x2, diffuse 24-32-3, color 28-64-64-3, renv 4-64-64-64-12",
             "max_steps": 1024, "T_thresh": 1e-4,
-            "schedule": "passes 1-2: the reference's iterative schedule (n_step = N // n_alive <= 8); main pass: one batch over the per-ray "
-                        "sample counts found by the geometry pass (RenderConfig.replay_main_pass)" if indir else "geometry-only iterative loop (reference schedule), then one shading batch over the composited samples "
+            "schedule": "passes 1-2: geometry-only iterative loops on the reference's schedule n_step = N // n_alive with the cap raised from 8 to 16 and a "
+                        "floor of 8 in the reflected-ray pass (batching only: same composited samples, frame bit-identical to cap 8 / floor 1, "
+                        "tests/test_gpu_render.py), shading deferred to one batch per pass; main pass: one batch over the per-ray sample counts found by "
+                        "the geometry pass (RenderConfig.replay_main_pass)" if indir else "geometry-only iterative loop (reference schedule, n_step cap 16), then one shading batch over the composited samples "
                         "(RenderConfig.defer_shading)",
             "parallelism": f"ray/frame sharding x{args.gpus} + all_gather",
             "cache": "inputs larger than L2 are not needed: 48.8 MB table + per-iteration sample buffers are re-written each step; "

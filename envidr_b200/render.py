@@ -44,8 +44,10 @@ class RenderConfig:
     # pass shades those (env_net + shading heads) instead of marching and evaluating the hash grid + sdf_net a second time
     reuse_geometry: bool = True
     # n_step floor of the secondary (reflected-ray) pass: it runs over few rays, so the reference schedule n_step = N // n_alive
-    # starts at 1 and issues ~50 launches of <= 71 k samples; a floor only changes the batching (same composited samples).  1 = reference
-    secondary_n_step_floor: int = 4
+    # starts at 1 and issues ~50 launches of <= 71 k samples; a floor only changes the batching (same composited samples).  1 = reference.
+    # 8 since the third session of round 2 (was 4): with deferred shading the image is bit-identical whatever the floor (run r3_22), and every
+    # iteration costs ~40 us of latency-bound march / composite launches and kernel set-up that does not shrink with the ray count
+    secondary_n_step_floor: int = 8
     # secondary pass with deferred shading (tensor-core field): its iterative loop runs geometry-only (ray termination depends on
     # the density alone) while logging the per-sample records, then env_net + the shading heads run ONCE over all composited
     # samples (envidr_field_forward_records) and envidr_composite_rays_replay composites -- the main pass's scheme, applied to
@@ -55,10 +57,12 @@ class RenderConfig:
     defer_shading: bool = True
     # cap of n_step in the geometry-only LOGGED passes of the batched schedule (the passes above): the reference caps n_step = N // n_alive
     # at 8 (cuda_ray.py:287), so the long tail of a pass -- a few thousand grazing rays -- runs as dozens of tiny iterations of 3 launches
-    # each; 16 halves their number.  Same composited samples (batching only); passes on the reference schedule always use 8.
-    # Measured (run 21): 44 -> 30 iterations per frame, 15.95 -> 15.85 ms (the tail iterations are cheap), +1.8 % marched samples:
-    # not worth leaving the reference's cap by default
-    logged_n_step_cap: int = 8
+    # each; 16 halves their number.  Batching only: the logged passes are geometry-only, shading and compositing run afterwards over the
+    # composited samples, and the frame is BIT-IDENTICAL for caps 8 and 16 (run r3_22: max |d image| = 0; +3.8 % marched samples past ray
+    # termination).  Measured: 800x800 frame 15.92 -> 15.47 ms together with the secondary floor of 8 (20 + 23 -> 14 + 12 iterations); one
+    # rank's share of the 1600x1600 frame at 8 GPUs 9.43 -> 9.03 ms.  Passes on the reference schedule (replay_main_pass=False, or any
+    # pass that shades inside the loop) always use the reference's 8; logged_n_step_cap=8, secondary_n_step_floor=1 reproduce its counts
+    logged_n_step_cap: int = 16
 
     def aabb6(self):
         return list(self.aabb) if self.aabb is not None else [-self.bound] * 3 + [self.bound] * 3

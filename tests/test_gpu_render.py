@@ -185,8 +185,8 @@ def test_main_pass_replay_equals_iterative_schedule(dev, W, env_width, deg):
     ro, rd = ro.to(dev), rd.to(dev)
     items = ("diffuse", "specular", "roughness")
     st_a, st_b = [], []
-    a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, secondary_n_step_floor=4), bg_color=1.0,
-                      visual_items=items, stats=st_a)
+    a = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=True, secondary_n_step_floor=4, logged_n_step_cap=8),
+                      bg_color=1.0, visual_items=items, stats=st_a)
     b = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, replay_main_pass=False, secondary_n_step_floor=1,
                                                           defer_secondary_shading=False), bg_color=1.0, visual_items=items, stats=st_b)
     # deferred shading of the secondary pass: the composited samples only, never more than were marched
@@ -230,7 +230,7 @@ def test_single_pass_deferred_shading_equals_loop(dev, W, env_width, deg):
     items = ("diffuse", "specular", "roughness")
     for kw in (dict(bg_color=1.0), dict(bg_color=bg, r_images=r_img), dict(bg_color=[0.2, 0.4, 0.6], env_rot_radian=0.7)):
         st_a, st_b = [], []
-        a = render.render(fp, bf, ro, rd, render.RenderConfig(defer_shading=True), visual_items=items, stats=st_a, **kw)
+        a = render.render(fp, bf, ro, rd, render.RenderConfig(defer_shading=True, logged_n_step_cap=8), visual_items=items, stats=st_a, **kw)
         b = render.render(fp, bf, ro, rd, render.RenderConfig(defer_shading=False), visual_items=items, stats=st_b, **kw)
         assert st_a[0]["samples"] == st_b[0]["samples"] and st_a[0]["iterations"] == st_b[0]["iterations"]
         assert 0.9 * st_b[0]["samples"] <= st_a[0]["shaded"] <= st_b[0]["samples"]
@@ -311,3 +311,28 @@ def test_relight_sweep_shares_the_rotation_independent_passes(dev):
         frames.append(fast["image"])
     hit = geom.ray_idx
     assert float((frames[1][hit] - frames[0][hit]).abs().mean()) > 1e-3          # the light really moved
+
+
+def test_batching_of_the_logged_passes_does_not_change_the_frame(dev):
+    """RenderConfig.logged_n_step_cap / secondary_n_step_floor only change how many samples a geometry-only logged pass marches per
+    iteration: shading and compositing run afterwards over the composited samples, so the three-pass frame is bit-identical for the
+    reference's cap (8, floor 4 or 1) and the default (16, floor 8); the default needs fewer iterations and marches a few more samples."""
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=256, ide_degree=5)
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    bf = torch.from_numpy(scene.make_bitfield()).to(dev)
+    ro, rd = scene.camera_rays(128, 128)
+    ro, rd = ro.to(dev), rd.to(dev)
+    out = {}
+    for name, kw in (("default", {}), ("ref_cap", dict(logged_n_step_cap=8, secondary_n_step_floor=4)), ("ref_cap_floor1", dict(logged_n_step_cap=8, secondary_n_step_floor=1))):
+        st = []
+        res = render.render(fp, bf, ro, rd, render.RenderConfig(indir_ref=True, **kw), bg_color=1.0, stats=st)
+        out[name] = (res, st)
+    d, r = out["default"], out["ref_cap"]
+    assert render.RenderConfig().logged_n_step_cap == 16 and render.RenderConfig().secondary_n_step_floor == 8
+    for k in ("image", "depth", "weights_sum", "normal_image"):
+        assert torch.equal(d[0][k], r[0][k]), k
+        assert torch.equal(d[0][k], out["ref_cap_floor1"][0][k]), k
+    assert d[1][0]["iterations"] < r[1][0]["iterations"] and r[1][0]["samples"] <= d[1][0]["samples"] <= 1.1 * r[1][0]["samples"]
+    assert d[1][2]["samples"] == r[1][2]["samples"]                      # the main pass shades the same composited samples
