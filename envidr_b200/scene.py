@@ -273,3 +273,80 @@ def neus_to_oracle(nf) -> dict:
     P.update(sdf=[(W.detach().cpu().numpy(), b.detach().cpu().numpy()) for W, b in nf.sdf], skip_layers=tuple(nf.skip_layers), multires=nf.multires,
              variance=float(nf.variance.reshape(-1)[0]), cos_anneal_ratio=nf.cos_anneal_ratio, geo_feat_dim=nf.geo_feat_dim)
     return P
+
+
+# ---------------------------------------------------------------------------------------------
+# Fitted variant of the synthetic toaster (SURVEY.md 8d recipe): the geometry is LEARNED through this library's operators instead of
+# being written into the dense levels, and the occupancy bit field comes from the field itself through update_extra_state.
+# ---------------------------------------------------------------------------------------------
+
+def analytic_sdf_torch(xyz: torch.Tensor, scale: float = 0.65) -> torch.Tensor:
+    """analytic_sdf on a torch tensor [..., 3] (any device / dtype)."""
+    p = xyz / scale
+    half = torch.tensor([0.55, 0.35, 0.30], dtype=p.dtype, device=p.device)
+    r = 0.08
+    q = p.abs() - (half - r)
+    box = q.clamp_min(0).norm(dim=-1) + q.max(dim=-1).values.clamp_max(0) - r
+    sph = (p - torch.tensor([0.3, 0.25, 0.0], dtype=p.dtype, device=p.device)).norm(dim=-1) - 0.25
+    return torch.minimum(box, sph) * scale
+
+
+def fit_synthetic_field(seed: int = 0, *, device="cuda", steps: int = 1000, batch: int = 1 << 18, lr_grid: float = 1e-2, lr_mlp: float = 2e-3,
+                        density_thresh: float = 10.0, density_updates: int = 17, **field_kw):
+    """The recipe of SURVEY.md 8d on the GPU: (1) hash table re-initialised to U(-1e-4, 1e-4) (hashgrid.py:104-106) and sdf_net to
+    Xavier weights, then `steps` Adam steps (betas (0.9, 0.99), eps 1e-15: main_nerf.py:150) on an L1 loss between sdf_net(hash_encode(x))[0]
+    and the analytic SDF over `batch` points per step (half uniform in the box, half within 0.1 of the surface), through the library's
+    hash_encode forward / backward kernels; (2) 1 + 16 update_extra_state calls (renderer.py:264-352) from an empty grid -> bit field.
+    Everything else (rendering MLPs, head biases) is the constructed scene's.  Returns (FieldParams on `device`, bitfield uint8 tensor, info)."""
+    from . import density, hashencoder
+    dev = torch.device(device)
+    fp = make_synthetic_field(seed, **field_kw).to(dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    emb = ((torch.rand(fp.embeddings.shape, generator=g, device=dev) * 2 - 1) * 1e-4).requires_grad_(True)
+    layers = []
+    for W, b in fp.sdf:
+        a = math.sqrt(6.0 / (W.shape[0] + W.shape[1]))
+        layers.append((((torch.rand(W.shape, generator=g, device=dev) * 2 - 1) * a).requires_grad_(True), torch.zeros_like(b).requires_grad_(True)))
+    offsets = fp.offsets.to(dev).int()
+    opt = torch.optim.Adam([{"params": [emb], "lr": lr_grid}, {"params": [t for Wb in layers for t in Wb], "lr": lr_mlp}], betas=(0.9, 0.99), eps=1e-15)
+    bound = float(fp.bound)
+
+    def sdf_of(x):
+        h = hashencoder.hash_encode((x + bound) / (2 * bound), emb, offsets, fp.per_level_scale, fp.base_resolution, False)
+        for i, (W, b) in enumerate(layers):
+            h = torch.nn.functional.linear(h, W, b)
+            if i != len(layers) - 1:
+                h = torch.relu(h)
+        return h[:, 0]
+
+    def draw(n):
+        x = (torch.rand(4 * n, 3, generator=g, device=dev) * 2 - 1) * 0.8 * bound
+        sd = analytic_sdf_torch(x)
+        near = torch.nonzero(sd.abs() < 0.1).flatten()[: n // 2]
+        return torch.cat([x[near], x[-(n - near.numel()):]], 0)
+
+    last = 0.0
+    for it in range(steps):
+        x = draw(batch)
+        loss = (sdf_of(x) - analytic_sdf_torch(x)).abs().mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if it == steps - 1:
+            last = float(loss.detach())
+    with torch.no_grad():
+        xt = draw(1 << 20)
+        err = (sdf_of(xt) - analytic_sdf_torch(xt)).abs()
+        info = {"steps": steps, "batch": batch, "train_loss_last": last, "sdf_l1_mean": float(err.mean()), "sdf_l1_p99": float(torch.quantile(err[:1 << 18], 0.99))}
+    fitted = FieldParams(**{**{f: getattr(fp, f) for f in fp.__dataclass_fields__ if not f.startswith("_")},
+                            "embeddings": emb.detach().contiguous(), "sdf": [(W.detach().contiguous(), b.detach().contiguous()) for W, b in layers]})
+    fitted.precision = "tc"
+    fitted.pack()
+    dg = density.DensityGrid(bound=bound, density_thresh=density_thresh, grid_size=128, device=dev)
+    for _ in range(density_updates):
+        dg.update_extra_state(fitted, decay=0.95, full_update=True)
+    bits = dg.density_bitfield
+    occ = int(torch.tensor([bin(v).count("1") for v in range(256)], device=dev)[bits.long()].sum())
+    info.update(occupied_cells=occ, occupied_fraction=occ / float(128 ** 3), mean_density=float(dg.mean_density), density_thresh=density_thresh,
+                density_updates=density_updates)
+    return fitted, bits, info
