@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 (third session) evidence run:  gpurun --timeout 2400 -- 'bash profiles/run_final_r3.sh'
 set -u
-OUT=gpurun_out; TAG=r3f; mkdir -p $OUT
+OUT=gpurun_out; TAG=${1:-r3g}; mkdir -p $OUT
 NOX="--no-cpu-baseline --no-gpu-reference --no-train --no-density --no-sweep --no-extra-warmup"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > $OUT/${TAG}_gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q > $OUT/${TAG}_tests.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_tests.log; tail -3 $OUT/${TAG}_tests.log
@@ -18,8 +18,8 @@ for KS in k_env_tc:5 k_geom_tc:60 k_shade_tc:5; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $S --launch-count 1 -f -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 $NOX > $OUT/${TAG}_full_$K.log 2>&1
   echo "ncu full $K exit $?"
 done
-for KS in k_env_bwd_tc:4 "k_env_tc<1, false, 1, true>:4"; do
-  K=${KS%%:*}; S=${KS##*:}; F=$(echo $K | tr -c 'a-z_' '_')
-  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$K" --launch-skip $S --launch-count 1 -f -o $OUT/${TAG}_train_$F python profiles/train_profile.py > $OUT/${TAG}_full_train_$F.log 2>&1
-  echo "ncu full $K exit $?"
-done
+# training kernels: profiles/train_profile.py launches only the SAVE instantiation of k_env_tc and the three modes of k_chain_tc
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_env_tc --launch-skip 4 --launch-count 1 -f -o $OUT/${TAG}_train_k_env_tc_save python profiles/train_profile.py > $OUT/${TAG}_full_train_k_env_tc_save.log 2>&1
+echo "ncu full k_env_tc<SAVE> exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_chain_tc<0>" --launch-skip 4 --launch-count 1 -f -o $OUT/${TAG}_train_k_chain_tc_0 python profiles/train_profile.py > $OUT/${TAG}_full_train_k_chain_tc_0.log 2>&1
+echo "ncu full k_chain_tc<0> exit $?"
