@@ -372,8 +372,11 @@ def config5(args, fp, bft, dev, world, rank, steps, flush, e2e=True):
                                     o, d, Wd, Wd, presharded=True)
 
     def frame_e2e(i):
+        # host rays of THIS rank's shard in, the assembled frame out to the host on rank 0 (the all-gather leaves the full frame on every rank;
+        # one reader is what a caller does -- until the third session of round 2 every rank copied the whole frame back: 8 x 30.7 MB at N = 8)
         out = frame(i, o_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True))
-        img_h.copy_(out["image"], non_blocking=True)
+        if rank == 0:
+            img_h.copy_(out["image"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     R = args.sweep_rotations
@@ -541,7 +544,7 @@ def run_multi(args, fp_cpu, bf, dev, world, rank, local):
                                              "(the exact strong-scaling denominator)"),
                 "samples_per_step_per_gpu": sum(s["samples"] for s in st),
                 "e2e": {"value": N5 / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 2 * c5["rays_per_frame_per_rank"] * 12,
-                        "d2h_bytes_per_step": N5 * 12, "ms_per_step": e2e_ms},
+                        "d2h_bytes_per_step": N5 * 12, "d2h_on": "rank 0 (the assembled frame)", "ms_per_step": e2e_ms},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": "k_env_tc (rank 0's share of the frame)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": ach / peak_tf, "traffic": None, "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": fl.value / steps,
