@@ -56,7 +56,7 @@ void* stream_scratch(int kind, size_t bytes, size_t fixed_bytes, cudaStream_t st
 
 extern "C" {
 const char* envidr_last_error(void) { return envidr::g_err; }
-int envidr_version(void) { return 102; }   // 1.02: envidr_get_scatter_idx takes M (bounded writes); + NeuS field, sweep shading entry points
+int envidr_version(void) { return 103; }   // 1.03: + envidr_env_mlp_* / envidr_mlp_* (fused training kernels); 1.02: envidr_get_scatter_idx takes M, NeuS field, sweep shading
 int envidr_abi_sizes(uint32_t out[5]) {
     out[0] = (uint32_t)sizeof(envidr_mlp_layer); out[1] = (uint32_t)sizeof(envidr_field); out[2] = (uint32_t)sizeof(envidr_field_out);
     out[3] = (uint32_t)sizeof(envidr_render_opts); out[4] = (uint32_t)sizeof(envidr_render_out);

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(lib):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in protos:
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
-    assert lib.envidr_version() == 102
+    assert lib.envidr_version() == 103
     assert {"envidr_density_grid_update", "envidr_mark_untrained_grid", "envidr_adam_step", "envidr_get_rays", "envidr_train_loss_forward",
             "envidr_train_loss_backward", "envidr_pow2_scales"} <= set(protos)
 
