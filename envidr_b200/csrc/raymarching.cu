@@ -386,6 +386,18 @@ __global__ void __launch_bounds__(256) k_scatter_rows4(const int32_t* __restrict
     for (uint32_t s = lane; s < cnt; s += 32) dst[off + s] = v;
 }
 
+// dst[p, :] = src[idx[p], :] for rows of `vec4` float4s (frame assembly after the all-gather of a sharded render: rows of 32 B per ray in
+// rank order -> pixel order).  torch's index_select moves these 82 MB at 62 GB/s (1.33 ms per 1600x1600 frame, run r3_27); one float4 per
+// thread moves them at HBM speed.
+__global__ void __launch_bounds__(256) k_gather_rows(const float4* __restrict__ src, const int32_t* __restrict__ idx, uint64_t n_rows, uint32_t vec4,
+                                                    float4* __restrict__ dst) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t row = t / vec4;
+    if (row >= n_rows) return;
+    const uint32_t part = (uint32_t)(t - row * vec4);
+    dst[t] = __ldg(src + (size_t)idx[row] * vec4 + part);
+}
+
 // Inference compositor (reference kernel_composite_rays, raymarching.cu:957-1046) over ray-contiguous samples: the pre-sample
 // transmittance T = 1 - sum w, w = alpha T, every image accumulated sample by sample in the same order.  One thread per ray.
 __global__ void __launch_bounds__(128) k_composite_replay(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
@@ -766,6 +778,19 @@ int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const 
                                                                    reinterpret_cast<float4*>(dst));
     g_launches += 1;
     return check_launch("scatter_ray_rows4");
+}
+
+int envidr_gather_rows(const float* src, const int32_t* idx, uint64_t n_rows, uint32_t row_floats, float* dst, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(src && idx && dst, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(row_floats > 0 && row_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                   ENVIDR_E_UNSUPPORTED, "rows must be whole float4s, 16-byte aligned");
+    if (n_rows == 0) return 0;
+    const uint32_t vec4 = row_floats / 4;
+    const uint64_t threads = n_rows * vec4;
+    k_gather_rows<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), idx, n_rows, vec4,
+                                                                                 reinterpret_cast<float4*>(dst));
+    g_launches += 1;
+    return check_launch("gather_rows");
 }
 
 int envidr_composite_rays_replay(const float* sigmas, const float* rgbs, const float* normals, const float* c_diffuse,

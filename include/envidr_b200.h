@@ -320,6 +320,9 @@ int envidr_field_forward_records(const envidr_field* field, const float* rec, co
 /* dst[offset_n + s, 0:4] = src[ray_n, 0:4] for every sample of every ray in `rays` [N,3] (per-ray r_images -> per-sample rows). */
 int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const float* src /* [N,4] */, float* dst /* [M,4] */,
                              envidr_stream_t stream);
+/* dst[p, 0:row_floats] = src[idx[p], 0:row_floats], p < n_rows (row_floats a multiple of 4, 16-byte aligned buffers): the de-interleave of a
+ * sharded frame after its all-gather (envidr_b200/dist.py; no reference counterpart: the reference has no reachable multi-GPU path). */
+int envidr_gather_rows(const float* src, const int32_t* idx, uint64_t n_rows, uint32_t row_floats, float* dst, envidr_stream_t stream);
 /* images may be NULL except weights_sum / image; sigmas [M], rgbs / normals / c_diffuse / c_specular [M,3], roughness [M];
  * nears [N] (start of the depth accumulation, may be NULL = 0). */
 int envidr_composite_rays_replay(const float* sigmas, const float* rgbs, const float* normals, const float* c_diffuse,

@@ -485,3 +485,18 @@ def test_ide_kernel_vs_reference_golden(dev, golden_dir, deg):
     got_t = enc(d2, 0.1)
     got_k = enc(d, 0.1)
     assert (np.abs(got_t.detach().cpu().numpy() - got_k.cpu().numpy()) <= atol_t + 2e-5 * np.abs(got_k.cpu().numpy())).all()
+
+
+def test_gather_rows_equals_index_select(dev):
+    """envidr_gather_rows (frame assembly after the all-gather of a sharded render, envidr_b200/dist.py) against torch.index_select: bit-exact,
+    rows of 8 floats (the packed per-ray outputs) and of 4, a count that is not a multiple of the block size; and through dist._deinterleave."""
+    from envidr_b200 import dist as D
+    from envidr_b200._lib import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(5)
+    for n, rf in ((100_003, 8), (257, 4), (1, 8)):
+        src = torch.rand(n + 17, rf, generator=g).to(dev)
+        idx = torch.randint(0, n + 17, (n,), generator=g).to(dev)
+        dst = torch.empty(n, rf, device=dev)
+        check(lib().envidr_gather_rows(ptr(src), ptr(idx.to(torch.int32)), n, rf, ptr(dst), stream()), "gather_rows")
+        assert torch.equal(dst, src.index_select(0, idx))
+        assert torch.equal(D._deinterleave(src, idx), src.index_select(0, idx))
