@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""n_step cap / secondary floor of the logged geometry passes: frame time, iterations, marched samples and max |d image| against the default, for the
+800x800 frame and for one rank's share of the 1600x1600 frame at 8 ranks (run r3_22).  GPU box: python profiles/batching_experiment.py"""
 import sys, torch
 sys.path.insert(0, ".")
 from envidr_b200 import dist as D, render, scene

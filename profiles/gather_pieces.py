@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""CUDA-event time of the pieces of dist.render_sharded's frame assembly (pack, all_gather_into_tensor, torch index_select, slicing) on synthetic
+per-ray outputs of a 1600x1600 frame (run r3_27b: the index_select was 1.33 ms of 1.5; it is envidr_gather_rows now).
+torchrun --nproc-per-node N profiles/gather_pieces.py"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, ".")
 from envidr_b200 import dist as D
