@@ -194,17 +194,29 @@ def _sample_log(device, need: int, slot: str = "primary") -> SampleLogBuffers:
     return lg
 
 
-def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor]) -> Dict:
+def _compact(mask: torch.Tensor, n: int) -> torch.Tensor:
+    """Indices of the n set entries of a boolean mask, ascending, WITHOUT a host synchronisation (mask.nonzero() has to read its output
+    size back; here the caller already knows n from one combined read-back): exclusive scan + scatter."""
+    N = mask.shape[0]
+    pos = torch.cumsum(mask, 0) - 1
+    out = torch.empty(n + 1, dtype=torch.int64, device=mask.device)
+    out.scatter_(0, torch.where(mask, pos, n), torch.arange(N, dtype=torch.int64, device=mask.device))
+    return out[:n]
+
+
+def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor], M: Optional[int] = None) -> Dict:
     """Ray-contiguous copy of the logged samples of the rays `ray_idx` (int64 indices into the logged pass's rays, ascending; None =
     all of them): envidr_permute_sample_log.  Nothing here depends on colour, r_images or the light rotation, so one prepared batch
-    serves every frame of a relight sweep.  One host synchronisation (the batch size M sizes the buffers)."""
+    serves every frame of a relight sweep.  M = number of samples of the selected rays if the caller already knows it (render() reads
+    it back together with the pass statistics); otherwise one host synchronisation (the batch size sizes the buffers)."""
     dev = counts.device
     f32 = dict(dtype=torch.float32, device=dev)
     n_all = counts.shape[0]
     cs = (counts if ray_idx is None else counts[ray_idx]).to(torch.int64)
     n_r = int(cs.shape[0])
     incl = torch.cumsum(cs, 0)
-    M = int(incl[-1].item()) if n_r else 0
+    if M is None:
+        M = int(incl[-1].item()) if n_r else 0
     off = (incl - cs).to(torch.int32)
     if ray_idx is None:
         ray_off = off
@@ -269,11 +281,11 @@ def shade_prepared(field: FieldParams, prep: Dict, cfg: RenderConfig, *, bg_colo
 
 def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor],
                          cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
-                         visual_items: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+                         visual_items: Sequence[str] = (), M: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """A pass shaded from a geometry-only pass's sample log: gather ray by ray (prepare_from_log), shade from the geometry records and
     composite (shade_prepared).  counts [N_all] = samples composited per ray of the logged pass; r_images [n_selected, 4] in the order
     of ray_idx.  Returns per-selected-ray images."""
-    return shade_prepared(field, prepare_from_log(log, total, counts, ray_idx), cfg, bg_color=bg_color, r_images=r_images,
+    return shade_prepared(field, prepare_from_log(log, total, counts, ray_idx, M), cfg, bg_color=bg_color, r_images=r_images,
                           visual_items=visual_items)
 
 
@@ -378,11 +390,12 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             log = _sample_log(rays_o.device, _log_need.get(("one", N), 8 * 1 << 20), "primary")
             geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
                               sample_count=True, log=log, n_step_cap=cfg.logged_n_step_cap)
-            st = last_stats()
+            m_all = int(geo["sample_count"].sum().item())                  # the ONE host synchronisation of the pass: composited samples ...
+            st = last_stats()                                              # ... after which the pass statistics are already on the host
             _log_need[("one", N)] = int(st["samples"] * 1.25) + 4096
             if st["samples"] <= log.capacity:
                 main = render_rays_from_log(field, log, st["samples"], geo["sample_count"], None, cfg, bg_color=bg_color, r_images=r_images,
-                                            visual_items=visual_items)
+                                            visual_items=visual_items, M=m_all)
                 st = dict(st, shaded=int(main.pop("_samples")))
                 results = dict(main, depth=geo["depth"], normal_image=geo["normal_image"])
                 if stats is not None:
@@ -398,13 +411,6 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         log = _sample_log(rays_o.device, _log_need.get(N, 8 * 1 << 20)) if reuse else None
         geo = render_rays(field, bitfield, rays_o, rays_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
                           sample_count=cfg.replay_main_pass, log=log, n_step_cap=cfg.logged_n_step_cap if log is not None else 8)
-        geo_stats = last_stats() if (stats is not None or reuse) else None
-        if stats is not None:
-            stats.append(geo_stats)
-        if reuse:
-            _log_need[N] = int(geo_stats["samples"] * 1.25) + 4096          # size the log for the next frame of this shape
-            if geo_stats["samples"] > log.capacity:                          # overflowed: this frame marches the main pass again
-                reuse = False
         normals = geo["normal_image"]
         depth = geo["depth"] - dt
         weights_sum = geo["weights_sum"]
@@ -417,8 +423,23 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             ref_mask = ref_mask & (ref_o > ob[:3]).all(-1) & (ref_o < ob[3:]).all(-1)
         # The reference indexes with the boolean masks at every use (each one a host synchronisation); here the two index lists are
         # built once and every later gather / scatter uses them.  ref_mask is a subset of ray_mask (ws > 0.9 vs > 0.3).
-        ref_idx = ref_mask.nonzero().squeeze(-1)
-        ray_idx = ray_mask.nonzero().squeeze(-1)
+        # ONE read-back for everything the host has to know after the geometry pass (third session of round 2; it used to be four:
+        # the pass statistics, the two nonzero() sizes and the main pass's sample count): sizes of the two index lists and the number of
+        # logged samples of the main-pass rays; the pass statistics are on the host once this returns.
+        if "sample_count" in geo:
+            m_main_t = (geo["sample_count"].to(torch.int64) * ray_mask).sum()
+        else:
+            m_main_t = ray_mask.sum() * 0
+        n_ref, n_ray, m_main = (int(v) for v in torch.stack([ref_mask.sum(), ray_mask.sum(), m_main_t]).tolist())
+        geo_stats = last_stats() if (stats is not None or reuse) else None
+        if stats is not None:
+            stats.append(geo_stats)
+        if reuse:
+            _log_need[N] = int(geo_stats["samples"] * 1.25) + 4096          # size the log for the next frame of this shape
+            if geo_stats["samples"] > log.capacity:                          # overflowed: this frame marches the main pass again
+                reuse = False
+        ref_idx = _compact(ref_mask, n_ref)
+        ray_idx = _compact(ray_mask, n_ray)
         pos_in_ray = torch.cumsum(ray_mask, 0) - 1                       # position of a ray among the main-pass rays
         sec_o, sec_d = ref_o[ref_idx], ref_d[ref_idx]
         n_sec = sec_o.shape[0]
@@ -428,10 +449,11 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
             geo2 = render_rays(field, bitfield, sec_o, sec_d, cfg, geometry_only=True, env_rot_radian=env_rot_radian,
                                max_steps=cfg.indir_max_steps, min_near=dt * 2, n_step_floor=cfg.secondary_n_step_floor,
                                sample_count=True, log=log2, n_step_cap=cfg.logged_n_step_cap)
+            m_sec = int(geo2["sample_count"].sum().item())                  # the pass's one read-back; its statistics are on the host afterwards
             st2 = last_stats()
             _log_need[("sec", N)] = int(st2["samples"] * 1.25) + 4096
             if st2["samples"] <= log2.capacity:
-                ref = render_rays_from_log(field, log2, st2["samples"], geo2["sample_count"], None, cfg, bg_color=0.0)
+                ref = render_rays_from_log(field, log2, st2["samples"], geo2["sample_count"], None, cfg, bg_color=0.0, M=m_sec)
                 st2 = dict(st2, shaded=int(ref.pop("_samples")))
             if stats is not None and ref is not None:
                 stats.append(st2)
@@ -446,7 +468,7 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
         r_img[pos_in_ray[ref_idx]] = ref_image                              # == r_img[ref_mask[ray_mask]] = ref_image (renderer.py:484-486)
         if reuse:
             main = render_rays_from_log(field, log, geo_stats["samples"], geo["sample_count"], ray_idx, cfg, bg_color=0.0, r_images=r_img,
-                                        visual_items=visual_items)
+                                        visual_items=visual_items, M=m_main)
             if stats is not None:
                 stats.append(dict(iterations=1, samples=int(main.pop("_samples"))))
             else:
