@@ -474,6 +474,20 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
         if (out->specular_image) fo.c_specular = B.s_cs;
         if (out->roughness_image) fo.roughness = B.s_rough;
     }
+    // The loop alternates between these small kernels and k_geom_tc (150 KB of dynamic shared memory per CTA).  Asking for the maximum
+    // shared-memory carve-out for the small ones as well spares the SMs a shared-memory / L1 reconfiguration at every kernel boundary
+    // (ENVIDR_LOOP_CARVEOUT=0 keeps the driver's default choice).
+    static int carve = -1;
+    if (carve < 0) {
+        const char* e = getenv("ENVIDR_LOOP_CARVEOUT");
+        carve = (e && e[0] == '0') ? 0 : 1;
+        if (carve) {
+            cudaFuncSetAttribute(k_march_compact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_composite_compact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_render_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_render_finish, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
     const uint32_t march_grid = min(ceil_div(N, kMarchBlock), (uint32_t)kSMs * 8);
     const uint32_t max_iters = opts->max_steps;       // n_step >= 1 per iteration
     static const uint32_t batch = [] { const char* e = getenv("ENVIDR_LOOP_BATCH"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 1 && v <= 64 ? v : 4); }();
