@@ -768,6 +768,11 @@ int envidr_field_forward(const envidr_field* field, const float* xyzs, const flo
 
 int envidr_field_forward_records(const envidr_field* field, const float* rec, const float* r_images, uint32_t M,
                                  const envidr_field_out* out, envidr_stream_t stream) {
+    return envidr_field_forward_records_indexed(field, rec, nullptr, r_images, M, out, stream);
+}
+
+int envidr_field_forward_records_indexed(const envidr_field* field, const float* rec, const int32_t* rec_index, const float* r_images, uint32_t M,
+                                         const envidr_field_out* out, envidr_stream_t stream) {
     ENVIDR_REQUIRE(field && out, ENVIDR_E_BADARG, "null pointer");
     ENVIDR_REQUIRE(field->precision == 1, ENVIDR_E_UNSUPPORTED, "field_forward_records: tensor-core field only (precision = 1)");
     if (M == 0) return 0;
@@ -790,11 +795,11 @@ int envidr_field_forward_records(const envidr_field* field, const float* rec, co
         tcenv.has_rot = 1;
         for (int i = 0; i < 9; i++) tcenv.rot[i] = field->env_rot[i];
     }
-    rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, nullptr, M, st);
+    rc = env_tc_launch(tcenv, field->ide_degree, rec, feat, nullptr, M, st, nullptr, rec_index);
     if (ev) { cudaEventRecord(ev[1], st); timing_commit(); }
     if (rc) return rc;
     g_launches += 2;
-    return shade_tc_launch(tcshade, rec, feat, r_images, nullptr, M, out, st);
+    return shade_tc_launch(tcshade, rec, feat, r_images, nullptr, M, out, st, rec_index);
 }
 
 }  // extern "C"

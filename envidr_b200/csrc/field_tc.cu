@@ -159,7 +159,7 @@ template <int CTAS, bool F8, int MC, bool SAVE = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat, const uint32_t* __restrict__ M_dev, uint32_t M_host,
          unsigned long long* __restrict__ prof, uint32_t prof_cap, const __grid_constant__ CUtensorMap tmap,
-         const __grid_constant__ CUtensorMap tmap1, const TcSave SV) {
+         const __grid_constant__ CUtensorMap tmap1, const TcSave SV, const int32_t* __restrict__ ridx) {
     constexpr int kTcStages = 3;
     constexpr uint32_t kTcStageBytes = kTcRingBytes / kTcStages;
     constexpr int GROUP = CTAS == 2 ? 2 : MC;             // CTAs per cluster
@@ -598,7 +598,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
             const bool valid = m < M;
             float dx = 0.f, dy = 0.f, dz = 1.f, kap = 0.f;
             if (valid) {
-                const float* q = rec + (size_t)m * kTcRecFloats;
+                const float* q = rec + (size_t)(ridx ? (uint32_t)ridx[m] : m) * kTcRecFloats;      // ridx: records stay where the geometry pass logged them
                 dx = q[22 + 3 * branch]; dy = q[23 + 3 * branch]; dz = q[24 + 3 * branch];
                 kap = branch ? q[20] : E.kappa_diffuse;
                 if (E.has_rot) {                                  // v @ rot_theta[:3,:3] (renderer.py:160-161, 171-172)
@@ -852,7 +852,7 @@ static int env_tc_multicast() {
 }
 
 int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st,
-                  const TcSave* save) {
+                  const TcSave* save, const int32_t* ridx) {
     if ((int)ide_degree != g_ide_tc_deg) {
         IdeTables tab;
         if (!ide_build_tables((int)ide_degree, &tab)) return ENVIDR_E_UNSUPPORTED;
@@ -882,7 +882,7 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         }
         const uint32_t grid_s = min((uint32_t)kSMs, n_tiles_host);
         if (grid_s == 0) return 0;
-        k_env_tc<1, false, 1, true><<<grid_s, kTcThreads, kTcSmem, st>>>(t_in, rec, feat, nullptr, M_host, nullptr, 0, g_no_tmap, g_no_tmap, *save);
+        k_env_tc<1, false, 1, true><<<grid_s, kTcThreads, kTcSmem, st>>>(t_in, rec, feat, nullptr, M_host, nullptr, 0, g_no_tmap, g_no_tmap, *save, nullptr);
         return check_launch("env_tc(train forward)");
     }
     static int reorder = -1;
@@ -904,7 +904,7 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false, 1>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, tmap[0], tmap[1], TcSave{});
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_env_tc<2, false, 1>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, tmap[0], tmap[1], TcSave{}, ridx);
         if (e != cudaSuccess) { set_error("env_tc (CTA pair) launch: %s", cudaGetErrorString(e)); return (int)e; }
         return check_launch("env_tc2");
     }
@@ -914,7 +914,7 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
     if (env_tc_mode() == 1) {
         TcEnv t8 = t;
         for (uint32_t i = 0; i < t8.n_layers; i++) if (t8.L[i].f8) t8.L[i].dscale = kF8DScale;
-        k_env_tc<1, true, 1><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
+        k_env_tc<1, true, 1><<<grid, kTcThreads, kTcSmem, st>>>(t8, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{}, ridx);
     } else if (env_tc_multicast() > 1) {
         // weight-multicast clusters (opt-in; measured no faster, run r3_09): whole clusters only; a cluster whose tiles are all past the end returns at once
         const uint32_t mc = (uint32_t)env_tc_multicast();
@@ -926,11 +926,11 @@ int env_tc_launch(const TcEnv& t_in, uint32_t ide_degree, const float* rec, floa
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = mc == 4 ? cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 4>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{})
-                                : cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
+        cudaError_t e = mc == 4 ? cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 4>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{}, ridx)
+                                : cudaLaunchKernelEx(&cfg, k_env_tc<1, false, 2>, t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{}, ridx);
         if (e != cudaSuccess) { set_error("env_tc (multicast cluster) launch: %s", cudaGetErrorString(e)); return (int)e; }
     } else {
-        k_env_tc<1, false, 1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{});
+        k_env_tc<1, false, 1><<<grid, kTcThreads, kTcSmem, st>>>(t, rec, feat, M_dev, M_host, g_prof, g_prof_cap, g_no_tmap, g_no_tmap, TcSave{}, ridx);
     }
     return check_launch("env_tc");
 }

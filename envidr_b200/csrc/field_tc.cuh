@@ -63,7 +63,7 @@ struct TcShade {
 bool shade_tc_layout(const envidr_field* f, uint64_t base_bytes, TcShade* out, uint64_t* total_bytes);
 int shade_tc_pack(const envidr_field* f, const TcShade& s, void* packed, cudaStream_t st);
 int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const float* r_images, const uint32_t* M_dev, uint32_t M_host,
-                    const envidr_field_out* out, cudaStream_t st);
+                    const envidr_field_out* out, cudaStream_t st, const int32_t* ridx = nullptr);
 
 // layout / packing / launch (field_tc.cu)
 bool tc_layout(const envidr_field* f, uint64_t base_bytes, TcEnv* out, uint64_t* total_bytes);
@@ -74,8 +74,9 @@ struct TcSave {
     uint32_t* mask[3];            // their ReLU bit masks, [2M, N_l / 32]
     uint32_t M;
 };
+// ridx (optional): sample m reads record rec[ridx[m]] instead of rec[m] (records left in the geometry pass's log, render.py)
 int env_tc_launch(const TcEnv& t, uint32_t ide_degree, const float* rec, float* feat, const uint32_t* M_dev, uint32_t M_host, cudaStream_t st,
-                  const TcSave* save = nullptr);
+                  const TcSave* save = nullptr, const int32_t* ridx = nullptr);
 int env_tc_mode();               // 0: three fp16 products per K step; 1 (default): fp16 main product + two e4m3 correction products
 
 }  // namespace envidr

@@ -322,18 +322,20 @@ __global__ void __launch_bounds__(kMarchBlock) k_composite_compact(uint32_t N, f
 __global__ void __launch_bounds__(256) k_permute_log(const float4* __restrict__ rec, const float* __restrict__ sigma, const float2* __restrict__ delta,
                                                     const int32_t* __restrict__ ray, const int32_t* __restrict__ seq, uint64_t total,
                                                     const int32_t* __restrict__ ray_offset, float4* __restrict__ rec_out,
-                                                    float* __restrict__ sigma_out, float2* __restrict__ delta_out) {
+                                                    float* __restrict__ sigma_out, float2* __restrict__ delta_out, int32_t* __restrict__ idx_out,
+                                                    uint32_t shift) {
+    // shift = 3: 8 lanes per entry move its 128-byte record; shift = 0 (index mode, rec_out == NULL): one thread per entry
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t g = t >> 3;
-    const uint32_t part = (uint32_t)t & 7u;
+    const uint64_t g = t >> shift;
+    const uint32_t part = (uint32_t)t & ((1u << shift) - 1u);
     if (g >= total) return;
     const int32_t r = ray[g];
     if (r < 0) return;
     const int32_t off = ray_offset[r];
     if (off < 0) return;
     const uint64_t dst = (uint64_t)off + (uint32_t)seq[g];
-    rec_out[dst * 8 + part] = rec[g * 8 + part];
-    if (part == 0) { sigma_out[dst] = sigma[g]; delta_out[dst] = delta[g]; }
+    if (rec_out) rec_out[dst * 8 + part] = rec[g * 8 + part];
+    if (part == 0) { sigma_out[dst] = sigma[g]; delta_out[dst] = delta[g]; if (idx_out) idx_out[dst] = (int32_t)g; }
 }
 
 // image += (1 - ws) * bg ; normal_image <- F.normalize(normal_image, eps=1e-10)   (cuda_ray.py:348-359)
@@ -535,16 +537,32 @@ int envidr_render_rays(const envidr_field* field, const uint8_t* bitfield, const
     return check_launch("render_finish");
 }
 
+static int permute_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out, float* sigma_out, float* delta_out,
+                       int32_t* idx_out, envidr_stream_t stream);
+
 int envidr_permute_sample_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out,
                               float* sigma_out, float* delta_out, envidr_stream_t stream) {
-    ENVIDR_REQUIRE(log && ray_offset && rec_out && sigma_out && delta_out, ENVIDR_E_BADARG, "null pointer");
+    ENVIDR_REQUIRE(rec_out, ENVIDR_E_BADARG, "null pointer");
+    return permute_log(log, total, ray_offset, rec_out, sigma_out, delta_out, nullptr, stream);
+}
+
+int envidr_permute_sample_log_index(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, int32_t* idx_out,
+                                    float* sigma_out, float* delta_out, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(idx_out && total <= 0x7FFFFFFFull, ENVIDR_E_BADARG, "null pointer / more than 2^31 log entries");
+    return permute_log(log, total, ray_offset, nullptr, sigma_out, delta_out, idx_out, stream);
+}
+
+static int permute_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out, float* sigma_out, float* delta_out,
+                       int32_t* idx_out, envidr_stream_t stream) {
+    ENVIDR_REQUIRE(log && ray_offset && sigma_out && delta_out, ENVIDR_E_BADARG, "null pointer");
     ENVIDR_REQUIRE(log->rec && log->sigma && log->delta && log->ray && log->seq, ENVIDR_E_BADARG, "sample log: null buffer");
     ENVIDR_REQUIRE(total <= log->capacity, ENVIDR_E_WORKSPACE, "sample log overflowed its capacity; the pass has to be marched again");
     if (total == 0) return 0;
-    const uint64_t threads = total * 8;
+    const uint32_t shift = rec_out ? 3u : 0u;
+    const uint64_t threads = total << shift;
     k_permute_log<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(log->rec), log->sigma, reinterpret_cast<const float2*>(log->delta), log->ray, log->seq, total,
-        ray_offset, reinterpret_cast<float4*>(rec_out), sigma_out, reinterpret_cast<float2*>(delta_out));
+        ray_offset, reinterpret_cast<float4*>(rec_out), sigma_out, reinterpret_cast<float2*>(delta_out), idx_out, shift);
     g_launches += 1;
     return check_launch("permute_sample_log");
 }

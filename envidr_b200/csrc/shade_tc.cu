@@ -29,7 +29,7 @@ __device__ __forceinline__ float s_sigmoid(float x) { return 1.0f / (1.0f + expf
 //   renv_net    : [ r*vis (3) rho | 0 ... ]   (K = 16)
 __global__ void __launch_bounds__(kSThreads, 1)
 k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restrict__ feat, const float* __restrict__ r_images,
-           const uint32_t* __restrict__ M_dev, uint32_t M_host, const ShadeOutDev O) {
+           const uint32_t* __restrict__ M_dev, uint32_t M_host, const ShadeOutDev O, const int32_t* __restrict__ ridx) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem;
     uint8_t* s_op = smem + S.res_bytes_al;
@@ -112,7 +112,8 @@ k_shade_tc(const TcShade S, const float* __restrict__ rec, const float* __restri
             const uint32_t tile = blockIdx.x + j * gridDim.x;
             const uint32_t m = tile * 128 + row;
             const bool valid = m < M;
-            const float4* q4 = reinterpret_cast<const float4*>(rec + (size_t)min(m, M - 1) * kTcRecFloats);
+            const uint32_t mc = min(m, M - 1);
+            const float4* q4 = reinterpret_cast<const float4*>(rec + (size_t)(ridx ? (uint32_t)ridx[mc] : mc) * kTcRecFloats);
             const float4* f4 = reinterpret_cast<const float4*>(feat + (size_t)min(m, M - 1) * kTcRecFloats);
             float geo[16];                         // geo 0..11, then n.xyz, n.w_o
             {
@@ -315,7 +316,7 @@ int shade_tc_pack(const envidr_field* f, const TcShade& s, void* packed, cudaStr
 }
 
 int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const float* r_images, const uint32_t* M_dev, uint32_t M_host,
-                    const envidr_field_out* out, cudaStream_t st) {
+                    const envidr_field_out* out, cudaStream_t st, const int32_t* ridx) {
     const size_t smem = (size_t)s.res_bytes_al + kSGroups * kSOperand + 128;
     static size_t attr_set = 0;
     if (attr_set < smem) {
@@ -327,7 +328,7 @@ int shade_tc_launch(const TcShade& s, const float* rec, const float* feat, const
     if (!M_dev) grid = min((uint32_t)kSMs, (M_host + 127) / 128);
     if (grid == 0) return 0;
     ShadeOutDev O{out->rgb, out->c_diffuse, out->c_specular};
-    k_shade_tc<<<grid, kSThreads, smem, st>>>(s, rec, feat, r_images, M_dev, M_host, O);
+    k_shade_tc<<<grid, kSThreads, smem, st>>>(s, rec, feat, r_images, M_dev, M_host, O, ridx);
     return check_launch("shade_tc");
 }
 

@@ -204,11 +204,15 @@ def _compact(mask: torch.Tensor, n: int) -> torch.Tensor:
     return out[:n]
 
 
-def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor], M: Optional[int] = None) -> Dict:
+def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ray_idx: Optional[torch.Tensor], M: Optional[int] = None,
+                     indexed: bool = False) -> Dict:
     """Ray-contiguous copy of the logged samples of the rays `ray_idx` (int64 indices into the logged pass's rays, ascending; None =
     all of them): envidr_permute_sample_log.  Nothing here depends on colour, r_images or the light rotation, so one prepared batch
     serves every frame of a relight sweep.  M = number of samples of the selected rays if the caller already knows it (render() reads
-    it back together with the pass statistics); otherwise one host synchronisation (the batch size sizes the buffers)."""
+    it back together with the pass statistics); otherwise one host synchronisation (the batch size sizes the buffers).
+    indexed: leave the 128-byte records in the log and return the log position of every ray-ordered sample instead
+    (envidr_permute_sample_log_index; the shading kernels then read rec[ridx[m]]): for a batch that is shaded ONCE (a frame) this saves
+    reading and writing 256 B per sample; a relight sweep, which shades the same batch for every rotation, keeps the copy."""
     dev = counts.device
     f32 = dict(dtype=torch.float32, device=dev)
     n_all = counts.shape[0]
@@ -223,14 +227,21 @@ def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ra
     else:
         ray_off = torch.full((n_all,), -1, dtype=torch.int32, device=dev)
         ray_off[ray_idx] = off
-    rec = torch.empty(M, 32, **f32)
     sigma, delta = torch.empty(M, **f32), torch.empty(M, 2, **f32)
     lstruct = log.cstruct()
-    check(lib().envidr_permute_sample_log(ctypes.byref(lstruct), total, ptr(ray_off), ptr(rec), ptr(sigma), ptr(delta), stream()),
-          "permute_sample_log")
+    ridx = None
+    if indexed and total < 2 ** 31:
+        rec = log.rec
+        ridx = torch.empty(M, dtype=torch.int32, device=dev)
+        check(lib().envidr_permute_sample_log_index(ctypes.byref(lstruct), total, ptr(ray_off), ptr(ridx), ptr(sigma), ptr(delta), stream()),
+              "permute_sample_log_index")
+    else:
+        rec = torch.empty(M, 32, **f32)
+        check(lib().envidr_permute_sample_log(ctypes.byref(lstruct), total, ptr(ray_off), ptr(rec), ptr(sigma), ptr(delta), stream()),
+              "permute_sample_log")
     # rays of the pass in selected order: (ray id = position among the selected rays, offset, count)
     rays = torch.stack([torch.arange(n_r, dtype=torch.int32, device=dev), off, cs.to(torch.int32)], -1).contiguous()
-    return dict(rec=rec, sigma=sigma, delta=delta, rays=rays, n_r=n_r, M=M)
+    return dict(rec=rec, ridx=ridx, sigma=sigma, delta=delta, rays=rays, n_r=n_r, M=M)
 
 
 def shade_prepared(field: FieldParams, prep: Dict, cfg: RenderConfig, *, bg_color=0.0, r_images: Optional[torch.Tensor] = None,
@@ -251,14 +262,18 @@ def shade_prepared(field: FieldParams, prep: Dict, cfg: RenderConfig, *, bg_colo
         want["c_diffuse"] = torch.empty(M, 3, **f32)
     if "specular" in visual_items:
         want["c_specular"] = torch.empty(M, 3, **f32)
-    rough = rec[:, 20].contiguous() if ("roughness" in visual_items or "specular" in visual_items) else None
+    ridx = prep.get("ridx")
+    rough = None
+    if "roughness" in visual_items or "specular" in visual_items:
+        rough = (rec[:, 20] if ridx is None else rec[ridx.long(), 20]).contiguous()
     if field._scratch is None or field._scratch.numel() < 32 * (M + 2):
         field._scratch = torch.empty(32 * (M + 2), **f32)
     fo = _lib.FieldOut()
     for k, t in want.items():
         setattr(fo, k, t.data_ptr())
     f = field.cstruct(env_rot_radian if rec_unrotated else None, rec_unrotated=rec_unrotated)
-    check(lib().envidr_field_forward_records(ctypes.byref(f), ptr(rec), ptr(r_s), M, ctypes.byref(fo), stream()), "field_forward_records")
+    check(lib().envidr_field_forward_records_indexed(ctypes.byref(f), ptr(rec), ptr(ridx), ptr(r_s), M, ctypes.byref(fo), stream()),
+          "field_forward_records")
     res = {"image": torch.empty(n_r, 3, **f32), "depth": torch.empty(n_r, **f32), "weights_sum": torch.empty(n_r, **f32)}
     if "c_diffuse" in want:
         res["diffuse_image"] = torch.empty(n_r, 3, **f32)
@@ -285,7 +300,7 @@ def render_rays_from_log(field: FieldParams, log: SampleLogBuffers, total: int, 
     """A pass shaded from a geometry-only pass's sample log: gather ray by ray (prepare_from_log), shade from the geometry records and
     composite (shade_prepared).  counts [N_all] = samples composited per ray of the logged pass; r_images [n_selected, 4] in the order
     of ray_idx.  Returns per-selected-ray images."""
-    return shade_prepared(field, prepare_from_log(log, total, counts, ray_idx, M), cfg, bg_color=bg_color, r_images=r_images,
+    return shade_prepared(field, prepare_from_log(log, total, counts, ray_idx, M, indexed=True), cfg, bg_color=bg_color, r_images=r_images,
                           visual_items=visual_items)
 
 

@@ -313,10 +313,18 @@ int envidr_march_rays_replay(const float* rays_o, const float* rays_d, const uin
  * sample counts over the rays of the next pass, -1 for rays that are not part of it. */
 int envidr_permute_sample_log(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, float* rec_out,
                               float* sigma_out, float* delta_out, envidr_stream_t stream);
+/* Index form: instead of copying the 128-byte records, idx_out [M] receives the log position of every ray-ordered sample (sigma / delta are
+ * still gathered: the compositor walks them sequentially); use with envidr_field_forward_records_indexed. */
+int envidr_permute_sample_log_index(const envidr_sample_log* log, uint64_t total, const int32_t* ray_offset, int32_t* idx_out,
+                                    float* sigma_out, float* delta_out, envidr_stream_t stream);
 /* env_net + shading heads on precomputed geometry records (tensor-core field only): rec [M,32], r_images [M,4] or NULL;
  * writes out->rgb (and c_diffuse / c_specular when set).  field->scratch needs 128 B per sample. */
 int envidr_field_forward_records(const envidr_field* field, const float* rec, const float* r_images, uint32_t M,
                                  const envidr_field_out* out, envidr_stream_t stream);
+/* The same with the records left where the geometry pass logged them: sample m uses rec[rec_index[m]] (rec_index from
+ * envidr_permute_sample_log_index; saves copying 128 B per sample into ray order).  rec_index == NULL: as above. */
+int envidr_field_forward_records_indexed(const envidr_field* field, const float* rec, const int32_t* rec_index, const float* r_images, uint32_t M,
+                                         const envidr_field_out* out, envidr_stream_t stream);
 /* dst[offset_n + s, 0:4] = src[ray_n, 0:4] for every sample of every ray in `rays` [N,3] (per-ray r_images -> per-sample rows). */
 int envidr_scatter_ray_rows4(const int32_t* rays, uint32_t N, uint32_t M, const float* src /* [N,4] */, float* dst /* [M,4] */,
                              envidr_stream_t stream);
