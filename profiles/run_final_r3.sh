@@ -13,7 +13,7 @@ timeout 120 python profiles/env_timeline.py > $OUT/${TAG}_env_timeline.txt 2>&1
 timeout 300 python profiles/train_profile.py > $OUT/${TAG}_train_profile.txt 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 $NOX > $OUT/${TAG}_launches.log 2>&1
 python profiles/summarize_launches.py $OUT/${TAG}_launches.csv --frames > $OUT/${TAG}_launches.md 2>&1; head -14 $OUT/${TAG}_launches.md
-for KS in k_env_tc:5 k_geom_tc:60 k_shade_tc:5; do
+for KS in k_env_tc:5 k_geom_tc:30 k_shade_tc:5; do
   K=${KS%%:*}; S=${KS##*:}
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $S --launch-count 1 -f -o $OUT/${TAG}_$K python bench.py --steps 1 --warmup 3 $NOX > $OUT/${TAG}_full_$K.log 2>&1
   echo "ncu full $K exit $?"
