@@ -137,3 +137,25 @@ assert worst <= BOUND, worst
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "WORST" in r.stdout
+
+
+@pytest.mark.parametrize("layers", [2, 3, 5, 6])
+def test_env_kernel_layer_counts(dev, layers):
+    """k_env_tc issues the NEXT tile's layer 0 ahead of the last layer and parks the last layer's accumulator in the buffer of the layer
+    before it; which buffer is free depends on the parity of the layer count (field_tc.cu, acc_buf).  env_net with 2, 3, 5 and 6 layers
+    (the shipped scenes have 4) against the FFMA path, several tiles per SM so that consecutive tiles of one CTA overlap."""
+    from envidr_b200 import scene
+    fp_cpu = scene.make_synthetic_field(2, hidden_dim_env=256, ide_degree=5)
+    e = fp_cpu.env                                   # 72 -> 256 -> 256 -> 256 -> 12
+    g = torch.Generator().manual_seed(layers)
+    extra = lambda: ((torch.rand(256, 256, generator=g) * 2 - 1) * (6.0 / 512) ** 0.5, torch.randn(256, generator=g) * 0.05)
+    mid = {2: [], 3: [e[1]], 5: [e[1], e[2], extra()], 6: [e[1], e[2], extra(), extra()]}[layers]
+    fp_cpu.env = [e[0]] + mid + [e[3]]
+    M = 64 * 148 * 3 + 11
+    x, d = _samples(M, 1)
+    xt, dt = torch.from_numpy(x).to(dev), torch.from_numpy(d).to(dev)
+    fp_cpu.precision = "fp32"
+    ref = fp_cpu.to(dev).pack().forward(xt, dt, want=("rgb",))["rgb"]
+    fp_cpu.precision = "tc"
+    out = fp_cpu.to(dev).pack().forward(xt, dt, want=("rgb",))["rgb"]
+    assert (out - ref).abs().max().item() <= 3e-5
