@@ -31,14 +31,14 @@ def _ref64(enc, normals, w_r, rough, layers, deg, kappa, lis):
     return outs
 
 
-@pytest.mark.parametrize("width,deg,M", [(256, 5, 5000), (64, 4, 300), (160, 4, 64 * 148 + 9)])
-def test_fused_env_forward_backward_match_float64(dev, width, deg, M):
+@pytest.mark.parametrize("width,deg,M,depth", [(256, 5, 5000, 4), (64, 4, 300, 4), (160, 4, 64 * 148 + 9, 4), (256, 5, 1500, 3), (128, 4, 700, 2)])
+def test_fused_env_forward_backward_match_float64(dev, width, deg, M, depth):
     from envidr_b200 import env_train, ide_encoder
     g = torch.Generator().manual_seed(width + M)
     P2 = 2 * (2 ** deg - 1 + deg)
-    dims = [P2, width, width, width, 12]
+    dims = [P2] + [width] * (depth - 1) + [12]
     layers64 = []
-    for i in range(4):
+    for i in range(depth):
         a = (6.0 / (dims[i] + dims[i + 1])) ** 0.5
         W = ((torch.rand(dims[i + 1], dims[i], generator=g, dtype=torch.float64) * 2 - 1) * a).requires_grad_(True)
         b = (torch.randn(dims[i + 1], generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
