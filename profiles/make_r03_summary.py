@@ -30,7 +30,9 @@ A(f"`k_env_tc` share under ncu {m.group(1) if m else '?'} %; in the bench line (
 A(f"## 3. `ncu --set full --clock-control none` captures (profiles/ncu_keys.py; inference kernels {T}, training kernels {T} / r3f)\n\n```\n" + open(KEYS).read().strip() + "\n```\n")
 A("""Reading: `k_env_tc` (main-pass launch, ~4.25 M samples): DRAM ~545 MB read + ~498 MB written for 0.95 GB algorithmic (ratio 1.1), tensor-memory pipe ~62 % of
 elapsed cycles, `sm__pipe_tensor_cycles_active_realtime` 50.8 % of elapsed (raw page of r3j_k_env_tc.ncu-rep; 53 % in round 1), issue slots ~37 %, shared-memory bank
-conflicts 217.6 M of 559.8 M LSU wavefronts = 38.9 % (loads 168.1 M, stores 49.3 M; 822.8 M tensor-core operand wavefronts go through the same port conflict-free).  `k_env_tc<SAVE>` (training forward, 70 k samples = 140 k rows): adds 430 MB of activation stores and 4.5 MB of masks.
+conflicts 217.6 M of 559.8 M LSU wavefronts = 38.9 % by the raw counter (loads 168.1 M, stores 49.3 M; 822.8 M tensor-core operand wavefronts go through the same port).  The source page
+attributes only 36.7 M excessive wavefronts to SASS instructions, ALL of them the IDE warps' 4-byte operand stores (STS at the layer-0 operand buffers, 4-way: rows 8 apart share a bank); the
+epilogue's 16-byte operand stores and bias loads are conflict-free, so what the code controls is 6.5 % of the LSU wavefronts, on warps that have ~4x the time they need.  `k_env_tc<SAVE>` (training forward, 70 k samples = 140 k rows): adds 430 MB of activation stores and 4.5 MB of masks.
 `k_chain_tc<0>` (= `k_env_bwd_tc` in the r3f build; training backward of env_net): 253 us, 431 MB written (three [140 k, 256] fp32 gradient tensors + d y + d x0 = 476 MB
 algorithmic) at 1.9 TB/s, a 7-tile-per-SM launch with the forward kernel's per-tile latency chain; no shared-memory bank conflicts (5 k of 3.8 M wavefronts).\n""")
 A("## 4. k_env_tc: clock64 timeline of CTA 0 and timing experiments\n")
