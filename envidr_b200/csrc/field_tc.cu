@@ -180,7 +180,8 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
     uint64_t* ide_empty = acc_ready + 3;             // issuer -> IDE warps (layer-0 MMAs retired)
     uint64_t* a_rdy = acc_ready + 4;                 // [8] epilogue warps -> issuer: 32-column chunk c of the next A operand is in
                                                      //     shared memory (128 arrivals per CTA: the 4 warps that own chunk parity c & 1)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 8);
+    uint64_t* last_read = a_rdy + 8;                 // epilogue group 1 -> issuer: the last layer's accumulator is in registers (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_rdy + 9);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay uniform (UR datapath)
@@ -220,6 +221,7 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
         // cluster-scope arrive to the leader (+1 below) instead of 128 / 512 remote arrives serialising on the leader's barrier
         const uint32_t fwd = (CTAS == 2 && rank == 0) ? 1u : 0u;
         for (int i = 0; i < 8; i++) tc::mbar_init(&a_rdy[i], 128 + fwd);
+        tc::mbar_init(last_read, 128);
         tc::mbar_init(ide_full, kTcIdeThreads + fwd);
         tc::mbar_init(ide_empty, 1);
         tc::mbar_fence_init();
@@ -446,8 +448,11 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                 if (l == nl - 1) w_a = w_f = 0;
             }
         };
-        uint32_t ti = 0;
+        uint32_t ti = 0, last_par = 0;
         for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ti++) {
+            // the last layer of the previous tile sits in an accumulator that one of this tile's layers overwrites; its epilogue is run by
+            // group 1 while group 0 already converts this tile's layer 0 (below), so "chunk 0 is ready" no longer implies "read"
+            if (CTAS == 1 && ti > 0) { tc::mbar_wait(last_read, last_par); last_par ^= 1; }
             if (unit == unit0 || !early_l0) issue_layer(0, ti);
             for (int l = 1; l < nl - 1; l++) issue_layer(l, ti);
             if (early_l0 && unit + unit_step < n_units) issue_layer(0, ti + 1);
@@ -558,10 +563,15 @@ k_env_tc(const TcEnv E, const float* __restrict__ rec, float* __restrict__ feat,
                         arrive_issuer(a_rdy_addr + cb * 8, 1 + g, 128, quarter == 0 && lane == 0);         // chunk cb of the next layer's A operand is ready
                         if (prof && l == 1 && lane == 0 && quarter == 0 && (cb >> 1) < 4) stamp(ti, (g ? 37 : 33) + (cb >> 1), clock64());
                     }
-                } else if (g4 == 0) {
+                } else if (CTAS == 1 ? g == 1 : g == 0) {
+                    // last layer: 16 columns.  Run by group 1 (one CTA per tile): group 0, which owns chunk 0 of every layer, goes straight on
+                    // to the next tile's layer-0 epilogue -- its accumulator has been ready since before this tile's last hidden layer was
+                    // drained -- so the next tile's layer 1 starts ~1 k cycles earlier.  Both groups have passed acc_ready of this layer, i.e.
+                    // its MMAs no longer read the A operand the next epilogue overwrites.
                     uint32_t r[16];
                     tc::tmem_ld16(acc, r);
                     tc::tmem_ld_wait();
+                    if (CTAS == 1) { tc::tc_fence_before(); tc::mbar_arrive(last_read); }      // the accumulator may be overwritten from here on
                     const int Ef = (int)E.E;
                     float f[16], ss = 0.f;
                     #pragma unroll
