@@ -6,8 +6,8 @@ import re
 import subprocess
 import sys
 
-T = sys.argv[1] if len(sys.argv) > 1 else "r3j"
-KEYS = sys.argv[2] if len(sys.argv) > 2 else "/tmp/r3j_keys.txt"
+T = sys.argv[1] if len(sys.argv) > 1 else "r3k"
+KEYS = sys.argv[2] if len(sys.argv) > 2 else "/tmp/r3k_keys.txt"
 G = "gpurun_out/"
 out = []
 A = out.append
@@ -29,7 +29,7 @@ m = re.search(r"k_env_tc[^|]*\|[^|]*\|[^|]*\|\s*([0-9.]+)%", open(f"{G}{T}_launc
 A(f"`k_env_tc` share under ncu {m.group(1) if m else '?'} %; in the bench line (`roofline.kernel_share_of_step`, CUDA events) {100 * d['roofline']['kernel_share_of_step']:.1f} %.\n")
 A(f"## 3. `ncu --set full --clock-control none` captures (profiles/ncu_keys.py; inference kernels {T}, training kernels {T} / r3f)\n\n```\n" + open(KEYS).read().strip() + "\n```\n")
 A("""Reading: `k_env_tc` (main-pass launch, ~4.25 M samples): DRAM ~545 MB read + ~498 MB written for 0.95 GB algorithmic (ratio 1.1), tensor-memory pipe ~62 % of
-elapsed cycles, `sm__pipe_tensor_cycles_active_realtime` 50.8 % of elapsed (raw page of r3j_k_env_tc.ncu-rep; 53 % in round 1), issue slots ~37 %, shared-memory bank
+elapsed cycles, `sm__pipe_tensor_cycles_active_realtime` 50.8 % of elapsed (raw page of the r3j capture; 53 % in round 1), issue slots ~37 %, shared-memory bank
 conflicts 217.6 M of 559.8 M LSU wavefronts = 38.9 % by the raw counter (loads 168.1 M, stores 49.3 M; 822.8 M tensor-core operand wavefronts go through the same port).  The source page
 attributes only 36.7 M excessive wavefronts to SASS instructions, ALL of them the IDE warps' 4-byte operand stores (STS at the layer-0 operand buffers, 4-way: rows 8 apart share a bank); the
 epilogue's 16-byte operand stores and bias loads are conflict-free, so what the code controls is 6.5 % of the LSU wavefronts, on warps that have ~4x the time they need.  `k_env_tc<SAVE>` (training forward, 70 k samples = 140 k rows): adds 430 MB of activation stores and 4.5 MB of masks.
@@ -43,7 +43,7 @@ A("""=> the tile is a latency chain: with a third of the MMA work, no weight tra
 real kernel).  Layer-2 detail of the timeline: the epilogue publishes a chunk pair (64 columns) every ~900 cycles whether 8 or 16 warps convert (r3_11 / r3_12), and the
 issuer needs ~850 cycles per chunk (two K steps behind a ring handshake of ~310-425 cycles each).\n""")
 A("Variants measured this session (frame = bench.py --no-cpu-baseline --no-gpu-reference --no-train --no-density --no-sweep, `k_env_tc` ms per frame from CUDA events; boxes differ by ~2 %):\n")
-A("| build | k_env_tc ms / frame | frame ms | run |\n|---|---:|---:|---|\n| start of session (round-2 build) | 8.04 | 15.96 | r3_02 (c1) |\n| CTA pair without relay warps (tensor-map TMA signalling the leader, named barrier + one remote arrive), 3 x 16 KB ring | 8.68 (9.39 with relays) | 16.71 | r3_01 |\n| + IDE warps sleeping while an epilogue drains (removed) | 8.04 | 15.96 | r3_02 |\n| + next tile's layer 0 issued ahead of the 16-wide last layer (kept) | 7.61 - 7.91 | 15.47 - 15.90 | r3_03, r3_14, r3_17, r3f |\n| + 6 x 8 KB ring stages, hi / lo halves of a K step separately (removed) | 8.02 | 15.87 | r3_04 |\n| + 16 epilogue warps on 16-column halves, 12 IDE warps (removed) | 7.90 | 15.76 | r3_12 |\n| weight multicast across clusters of 2 / 4 CTAs (opt-in) | same as default / 1.7x slower (2 M-sample forward 4.98 vs 4.94 / 8.43 ms) | | r3_09 |\n| + n_step cap 16 / secondary floor 8 in the logged geometry passes (kept; not a k_env_tc change) | 7.74 - 7.87 | 15.30 - 15.40 | r3_23, r3g |\n| + 2 host synchronisations per frame instead of 6 (kept, neutral) | 7.84 | 15.38 | r3_28 |\n| + records read in place through an index instead of a ray-ordered copy (kept) | 7.78 - 7.91 | 15.19 - 15.33 | r3_29, r3j |\n")
+A("| build | k_env_tc ms / frame | frame ms | run |\n|---|---:|---:|---|\n| start of session (round-2 build) | 8.04 | 15.96 | r3_02 (c1) |\n| CTA pair without relay warps (tensor-map TMA signalling the leader, named barrier + one remote arrive), 3 x 16 KB ring | 8.68 (9.39 with relays) | 16.71 | r3_01 |\n| + IDE warps sleeping while an epilogue drains (removed) | 8.04 | 15.96 | r3_02 |\n| + next tile's layer 0 issued ahead of the 16-wide last layer (kept) | 7.61 - 7.91 | 15.47 - 15.90 | r3_03, r3_14, r3_17, r3f |\n| + 6 x 8 KB ring stages, hi / lo halves of a K step separately (removed) | 8.02 | 15.87 | r3_04 |\n| + 16 epilogue warps on 16-column halves, 12 IDE warps (removed) | 7.90 | 15.76 | r3_12 |\n| weight multicast across clusters of 2 / 4 CTAs (opt-in) | same as default / 1.7x slower (2 M-sample forward 4.98 vs 4.94 / 8.43 ms) | | r3_09 |\n| + n_step cap 16 / secondary floor 8 in the logged geometry passes (kept; not a k_env_tc change) | 7.74 - 7.87 | 15.30 - 15.40 | r3_23, r3g |\n| + 2 host synchronisations per frame instead of 6 (kept, neutral) | 7.84 | 15.38 | r3_28 |\n| + records read in place through an index instead of a ray-ordered copy (kept) | 7.78 - 7.91 | 15.19 - 15.33 | r3_29, r3j |\n| + 16-column accumulator read-out with the next tcgen05.ld in flight / no proxy fence (timing experiment) / critical warps on the highest ids (all reverted, neutral) | 7.92 - 7.93 | 15.24 - 15.28 | r3_30, r3_31 |\n| + last layer's epilogue on epilogue group 1, group 0 goes straight to the next tile's layer 0 (kept) | 7.74 - 7.78 | 15.03 - 15.22 | r3_32, r3k |\n")
 A("## 5. Frame phases, fixed cost per frame, batching of the logged passes\n")
 A("`profiles/frame_phases.py` (CUDA events around the phases of `render.render`, 800x800): before the index form of the log gather (run r3_25) and after (run r3_29):\n\n```\n" + open(f"{G}r3_25_phases.txt").read().strip().splitlines()[-1] + "\n" +
   "frame 15.41 ms | render_rays 3.12, last_stats 0.02, render_rays 1.30, last_stats 0.01, prepare_from_log 0.12, shade_prepared 2.23, prepare_from_log 0.16, shade_prepared 7.67 | rest 0.78 ms\n```\n")
