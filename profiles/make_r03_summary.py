@@ -63,7 +63,8 @@ A("ncu over 12 mid-loop launches (`--launch-skip 120 --launch-count 12`), averag
 A("## 8. Fitted scene (run r3_26; `fitted_scene` key of the bench line above)\n\n```\n" + open(f"{G}r3_26_fit.txt").read().strip().split("\n", 3)[-1] + "\n```\n")
 A("## 9. Multi-GPU runs of the session (gpurun --gpus N; `torchrun ... bench.py --gpus N --steps 6 --warmup 3`)\n")
 for name, f in (("N = 2 (run r3h)", f"{G}r3h_bench_n2.json"), ("N = 8 before the gather kernel (run r3h: torch index_select de-interleave, every rank reads the frame back in e2e)", f"{G}r3h_bench_n8.json"),
-                ("N = 8 with envidr_gather_rows and the e2e read-back on rank 0 (run r3i)", f"{G}r3i_bench_n8.json")):
+                ("N = 8 with envidr_gather_rows and the e2e read-back on rank 0 (run r3i)", f"{G}r3i_bench_n8.json"),
+                ("N = 4, final build (run r3l)", f"{G}r3l_bench_n4.json")):
     A(f"### {name}\n\n```json\n" + last(f) + "\n```\n")
 A("`profiles/shard_breakdown.py` at N = 8 (run r3_27, before the gather kernel): per rank (frame ms, render ms):\n\n```\n" + "\n".join(l for l in open(f"{G}r3_27_shard8.txt").read().splitlines() if l.startswith("world") or l.startswith("   max")) + "\n```\n")
 A("`profiles/gather_pieces.py` at N = 2 (`[1.28 M, 8]` fp32 per rank): pack 0.077 ms, all_gather_into_tensor 0.120 ms, torch index_select 1.326 ms, slicing 0.003 ms -> the de-interleave is now `envidr_gather_rows` (one float4 per thread).\n")
