@@ -100,6 +100,16 @@ def render_rays(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor
     f32 = dict(dtype=torch.float32, device=dev)
     out = _lib.RenderOut()
     res: Dict[str, torch.Tensor] = {}
+    if N == 0:                                       # empty ray set (e.g. no pixel of a frame qualifies for the reflected pass): empty outputs
+        res = {"depth": torch.empty(0, **f32), "weights_sum": torch.empty(0, **f32), "normal_image": torch.empty(0, 3, **f32)}
+        if not geometry_only:
+            res["image"] = torch.empty(0, 3, **f32)
+            for k, c in (("diffuse", 3), ("specular", 3), ("roughness", 1)):
+                if k in visual_items:
+                    res[f"{k}_image"] = torch.empty(0, c, **f32)
+        if sample_count or log is not None:
+            res["sample_count"] = torch.empty(0, dtype=torch.int32, device=dev)
+        return res
     res["depth"] = torch.empty(N, **f32)
     res["weights_sum"] = torch.empty(N, **f32)
     if not geometry_only:
@@ -230,7 +240,9 @@ def prepare_from_log(log: SampleLogBuffers, total: int, counts: torch.Tensor, ra
     sigma, delta = torch.empty(M, **f32), torch.empty(M, 2, **f32)
     lstruct = log.cstruct()
     ridx = None
-    if indexed and total < 2 ** 31:
+    if M == 0:                                       # no composited sample among the selected rays: nothing to gather
+        rec = torch.empty(0, 32, **f32)
+    elif indexed and total < 2 ** 31:
         rec = log.rec
         ridx = torch.empty(M, dtype=torch.int32, device=dev)
         check(lib().envidr_permute_sample_log_index(ctypes.byref(lstruct), total, ptr(ray_off), ptr(ridx), ptr(sigma), ptr(delta), stream()),
@@ -252,6 +264,13 @@ def shade_prepared(field: FieldParams, prep: Dict, cfg: RenderConfig, *, bg_colo
     rec, sigma, delta, rays, n_r, M = (prep[k] for k in ("rec", "sigma", "delta", "rays", "n_r", "M"))
     dev = rec.device
     f32 = dict(dtype=torch.float32, device=dev)
+    if M == 0:                                       # rays without a single composited sample: empty images over the background
+        bg0 = bg_color if torch.is_tensor(bg_color) else torch.tensor(bg_color, **f32)
+        res = {"image": torch.zeros(n_r, 3, **f32) + bg0, "depth": torch.zeros(n_r, **f32), "weights_sum": torch.zeros(n_r, **f32), "_samples": 0}
+        for k, c in (("diffuse", 3), ("specular", 3), ("roughness", 1)):
+            if k in visual_items or (k == "roughness" and "specular" in visual_items):
+                res[f"{k}_image"] = torch.zeros(n_r, c, **f32)
+        return res
     r_s = None
     if r_images is not None:
         r_s = torch.empty(M, 4, **f32)
@@ -477,11 +496,15 @@ def render(field: FieldParams, bitfield: torch.Tensor, rays_o: torch.Tensor, ray
                               get_normal_image=False, max_steps=cfg.indir_max_steps, min_near=dt * 2,
                               n_step_floor=cfg.secondary_n_step_floor)
             if stats is not None:
-                stats.append(last_stats())
+                stats.append(last_stats() if n_sec > 0 else dict(iterations=0, samples=0))
         ref_image = torch.cat([ref["image"], ref["weights_sum"][:, None]], -1)
         r_img = ref_image.new_zeros(ray_idx.shape[0], 4)
         r_img[pos_in_ray[ref_idx]] = ref_image                              # == r_img[ref_mask[ray_mask]] = ref_image (renderer.py:484-486)
-        if reuse:
+        if n_ray == 0:                                                      # nothing on screen: the main pass has no ray
+            main = {"image": normals.new_zeros(0, 3), "weights_sum": normals.new_zeros(0)}
+            if stats is not None:
+                stats.append(dict(iterations=0, samples=0))
+        elif reuse:
             main = render_rays_from_log(field, log, geo_stats["samples"], geo["sample_count"], ray_idx, cfg, bg_color=0.0, r_images=r_img,
                                         visual_items=visual_items, M=m_main)
             if stats is not None:

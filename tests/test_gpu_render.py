@@ -336,3 +336,22 @@ def test_batching_of_the_logged_passes_does_not_change_the_frame(dev):
         assert torch.equal(d[0][k], out["ref_cap_floor1"][0][k]), k
     assert d[1][0]["iterations"] < r[1][0]["iterations"] and r[1][0]["samples"] <= d[1][0]["samples"] <= 1.1 * r[1][0]["samples"]
     assert d[1][2]["samples"] == r[1][2]["samples"]                      # the main pass shades the same composited samples
+
+
+def test_three_pass_frame_with_no_hit_at_all(dev):
+    """Every ray misses the object (camera looking away): both index lists of the indirect-reflection frame are empty, the secondary pass
+    has nothing to trace and the main pass nothing to shade -- background everywhere, no crash, default (batched) and reference schedule."""
+    from envidr_b200 import render, scene
+    fp = scene.make_synthetic_field(0, hidden_dim_env=64, ide_degree=4)
+    fp.precision = "tc"
+    fp = fp.to(dev).pack()
+    bft = torch.from_numpy(scene.make_bitfield()).to(dev)
+    ro, rd = [t.to(dev) for t in scene.camera_rays(32, 32)]
+    rd = -rd                                                   # look away from the scene
+    for kw in ({}, dict(replay_main_pass=False, secondary_n_step_floor=1)):
+        out = render.render(fp, bft, ro, rd, render.RenderConfig(indir_ref=True, **kw), bg_color=[0.2, 0.4, 0.6])
+        assert float(out["weights_sum"].abs().max()) == 0.0
+        want = torch.tensor([0.2, 0.4, 0.6], device=dev).expand(32 * 32, 3)
+        assert torch.equal(out["image"], want)
+    one = render.render(fp, bft, ro, rd, render.RenderConfig(), bg_color=1.0)
+    assert float(one["weights_sum"].abs().max()) == 0.0 and float((one["image"] - 1.0).abs().max()) == 0.0
